@@ -1,0 +1,249 @@
+/*
+ * msort.h — C ABI of libmsort.so, the B200 (sm_100a) batched simulator for the
+ * step()/reset() dynamics of MARL-SortingEnv's Env_1_Sorting / Env_2_Pressing /
+ * Env_3_Monolith.
+ *
+ * Boundary.  The reference has no FFI: its boundary is the Gymnasium
+ * surface of three Python classes.  Each entry point below replaces the reference
+ * interface cited next to it ("ref:" paths are relative to the reference checkout).
+ * A maintainer binds these with ctypes; the in-repo Python host
+ * (marl-sortingenv_b200/) is exactly such a binding.
+ *
+ * Ownership.  Every device buffer (state, actions, obs, reward, flags, masks, replay
+ * streams, stats) is allocated by the CALLER (torch tensors in the Python host) and
+ * passed as a raw device pointer.  The library allocates only its small host handle.
+ * It never frees caller memory and never synchronises the device, except in
+ * msort_sync_check().
+ *
+ * Errors.  Every call returns 0 (MSORT_OK) or a negative msort_status; the text is in
+ * msort_last_error() (thread-local).  No C++ exception crosses the ABI.  There is NO
+ * CPU fallback: msort_create() fails unless the device reports compute capability 10.x.
+ *
+ * Threading.  A handle is not thread-safe; distinct handles are independent.
+ */
+#ifndef MSORT_H_
+#define MSORT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSORT_ABI_VERSION 1
+
+/* ------------------------------------------------------------------ enums */
+typedef enum msort_status {
+  MSORT_OK = 0,
+  MSORT_E_INVALID = -1,     /* bad argument (null, misaligned, out of range, bad struct_size) */
+  MSORT_E_UNSUPPORTED = -2, /* configuration the device path does not implement             */
+  MSORT_E_NO_DEVICE = -3,   /* no CUDA device / not compute capability 10.x                 */
+  MSORT_E_CUDA = -4,        /* CUDA runtime error (launch, sticky fault)                    */
+  MSORT_E_REPLAY = -5       /* replay stream exhausted / missing in REPLAY mode             */
+} msort_status;
+
+/* ref: `name` attribute "sort" / "press" / "mono" (env_1_sort.py:26, env_2_press.py:26,
+ * env_monolith.py:28) */
+typedef enum msort_env_kind { MSORT_ENV_SORT = 1, MSORT_ENV_PRESS = 2, MSORT_ENV_MONO = 3 } msort_env_kind;
+
+/* Random source of the plant.
+ *  PHILOX : counter-based Philox4x32-10 keyed by cfg.seed, counter =
+ *           (global env id, draw block, episode, step) — production mode; same
+ *           distributions as the reference's numpy streams, different bits.
+ *  REPLAY : consumes streams recorded from the reference's own numpy generators
+ *           (ref: env_super.py:170-174) so both implementations can be compared
+ *           bit for bit. */
+typedef enum msort_rng_mode { MSORT_RNG_PHILOX = 0, MSORT_RNG_REPLAY = 1 } msort_rng_mode;
+
+enum {
+  /* ref: step(..., use_action_masking=True) — env_2_press.py:88, env_monolith.py:109 */
+  MSORT_F_ACTION_MASKING = 1u << 0,
+  /* ref: step(..., check_overflow=False) — env_1_sort.py:133, env_2_press.py:145, env_monolith.py:265 */
+  MSORT_F_CHECK_OVERFLOW = 1u << 1,
+  /* SB3 VecEnv semantics: on `terminated` keep the terminal obs aside and reset() unseeded */
+  MSORT_F_AUTO_RESET = 1u << 2,
+  /* Env_2 only: sort mode from the embedded MLP (ref: env_2_press.py:106-109) instead of
+   * sorting_rules() (ref: env_2_press.py:112, env_super.py:469-482) */
+  MSORT_F_SORT_POLICY_MLP = 1u << 3
+};
+
+#define MSORT_OBS_DIM_SORT 13
+#define MSORT_OBS_DIM_PRESS 16
+#define MSORT_OBS_DIM_MONO 29
+#define MSORT_NUM_ACTIONS_SORT 2
+#define MSORT_NUM_ACTIONS_PRESS 11
+#define MSORT_NUM_ACTIONS_MONO 22
+#define MSORT_POLICY_WEIGHTS 1570 /* 13*32+32 + 32*32+32 + 32*2+2 ; ref: training.py:115 */
+#define MSORT_NUM_STATS 16
+
+/* ------------------------------------------------------------------ config */
+/* All live config.yml scalars + ctor arguments.
+ * ref: Env_Super.__init__ (env_super.py:25-137), config.yml:1-59. */
+typedef struct msort_config {
+  uint32_t struct_size;        /* = sizeof(msort_config_t) */
+  int32_t env_kind;            /* msort_env_kind */
+  int64_t num_envs;            /* N on this device */
+  int64_t global_env_offset;   /* global id of local env 0 (multi-GPU sharding; Philox counter) */
+  int32_t max_steps;           /* ctor max_steps (env_1_sort.py:19) */
+  uint32_t flags;              /* MSORT_F_* */
+  int32_t rng_mode;            /* msort_rng_mode */
+  int32_t reserved0;
+  uint64_t seed;               /* Philox key */
+  /* simulation: */
+  int32_t input_batch_size;    /* simulation.input_batch_size (env_super.py:33,445) ; <= 255 */
+  int32_t steps_per_pattern;   /* 20: the generator is rebuilt by every reset() with its ctor
+                                  default (env_super.py:375, input_generator.py:15) */
+  int32_t pattern_counts[2][4];/* floor(ratio*batch) for pattern 1 / 2 (input_generator.py:17-20,49) */
+  /* sorting_station: */
+  double baseline_accuracy[4]; /* env_super.py:58 */
+  double boost;                /* env_super.py:59 */
+  double noise;                /* ctor noise_sorting or sorting_station.noise (env_super.py:71) */
+  int32_t stage_capacity;      /* env_super.py:62 (obs normaliser) */
+  /* pressing_station: */
+  int32_t press_time[2];       /* env_super.py:97 */
+  int32_t container_capacity;  /* env_super.py:99 */
+  int32_t bale_size;           /* ctor balesize or bale_standard_size (env_super.py:87) */
+  int32_t reserved1;
+  double bale_remainder_threshold; /* env_super.py:88 */
+  double quality_threshold[4];     /* env_super.py:98 */
+  /* rewards: */
+  double purity_theta;         /* env_super.py:119 */
+  double purity_scaling;       /* 2.0, hard-coded at env_super.py:971 */
+  double tanh_temperature;     /* env_super.py:124 */
+  double overflow_penalty_catastrophic; /* env_super.py:1023 */
+  double overflow_penalty_severe;       /* env_super.py:1025 */
+  double overflow_penalty_mild;         /* env_super.py:1027 */
+  double bale_efficiency_factor;        /* env_super.py:1059 */
+  double max_state_reward;              /* env_super.py:132 */
+  double overflow_termination_penalty;  /* env_super.py:133 */
+} msort_config_t;
+
+/* ------------------------------------------------------------------ plain state */
+/* One env's full plant state as plain integers/doubles — the exchange format of
+ * msort_export_state()/msort_import_state() and the native state of the CPU oracle.
+ * ref: the attributes set in Env_Super.reset (env_super.py:365-420). */
+typedef struct msort_env_state {
+  int32_t input[4], belt[4], sorting[4]; /* current_material_{input,belt,sorting}            */
+  int32_t cont_true[4], cont_false[4];   /* container_materials[m], [m+"_False"]              */
+  int32_t cont_e;                        /* container_materials["E"]                          */
+  int32_t press_timer[2];                /* press_state["press_i"]                            */
+  int32_t press_mat[2];                  /* press_state["material_i"] as index 0..4 (0 if idle)*/
+  int32_t press_n[2];                    /* press_state["n_i"]                                */
+  int32_t press_q[2];                    /* rint(press_state["q_i"]*100), 0..100              */
+  int32_t last_press_started;            /* _last_press_started                               */
+  int32_t last_press_amount;             /* _last_press_amount                                */
+  int32_t gen_first;                     /* input_generator.pattern_sequence[0] : 1 or 2      */
+  int32_t gen_idx;                       /* input_generator.current_pattern_idx               */
+  int32_t gen_counter;                   /* input_generator.step_counter                      */
+  int32_t step;                          /* current_step                                      */
+  int32_t episode;                       /* resets seen (Philox counter word)                 */
+  int32_t sensor_mode;                   /* sensor_current_setting                            */
+  int32_t replay_cursor;                 /* next unread element of the redistribution stream  */
+  int32_t bale_n[5];                     /* len(bale_count[m])                                */
+  int32_t bale_last_size[5];             /* bale_count[m][-1][0]                              */
+  int32_t bale_last_q[5];                /* bale_count[m][-1][1]                              */
+  int32_t bale_sum[5];                   /* sum of bale sizes of m                            */
+  int32_t reserved;
+  double acc_belt[4];                    /* accuracy_belt                                     */
+  double ep_return;                      /* sum of rewards of the running episode (Monitor)   */
+} msort_env_state_t;
+
+/* ------------------------------------------------------------------ per-step I/O */
+/* Replay streams for ONE step (REPLAY mode; all device pointers).
+ * ref: SURVEY.md §8c / Appendix B. */
+typedef struct msort_replay {
+  uint32_t struct_size;
+  uint32_t reserved;
+  const double* noise_u;        /* [N,4] raw uniforms of rng_noise (env_super.py:508): noise = -n + 2n*u.  required */
+  const double* redis_u;        /* [N,redis_len] uniforms of `rng` (env_super.py:563), read at the env's cursor. required */
+  int64_t redis_len;
+  const uint32_t* input_counts; /* [N] packed A|B<<8|C<<16|D<<24 emitted by the generator this step; NULL = generator rule */
+  const uint8_t* press_choice;  /* [N] Env_1: internally sampled press action 0..10 (env_super.py:291-300). required for Env_1 */
+  const uint8_t* sort_mode;     /* [N] Env_2: sort mode actually applied; NULL = MLP / sorting_rules */
+} msort_replay_t;
+
+/* Optional per-step outputs (every pointer nullable; device memory). */
+typedef struct msort_info_out {
+  uint32_t struct_size;
+  uint32_t reserved;
+  int64_t* action;              /* [N] info["action"] echo (clamped into range)                 */
+  uint8_t* overflow;            /* [N] info["overflow"]                                          */
+  int8_t* overflow_material;    /* [N] index 0..4 of info["overflow_material"], -1 if none      */
+  uint8_t* sort_mode;           /* [N] sort mode applied this step                               */
+  uint8_t* press_action;        /* [N] press action applied (after sanitising / Env_1 sampling) */
+  uint8_t* invalid_action;      /* [N] 1 if the press action was rejected (log codes 111/222)   */
+  float* terminal_obs;          /* [N,D] rows written only where terminated (AUTO_RESET)        */
+  double* episode_return;       /* [N] written where terminated                                  */
+  int32_t* episode_length;      /* [N] written where terminated                                  */
+  double* stats;                /* [MSORT_NUM_STATS] accumulators, atomically added to:
+                                   0 episodes finished, 1 sum episode return, 2 sum episode length,
+                                   3 env-steps, 4 sum reward, 5 overflows, 6 bales pressed,
+                                   7 invalid actions, 8 clamped actions, 9 replay under-runs */
+} msort_info_out_t;
+
+typedef struct msort_handle msort_t;
+
+/* ------------------------------------------------------------------ entry points */
+int msort_abi_version(void);
+const char* msort_last_error(void);
+
+/* Fill `cfg` with the reference's defaults (config.yml + ctor defaults of the env kind).
+ * ref: config.yml:1-59; Env_X.__init__ defaults (env_1_sort.py:19-20). */
+int msort_default_config(int env_kind, msort_config_t* cfg);
+
+/* ref: Env_X.__init__ (env_1_sort.py:19-29, env_2_press.py:19-34, env_monolith.py:22-35). */
+int msort_create(const msort_config_t* cfg, int device, msort_t** out);
+int msort_destroy(msort_t* h);
+
+/* Size in bytes of the opaque device state blob the caller must allocate (16-B aligned). */
+size_t msort_state_bytes(const msort_t* h);
+int msort_obs_dim(const msort_t* h);
+int msort_num_actions(const msort_t* h);
+
+/* ref: Env_X.reset(seed) (env_super.py:365-420 ; env_1_sort.py:81-85).
+ *  which         : nullable u8[N]; reset only envs with which[i]!=0 (NULL = all)
+ *  first_pattern : nullable u8[N] with 1|2 = pattern_sequence[0] of the freshly seeded
+ *                  generator (input_generator.py:30); NULL = drawn from Philox
+ *  obs, mask     : nullable outputs [N,D] f32 / [N,A] u8 (rows of reset envs only) */
+int msort_reset(msort_t* h, void* state, const uint8_t* which, const uint8_t* first_pattern,
+                float* obs, uint8_t* mask, void* stream);
+
+/* Re-key the Philox generator and restart episode numbering (reset(seed=s) with a new seed). */
+int msort_set_seed(msort_t* h, uint64_t seed);
+
+/* ref: Env_X.step(action, use_action_masking, check_overflow) (env_1_sort.py:97-154,
+ * env_2_press.py:88-165, env_monolith.py:109-284) followed by Env_X.action_masks()
+ * (env_super.py:869-898) on the new state.  One fused kernel launch.
+ *  actions    : i64[N]    obs : f32[N,D]   reward : f32[N]   terminated : u8[N]
+ *  mask       : u8[N,A] (nullable)   info / replay : nullable */
+int msort_step(msort_t* h, void* state, const int64_t* actions, float* obs, float* reward,
+               uint8_t* terminated, uint8_t* mask, const msort_info_out_t* info,
+               const msort_replay_t* replay, void* stream);
+
+/* ref: sort_agent.predict(sort_obs, deterministic=True) (env_2_press.py:106-109) —
+ * uploads the 1570 fp32 weights [W1(32x13) b1 W2(32x32) b2 W3(2x32) b3] (device or host ptr). */
+int msort_set_policy(msort_t* h, const float* weights, int weights_on_device, void* stream);
+
+/* ref: Env_X.get_obs() / action_masks() on the current state, no transition. */
+int msort_observe(msort_t* h, const void* state, float* obs, uint8_t* mask, void* stream);
+
+/* SoA device blob <-> plain msort_env_state_t[N] (device memory). */
+int msort_export_state(msort_t* h, const void* state, msort_env_state_t* out, void* stream);
+int msort_import_state(msort_t* h, void* state, const msort_env_state_t* in, void* stream);
+
+/* State-wide sums for the episode-statistics all-reduce (out16: device, f64[16], overwritten):
+ * 0 N, 1 sum container level, 2..6 bales A..E, 7..11 bale size sums A..E, 12 sum mean purity,
+ * 13 busy presses, 14 sum running episode return, 15 sum current step. */
+int msort_reduce_stats(msort_t* h, const void* state, double* out16, void* stream);
+
+/* The only call that synchronises: waits for `stream` and reports sticky faults. */
+int msort_sync_check(msort_t* h, void* stream);
+
+/* Number of kernels this handle has launched (bench.py's gpu_launches). */
+int64_t msort_launch_count(const msort_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSORT_H_ */

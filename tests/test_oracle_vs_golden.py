@@ -1,0 +1,70 @@
+"""The CPU oracle (oracle/msort_oracle.c) is pinned against trajectories recorded from the
+unmodified reference (tests/golden/reference_trajectories.npz, made by make_golden.py).
+Integer state / masks / flags bit-exact; float64 rewards to 1e-12; f32 obs bit-identical."""
+import numpy as np
+import pytest
+
+from oracle.cpu_oracle import OracleEnv
+from parity_util import (config_for, golden_group, golden_group_names, replay_and_compare)
+
+NAMES = golden_group_names()
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_oracle_replays_reference(name):
+    meta, batch = golden_group(name)
+    n = batch["action"].shape[1]
+    env = OracleEnv(config_for(meta, n))
+    if meta.get("mlp"):
+        env.set_policy(batch["mlp_weights"])
+    use_counts = not name.startswith("gen_")      # gen_*: exercise the generator rule itself
+    steps = replay_and_compare(env, batch, meta, use_input_counts=use_counts, reward_rtol=1e-12,
+                               exact_obs=True)
+    assert steps == meta["steps"] * n
+
+
+def test_oracle_embedded_mlp_matches_reference_argmax():
+    """Env_2's embedded sort policy evaluated by the oracle's own fp32 MLP (no recorded sort
+    modes): identical argmax on every step (fixture margins are > 1e-2)."""
+    meta, batch = golden_group("mlp_press")
+    env = OracleEnv(config_for(meta, batch["action"].shape[1]))
+    env.set_policy(batch["mlp_weights"])
+    replay_and_compare(env, batch, meta, check_mlp=True, reward_rtol=1e-12)
+    assert 0.1 < batch["sort_mode"].mean() < 0.9, "fixture must exercise both sort modes"
+
+
+def test_known_answers_appendix_c():
+    """200-step returns of the reference at seed 42, noise 0."""
+    want = {"kat_sort": 74.3138315323, "kat_press": -162.6947619048, "kat_mono": -101.6453411013}
+    for name, ret in want.items():
+        meta, batch = golden_group(name)
+        assert abs(batch["reward"].sum() - ret) < 1e-9
+        env = OracleEnv(config_for(meta, 1))
+        env.reset(first_pattern=batch["first_pattern0"])
+        total = 0.0
+        for t in range(meta["steps"]):
+            kw = dict(noise_u=batch["noise_u"][t], redis_u=batch["redis_u"])
+            if meta["kind"] == "sort":
+                kw["press_choice"] = batch["press_choice"][t]
+            _, r, term, _, _ = env.step(batch["action"][t], **kw)
+            total += float(r[0])
+        assert abs(total - ret) < 1e-9
+        assert bool(term[0])
+        assert abs(float(env.state["ep_return"][0]) - ret) < 1e-9
+
+
+def test_material_conservation_invariant():
+    """SURVEY.md Appendix C invariant: containers + presses + bales + input + belt == 100*steps."""
+    for name in ("grid_mono_m1_o0_n05", "grid_press_m0_o0_n05", "grid_sort_m1_o0_n00"):
+        meta, batch = golden_group(name)
+        meta = dict(meta, auto_reset=False, max_steps=10 ** 6)
+        n = batch["action"].shape[1]
+        env = OracleEnv(config_for(meta, n, rng_mode="philox", seed=5))
+        env.reset()
+        for t in range(150):
+            a = env.sample_masked_actions(9, t)
+            env.step(a)
+            s = env.state
+            total = (s["cont_true"].sum(1) + s["cont_false"].sum(1) + s["cont_e"] + s["press_n"].sum(1)
+                     + s["bale_sum"].sum(1) + s["input"].sum(1) + s["belt"].sum(1))
+            assert np.all(total == 100 * (t + 1))
