@@ -68,6 +68,8 @@ enum {
   MSORT_F_SORT_POLICY_MLP = 1u << 3
 };
 
+#define MSORT_RESET_KEEP_STREAMS 1u
+
 #define MSORT_OBS_DIM_SORT 13
 #define MSORT_OBS_DIM_PRESS 16
 #define MSORT_OBS_DIM_MONO 29
@@ -205,9 +207,17 @@ int msort_num_actions(const msort_t* h);
  *  which         : nullable u8[N]; reset only envs with which[i]!=0 (NULL = all)
  *  first_pattern : nullable u8[N] with 1|2 = pattern_sequence[0] of the freshly seeded
  *                  generator (input_generator.py:30); NULL = drawn from Philox
- *  obs, mask     : nullable outputs [N,D] f32 / [N,A] u8 (rows of reset envs only) */
+ *  obs, mask     : nullable outputs [N,D] f32 / [N,A] u8 (rows of reset envs only)
+ *  reset_flags   : 0 = reset(seed=s): episode counter and replay cursor restart;
+ *                  MSORT_RESET_KEEP_STREAMS = reset(seed=None): the RNG streams run on
+ *                  (env_super.py:377-378) — episode counter +1, replay cursor kept */
 int msort_reset(msort_t* h, void* state, const uint8_t* which, const uint8_t* first_pattern,
-                float* obs, uint8_t* mask, void* stream);
+                float* obs, uint8_t* mask, uint32_t reset_flags, void* stream);
+
+/* Change the per-call switches of step() (MSORT_F_ACTION_MASKING / MSORT_F_CHECK_OVERFLOW /
+ * MSORT_F_AUTO_RESET / MSORT_F_SORT_POLICY_MLP) — the reference passes the first two as step()
+ * keyword arguments (env_monolith.py:109). */
+int msort_set_flags(msort_t* h, uint32_t flags);
 
 /* Re-key the Philox generator and restart episode numbering (reset(seed=s) with a new seed). */
 int msort_set_seed(msort_t* h, uint64_t seed);

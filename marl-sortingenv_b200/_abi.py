@@ -19,6 +19,8 @@ NUM_ACTIONS = {ENV_SORT: 2, ENV_PRESS: 11, ENV_MONO: 22}
 POLICY_WEIGHTS = 1570
 NUM_STATS = 16
 
+RESET_KEEP_STREAMS = 1
+
 OK, E_INVALID, E_UNSUPPORTED, E_NO_DEVICE, E_CUDA, E_REPLAY = 0, -1, -2, -3, -4, -5
 
 
@@ -131,7 +133,8 @@ SYMBOLS = {
     "msort_state_bytes": (C.c_size_t, [_P]),
     "msort_obs_dim": (C.c_int, [_P]),
     "msort_num_actions": (C.c_int, [_P]),
-    "msort_reset": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "msort_reset": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_uint32, _P]),
+    "msort_set_flags": (C.c_int, [_P, C.c_uint32]),
     "msort_set_seed": (C.c_int, [_P, C.c_uint64]),
     "msort_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.POINTER(MsortInfoOut),
                              C.POINTER(MsortReplay), _P]),

@@ -1,0 +1,301 @@
+"""Batched device environments: the Python host over libmsort.so.
+
+`BatchedSortingEnv / BatchedPressingEnv / BatchedMonolithEnv` keep the reference's Gymnasium
+surface (ref: env_1_sort.py:19-154, env_2_press.py:19-165, env_monolith.py:22-284) for N
+environments at once: same constructor arguments, observation/action spaces, `reset`,
+`step`, `action_masks`, info keys and reward terms.  All buffers are torch CUDA tensors owned
+here and handed to the C ABI as raw pointers; the computation is the fused CUDA step kernel.
+There is no CPU path: constructing an env without a B200 raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _abi
+from .config import make_config
+from .spaces import make_spaces
+
+_KIND_NAME = {_abi.ENV_SORT: "sort", _abi.ENV_PRESS: "press", _abi.ENV_MONO: "mono"}
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class BatchedEnv:
+    """N independent plants stepped by one kernel launch per `step()`."""
+
+    kind = "mono"
+
+    def __init__(self, num_envs: int, device="cuda:0", max_steps: int = 50, seed: int | None = None,
+                 noise_sorting: float | None = 0.05, balesize: int | None = 200, simulation=False,
+                 config_path: str | None = None, config: dict | None = None,
+                 use_action_masking: bool = True, check_overflow: bool = False,
+                 auto_reset: bool = True, rng_mode: str = "philox", sort_policy=None,
+                 global_env_offset: int = 0, info_level: str = "full", track_stats: bool = True):
+        self.lib = _abi.load_library()              # raises when the CUDA extension is missing
+        if not torch.cuda.is_available():
+            raise RuntimeError("marl_sortingenv_b200 needs a CUDA device (B200); there is no CPU fallback")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("marl_sortingenv_b200 runs on CUDA devices only")
+        self.num_envs = int(num_envs)
+        self.name = self.kind                        # ref: training.py:63 keys on env.name
+        self.max_steps = int(max_steps)
+        self.seed = seed
+        self.cfg = make_config(self.kind, self.num_envs, max_steps=max_steps, seed=seed,
+                               noise_sorting=noise_sorting, balesize=balesize, config=config,
+                               config_path=config_path, use_action_masking=use_action_masking,
+                               check_overflow=check_overflow, auto_reset=auto_reset,
+                               rng_mode=rng_mode, sort_policy_mlp=sort_policy is not None,
+                               global_env_offset=global_env_offset)
+        self.rng_mode = rng_mode
+        self.D = _abi.OBS_DIM[self.cfg.env_kind]
+        self.A = _abi.NUM_ACTIONS[self.cfg.env_kind]
+        self.observation_space, self.action_space = make_spaces(self.kind)
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", dev_index)
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _abi.check(self.lib, self.lib.msort_create(C.byref(self.cfg), dev_index, C.byref(handle)),
+                       "msort_create")
+        self._h = handle
+        n, D, A, dev = self.num_envs, self.D, self.A, self.device
+        nbytes = self.lib.msort_state_bytes(self._h)
+        self.state = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        self.obs = torch.zeros((n, D), dtype=torch.float32, device=dev)
+        self.reward = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.terminated = torch.zeros(n, dtype=torch.bool, device=dev)
+        self.truncated = torch.zeros(n, dtype=torch.bool, device=dev)     # always False (ref: step returns False)
+        self.mask = torch.zeros((n, A), dtype=torch.bool, device=dev)
+        self.stats = torch.zeros(_abi.NUM_STATS, dtype=torch.float64, device=dev) if track_stats else None
+        self._info = _abi.MsortInfoOut()
+        self._info.struct_size = C.sizeof(self._info)
+        self.info_buffers = {}
+        if info_level not in ("none", "episode", "full"):
+            raise ValueError("info_level must be 'none', 'episode' or 'full'")
+        if info_level in ("episode", "full"):
+            self.info_buffers["episode_return"] = torch.zeros(n, dtype=torch.float64, device=dev)
+            self.info_buffers["episode_length"] = torch.zeros(n, dtype=torch.int32, device=dev)
+            self.info_buffers["terminal_observation"] = torch.zeros((n, D), dtype=torch.float32, device=dev)
+        if info_level == "full":
+            self.info_buffers["action"] = torch.zeros(n, dtype=torch.int64, device=dev)
+            self.info_buffers["overflow"] = torch.zeros(n, dtype=torch.bool, device=dev)
+            self.info_buffers["overflow_material"] = torch.full((n,), -1, dtype=torch.int8, device=dev)
+            self.info_buffers["sort_mode"] = torch.zeros(n, dtype=torch.uint8, device=dev)
+            self.info_buffers["press_action"] = torch.zeros(n, dtype=torch.uint8, device=dev)
+            self.info_buffers["invalid_action"] = torch.zeros(n, dtype=torch.bool, device=dev)
+        b = self.info_buffers
+        self._info.action = _ptr(b.get("action"))
+        self._info.overflow = _ptr(b.get("overflow"))
+        self._info.overflow_material = _ptr(b.get("overflow_material"))
+        self._info.sort_mode = _ptr(b.get("sort_mode"))
+        self._info.press_action = _ptr(b.get("press_action"))
+        self._info.invalid_action = _ptr(b.get("invalid_action"))
+        self._info.terminal_obs = _ptr(b.get("terminal_observation"))
+        self._info.episode_return = _ptr(b.get("episode_return"))
+        self._info.episode_length = _ptr(b.get("episode_length"))
+        self._info.stats = _ptr(self.stats)
+        self._has_info = info_level != "none" or track_stats
+        self._was_reset = False
+        self.sort_agent = None
+        if sort_policy is not None:
+            self.set_sort_policy(sort_policy)
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.msort_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def unwrapped(self):
+        return self
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.msort_launch_count(self._h))
+
+    def set_flags(self, *, use_action_masking=None, check_overflow=None, auto_reset=None):
+        f = int(self.cfg.flags)
+        for val, bit in ((use_action_masking, _abi.F_ACTION_MASKING), (check_overflow, _abi.F_CHECK_OVERFLOW),
+                         (auto_reset, _abi.F_AUTO_RESET)):
+            if val is not None:
+                f = (f | bit) if val else (f & ~bit)
+        self.cfg.flags = f
+        _abi.check(self.lib, self.lib.msort_set_flags(self._h, f), "msort_set_flags")
+
+    # ------------------------------------------------------------------ Gymnasium surface
+    def reset(self, seed: int | None = None, options=None, *, which=None, first_pattern=None):
+        """ref: Env_X.reset(seed) → (obs, {}).  `seed` re-keys the Philox generator and restarts
+        episode numbering; `seed=None` after the first reset keeps the streams running
+        (env_super.py:377-378)."""
+        flags = 0
+        if seed is not None:
+            self.seed = seed
+            _abi.check(self.lib, self.lib.msort_set_seed(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF), "msort_set_seed")
+        elif self._was_reset:
+            flags = _abi.RESET_KEEP_STREAMS
+        w = None if which is None else torch.as_tensor(which, device=self.device).to(torch.uint8).contiguous()
+        fp = None if first_pattern is None else torch.as_tensor(first_pattern, device=self.device).to(torch.uint8).contiguous()
+        with torch.cuda.device(self.device):
+            rc = self.lib.msort_reset(self._h, _ptr(self.state), _ptr(w), _ptr(fp), _ptr(self.obs),
+                                      _ptr(self.mask), flags, self._stream())
+        _abi.check(self.lib, rc, "msort_reset")
+        self._was_reset = True
+        return self.obs, {}
+
+    def step(self, actions, replay: dict | None = None):
+        """ref: Env_X.step(action) → (obs, reward, terminated, truncated, info), batched.
+        `actions`: int64 CUDA tensor [N].  Returned tensors are views of internal buffers that
+        the next step() overwrites."""
+        if not self._was_reset:
+            # the reference raises AttributeError on step() before reset() (env_super.py:394,402)
+            raise AttributeError("step() called before reset()")
+        if not (isinstance(actions, torch.Tensor) and actions.dtype == torch.int64 and actions.is_cuda
+                and actions.is_contiguous()):
+            actions = torch.as_tensor(actions, device=self.device).to(torch.int64).contiguous()
+        if actions.numel() != self.num_envs:
+            raise ValueError(f"expected {self.num_envs} actions, got {actions.numel()}")
+        rp = None
+        if self.rng_mode == "replay":
+            rp, _keep = self._make_replay(replay or {})
+        with torch.cuda.device(self.device):
+            rc = self.lib.msort_step(self._h, _ptr(self.state), _ptr(actions), _ptr(self.obs),
+                                     _ptr(self.reward), _ptr(self.terminated), _ptr(self.mask),
+                                     C.byref(self._info) if self._has_info else None,
+                                     C.byref(rp) if rp is not None else None, self._stream())
+        _abi.check(self.lib, rc, "msort_step")
+        return self.obs, self.reward, self.terminated, self.truncated, self.info_buffers
+
+    def action_masks(self):
+        """ref: Env_X.action_masks() (env_super.py:869-898) on the current state: bool [N, A]."""
+        return self.mask
+
+    def get_obs(self):
+        with torch.cuda.device(self.device):
+            rc = self.lib.msort_observe(self._h, _ptr(self.state), _ptr(self.obs), _ptr(self.mask), self._stream())
+        _abi.check(self.lib, rc, "msort_observe")
+        return self.obs
+
+    # ------------------------------------------------------------------ embedded sort agent (Env_2)
+    def set_agents(self, sort_agent=None, **_):
+        """ref: Env_2_Pressing.set_agents(sort_agent) (env_2_press.py:39-40).  Accepts a flat
+        1570-float weight vector, or an object exposing SB3's `policy.state_dict()` layout."""
+        self.set_sort_policy(sort_agent)
+
+    def set_sort_policy(self, agent):
+        from .policy import flatten_sort_policy
+        self.sort_agent = agent
+        if agent is None:
+            self.set_flags_mlp(False)
+            return
+        w = flatten_sort_policy(agent).to(device=self.device, dtype=torch.float32).contiguous()
+        with torch.cuda.device(self.device):
+            rc = self.lib.msort_set_policy(self._h, _ptr(w), 1, self._stream())
+        _abi.check(self.lib, rc, "msort_set_policy")
+        torch.cuda.current_stream(self.device).synchronize()   # `w` may be freed after return
+        self.set_flags_mlp(True)
+
+    def set_flags_mlp(self, on: bool):
+        f = int(self.cfg.flags)
+        f = (f | _abi.F_SORT_POLICY_MLP) if on else (f & ~_abi.F_SORT_POLICY_MLP)
+        self.cfg.flags = f
+        _abi.check(self.lib, self.lib.msort_set_flags(self._h, f), "msort_set_flags")
+
+    # ------------------------------------------------------------------ replay / state exchange
+    def _make_replay(self, r: dict):
+        rp = _abi.MsortReplay()
+        rp.struct_size = C.sizeof(rp)
+        keep = []
+
+        def dev(x, dtype, shape):
+            t = torch.as_tensor(x, device=self.device)
+            t = t.to(dtype).reshape(shape).contiguous()
+            keep.append(t)
+            return t
+        n = self.num_envs
+        if "noise_u" in r:
+            rp.noise_u = _ptr(dev(r["noise_u"], torch.float64, (n, 4)))
+        if "redis_u" in r:
+            t = r["redis_u"]
+            if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()):
+                t = dev(t, torch.float64, (n, -1))
+            rp.redis_u = _ptr(t)
+            rp.redis_len = t.shape[1]
+        if r.get("input_counts") is not None:
+            ic = r["input_counts"]
+            if isinstance(ic, torch.Tensor):
+                ic = ic.detach().cpu().numpy()
+            ic = np.ascontiguousarray(np.asarray(ic).astype(np.uint32)).view(np.int32).reshape(n)
+            t = torch.from_numpy(ic.copy()).to(self.device)
+            keep.append(t)
+            rp.input_counts = _ptr(t)
+        if r.get("press_choice") is not None:
+            rp.press_choice = _ptr(dev(r["press_choice"], torch.uint8, (n,)))
+        if r.get("sort_mode") is not None:
+            rp.sort_mode = _ptr(dev(r["sort_mode"], torch.uint8, (n,)))
+        self._replay_keep = keep
+        return rp, keep
+
+    def export_state(self) -> np.ndarray:
+        """SoA device blob → numpy structured array of msort_env_state_t (synchronises)."""
+        dt = _abi.env_state_dtype()
+        buf = torch.zeros(self.num_envs * dt.itemsize, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.msort_export_state(self._h, _ptr(self.state), _ptr(buf), self._stream())
+        _abi.check(self.lib, rc, "msort_export_state")
+        return buf.cpu().numpy().view(dt).copy()
+
+    def import_state(self, arr: np.ndarray):
+        dt = _abi.env_state_dtype()
+        a = np.ascontiguousarray(arr, dtype=dt)
+        assert a.shape == (self.num_envs,)
+        buf = torch.from_numpy(a.view(np.uint8).copy()).to(self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.msort_import_state(self._h, _ptr(self.state), _ptr(buf), self._stream())
+        _abi.check(self.lib, rc, "msort_import_state")
+        torch.cuda.current_stream(self.device).synchronize()
+        self._was_reset = True
+        self.get_obs()
+
+    def state_stats(self) -> torch.Tensor:
+        """16 state-wide sums (include/msort.h msort_reduce_stats) as a CUDA f64 tensor."""
+        out = torch.zeros(_abi.NUM_STATS, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.msort_reduce_stats(self._h, _ptr(self.state), _ptr(out), self._stream())
+        _abi.check(self.lib, rc, "msort_reduce_stats")
+        return out
+
+    def sync_check(self):
+        _abi.check(self.lib, self.lib.msort_sync_check(self._h, self._stream()), "msort_sync_check")
+
+
+class BatchedSortingEnv(BatchedEnv):
+    """ref: Env_1_Sorting (env_1_sort.py:12-154): Box(13) / Discrete(2)."""
+    kind = "sort"
+
+
+class BatchedPressingEnv(BatchedEnv):
+    """ref: Env_2_Pressing (env_2_press.py:12-165): Box(16) / Discrete(11)."""
+    kind = "press"
+
+
+class BatchedMonolithEnv(BatchedEnv):
+    """ref: Env_3_Monolith (env_monolith.py:12-284): Box(29) / Discrete(22)."""
+    kind = "mono"
+
+
+ENV_CLASSES = {"sort": BatchedSortingEnv, "press": BatchedPressingEnv, "mono": BatchedMonolithEnv}

@@ -1,0 +1,314 @@
+// msort_api.cu — the C ABI of libmsort.so (include/msort.h): argument validation, config
+// digestion (host float64 arithmetic identical to the reference's), handle management and
+// kernel launches.  No torch types, no exceptions across the boundary, no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "msort_device.cuh"
+#include "msort_launch.h"
+
+using namespace msort;
+
+struct msort_handle {
+  msort_config_t cfg;
+  DevConfig dev;
+  int device;
+  int sm_count;
+  float* policy_dev;  // owned: 1570 floats (tiny, allocated at create)
+  bool policy_set;
+  int64_t launches;
+};
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+static int cuda_fail(cudaError_t e, const char* where) {
+  return fail(MSORT_E_CUDA, "%s: %s (%s)", where, cudaGetErrorString(e), cudaGetErrorName(e));
+}
+
+#define MSORT_TRY_CUDA(expr, where)                 \
+  do {                                              \
+    cudaError_t e__ = (expr);                       \
+    if (e__ != cudaSuccess) return cuda_fail(e__, where); \
+  } while (0)
+
+static bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+extern "C" int msort_abi_version(void) { return MSORT_ABI_VERSION; }
+extern "C" const char* msort_last_error(void) { return g_err; }
+
+extern "C" int msort_default_config(int env_kind, msort_config_t* cfg) {
+  if (!cfg) return fail(MSORT_E_INVALID, "msort_default_config: cfg is NULL");
+  if (env_kind < MSORT_ENV_SORT || env_kind > MSORT_ENV_MONO)
+    return fail(MSORT_E_INVALID, "msort_default_config: unknown env kind %d", env_kind);
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->struct_size = sizeof(*cfg);
+  cfg->env_kind = env_kind;
+  cfg->num_envs = 1;
+  cfg->max_steps = 50;                                  // ctor default (env_1_sort.py:19)
+  cfg->flags = MSORT_F_ACTION_MASKING | MSORT_F_AUTO_RESET;
+  cfg->rng_mode = MSORT_RNG_PHILOX;
+  cfg->input_batch_size = 100;                          // config.yml simulation.input_batch_size
+  cfg->steps_per_pattern = 20;                          // input_generator.py:15 (env_super.py:375)
+  const double ratios[2][4] = {{0.40, 0.15, 0.35, 0.10}, {0.15, 0.40, 0.10, 0.35}};  // input_generator.py:17-20
+  for (int p = 0; p < 2; ++p)
+    for (int m = 0; m < 4; ++m) cfg->pattern_counts[p][m] = (int32_t)std::floor(ratios[p][m] * 100);
+  for (int m = 0; m < 4; ++m) { cfg->baseline_accuracy[m] = 0.75; cfg->quality_threshold[m] = 0.9; }
+  cfg->boost = 0.5;
+  cfg->noise = 0.05;
+  cfg->stage_capacity = 100;
+  cfg->press_time[0] = 12; cfg->press_time[1] = 15;
+  cfg->container_capacity = 700;
+  cfg->bale_size = 200;
+  cfg->bale_remainder_threshold = 0.5;
+  cfg->purity_theta = 0.80; cfg->purity_scaling = 2.0; cfg->tanh_temperature = 0.5;
+  cfg->overflow_penalty_catastrophic = -1.0; cfg->overflow_penalty_severe = -0.5; cfg->overflow_penalty_mild = -0.2;
+  cfg->bale_efficiency_factor = 1.0; cfg->max_state_reward = 0.5;
+  cfg->overflow_termination_penalty = -10.0;
+  return MSORT_OK;
+}
+
+// smallest integer level L in [0, hi] with (double)L / cap > thr, in the reference's own float64
+// arithmetic (`fill_ratio = level / container_max`, env_super.py:1020-1027); hi+1 if none.
+static int level_threshold(int cap, double thr, int hi) {
+  for (int L = 0; L <= hi; ++L)
+    if ((double)L / (double)cap > thr) return L;
+  return hi + 1;
+}
+
+static int digest_config(const msort_config_t& c, DevConfig& d) {
+  if (c.struct_size != sizeof(msort_config_t))
+    return fail(MSORT_E_INVALID, "config struct_size %u != %zu", c.struct_size, sizeof(msort_config_t));
+  if (c.env_kind < MSORT_ENV_SORT || c.env_kind > MSORT_ENV_MONO) return fail(MSORT_E_INVALID, "unknown env kind %d", c.env_kind);
+  if (c.num_envs <= 0) return fail(MSORT_E_INVALID, "num_envs must be > 0");
+  if (c.num_envs > (1ll << 31) - kTile) return fail(MSORT_E_UNSUPPORTED, "num_envs too large for one device");
+  if (c.global_env_offset < 0 || c.global_env_offset + c.num_envs > (1ll << 48))
+    return fail(MSORT_E_INVALID, "global env ids must fit 48 bits");
+  if (c.max_steps <= 0) return fail(MSORT_E_INVALID, "max_steps must be > 0");
+  if (c.rng_mode != MSORT_RNG_PHILOX && c.rng_mode != MSORT_RNG_REPLAY) return fail(MSORT_E_INVALID, "unknown rng mode");
+  if (c.input_batch_size < 0 || c.input_batch_size > 255)
+    return fail(MSORT_E_UNSUPPORTED, "input_batch_size %d outside [0,255] (stage counts are stored as bytes)", c.input_batch_size);
+  if (c.steps_per_pattern < 1 || c.steps_per_pattern > 255) return fail(MSORT_E_UNSUPPORTED, "steps_per_pattern outside [1,255]");
+  if (c.container_capacity <= 0 || c.bale_size <= 0 || c.stage_capacity <= 0) return fail(MSORT_E_INVALID, "capacities must be > 0");
+  if (c.bale_size > (1 << 22)) return fail(MSORT_E_UNSUPPORTED, "bale_size too large");
+  for (int p = 0; p < 2; ++p)
+    if (c.press_time[p] < 1 || c.press_time[p] > 255) return fail(MSORT_E_UNSUPPORTED, "press_time outside [1,255]");
+  if (!(c.noise >= 0.0)) return fail(MSORT_E_INVALID, "noise must be >= 0");
+  if (c.tanh_temperature == 0.0) return fail(MSORT_E_INVALID, "tanh_temperature must be non-zero");
+
+  memset(&d, 0, sizeof(d));
+  d.n = c.num_envs;
+  d.n_pad = (c.num_envs + kTile - 1) / kTile * kTile;
+  d.gid0 = c.global_env_offset;
+  d.kind = c.env_kind;
+  d.max_steps = c.max_steps;
+  d.flags = c.flags;
+  d.key0 = (unsigned)(c.seed & 0xffffffffu);
+  d.key1 = (unsigned)(c.seed >> 32);
+  d.batch = c.input_batch_size;
+  d.spp = c.steps_per_pattern;
+  int tot[2] = {0, 0};
+  for (int p = 0; p < 2; ++p) {
+    d.pat[p] = 0;
+    for (int m = 0; m < 4; ++m) {
+      int v = c.pattern_counts[p][m];
+      if (v < 0 || v > 255) return fail(MSORT_E_INVALID, "pattern count outside [0,255]");
+      d.pat[p] |= (unsigned)v << (8 * m);
+      tot[p] += v;
+    }
+    if (tot[p] > c.input_batch_size) return fail(MSORT_E_INVALID, "pattern counts exceed input_batch_size");
+  }
+  if (tot[0] != tot[1]) return fail(MSORT_E_UNSUPPORTED, "patterns with different totals");
+  d.pat_remainder = c.input_batch_size - tot[0];  // input_generator.py:52-55
+  d.stage_cap = c.stage_capacity;
+  d.cap = c.container_capacity;
+  d.S = c.bale_size;
+  d.press_time[0] = c.press_time[0];
+  d.press_time[1] = c.press_time[1];
+  d.lvl_cat = level_threshold(c.container_capacity, 1.0, 2 * c.container_capacity + 2);
+  d.lvl_sev = level_threshold(c.container_capacity, 0.95, 2 * c.container_capacity + 2);
+  d.lvl_mild = level_threshold(c.container_capacity, 0.90, 2 * c.container_capacity + 2);
+  d.rem_new_bale = c.bale_size + 1;  // `rem > S*threshold` (env_super.py:675); rem < S always
+  for (int r = 0; r <= c.bale_size; ++r)
+    if ((double)r > (double)c.bale_size * c.bale_remainder_threshold) { d.rem_new_bale = r; break; }
+  for (int m = 0; m < 4; ++m) { d.base_acc[m] = c.baseline_accuracy[m]; d.qthr[m] = c.quality_threshold[m]; }
+  d.boost = c.boost;
+  d.noise_low = -c.noise;                 // numpy uniform(low, high): low + (high-low)*u
+  d.noise_range = c.noise - d.noise_low;
+  d.theta = c.purity_theta; d.scaling = c.purity_scaling; d.temperature = c.tanh_temperature;
+  d.pen_cat = c.overflow_penalty_catastrophic; d.pen_sev = c.overflow_penalty_severe; d.pen_mild = c.overflow_penalty_mild;
+  d.bef = c.bale_efficiency_factor; d.max_state = c.max_state_reward; d.ovf_pen = c.overflow_termination_penalty;
+  d.policy = nullptr;
+  return MSORT_OK;
+}
+
+extern "C" int msort_create(const msort_config_t* cfg, int device, msort_t** out) {
+  if (!cfg || !out) return fail(MSORT_E_INVALID, "msort_create: NULL argument");
+  *out = nullptr;
+  DevConfig d;
+  int rc = digest_config(*cfg, d);
+  if (rc != MSORT_OK) return rc;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) return fail(MSORT_E_NO_DEVICE, "no CUDA device (%s); there is no CPU fallback", cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(MSORT_E_INVALID, "device %d out of range (%d devices)", device, count);
+  cudaDeviceProp prop;
+  MSORT_TRY_CUDA(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties");
+  if (prop.major != 10)
+    return fail(MSORT_E_NO_DEVICE, "device %d is sm_%d%d; libmsort is built for sm_100a (B200) only", device, prop.major, prop.minor);
+  int prev_device = 0;
+  MSORT_TRY_CUDA(cudaGetDevice(&prev_device), "cudaGetDevice");
+  MSORT_TRY_CUDA(cudaSetDevice(device), "cudaSetDevice");
+  msort_handle* h = new (std::nothrow) msort_handle();
+  if (!h) return fail(MSORT_E_INVALID, "out of host memory");
+  h->cfg = *cfg;
+  h->dev = d;
+  h->device = device;
+  h->sm_count = prop.multiProcessorCount;
+  h->policy_dev = nullptr;
+  h->policy_set = false;
+  h->launches = 0;
+  e = cudaMalloc(&h->policy_dev, sizeof(float) * MSORT_POLICY_WEIGHTS);
+  if (e != cudaSuccess) { delete h; cudaSetDevice(prev_device); return cuda_fail(e, "cudaMalloc(policy)"); }
+  cudaMemset(h->policy_dev, 0, sizeof(float) * MSORT_POLICY_WEIGHTS);
+  cudaSetDevice(prev_device);  // launches run on the caller's current device, which must be `device`
+  h->dev.policy = h->policy_dev;
+  *out = h;
+  return MSORT_OK;
+}
+
+extern "C" int msort_destroy(msort_t* h) {
+  if (!h) return MSORT_OK;
+  if (h->policy_dev) cudaFree(h->policy_dev);
+  delete h;
+  return MSORT_OK;
+}
+
+extern "C" size_t msort_state_bytes(const msort_t* h) { return h ? (size_t)kPlanes * (size_t)h->dev.n_pad * 16u : 0; }
+extern "C" int msort_obs_dim(const msort_t* h) {
+  if (!h) return 0;
+  return h->dev.kind == MSORT_ENV_SORT ? MSORT_OBS_DIM_SORT : (h->dev.kind == MSORT_ENV_PRESS ? MSORT_OBS_DIM_PRESS : MSORT_OBS_DIM_MONO);
+}
+extern "C" int msort_num_actions(const msort_t* h) {
+  if (!h) return 0;
+  return h->dev.kind == MSORT_ENV_SORT ? MSORT_NUM_ACTIONS_SORT : (h->dev.kind == MSORT_ENV_PRESS ? MSORT_NUM_ACTIONS_PRESS : MSORT_NUM_ACTIONS_MONO);
+}
+extern "C" int64_t msort_launch_count(const msort_t* h) { return h ? h->launches : 0; }
+
+extern "C" int msort_set_seed(msort_t* h, uint64_t seed) {
+  if (!h) return fail(MSORT_E_INVALID, "msort_set_seed: NULL handle");
+  h->cfg.seed = seed;
+  h->dev.key0 = (unsigned)(seed & 0xffffffffu);
+  h->dev.key1 = (unsigned)(seed >> 32);
+  return MSORT_OK;
+}
+
+extern "C" int msort_set_flags(msort_t* h, uint32_t flags) {
+  if (!h) return fail(MSORT_E_INVALID, "msort_set_flags: NULL handle");
+  h->cfg.flags = flags;
+  h->dev.flags = flags;
+  return MSORT_OK;
+}
+
+extern "C" int msort_reset(msort_t* h, void* state, const uint8_t* which, const uint8_t* first_pattern, float* obs,
+                           uint8_t* mask, uint32_t reset_flags, void* stream) {
+  if (!h || !state) return fail(MSORT_E_INVALID, "msort_reset: NULL handle/state");
+  if (!aligned(state, 16)) return fail(MSORT_E_INVALID, "msort_reset: state must be 16-byte aligned");
+  if (obs && !aligned(obs, 4)) return fail(MSORT_E_INVALID, "msort_reset: obs misaligned");
+  MSORT_TRY_CUDA(launch_reset(h->dev, state, which, first_pattern, obs, mask, reset_flags, (cudaStream_t)stream), "reset kernel");
+  h->launches += 1;
+  return MSORT_OK;
+}
+
+extern "C" int msort_step(msort_t* h, void* state, const int64_t* actions, float* obs, float* reward, uint8_t* terminated,
+                          uint8_t* mask, const msort_info_out_t* info, const msort_replay_t* replay, void* stream) {
+  if (!h || !state || !actions || !obs || !reward || !terminated)
+    return fail(MSORT_E_INVALID, "msort_step: NULL required argument");
+  if (!aligned(state, 16)) return fail(MSORT_E_INVALID, "msort_step: state must be 16-byte aligned");
+  if (!aligned(actions, 8)) return fail(MSORT_E_INVALID, "msort_step: actions must be int64-aligned");
+  if (!aligned(obs, 4) || !aligned(reward, 4)) return fail(MSORT_E_INVALID, "msort_step: obs/reward must be float-aligned");
+  if (mask && !aligned(mask, 4)) return fail(MSORT_E_INVALID, "msort_step: mask must be 4-byte aligned");
+  if (info && info->struct_size != sizeof(msort_info_out_t)) return fail(MSORT_E_INVALID, "msort_step: bad info struct_size");
+  if (info && info->stats && !aligned(info->stats, 8)) return fail(MSORT_E_INVALID, "msort_step: stats misaligned");
+  if (h->cfg.rng_mode == MSORT_RNG_REPLAY) {
+    if (!replay) return fail(MSORT_E_REPLAY, "msort_step: REPLAY mode needs a replay descriptor");
+    if (replay->struct_size != sizeof(msort_replay_t)) return fail(MSORT_E_INVALID, "msort_step: bad replay struct_size");
+    if (!replay->noise_u || !replay->redis_u || replay->redis_len <= 0)
+      return fail(MSORT_E_REPLAY, "msort_step: REPLAY mode needs noise_u and redis_u streams");
+    if (!aligned(replay->noise_u, 16) || !aligned(replay->redis_u, 8))
+      return fail(MSORT_E_INVALID, "msort_step: replay streams misaligned");
+    if (h->dev.kind == MSORT_ENV_SORT && !replay->press_choice)
+      return fail(MSORT_E_REPLAY, "msort_step: Env_1 REPLAY mode needs the press_choice stream");
+    if (replay->input_counts && !aligned(replay->input_counts, 4)) return fail(MSORT_E_INVALID, "msort_step: input_counts misaligned");
+  } else if (replay) {
+    return fail(MSORT_E_INVALID, "msort_step: replay descriptor given but the handle is in PHILOX mode");
+  }
+  if (h->dev.kind == MSORT_ENV_PRESS && (h->dev.flags & MSORT_F_SORT_POLICY_MLP) && !h->policy_set &&
+      !(replay && replay->sort_mode))
+    return fail(MSORT_E_INVALID, "msort_step: embedded sort policy requested but msort_set_policy() was never called");
+  StepLaunch l{state, actions, obs, reward, terminated, mask, info, replay};
+  MSORT_TRY_CUDA(launch_step(h->dev, l, h->cfg.rng_mode, (cudaStream_t)stream), "step kernel");
+  h->launches += 1;
+  return MSORT_OK;
+}
+
+extern "C" int msort_set_policy(msort_t* h, const float* weights, int weights_on_device, void* stream) {
+  if (!h || !weights) return fail(MSORT_E_INVALID, "msort_set_policy: NULL argument");
+  MSORT_TRY_CUDA(cudaMemcpyAsync(h->policy_dev, weights, sizeof(float) * MSORT_POLICY_WEIGHTS,
+                                 weights_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                 (cudaStream_t)stream), "cudaMemcpyAsync(policy)");
+  h->policy_set = true;
+  return MSORT_OK;
+}
+
+extern "C" int msort_observe(msort_t* h, const void* state, float* obs, uint8_t* mask, void* stream) {
+  if (!h || !state) return fail(MSORT_E_INVALID, "msort_observe: NULL handle/state");
+  if (!aligned(state, 16) || (obs && !aligned(obs, 4)) || (mask && !aligned(mask, 4)))
+    return fail(MSORT_E_INVALID, "msort_observe: misaligned buffer");
+  MSORT_TRY_CUDA(launch_observe(h->dev, state, obs, mask, (cudaStream_t)stream), "observe kernel");
+  h->launches += 1;
+  return MSORT_OK;
+}
+
+extern "C" int msort_export_state(msort_t* h, const void* state, msort_env_state_t* out, void* stream) {
+  if (!h || !state || !out) return fail(MSORT_E_INVALID, "msort_export_state: NULL argument");
+  if (!aligned(state, 16) || !aligned(out, 8)) return fail(MSORT_E_INVALID, "msort_export_state: misaligned buffer");
+  MSORT_TRY_CUDA(launch_export(h->dev, state, out, (cudaStream_t)stream), "export kernel");
+  h->launches += 1;
+  return MSORT_OK;
+}
+
+extern "C" int msort_import_state(msort_t* h, void* state, const msort_env_state_t* in, void* stream) {
+  if (!h || !state || !in) return fail(MSORT_E_INVALID, "msort_import_state: NULL argument");
+  if (!aligned(state, 16) || !aligned(in, 8)) return fail(MSORT_E_INVALID, "msort_import_state: misaligned buffer");
+  MSORT_TRY_CUDA(launch_import(h->dev, state, in, (cudaStream_t)stream), "import kernel");
+  h->launches += 1;
+  return MSORT_OK;
+}
+
+extern "C" int msort_reduce_stats(msort_t* h, const void* state, double* out16, void* stream) {
+  if (!h || !state || !out16) return fail(MSORT_E_INVALID, "msort_reduce_stats: NULL argument");
+  if (!aligned(state, 16) || !aligned(out16, 8)) return fail(MSORT_E_INVALID, "msort_reduce_stats: misaligned buffer");
+  MSORT_TRY_CUDA(launch_stats(h->dev, state, out16, h->sm_count, (cudaStream_t)stream), "stats kernel");
+  h->launches += 1;
+  return MSORT_OK;
+}
+
+extern "C" int msort_sync_check(msort_t* h, void* stream) {
+  if (!h) return fail(MSORT_E_INVALID, "msort_sync_check: NULL handle");
+  MSORT_TRY_CUDA(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize");
+  MSORT_TRY_CUDA(cudaGetLastError(), "sticky error");
+  return MSORT_OK;
+}

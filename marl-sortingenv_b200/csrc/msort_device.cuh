@@ -1,0 +1,287 @@
+// msort_device.cuh — device-side plant model shared by all kernels (sm_100a).
+//
+// State layout in HBM (DESIGN.md "Data layout"): structure-of-arrays in 16-byte planes,
+//   plane p, env i  ->  ((uint4*)state)[p * n_pad + i]
+// so a warp reads/writes 512 contiguous bytes per plane with one LDG.128/STG.128 per lane.
+//   hot planes (touched every step)
+//     P0  u8 input[4] | u8 belt[4] | u8 sorting[4] | timer1, timer2, mat1|mat2<<4, flags
+//     P1  i32 true[A..D]          P2  i32 false[A..D]
+//     P3  i32 E, n1, n2, last_press_amount
+//     P4  u32 step | q1,q2,gen_counter,0 | u32 episode | i32 replay_cursor
+//     P5  f64 episode_return | 8 B spare
+//     P6  f64 acc_belt[A,B]       P7  f64 acc_belt[C,D]
+//   cold planes (one per material, touched only when a press finishes that material)
+//     P8+m  u32 bale_n[m], bale_sum[m], last_size[m] | last_q[m]<<24, spare
+//
+// Every float64 operation whose result can reach integer state or a 2-decimal rounding is
+// written with explicit round-to-nearest intrinsics so nvcc never contracts it into an FMA
+// (numpy does not fuse): see SURVEY.md §7 "Hard parts".
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/msort.h"
+
+namespace msort {
+
+constexpr int kHotPlanes = 8;
+constexpr int kColdPlanes = 5;
+constexpr int kPlanes = kHotPlanes + kColdPlanes;
+constexpr int kTile = 128;  // envs per CTA tile == threads per CTA
+
+// Philox draw blocks (shared with oracle/msort_oracle.c)
+constexpr uint32_t kBlkNoise = 0, kBlkPress = 1, kBlkReset = 2, kBlkInput = 3, kBlkRedis = 16;
+
+// Kernel-parameter copy of msort_config_t plus host-precomputed integer thresholds.
+struct DevConfig {
+  long long n, n_pad, gid0;
+  int kind, max_steps;
+  unsigned flags;
+  unsigned key0, key1;
+  int batch, spp;
+  unsigned pat[2];  // packed u8x4 counts of pattern 1 / 2
+  int pat_remainder;
+  int stage_cap, cap, S;
+  int press_time[2];
+  int lvl_cat, lvl_sev, lvl_mild;  // smallest level with level/cap > 1.0 / 0.95 / 0.90 (f64)
+  int rem_new_bale;                // smallest remainder with rem > S*threshold (f64)
+  double base_acc[4], boost, noise_low, noise_range;
+  double qthr[4];
+  double theta, scaling, temperature;
+  double pen_cat, pen_sev, pen_mild, bef, max_state, ovf_pen;
+  const float* policy;  // 1570 fp32 weights in device memory (Env_2 embedded MLP) or nullptr
+};
+
+// ---------------------------------------------------------------- exact f64 helpers
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+// numpy-scalar round(x, 2) == rint(x*100)/100
+__device__ __forceinline__ double round2(double x) { return ddiv(rint(dmul(x, 100.0)), 100.0); }
+__device__ __forceinline__ double clipd(double x, double lo, double hi) {
+  return x < lo ? lo : (x > hi ? hi : x);
+}
+__device__ __forceinline__ float clipf(float x, float lo, float hi) {
+  return x < lo ? lo : (x > hi ? hi : x);
+}
+
+// ---------------------------------------------------------------- Philox4x32-10
+struct U4 { uint32_t x, y, z, w; };
+
+__device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                            uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return U4{c0, c1, c2, c3};
+}
+
+// counter = {gid_lo, (gid_hi & 0xffff) | block<<16, episode, step}, key = seed
+__device__ __forceinline__ U4 env_draw(const DevConfig& c, long long gid, uint32_t block,
+                                       uint32_t episode, uint32_t step) {
+  unsigned long long g = (unsigned long long)gid;
+  return philox4x32_10((uint32_t)g, (uint32_t)((g >> 32) & 0xffffu) | (block << 16), episode, step,
+                       c.key0, c.key1);
+}
+
+__device__ __forceinline__ uint32_t u4_get(const U4& v, int i) {
+  return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
+}
+
+// ---------------------------------------------------------------- env registers
+struct Env {
+  uint32_t in4, belt4, sort4;  // packed u8x4 stage counts (A | B<<8 | C<<16 | D<<24)
+  int tr[4], fl[4], e;         // containers
+  int timer[2], mat[2], pn[2], pq[2];
+  int started, last_amt;
+  int gfirst, gidx, gcount;    // generator: gfirst 0 -> pattern 1 first, 1 -> pattern 2 first
+  int mode;
+  uint32_t step, episode;
+  int cursor;
+  double ep_ret;
+  double acc[4];
+};
+
+__device__ __forceinline__ int b4(uint32_t v, int m) { return (int)((v >> (8 * m)) & 0xffu); }
+__device__ __forceinline__ int sum4(uint32_t v) { return (int)__dp4a(v, 0x01010101u, 0u); }
+
+__device__ __forceinline__ void load_env(const uint4* __restrict__ st, long long n_pad, long long i, Env& s) {
+  uint4 p0 = st[0 * n_pad + i], p1 = st[1 * n_pad + i], p2 = st[2 * n_pad + i], p3 = st[3 * n_pad + i];
+  uint4 p4 = st[4 * n_pad + i], p5 = st[5 * n_pad + i], p6 = st[6 * n_pad + i], p7 = st[7 * n_pad + i];
+  s.in4 = p0.x; s.belt4 = p0.y; s.sort4 = p0.z;
+  s.timer[0] = p0.w & 0xff; s.timer[1] = (p0.w >> 8) & 0xff;
+  s.mat[0] = (p0.w >> 16) & 0xf; s.mat[1] = (p0.w >> 20) & 0xf;
+  uint32_t fl = p0.w >> 24;
+  s.gfirst = fl & 1; s.gidx = (fl >> 1) & 1; s.started = (fl >> 2) & 1; s.mode = (fl >> 3) & 1;
+  s.tr[0] = (int)p1.x; s.tr[1] = (int)p1.y; s.tr[2] = (int)p1.z; s.tr[3] = (int)p1.w;
+  s.fl[0] = (int)p2.x; s.fl[1] = (int)p2.y; s.fl[2] = (int)p2.z; s.fl[3] = (int)p2.w;
+  s.e = (int)p3.x; s.pn[0] = (int)p3.y; s.pn[1] = (int)p3.z; s.last_amt = (int)p3.w;
+  s.step = p4.x; s.pq[0] = p4.y & 0xff; s.pq[1] = (p4.y >> 8) & 0xff; s.gcount = (p4.y >> 16) & 0xff;
+  s.episode = p4.z; s.cursor = (int)p4.w;
+  s.ep_ret = __hiloint2double((int)p5.y, (int)p5.x);
+  s.acc[0] = __hiloint2double((int)p6.y, (int)p6.x); s.acc[1] = __hiloint2double((int)p6.w, (int)p6.z);
+  s.acc[2] = __hiloint2double((int)p7.y, (int)p7.x); s.acc[3] = __hiloint2double((int)p7.w, (int)p7.z);
+}
+
+__device__ __forceinline__ uint2 d2u(double d) {
+  return make_uint2((uint32_t)__double2loint(d), (uint32_t)__double2hiint(d));
+}
+
+__device__ __forceinline__ void store_env(uint4* __restrict__ st, long long n_pad, long long i, const Env& s) {
+  uint32_t fl = (uint32_t)(s.gfirst | (s.gidx << 1) | (s.started << 2) | ((s.mode & 1) << 3));
+  uint32_t w = (uint32_t)s.timer[0] | ((uint32_t)s.timer[1] << 8) | ((uint32_t)s.mat[0] << 16) |
+               ((uint32_t)s.mat[1] << 20) | (fl << 24);
+  st[0 * n_pad + i] = make_uint4(s.in4, s.belt4, s.sort4, w);
+  st[1 * n_pad + i] = make_uint4((uint32_t)s.tr[0], (uint32_t)s.tr[1], (uint32_t)s.tr[2], (uint32_t)s.tr[3]);
+  st[2 * n_pad + i] = make_uint4((uint32_t)s.fl[0], (uint32_t)s.fl[1], (uint32_t)s.fl[2], (uint32_t)s.fl[3]);
+  st[3 * n_pad + i] = make_uint4((uint32_t)s.e, (uint32_t)s.pn[0], (uint32_t)s.pn[1], (uint32_t)s.last_amt);
+  st[4 * n_pad + i] = make_uint4(s.step, (uint32_t)s.pq[0] | ((uint32_t)s.pq[1] << 8) | ((uint32_t)s.gcount << 16),
+                                 s.episode, (uint32_t)s.cursor);
+  uint2 r = d2u(s.ep_ret);
+  st[5 * n_pad + i] = make_uint4(r.x, r.y, 0u, 0u);
+  uint2 a0 = d2u(s.acc[0]), a1 = d2u(s.acc[1]), a2 = d2u(s.acc[2]), a3 = d2u(s.acc[3]);
+  st[6 * n_pad + i] = make_uint4(a0.x, a0.y, a1.x, a1.y);
+  st[7 * n_pad + i] = make_uint4(a2.x, a2.y, a3.x, a3.y);
+}
+
+__device__ __forceinline__ int level_of(const Env& s, int m) {
+  int l = s.e;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) if (m == k) l = s.tr[k] + s.fl[k];
+  return l;
+}
+
+// ref: press_action_masks env_super.py:869-885 (11 information bits)
+__device__ __forceinline__ uint32_t press_mask_bits(const DevConfig& c, const Env& s) {
+  uint32_t ready = 0;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) ready |= (uint32_t)(s.tr[m] + s.fl[m] >= c.S) << m;
+  ready |= (uint32_t)(s.e >= c.S) << 4;
+  uint32_t b = 1u;
+  if (s.timer[0] == 0) b |= ready << 1;
+  if (s.timer[1] == 0) b |= ready << 6;
+  return b;
+}
+
+// ref: validate_press_action env_super.py:811-836
+__device__ __forceinline__ bool press_action_valid(const DevConfig& c, const Env& s, int pa) {
+  return (press_mask_bits(c, s) >> pa) & 1u;
+}
+
+// ref: get_container_purity env_super.py:771-791
+__device__ __forceinline__ void container_purity(const DevConfig& c, const Env& s, double pur[4]) {
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    int tot = s.tr[m] + s.fl[m];
+    pur[m] = tot > 0 ? round2(ddiv((double)s.tr[m], (double)tot)) : c.qthr[m];
+  }
+}
+
+// ref: get_sort_obs env_super.py:306-325, compute_purity_differences :212-227,
+// compute_belt_proportions :199-210
+__device__ __forceinline__ void sort_obs(const DevConfig& c, const Env& s, const double pur[4], float* o) {
+  int bt = sum4(s.belt4);
+  o[0] = clipf((float)ddiv((double)bt, 100.0), -1.f, 1.f);
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    double p = bt > 0 ? ddiv((double)b4(s.belt4, m), (double)bt) : 0.0;
+    o[1 + m] = clipf((float)p, -1.f, 1.f);
+    o[5 + m] = clipf((float)s.acc[m], -1.f, 1.f);
+    int tot = s.tr[m] + s.fl[m];
+    double diff = dsub(pur[m], c.qthr[m]);
+    o[9 + m] = clipf((float)(tot > 0 ? round2(diff) : diff), -1.f, 1.f);
+  }
+}
+
+// ref: get_press_obs env_super.py:327-359
+__device__ __forceinline__ void press_obs(const DevConfig& c, const Env& s, float* o) {
+#pragma unroll
+  for (int m = 0; m < 5; ++m) {
+    int l = m < 4 ? s.tr[m] + s.fl[m] : s.e;
+    float v = clipf((float)ddiv((double)l, (double)c.cap), 0.f, 1.f);
+    o[m] = v; o[5 + m] = v;
+  }
+#pragma unroll
+  for (int m = 0; m < 4; ++m)
+    o[10 + m] = clipf((float)ddiv((double)b4(s.sort4, m), (double)c.stage_cap), 0.f, 1.f);
+#pragma unroll
+  for (int p = 0; p < 2; ++p)
+    o[14 + p] = clipf((float)ddiv((double)s.timer[p], (double)c.press_time[p]), 0.f, 1.f);
+}
+
+template <int KIND>
+__device__ __forceinline__ void env_obs(const DevConfig& c, const Env& s, float* o) {
+  if (KIND != MSORT_ENV_PRESS) {
+    double pur[4];
+    container_purity(c, s, pur);
+    sort_obs(c, s, pur, o);
+  }
+  if (KIND == MSORT_ENV_PRESS) press_obs(c, s, o);
+  if (KIND == MSORT_ENV_MONO) press_obs(c, s, o + 13);
+}
+
+// fresh plant (ref: Env_Super.reset env_super.py:365-420); keeps what the caller sets after
+__device__ __forceinline__ void reset_env(const DevConfig& c, Env& s) {
+  s.in4 = s.belt4 = s.sort4 = 0;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) { s.tr[m] = 0; s.fl[m] = 0; s.acc[m] = c.base_acc[m]; }
+  s.e = 0;
+  s.timer[0] = s.timer[1] = s.mat[0] = s.mat[1] = s.pn[0] = s.pn[1] = s.pq[0] = s.pq[1] = 0;
+  s.started = 0; s.last_amt = 0; s.gidx = 0; s.gcount = 0; s.mode = 0; s.step = 0; s.ep_ret = 0.0;
+}
+
+__device__ __forceinline__ void zero_cold(uint4* __restrict__ st, long long n_pad, long long i) {
+#pragma unroll
+  for (int m = 0; m < kColdPlanes; ++m) st[(kHotPlanes + m) * n_pad + i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// ref: press_bale env_super.py:661-687 — updates the material's cold plane in place
+__device__ __forceinline__ int press_bale(const DevConfig& c, uint4* __restrict__ st, long long n_pad,
+                                          long long i, int m, int n, int qk) {
+  uint4* cell = &st[(kHotPlanes + m) * n_pad + i];
+  uint4 v = *cell;
+  uint32_t cnt = v.x, sum = v.y, last_size = v.z & 0xffffffu, last_q = v.z >> 24;
+  double q = ddiv((double)qk, 100.0);
+  uint32_t q100 = (uint32_t)__double2int_rz(dmul(q, 100.0));  // int(q*100): truncation (:663)
+  int S = c.S, full = n / S, rem = n - full * S, made = 0;
+  if (full > 0) { cnt += full; sum += (uint32_t)(full * S); last_size = (uint32_t)S; last_q = q100; made += full; }
+  if (rem > 0) {
+    if (rem >= c.rem_new_bale || cnt == 0) { cnt += 1; last_size = (uint32_t)rem; last_q = q100; made += 1; }
+    else last_size += (uint32_t)rem;
+    sum += (uint32_t)rem;
+  }
+  *cell = make_uint4(cnt, sum, (last_size & 0xffffffu) | (last_q << 24), 0u);
+  return made;
+}
+
+// fp32 MLP 13->32->32->2 with tanh; weights staged in shared memory by the CTA
+// (ref: sort_agent.predict env_2_press.py:106-109; arch training.py:115)
+__device__ __forceinline__ int mlp_sort_mode(const float* __restrict__ w, const float* x) {
+  const float *W1 = w, *b1 = w + 416, *W2 = w + 448, *b2 = w + 1472, *W3 = w + 1504, *b3 = w + 1568;
+  float h1[32], h2[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float a = b1[j];
+#pragma unroll
+    for (int k = 0; k < 13; ++k) a = fmaf(W1[j * 13 + k], x[k], a);
+    h1[j] = tanhf(a);
+  }
+#pragma unroll 4
+  for (int j = 0; j < 32; ++j) {
+    float a = b2[j];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) a = fmaf(W2[j * 32 + k], h1[k], a);
+    h2[j] = tanhf(a);
+  }
+  float l0 = b3[0], l1 = b3[1];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) { l0 = fmaf(W3[k], h2[k], l0); l1 = fmaf(W3[32 + k], h2[k], l1); }
+  return l1 > l0 ? 1 : 0;
+}
+
+}  // namespace msort

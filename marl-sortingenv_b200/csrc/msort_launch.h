@@ -1,0 +1,32 @@
+// msort_launch.h — host-side declarations of the kernel launch wrappers (msort_kernels.cu),
+// used by the C-ABI layer (msort_api.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/msort.h"
+
+namespace msort {
+
+struct DevConfig;
+
+struct StepLaunch {
+  void* state;
+  const int64_t* actions;
+  float* obs;
+  float* reward;
+  uint8_t* terminated;
+  uint8_t* mask;
+  const msort_info_out_t* info;
+  const msort_replay_t* replay;
+};
+
+cudaError_t launch_step(const DevConfig& c, const StepLaunch& l, int rng, cudaStream_t st);
+cudaError_t launch_reset(const DevConfig& c, void* state, const uint8_t* which, const uint8_t* first_pattern,
+                         float* obs, uint8_t* mask, uint32_t reset_flags, cudaStream_t st);
+cudaError_t launch_observe(const DevConfig& c, const void* state, float* obs, uint8_t* mask, cudaStream_t st);
+cudaError_t launch_export(const DevConfig& c, const void* state, msort_env_state_t* out, cudaStream_t st);
+cudaError_t launch_import(const DevConfig& c, void* state, const msort_env_state_t* in, cudaStream_t st);
+cudaError_t launch_stats(const DevConfig& c, const void* state, double* out16, int sm_count, cudaStream_t st);
+
+}  // namespace msort
