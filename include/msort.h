@@ -238,6 +238,13 @@ int msort_set_policy(msort_t* h, const float* weights, int weights_on_device, vo
 /* ref: Env_X.get_obs() / action_masks() on the current state, no transition. */
 int msort_observe(msort_t* h, const void* state, float* obs, uint8_t* mask, void* stream);
 
+/* Masked-random action source: actions[i] = uniform choice among the valid entries of
+ * mask[i, :] (all-zero row -> 0), Philox-keyed by (seed, t, global env id).
+ * ref: Env_3 step(mode='random', use_action_masking=True): np.random.choice(flatnonzero(mask))
+ * (env_monolith.py:152-158); sample_masked_press_action (env_super.py:291-300). */
+int msort_sample_actions(msort_t* h, const uint8_t* mask, int64_t* actions, uint64_t seed, uint32_t t,
+                         void* stream);
+
 /* SoA device blob <-> plain msort_env_state_t[N] (device memory). */
 int msort_export_state(msort_t* h, const void* state, msort_env_state_t* out, void* stream);
 int msort_import_state(msort_t* h, void* state, const msort_env_state_t* in, void* stream);

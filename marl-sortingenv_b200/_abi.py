@@ -139,6 +139,7 @@ SYMBOLS = {
     "msort_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.POINTER(MsortInfoOut),
                              C.POINTER(MsortReplay), _P]),
     "msort_set_policy": (C.c_int, [_P, _P, C.c_int, _P]),
+    "msort_sample_actions": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint32, _P]),
     "msort_observe": (C.c_int, [_P, _P, _P, _P, _P]),
     "msort_export_state": (C.c_int, [_P, _P, _P, _P]),
     "msort_import_state": (C.c_int, [_P, _P, _P, _P]),

@@ -184,6 +184,55 @@ class BatchedEnv:
         """ref: Env_X.action_masks() (env_super.py:869-898) on the current state: bool [N, A]."""
         return self.mask
 
+    def sample_actions(self, seed: int = 0, t: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Uniform random valid action per env under the current mask (one kernel launch).
+        ref: Env_3 step(mode='random', use_action_masking=True) (env_monolith.py:152-158)."""
+        if out is None:
+            out = torch.empty(self.num_envs, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.msort_sample_actions(self._h, _ptr(self.mask), _ptr(out), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                               int(t) & 0xFFFFFFFF, self._stream())
+        _abi.check(self.lib, rc, "msort_sample_actions")
+        return out
+
+    # ------------------------------------------------------------------ host-buffer surface
+    def _host_buffers(self):
+        if getattr(self, "_hb", None) is None:
+            n, D, A = self.num_envs, self.D, self.A
+            pin = dict(pin_memory=True)
+            self._hb = dict(actions=torch.zeros(n, dtype=torch.int64, **pin),
+                            obs=torch.zeros((n, D), dtype=torch.float32, **pin),
+                            reward=torch.zeros(n, dtype=torch.float32, **pin),
+                            terminated=torch.zeros(n, dtype=torch.bool, **pin),
+                            mask=torch.zeros((n, A), dtype=torch.bool, **pin))
+            self._dev_actions = torch.zeros(n, dtype=torch.int64, device=self.device)
+        return self._hb
+
+    def step_host(self, actions):
+        """step() for callers that live on the host (SB3-style loops): `actions` is a numpy array /
+        CPU tensor [N]; obs, reward, terminated and the next action mask come back as numpy views
+        of pinned host buffers.  Host->device and device->host copies are part of the call.
+        Returns (obs, reward, terminated, truncated, mask); also counts the bytes moved in
+        `self.h2d_bytes` / `self.d2h_bytes`."""
+        hb = self._host_buffers()
+        a = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions))
+        if a.is_pinned() and a.dtype == torch.int64 and a.is_contiguous():
+            src = a                                    # the caller already holds a pinned buffer
+        else:
+            hb["actions"].copy_(a.reshape(-1))
+            src = hb["actions"]
+        self._dev_actions.copy_(src, non_blocking=True)
+        obs, rew, term, _, _ = self.step(self._dev_actions)
+        hb["obs"].copy_(obs, non_blocking=True)
+        hb["reward"].copy_(rew, non_blocking=True)
+        hb["terminated"].copy_(term, non_blocking=True)
+        hb["mask"].copy_(self.mask, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        self.h2d_bytes = src.numel() * 8
+        self.d2h_bytes = sum(hb[k].numel() * hb[k].element_size() for k in ("obs", "reward", "terminated", "mask"))
+        return (hb["obs"].numpy(), hb["reward"].numpy(), hb["terminated"].numpy(),
+                np.zeros(self.num_envs, dtype=bool), hb["mask"].numpy())
+
     def get_obs(self):
         with torch.cuda.device(self.device):
             rc = self.lib.msort_observe(self._h, _ptr(self.state), _ptr(self.obs), _ptr(self.mask), self._stream())

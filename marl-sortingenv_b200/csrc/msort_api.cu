@@ -282,6 +282,15 @@ extern "C" int msort_observe(msort_t* h, const void* state, float* obs, uint8_t*
   return MSORT_OK;
 }
 
+extern "C" int msort_sample_actions(msort_t* h, const uint8_t* mask, int64_t* actions, uint64_t seed, uint32_t t,
+                                    void* stream) {
+  if (!h || !mask || !actions) return fail(MSORT_E_INVALID, "msort_sample_actions: NULL argument");
+  if (!aligned(mask, 4) || !aligned(actions, 8)) return fail(MSORT_E_INVALID, "msort_sample_actions: misaligned buffer");
+  MSORT_TRY_CUDA(launch_sample(h->dev, mask, actions, seed, t, (cudaStream_t)stream), "sample kernel");
+  h->launches += 1;
+  return MSORT_OK;
+}
+
 extern "C" int msort_export_state(msort_t* h, const void* state, msort_env_state_t* out, void* stream) {
   if (!h || !state || !out) return fail(MSORT_E_INVALID, "msort_export_state: NULL argument");
   if (!aligned(state, 16) || !aligned(out, 8)) return fail(MSORT_E_INVALID, "msort_export_state: misaligned buffer");

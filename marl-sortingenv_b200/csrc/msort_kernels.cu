@@ -459,6 +459,37 @@ observe_kernel(const __grid_constant__ DevConfig c, const uint4* __restrict__ st
   if (mask) flush_mask_tile<A>(s_bits, mask, row0, rows);
 }
 
+// ---------------------------------------------------------------- masked-random action source
+// One thread per env; the CTA's mask rows (contiguous kTile*A bytes) are staged through shared
+// memory with coalesced 4-byte loads, then each thread scans its own row.
+template <int A>
+__global__ void __launch_bounds__(kTile)
+sample_kernel(const __grid_constant__ DevConfig c, const uint8_t* __restrict__ mask, long long* __restrict__ actions,
+              unsigned key0, unsigned key1, unsigned t) {
+  __shared__ uint32_t s_rows[kTile * A / 4];
+  const long long row0 = (long long)blockIdx.x * kTile;
+  const int rows = (int)min((long long)kTile, c.n - row0);
+  const uint8_t* src = mask + row0 * A;
+  const int total = rows * A, words = total >> 2;
+  for (int w = threadIdx.x; w < words; w += kTile) s_rows[w] = reinterpret_cast<const uint32_t*>(src)[w];
+  for (int e = 4 * words + threadIdx.x; e < total; e += kTile) reinterpret_cast<uint8_t*>(s_rows)[e] = src[e];
+  __syncthreads();
+  if ((int)threadIdx.x >= rows) return;
+  const uint8_t* row = reinterpret_cast<const uint8_t*>(s_rows) + threadIdx.x * A;
+  uint32_t bits = 0;
+#pragma unroll
+  for (int k = 0; k < A; ++k) bits |= (uint32_t)(row[k] != 0) << k;
+  unsigned long long g = (unsigned long long)(c.gid0 + row0 + threadIdx.x);
+  U4 r = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), 0x5A3Cu, t, key0, key1);
+  int nv = __popc(bits), a = 0;
+  if (nv > 0) {
+    int pick = (int)__umulhi(r.x, (uint32_t)nv);
+    for (int q = 0; q < pick; ++q) bits &= bits - 1;
+    a = __ffs(bits) - 1;
+  }
+  actions[row0 + threadIdx.x] = a;
+}
+
 // ---------------------------------------------------------------- K6: export / import
 __global__ void __launch_bounds__(kTile)
 export_kernel(const __grid_constant__ DevConfig c, const uint4* __restrict__ state, msort_env_state_t* __restrict__ out) {
@@ -609,6 +640,17 @@ cudaError_t launch_observe(const DevConfig& c, const void* state, float* obs, ui
     case MSORT_ENV_SORT: observe_kernel<MSORT_ENV_SORT><<<tiles(c.n), kTile, 0, st>>>(c, (const uint4*)state, obs, mask); break;
     case MSORT_ENV_PRESS: observe_kernel<MSORT_ENV_PRESS><<<tiles(c.n), kTile, 0, st>>>(c, (const uint4*)state, obs, mask); break;
     default: observe_kernel<MSORT_ENV_MONO><<<tiles(c.n), kTile, 0, st>>>(c, (const uint4*)state, obs, mask); break;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_sample(const DevConfig& c, const uint8_t* mask, int64_t* actions, uint64_t seed, uint32_t t,
+                          cudaStream_t st) {
+  unsigned k0 = (unsigned)(seed & 0xffffffffu), k1 = (unsigned)(seed >> 32);
+  switch (c.kind) {
+    case MSORT_ENV_SORT: sample_kernel<2><<<tiles(c.n), kTile, 0, st>>>(c, mask, (long long*)actions, k0, k1, t); break;
+    case MSORT_ENV_PRESS: sample_kernel<11><<<tiles(c.n), kTile, 0, st>>>(c, mask, (long long*)actions, k0, k1, t); break;
+    default: sample_kernel<22><<<tiles(c.n), kTile, 0, st>>>(c, mask, (long long*)actions, k0, k1, t); break;
   }
   return cudaGetLastError();
 }

@@ -25,6 +25,8 @@ cudaError_t launch_step(const DevConfig& c, const StepLaunch& l, int rng, cudaSt
 cudaError_t launch_reset(const DevConfig& c, void* state, const uint8_t* which, const uint8_t* first_pattern,
                          float* obs, uint8_t* mask, uint32_t reset_flags, cudaStream_t st);
 cudaError_t launch_observe(const DevConfig& c, const void* state, float* obs, uint8_t* mask, cudaStream_t st);
+cudaError_t launch_sample(const DevConfig& c, const uint8_t* mask, int64_t* actions, uint64_t seed, uint32_t t,
+                          cudaStream_t st);
 cudaError_t launch_export(const DevConfig& c, const void* state, msort_env_state_t* out, cudaStream_t st);
 cudaError_t launch_import(const DevConfig& c, void* state, const msort_env_state_t* in, cudaStream_t st);
 cudaError_t launch_stats(const DevConfig& c, const void* state, double* out16, int sm_count, cudaStream_t st);
