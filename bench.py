@@ -45,7 +45,7 @@ NCU_TRAFFIC_BYTES_PER_LAUNCH = None
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="msort", choices=["msort", "reference"])
     ap.add_argument("--kind", default="mono", choices=["sort", "press", "mono"])

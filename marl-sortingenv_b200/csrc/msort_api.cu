@@ -19,7 +19,8 @@ struct msort_handle {
   DevConfig dev;
   int device;
   int sm_count;
-  float* policy_dev;  // owned: 1570 floats (tiny, allocated at create)
+  float* policy_dev;  // owned device constants (tiny, allocated at create): 1570 policy floats ...
+  double* lut_dev;    // ... and the kSortLut-entry float64 sorting-reward table
   bool policy_set;
   int64_t launches;
 };
@@ -88,6 +89,21 @@ static int level_threshold(int cap, double thr, int hi) {
   return hi + 1;
 }
 
+// Philox4x32 key schedule (key += W per round), precomputed because the key is launch-uniform.
+static void set_round_keys(DevConfig& d, uint64_t seed) {
+  unsigned k0 = (unsigned)(seed & 0xffffffffu), k1 = (unsigned)(seed >> 32);
+  for (int r = 0; r < 10; ++r) {
+    d.rk[2 * r] = k0; d.rk[2 * r + 1] = k1;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+// float64 restatement of the reference's obs purity difference, used to validate the fast path
+static float pdiff_reference(int k, double qthr) {
+  double d = (double)k / 100.0 - qthr;
+  return (float)(std::rint(d * 100.0) / 100.0);
+}
+
 static int digest_config(const msort_config_t& c, DevConfig& d) {
   if (c.struct_size != sizeof(msort_config_t))
     return fail(MSORT_E_INVALID, "config struct_size %u != %zu", c.struct_size, sizeof(msort_config_t));
@@ -115,8 +131,7 @@ static int digest_config(const msort_config_t& c, DevConfig& d) {
   d.kind = c.env_kind;
   d.max_steps = c.max_steps;
   d.flags = c.flags;
-  d.key0 = (unsigned)(c.seed & 0xffffffffu);
-  d.key1 = (unsigned)(c.seed >> 32);
+  set_round_keys(d, c.seed);
   d.batch = c.input_batch_size;
   d.spp = c.steps_per_pattern;
   int tot[2] = {0, 0};
@@ -147,9 +162,26 @@ static int digest_config(const msort_config_t& c, DevConfig& d) {
   d.boost = c.boost;
   d.noise_low = -c.noise;                 // numpy uniform(low, high): low + (high-low)*u
   d.noise_range = c.noise - d.noise_low;
-  d.theta = c.purity_theta; d.scaling = c.purity_scaling; d.temperature = c.tanh_temperature;
+  d.theta4 = 4.0 * c.purity_theta;
+  d.c_sort = (c.purity_scaling / 4.0) / c.tanh_temperature;
+  d.c_state = c.max_state_reward / (double)(5 * c.container_capacity);
+  d.c_eff = 4.0 / (double)c.bale_size;
   d.pen_cat = c.overflow_penalty_catastrophic; d.pen_sev = c.overflow_penalty_severe; d.pen_mild = c.overflow_penalty_mild;
-  d.bef = c.bale_efficiency_factor; d.max_state = c.max_state_reward; d.ovf_pen = c.overflow_termination_penalty;
+  d.bef = c.bale_efficiency_factor; d.ovf_pen = c.overflow_termination_penalty;
+  d.inv_cap = 1.0f / (float)c.container_capacity;
+  d.inv_stage = 1.0f / (float)c.stage_capacity;
+  d.inv_pt[0] = 1.0f / (float)c.press_time[0];
+  d.inv_pt[1] = 1.0f / (float)c.press_time[1];
+  // obs purity difference: (k - 100*qthr)/100 in float32 when that reproduces the float64 pipeline
+  d.fast_pdiff = 1;
+  for (int m = 0; m < 4; ++m) {
+    d.qthr100[m] = (int)std::lrint(c.quality_threshold[m] * 100.0);
+    for (int k = 0; k <= 100 && d.fast_pdiff; ++k) {
+      float ref = pdiff_reference(k, c.quality_threshold[m]);
+      float fast = (float)(k - d.qthr100[m]) * 0.01f;
+      if (std::fabs((double)ref - (double)fast) > 1e-7 + 2e-6 * std::fabs((double)ref)) d.fast_pdiff = 0;
+    }
+  }
   d.policy = nullptr;
   return MSORT_OK;
 }
@@ -178,6 +210,7 @@ extern "C" int msort_create(const msort_config_t* cfg, int device, msort_t** out
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
   h->policy_dev = nullptr;
+  h->lut_dev = nullptr;
   h->policy_set = false;
   h->launches = 0;
   e = cudaMalloc(&h->policy_dev, sizeof(float) * MSORT_POLICY_WEIGHTS);
@@ -185,6 +218,20 @@ extern "C" int msort_create(const msort_config_t* cfg, int device, msort_t** out
   cudaMemset(h->policy_dev, 0, sizeof(float) * MSORT_POLICY_WEIGHTS);
   cudaSetDevice(prev_device);  // launches run on the caller's current device, which must be `device`
   h->dev.policy = h->policy_dev;
+  // sorting-reward table (see sort_reward_f64 in msort_device.cuh): same formula, host float64
+  {
+    double lut[kSortLut];
+    for (int kt = 0; kt < kSortLut; ++kt) lut[kt] = std::tanh(((double)kt * 0.01 - h->dev.theta4) * h->dev.c_sort);
+    cudaSetDevice(device);
+    e = cudaMalloc(&h->lut_dev, sizeof(lut));
+    if (e == cudaSuccess) e = cudaMemcpy(h->lut_dev, lut, sizeof(lut), cudaMemcpyHostToDevice);
+    cudaSetDevice(prev_device);
+    if (e != cudaSuccess) { cudaFree(h->policy_dev); delete h; return cuda_fail(e, "cudaMalloc(sort lut)"); }
+    h->dev.sort_lut = h->lut_dev;
+    // the table is exact only when every threshold is a whole percent; otherwise the kernel evaluates float64
+    for (int m = 0; m < 4; ++m)
+      if (std::fabs(cfg->quality_threshold[m] * 100.0 - (double)h->dev.qthr100[m]) > 1e-9) h->dev.fast_pdiff = 0;
+  }
   *out = h;
   return MSORT_OK;
 }
@@ -192,6 +239,7 @@ extern "C" int msort_create(const msort_config_t* cfg, int device, msort_t** out
 extern "C" int msort_destroy(msort_t* h) {
   if (!h) return MSORT_OK;
   if (h->policy_dev) cudaFree(h->policy_dev);
+  if (h->lut_dev) cudaFree(h->lut_dev);
   delete h;
   return MSORT_OK;
 }
@@ -210,8 +258,7 @@ extern "C" int64_t msort_launch_count(const msort_t* h) { return h ? h->launches
 extern "C" int msort_set_seed(msort_t* h, uint64_t seed) {
   if (!h) return fail(MSORT_E_INVALID, "msort_set_seed: NULL handle");
   h->cfg.seed = seed;
-  h->dev.key0 = (unsigned)(seed & 0xffffffffu);
-  h->dev.key1 = (unsigned)(seed >> 32);
+  set_round_keys(h->dev, seed);
   return MSORT_OK;
 }
 

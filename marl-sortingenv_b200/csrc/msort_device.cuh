@@ -13,9 +13,16 @@
 //   cold planes (one per material, touched only when a press finishes that material)
 //     P8+m  u32 bale_n[m], bale_sum[m], last_size[m] | last_q[m]<<24, spare
 //
-// Every float64 operation whose result can reach integer state or a 2-decimal rounding is
-// written with explicit round-to-nearest intrinsics so nvcc never contracts it into an FMA
-// (numpy does not fuse): see SURVEY.md §7 "Hard parts".
+// Arithmetic policy.  Everything that can reach INTEGER state is computed so
+// that it equals the reference's float64 result exactly:
+//   * rint(t*acc), the accuracy noise: float64 with explicit round-to-nearest intrinsics
+//     (never contracted to FMA; numpy does not fuse);
+//   * 2-decimal purity / bale quality rint(true/total*100): exact integer rounding, which
+//     provably equals the float64 pipeline except on exact .5 ties, where the float64
+//     pipeline itself is evaluated (purity_k);
+//   * fill-ratio and bale-remainder comparisons: host-precomputed integer thresholds.
+// Observations and rewards are emitted as float32 within 1e-5 relative of the reference
+// (they never feed back into state), so they use float32 / reciprocal arithmetic.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -32,12 +39,12 @@ constexpr int kTile = 128;  // envs per CTA tile == threads per CTA
 // Philox draw blocks (shared with oracle/msort_oracle.c)
 constexpr uint32_t kBlkNoise = 0, kBlkPress = 1, kBlkReset = 2, kBlkInput = 3, kBlkRedis = 16;
 
-// Kernel-parameter copy of msort_config_t plus host-precomputed integer thresholds.
+// Kernel-parameter copy of msort_config_t plus host-precomputed constants.
 struct DevConfig {
   long long n, n_pad, gid0;
   int kind, max_steps;
   unsigned flags;
-  unsigned key0, key1;
+  unsigned rk[20];  // Philox round keys: rk[2r] = key0 + r*W0, rk[2r+1] = key1 + r*W1
   int batch, spp;
   unsigned pat[2];  // packed u8x4 counts of pattern 1 / 2
   int pat_remainder;
@@ -45,12 +52,19 @@ struct DevConfig {
   int press_time[2];
   int lvl_cat, lvl_sev, lvl_mild;  // smallest level with level/cap > 1.0 / 0.95 / 0.90 (f64)
   int rem_new_bale;                // smallest remainder with rem > S*threshold (f64)
+  int qthr100[4];                  // 100*quality_threshold when that is an integer (fast_pdiff)
+  int fast_pdiff;                  // 1: obs purity diff == (k - qthr100)/100 within tolerance for all k
+  float inv_cap, inv_stage, inv_pt[2];
   double base_acc[4], boost, noise_low, noise_range;
   double qthr[4];
-  double theta, scaling, temperature;
-  double pen_cat, pen_sev, pen_mild, bef, max_state, ovf_pen;
-  const float* policy;  // 1570 fp32 weights in device memory (Env_2 embedded MLP) or nullptr
+  double theta4, c_sort;           // sum of 4 thetas; (scaling/4)/temperature
+  double c_state, c_eff;           // max_state/(5*cap); 4/S
+  double pen_cat, pen_sev, pen_mild, bef, ovf_pen;
+  const float* policy;             // 1570 fp32 weights in device memory (Env_2 embedded MLP)
+  const double* sort_lut;          // kSortLut float64 sorting rewards indexed by the purity sum (see sort_reward)
 };
+
+constexpr int kSortLut = 401;      // purity sum in hundredths: 4 containers x (0..100)
 
 // ---------------------------------------------------------------- exact f64 helpers
 __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
@@ -62,13 +76,27 @@ __device__ __forceinline__ double round2(double x) { return ddiv(rint(dmul(x, 10
 __device__ __forceinline__ double clipd(double x, double lo, double hi) {
   return x < lo ? lo : (x > hi ? hi : x);
 }
-__device__ __forceinline__ float clipf(float x, float lo, float hi) {
-  return x < lo ? lo : (x > hi ? hi : x);
-}
+__device__ __forceinline__ float clipf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 
 // ---------------------------------------------------------------- Philox4x32-10
 struct U4 { uint32_t x, y, z, w; };
 
+// 10 rounds, round keys precomputed on the host (uniform kernel parameters).
+__device__ __forceinline__ U4 philox_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                        const unsigned (&rk)[20]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+    unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+    c0 = (uint32_t)(p1 >> 32) ^ c1 ^ rk[2 * r];
+    c1 = (uint32_t)p1;
+    c2 = (uint32_t)(p0 >> 32) ^ c3 ^ rk[2 * r + 1];
+    c3 = (uint32_t)p0;
+  }
+  return U4{c0, c1, c2, c3};
+}
+
+// plain form (explicit key) for kernels off the hot path
 __device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                             uint32_t k0, uint32_t k1) {
 #pragma unroll
@@ -82,15 +110,9 @@ __device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c
 }
 
 // counter = {gid_lo, (gid_hi & 0xffff) | block<<16, episode, step}, key = seed
-__device__ __forceinline__ U4 env_draw(const DevConfig& c, long long gid, uint32_t block,
+__device__ __forceinline__ U4 env_draw(const DevConfig& c, uint32_t gid_lo, uint32_t gid_hi16, uint32_t block,
                                        uint32_t episode, uint32_t step) {
-  unsigned long long g = (unsigned long long)gid;
-  return philox4x32_10((uint32_t)g, (uint32_t)((g >> 32) & 0xffffu) | (block << 16), episode, step,
-                       c.key0, c.key1);
-}
-
-__device__ __forceinline__ uint32_t u4_get(const U4& v, int i) {
-  return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
+  return philox_rk(gid_lo, gid_hi16 | (block << 16), episode, step, c.rk);
 }
 
 // ---------------------------------------------------------------- env registers
@@ -110,9 +132,11 @@ struct Env {
 __device__ __forceinline__ int b4(uint32_t v, int m) { return (int)((v >> (8 * m)) & 0xffu); }
 __device__ __forceinline__ int sum4(uint32_t v) { return (int)__dp4a(v, 0x01010101u, 0u); }
 
-__device__ __forceinline__ void load_env(const uint4* __restrict__ st, long long n_pad, long long i, Env& s) {
-  uint4 p0 = st[0 * n_pad + i], p1 = st[1 * n_pad + i], p2 = st[2 * n_pad + i], p3 = st[3 * n_pad + i];
-  uint4 p4 = st[4 * n_pad + i], p5 = st[5 * n_pad + i], p6 = st[6 * n_pad + i], p7 = st[7 * n_pad + i];
+__device__ __forceinline__ double u2d(uint32_t lo, uint32_t hi) { return __hiloint2double((int)hi, (int)lo); }
+
+__device__ __forceinline__ void unpack_env(const uint4& p0, const uint4& p1, const uint4& p2, const uint4& p3,
+                                           const uint4& p4, const uint4& p5, const uint4& p6, const uint4& p7,
+                                           Env& s) {
   s.in4 = p0.x; s.belt4 = p0.y; s.sort4 = p0.z;
   s.timer[0] = p0.w & 0xff; s.timer[1] = (p0.w >> 8) & 0xff;
   s.mat[0] = (p0.w >> 16) & 0xf; s.mat[1] = (p0.w >> 20) & 0xf;
@@ -123,9 +147,15 @@ __device__ __forceinline__ void load_env(const uint4* __restrict__ st, long long
   s.e = (int)p3.x; s.pn[0] = (int)p3.y; s.pn[1] = (int)p3.z; s.last_amt = (int)p3.w;
   s.step = p4.x; s.pq[0] = p4.y & 0xff; s.pq[1] = (p4.y >> 8) & 0xff; s.gcount = (p4.y >> 16) & 0xff;
   s.episode = p4.z; s.cursor = (int)p4.w;
-  s.ep_ret = __hiloint2double((int)p5.y, (int)p5.x);
-  s.acc[0] = __hiloint2double((int)p6.y, (int)p6.x); s.acc[1] = __hiloint2double((int)p6.w, (int)p6.z);
-  s.acc[2] = __hiloint2double((int)p7.y, (int)p7.x); s.acc[3] = __hiloint2double((int)p7.w, (int)p7.z);
+  s.ep_ret = u2d(p5.x, p5.y);
+  s.acc[0] = u2d(p6.x, p6.y); s.acc[1] = u2d(p6.z, p6.w);
+  s.acc[2] = u2d(p7.x, p7.y); s.acc[3] = u2d(p7.z, p7.w);
+}
+
+__device__ __forceinline__ void load_env(const uint4* __restrict__ st, long long n_pad, long long i, Env& s) {
+  uint4 p0 = st[0 * n_pad + i], p1 = st[1 * n_pad + i], p2 = st[2 * n_pad + i], p3 = st[3 * n_pad + i];
+  uint4 p4 = st[4 * n_pad + i], p5 = st[5 * n_pad + i], p6 = st[6 * n_pad + i], p7 = st[7 * n_pad + i];
+  unpack_env(p0, p1, p2, p3, p4, p5, p6, p7, s);
 }
 
 __device__ __forceinline__ uint2 d2u(double d) {
@@ -173,28 +203,59 @@ __device__ __forceinline__ bool press_action_valid(const DevConfig& c, const Env
   return (press_mask_bits(c, s) >> pa) & 1u;
 }
 
-// ref: get_container_purity env_super.py:771-791
-__device__ __forceinline__ void container_purity(const DevConfig& c, const Env& s, double pur[4]) {
-#pragma unroll
-  for (int m = 0; m < 4; ++m) {
-    int tot = s.tr[m] + s.fl[m];
-    pur[m] = tot > 0 ? round2(ddiv((double)s.tr[m], (double)tot)) : c.qthr[m];
-  }
+// ---------------------------------------------------------------- 2-decimal purity, exactly
+// k = rint(fl(fl(tr/tot)*100)) as the reference computes round(true/total, 2)*100
+// (env_super.py:754,789).  For tot < 2^22 the float64 pipeline is within 2.3e-14 of the exact
+// value 100*tr/tot while a non-tie is at least 1/(2*tot) away from a rounding boundary, so
+// exact integer rounding gives the same k; on an exact .5 tie (remainder 0) the float64
+// pipeline itself decides (its result depends on how tr/tot rounds).
+static __device__ __noinline__ int purity_k_f64(int tr, int tot) {
+  return __double2int_rn(dmul(ddiv((double)tr, (double)tot), 100.0));
 }
 
-// ref: get_sort_obs env_super.py:306-325, compute_purity_differences :212-227,
-// compute_belt_proportions :199-210
-__device__ __forceinline__ void sort_obs(const DevConfig& c, const Env& s, const double pur[4], float* o) {
+__device__ __forceinline__ int purity_k(int tr, int tot) {  // tot > 0, 0 <= tr <= tot
+  if (tot < (1 << 22)) {
+    unsigned a = 200u * (unsigned)tr + (unsigned)tot, b = 2u * (unsigned)tot;
+    unsigned q = a / b;
+    if (a != q * b) return (int)q;
+  }
+  return purity_k_f64(tr, tot);
+}
+
+// Sorting reward tanh(((sum_m(p_m - theta))/4*scaling)/T) (calculate_sorting_reward env_super.py:963-1003).
+// With thresholds that are whole percents (fast_pdiff) the argument depends only on the integer
+// purity sum kt = sum_m (k_m, or 100*qthr_m for an empty container), so the reward is a float64
+// table built on the host with the same formula; otherwise the float64 formula is evaluated here.
+static __device__ __noinline__ double sort_reward_f64(const DevConfig& c, int k0, int k1, int k2, int k3) {
+  int ksum = 0;
+  double extra = 0.0;
+  if (k0 >= 0) ksum += k0; else extra += c.qthr[0];
+  if (k1 >= 0) ksum += k1; else extra += c.qthr[1];
+  if (k2 >= 0) ksum += k2; else extra += c.qthr[2];
+  if (k3 >= 0) ksum += k3; else extra += c.qthr[3];
+  return tanh(((double)ksum * 0.01 + (extra - c.theta4)) * c.c_sort);
+}
+
+// Observation value of one purity difference: round(purity - threshold, 2)
+// (compute_purity_differences env_super.py:212-227) for a non-empty container with purity k/100.
+static __device__ __noinline__ float pdiff_f64(int k, double qthr) {
+  return (float)round2(dsub(ddiv((double)k, 100.0), qthr));
+}
+
+// ---------------------------------------------------------------- observations (float32 out)
+// ref: get_sort_obs env_super.py:306-325, compute_belt_proportions :199-210.
+// kq[m] = purity k (0..100) of container m, or -1 when the container is empty.
+__device__ __forceinline__ void sort_obs(const DevConfig& c, const Env& s, const int kq[4], float* o) {
   int bt = sum4(s.belt4);
-  o[0] = clipf((float)ddiv((double)bt, 100.0), -1.f, 1.f);
+  float inv_bt = bt > 0 ? __frcp_rn((float)bt) : 0.f;
+  o[0] = fminf((float)bt * 0.01f, 1.f);
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
-    double p = bt > 0 ? ddiv((double)b4(s.belt4, m), (double)bt) : 0.0;
-    o[1 + m] = clipf((float)p, -1.f, 1.f);
-    o[5 + m] = clipf((float)s.acc[m], -1.f, 1.f);
-    int tot = s.tr[m] + s.fl[m];
-    double diff = dsub(pur[m], c.qthr[m]);
-    o[9 + m] = clipf((float)(tot > 0 ? round2(diff) : diff), -1.f, 1.f);
+    o[1 + m] = fminf((float)b4(s.belt4, m) * inv_bt, 1.f);
+    o[5 + m] = (float)s.acc[m];  // already clipped to [0,1]
+    float d = 0.f;               // empty container: purity == threshold -> 0
+    if (kq[m] >= 0) d = c.fast_pdiff ? (float)(kq[m] - c.qthr100[m]) * 0.01f : pdiff_f64(kq[m], c.qthr[m]);
+    o[9 + m] = clipf(d, -1.f, 1.f);
   }
 }
 
@@ -203,23 +264,29 @@ __device__ __forceinline__ void press_obs(const DevConfig& c, const Env& s, floa
 #pragma unroll
   for (int m = 0; m < 5; ++m) {
     int l = m < 4 ? s.tr[m] + s.fl[m] : s.e;
-    float v = clipf((float)ddiv((double)l, (double)c.cap), 0.f, 1.f);
+    float v = fminf((float)l * c.inv_cap, 1.f);
     o[m] = v; o[5 + m] = v;
   }
 #pragma unroll
-  for (int m = 0; m < 4; ++m)
-    o[10 + m] = clipf((float)ddiv((double)b4(s.sort4, m), (double)c.stage_cap), 0.f, 1.f);
+  for (int m = 0; m < 4; ++m) o[10 + m] = fminf((float)b4(s.sort4, m) * c.inv_stage, 1.f);
 #pragma unroll
-  for (int p = 0; p < 2; ++p)
-    o[14 + p] = clipf((float)ddiv((double)s.timer[p], (double)c.press_time[p]), 0.f, 1.f);
+  for (int p = 0; p < 2; ++p) o[14 + p] = fminf((float)s.timer[p] * c.inv_pt[p], 1.f);
+}
+
+__device__ __forceinline__ void purity_ks(const Env& s, int kq[4]) {
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    int tot = s.tr[m] + s.fl[m];
+    kq[m] = tot > 0 ? purity_k(s.tr[m], tot) : -1;
+  }
 }
 
 template <int KIND>
 __device__ __forceinline__ void env_obs(const DevConfig& c, const Env& s, float* o) {
   if (KIND != MSORT_ENV_PRESS) {
-    double pur[4];
-    container_purity(c, s, pur);
-    sort_obs(c, s, pur, o);
+    int kq[4];
+    purity_ks(s, kq);
+    sort_obs(c, s, kq, o);
   }
   if (KIND == MSORT_ENV_PRESS) press_obs(c, s, o);
   if (KIND == MSORT_ENV_MONO) press_obs(c, s, o + 13);
@@ -241,8 +308,8 @@ __device__ __forceinline__ void zero_cold(uint4* __restrict__ st, long long n_pa
 }
 
 // ref: press_bale env_super.py:661-687 — updates the material's cold plane in place
-__device__ __forceinline__ int press_bale(const DevConfig& c, uint4* __restrict__ st, long long n_pad,
-                                          long long i, int m, int n, int qk) {
+static __device__ __noinline__ int press_bale(const DevConfig& c, uint4* __restrict__ st, long long n_pad,
+                                       long long i, int m, int n, int qk) {
   uint4* cell = &st[(kHotPlanes + m) * n_pad + i];
   uint4 v = *cell;
   uint32_t cnt = v.x, sum = v.y, last_size = v.z & 0xffffffu, last_q = v.z >> 24;
@@ -263,7 +330,7 @@ __device__ __forceinline__ int press_bale(const DevConfig& c, uint4* __restrict_
 // (ref: sort_agent.predict env_2_press.py:106-109; arch training.py:115)
 __device__ __forceinline__ int mlp_sort_mode(const float* __restrict__ w, const float* x) {
   const float *W1 = w, *b1 = w + 416, *W2 = w + 448, *b2 = w + 1472, *W3 = w + 1504, *b3 = w + 1568;
-  float h1[32], h2[32];
+  float h1[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     float a = b1[j];
@@ -271,16 +338,16 @@ __device__ __forceinline__ int mlp_sort_mode(const float* __restrict__ w, const 
     for (int k = 0; k < 13; ++k) a = fmaf(W1[j * 13 + k], x[k], a);
     h1[j] = tanhf(a);
   }
-#pragma unroll 4
+  float l0 = b3[0], l1 = b3[1];
+#pragma unroll 2
   for (int j = 0; j < 32; ++j) {
     float a = b2[j];
 #pragma unroll
     for (int k = 0; k < 32; ++k) a = fmaf(W2[j * 32 + k], h1[k], a);
-    h2[j] = tanhf(a);
+    float h = tanhf(a);
+    l0 = fmaf(W3[j], h, l0);
+    l1 = fmaf(W3[32 + j], h, l1);
   }
-  float l0 = b3[0], l1 = b3[1];
-#pragma unroll
-  for (int k = 0; k < 32; ++k) { l0 = fmaf(W3[k], h2[k], l0); l1 = fmaf(W3[32 + k], h2[k], l1); }
   return l1 > l0 ? 1 : 0;
 }
 

@@ -10,44 +10,51 @@
 namespace msort {
 
 template <int KIND> struct Dims;
-template <> struct Dims<MSORT_ENV_SORT> { static constexpr int D = 13, DP = 13, A = 2; };
-template <> struct Dims<MSORT_ENV_PRESS> { static constexpr int D = 16, DP = 17, A = 11; };
-template <> struct Dims<MSORT_ENV_MONO> { static constexpr int D = 29, DP = 29, A = 22; };
+template <> struct Dims<MSORT_ENV_SORT> { static constexpr int D = 13, A = 2; };
+template <> struct Dims<MSORT_ENV_PRESS> { static constexpr int D = 16, A = 11; };
+template <> struct Dims<MSORT_ENV_MONO> { static constexpr int D = 29, A = 22; };
 
 // ---------------------------------------------------------------- tile output helpers
-// Copy the CTA's obs tile (smem, row stride DP) to global rows [row0, row0+rows) of obs[N,D].
-template <int D, int DP>
-__device__ __forceinline__ void flush_obs_tile(const float* __restrict__ tile, float* __restrict__ obs,
-                                               long long row0, int rows) {
-  float* dst = obs + row0 * D;
-  const int total = rows * D;
-  for (int e = threadIdx.x; e < total; e += kTile) {
-    int r = e / D, k = e - r * D;
-    dst[e] = tile[r * DP + k];
-  }
+// The CTA's obs rows / mask rows are staged in shared memory in exactly the row-major layout of
+// the global tensors, so the flush is a straight 16-byte-vector copy of a contiguous range
+// (128 rows * D * 4 B and 128 * A B are multiples of 16 for every env kind).
+__device__ __forceinline__ void flush_tile(const void* __restrict__ tile, void* __restrict__ dst, int bytes) {
+  const int n16 = bytes >> 4;
+  const uint4* s4 = reinterpret_cast<const uint4*>(tile);
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+  for (int e = threadIdx.x; e < n16; e += kTile) d4[e] = s4[e];
+  const uint8_t* sb = reinterpret_cast<const uint8_t*>(tile);
+  uint8_t* db = reinterpret_cast<uint8_t*>(dst);
+  for (int e = (n16 << 4) + threadIdx.x; e < bytes; e += kTile) db[e] = sb[e];  // partial last tile only
 }
 
-// Expand per-env 11-bit press masks (smem) into mask[N,A] bytes, 4 bytes per lane per store.
+// bits 0..3 of x -> bytes 0..3 (0/1 each): bit i lands at 8i through the 2^(7i) term
+__device__ __forceinline__ uint32_t spread4(uint32_t x) { return (x * 0x00204081u) & 0x01010101u; }
+
+// Write one env's action-mask row (A bytes) into the dense shared tile.
 template <int A>
-__device__ __forceinline__ void flush_mask_tile(const uint16_t* __restrict__ bits, uint8_t* __restrict__ mask,
-                                                long long row0, int rows) {
-  uint8_t* dst = mask + row0 * A;  // row0 is a multiple of 128 -> 4-byte aligned for every A
-  const int total = rows * A;
-  const int words = total >> 2;
-  for (int w = threadIdx.x; w < words; w += kTile) {
-    uint32_t v = 0;
+__device__ __forceinline__ void put_mask_row(uint8_t* __restrict__ tile, int t, uint32_t bits) {
+  if (A == 2) {
+    reinterpret_cast<uint16_t*>(tile)[t] = 0x0101;
+  } else {
+    const uint32_t w0 = spread4(bits & 0xfu), w1 = spread4((bits >> 4) & 0xfu), w2 = spread4((bits >> 8) & 0x7u);
+    if (A == 11) {
+      uint8_t* r = tile + 11 * t;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      int e = 4 * w + q;
-      int r = e / A, k = e - r * A;
-      uint32_t bit = A == 2 ? 1u : (bits[r] >> (k >= 11 ? k - 11 : k)) & 1u;
-      v |= bit << (8 * q);
+      for (int k = 0; k < 4; ++k) { r[k] = (uint8_t)(w0 >> (8 * k)); r[4 + k] = (uint8_t)(w1 >> (8 * k)); }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) r[8 + k] = (uint8_t)(w2 >> (8 * k));
+    } else {  // A == 22: the 11 press bytes twice (monolith_action_masks env_super.py:887-898); row is 2-byte aligned
+      uint16_t* r = reinterpret_cast<uint16_t*>(tile + 22 * t);
+      r[0] = (uint16_t)w0; r[1] = (uint16_t)(w0 >> 16); r[2] = (uint16_t)w1; r[3] = (uint16_t)(w1 >> 16);
+      r[4] = (uint16_t)w2;
+      r[5] = (uint16_t)((w2 >> 16) | (w0 << 8));
+      r[6] = (uint16_t)(w0 >> 8);
+      r[7] = (uint16_t)((w0 >> 24) | (w1 << 8));
+      r[8] = (uint16_t)(w1 >> 8);
+      r[9] = (uint16_t)((w1 >> 24) | (w2 << 8));
+      r[10] = (uint16_t)(w2 >> 8);
     }
-    reinterpret_cast<uint32_t*>(dst)[w] = v;
-  }
-  for (int e = 4 * words + threadIdx.x; e < total; e += kTile) {
-    int r = e / A, k = e - r * A;
-    dst[e] = A == 2 ? 1 : (uint8_t)((bits[r] >> (k >= 11 ? k - 11 : k)) & 1u);
   }
 }
 
@@ -79,44 +86,67 @@ struct StepArgs {
   const uint8_t* sort_mode_in;
 };
 
-constexpr int kNumAcc = 10;  // stats slots accumulated by the step kernel
+// stats slots accumulated by the step kernel (include/msort.h msort_info_out_t.stats)
+enum { ST_EPISODES = 0, ST_RETURN = 1, ST_LENGTH = 2, ST_STEPS = 3, ST_REWARD = 4, ST_OVERFLOW = 5,
+       ST_BALES = 6, ST_INVALID = 7, ST_CLAMPED = 8, ST_UNDERRUN = 9, ST_COUNT = 10 };
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 
 template <int KIND, int RNG>
-__global__ void __launch_bounds__(kTile)
+__global__ void __launch_bounds__(kTile, 5)
 step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArgs a) {
-  constexpr int D = Dims<KIND>::D, DP = Dims<KIND>::DP, A = Dims<KIND>::A;
-  __shared__ float s_obs[kTile * DP];
-  __shared__ uint16_t s_bits[kTile];
+  constexpr int D = Dims<KIND>::D, A = Dims<KIND>::A;
+  __shared__ __align__(16) float s_obs[kTile * D];
+  __shared__ __align__(16) uint8_t s_mask[kTile * A];
+  __shared__ double s_accs[4][kTile];  // accuracy_sorter (last step's accuracy_belt), per thread
   __shared__ float s_policy[KIND == MSORT_ENV_PRESS ? MSORT_POLICY_WEIGHTS : 1];
-  __shared__ double s_acc[kNumAcc][kTile / 32];
+  __shared__ double s_stat[ST_COUNT];
+  __shared__ double s_lut[KIND == MSORT_ENV_PRESS ? 1 : kSortLut];
 
   const bool masking = c.flags & MSORT_F_ACTION_MASKING;
   const bool auto_reset = c.flags & MSORT_F_AUTO_RESET;
   const bool use_mlp = KIND == MSORT_ENV_PRESS && (c.flags & MSORT_F_SORT_POLICY_MLP) &&
                        !(RNG == MSORT_RNG_REPLAY && a.sort_mode_in);
-  if (use_mlp) {
-    for (int k = threadIdx.x; k < MSORT_POLICY_WEIGHTS; k += kTile) s_policy[k] = c.policy[k];
-    __syncthreads();
-  }
+  const int tid = threadIdx.x;
+  if (use_mlp) for (int k = tid; k < MSORT_POLICY_WEIGHTS; k += kTile) s_policy[k] = c.policy[k];
+  if (a.stats && tid < ST_COUNT) s_stat[tid] = 0.0;
+  if (KIND != MSORT_ENV_PRESS && c.fast_pdiff)
+    for (int k = tid; k < kSortLut; k += kTile) s_lut[k] = c.sort_lut[k];
+  __syncthreads();
 
   const long long row0 = (long long)blockIdx.x * kTile;
-  const long long i = row0 + threadIdx.x;
+  const long long i = row0 + tid;
   const bool live = i < c.n;
   const int rows = (int)min((long long)kTile, c.n - row0);
-  const long long gid = c.gid0 + i;
 
-  double acc_stat[kNumAcc];
-#pragma unroll
-  for (int k = 0; k < kNumAcc; ++k) acc_stat[k] = 0.0;
+  // per-thread statistics (reduced per warp at the end)
+  uint32_t st_flags = 0;   // done | overflow<<8 | invalid<<16 | clamped<<24
+  uint32_t st_bales = 0, st_len = 0, st_underrun = 0;
+  double st_reward = 0.0, st_return = 0.0;
 
   if (live) {
+    const unsigned long long gid = (unsigned long long)(c.gid0 + i);
+    const uint32_t gid_lo = (uint32_t)gid, gid_hi = (uint32_t)(gid >> 32) & 0xffffu;
     Env s;
-    load_env(a.state, c.n_pad, i, s);
+    {
+      const uint4* st = a.state;
+      const long long np = c.n_pad;
+      uint4 p0 = st[i], p1 = st[np + i], p2 = st[2 * np + i], p3 = st[3 * np + i];
+      uint4 p4 = st[4 * np + i], p5 = st[5 * np + i], p6 = st[6 * np + i], p7 = st[7 * np + i];
+      unpack_env(p0, p1, p2, p3, p4, p5, p6, p7, s);
+    }
     long long act = a.actions[i];
     const uint32_t ep = s.episode, stp = s.step;
+    if (act < 0) { act = 0; st_flags += 1u << 24; }
+    if (act >= A) { act = A - 1; st_flags += 1u << 24; }
 
-    if (act < 0) { act = 0; acc_stat[8] += 1.0; }
-    if (act >= A) { act = A - 1; acc_stat[8] += 1.0; }
+    // accuracy_sorter <- accuracy_belt (env_super.py:457), parked in shared memory for the sort loop
+#pragma unroll
+    for (int m = 0; m < 4; ++m) s_accs[m][tid] = s.acc[m];
 
     // 1: material flow (update_environment env_super.py:440-442)
     s.sort4 = s.belt4; s.belt4 = s.in4;
@@ -129,15 +159,13 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       if (c.pat_remainder > 0) {
         U4 r4 = {0, 0, 0, 0};
         for (int k = 0; k < c.pat_remainder; ++k) {
-          if ((k & 3) == 0) r4 = env_draw(c, gid, kBlkInput + 0x100u * (uint32_t)(k >> 2), ep, stp);
-          s.in4 += 1u << (8 * (u4_get(r4, k & 3) & 3u));
+          if ((k & 3) == 0) r4 = env_draw(c, gid_lo, gid_hi, kBlkInput + 0x100u * (uint32_t)(k >> 2), ep, stp);
+          uint32_t x = (k & 3) == 0 ? r4.x : ((k & 3) == 1 ? r4.y : ((k & 3) == 2 ? r4.z : r4.w));
+          s.in4 += 1u << (8 * (x & 3u));
         }
       }
       s.gcount += 1;
     }
-    double acc_sorter[4];
-#pragma unroll
-    for (int m = 0; m < 4; ++m) acc_sorter[m] = s.acc[m];  // env_super.py:457
 
     // 3: decode the action
     int mode = 0, pa = 0;
@@ -145,7 +173,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     if (KIND == MSORT_ENV_SORT) {
       mode = (int)act;
     } else if (KIND == MSORT_ENV_MONO) {
-      mode = (int)act / 11; pa = (int)act - 11 * mode;
+      mode = (int)act >= 11 ? 1 : 0; pa = (int)act - 11 * mode;
       if (!masking && !press_action_valid(c, s, pa)) { pa = 0; skip_press = true; invalid = true; }
     } else {
       pa = (int)act;
@@ -153,16 +181,20 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
         mode = a.sort_mode_in[i] & 1;
       } else if (use_mlp) {
         float so[13];
-        double pur[4];
-        container_purity(c, s, pur);
-        sort_obs(c, s, pur, so);
+        int kq[4];
+        purity_ks(s, kq);
+        sort_obs(c, s, kq, so);
         mode = mlp_sort_mode(s_policy, so);
-      } else {  // sorting_rules env_super.py:469-482 (float64 proportions, as the reference)
-        int bt = sum4(s.belt4);
-        double p[4];
+      } else {  // sorting_rules env_super.py:469-482: pA+pC > pB+pD on float64 proportions
+        int ac = b4(s.belt4, 0) + b4(s.belt4, 2), bd = b4(s.belt4, 1) + b4(s.belt4, 3);
+        if (ac != bd) mode = ac > bd ? 0 : 1;  // strict integer inequality survives the float64 rounding
+        else {                                  // integer tie: the float64 sums decide, as in the reference
+          int bt = ac + bd;
+          double p[4];
 #pragma unroll
-        for (int m = 0; m < 4; ++m) p[m] = bt > 0 ? ddiv((double)b4(s.belt4, m), (double)bt) : 0.0;
-        mode = dadd(p[0], p[2]) > dadd(p[1], p[3]) ? 0 : 1;
+          for (int m = 0; m < 4; ++m) p[m] = bt > 0 ? ddiv((double)b4(s.belt4, m), (double)bt) : 0.0;
+          mode = dadd(p[0], p[2]) > dadd(p[1], p[3]) ? 0 : 1;
+        }
       }
     }
     s.mode = mode;
@@ -175,7 +207,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
         double2 n0 = nz[0], n1 = nz[1];
         u[0] = n0.x; u[1] = n0.y; u[2] = n1.x; u[3] = n1.y;
       } else {
-        U4 r4 = env_draw(c, gid, kBlkNoise, ep, stp);
+        U4 r4 = env_draw(c, gid_lo, gid_hi, kBlkNoise, ep, stp);
         u[0] = (double)r4.x * 2.3283064365386963e-10; u[1] = (double)r4.y * 2.3283064365386963e-10;
         u[2] = (double)r4.z * 2.3283064365386963e-10; u[3] = (double)r4.w * 2.3283064365386963e-10;
       }
@@ -188,53 +220,73 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       }
     }
 
-    // 5: sort_material env_super.py:511-609 — one flattened loop over all redistribution draws
+    // 5: sort_material env_super.py:511-609.  One loop over "events"; an event (optionally) starts
+    //    the next station and then (optionally) performs one redistribution draw, so the warp
+    //    iterates max-over-lanes of (stations without draws + total draws).  In PHILOX mode event
+    //    `it` owns random word it&3 of Philox block it>>2 whether or not it draws; the loop is
+    //    unrolled by four so the word selection is static.
     {
-      uint32_t L = s.sort4, T4 = 0, F4 = 0;
-      int m = 0, rem = 0, k = 0;
-      U4 r4 = {0, 0, 0, 0};
-      while (true) {
-        while (rem == 0 && m < 4) {
-          int t = b4(L, m);
-          double am = m == 0 ? acc_sorter[0] : (m == 1 ? acc_sorter[1] : (m == 2 ? acc_sorter[2] : acc_sorter[3]));
-          int tv = __double2int_rn(dmul((double)t, am));  // int(round(t*acc)) half-to-even (:539)
-          int f = t - tv;
-          T4 |= (uint32_t)tv << (8 * m); F4 |= (uint32_t)f << (8 * m);
-          L = (L & ~(0xffu << (8 * m))) | ((uint32_t)f << (8 * m));
-          rem = f; ++m;
-        }
-        if (rem == 0) break;
-        int tot = sum4(L);
-        if (tot == 0) { rem = 0; continue; }  // :557-559
-        int j;
-        if (RNG == MSORT_RNG_REPLAY) {
+      uint32_t L = s.sort4, T4 = 0, F4 = 0;  // leftover / true / false counts, packed bytes
+      int m = 0, rem = 0, tot = sum4(L);     // tot == sum of the bytes of L, maintained incrementally
+      uint32_t sh = 0;
+
+#define MSORT_STATION_START()                                                                          \
+      if (rem == 0 && m < 4) {                                                                         \
+        const int t = (int)((L >> sh) & 0xffu);                                                        \
+        const int tv = __double2int_rn(dmul((double)t, s_accs[m][tid])); /* int(round(t*acc)) (:539) */ \
+        T4 += (uint32_t)tv << sh;                                                                      \
+        L -= (uint32_t)tv << sh; /* leftover[m] = false_val (:546) */                                  \
+        tot -= tv;                                                                                     \
+        rem = t - tv;                                                                                  \
+        F4 += (uint32_t)rem << sh;                                                                     \
+        ++m; sh += 8;                                                                                  \
+      }
+#define MSORT_REMOVE(j)  { L -= 1u << (8 * (j)); --rem; --tot; }
+
+      if (RNG == MSORT_RNG_REPLAY) {
+        while (true) {
+          MSORT_STATION_START();
+          if (rem == 0) { if (m == 4) break; continue; }
+          uint32_t j;
           if ((long long)s.cursor >= a.redis_len) {
-            acc_stat[9] += 1.0;
-            j = 0; while (b4(L, j) == 0) ++j;  // defined fallback; reported as an under-run
+            st_underrun += 1;
+            j = 0; while (((L >> (8 * j)) & 0xffu) == 0) ++j;  // defined fallback; reported as an under-run
           } else {
-            double uu = a.redis_u[i * a.redis_len + s.cursor];
+            const double uu = a.redis_u[i * a.redis_len + s.cursor];
             s.cursor += 1;
-            double cdf[4], cs = 0.0;  // numpy Generator.choice(4, p=): cumsum, /= last, searchsorted right
+            double cdf[3], cs = 0.0;  // numpy Generator.choice(4, p=): cumsum, /= last, searchsorted right
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { cs = dadd(cs, ddiv((double)b4(L, q), (double)tot)); cdf[q] = cs; }
+            for (int q = 0; q < 4; ++q) { cs = dadd(cs, ddiv((double)b4(L, q), (double)tot)); if (q < 3) cdf[q] = cs; }
             j = 0;
 #pragma unroll
-            for (int q = 0; q < 3; ++q) j += ddiv(cdf[q], cs) <= uu ? 1 : 0;
+            for (int q = 0; q < 3; ++q) j += ddiv(cdf[q], cs) <= uu ? 1u : 0u;
           }
-        } else {
-          if ((k & 3) == 0) r4 = env_draw(c, gid, kBlkRedis + (uint32_t)(k >> 2), ep, stp);
-          uint32_t x = u4_get(r4, k & 3);
-          uint32_t r = __umulhi(x, (uint32_t)tot);
-          uint32_t pre = L * 0x01010101u;  // byte q = L0+..+Lq (tot <= 255: no carries)
-          j = (r >= (pre & 0xffu)) + (r >= ((pre >> 8) & 0xffu)) + (r >= ((pre >> 16) & 0xffu));
+          MSORT_REMOVE(j);
         }
-        ++k;
-        L -= 1u << (8 * j);
-        --rem;
+      } else {
+        // tot >= rem > 0 whenever a draw happens: the pool always contains this station's own false units
+#define MSORT_EVENT(x)                                                                                 \
+        {                                                                                              \
+          MSORT_STATION_START();                                                                       \
+          if (rem > 0) {                                                                               \
+            const uint32_t r = __umulhi((x), (uint32_t)tot);                                           \
+            const uint32_t pre = L * 0x01010101u; /* byte q = L0+..+Lq (tot <= 255: no carries) */     \
+            const uint32_t j = (r >= (pre & 0xffu)) + (r >= __byte_perm(pre, 0, 0x4441)) +             \
+                               (r >= __byte_perm(pre, 0, 0x4442));                                     \
+            MSORT_REMOVE(j);                                                                           \
+          }                                                                                            \
+        }
+        for (uint32_t blk = 0; !(rem == 0 && m == 4); ++blk) {
+          const U4 r4 = env_draw(c, gid_lo, gid_hi, kBlkRedis + blk, ep, stp);
+          MSORT_EVENT(r4.x); MSORT_EVENT(r4.y); MSORT_EVENT(r4.z); MSORT_EVENT(r4.w);
+        }
+#undef MSORT_EVENT
       }
-      s.e += sum4(L);
+#undef MSORT_REMOVE
+#undef MSORT_STATION_START
+      s.e += sum4(L);                                            // :579,597
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { s.tr[q] += b4(T4, q); s.fl[q] += b4(F4, q); }
+      for (int q = 0; q < 4; ++q) { s.tr[q] += b4(T4, q); s.fl[q] += b4(F4, q); }  // :600-602
     }
 
     // 6: Env_1 samples its own press action under the mask (env_super.py:291-300)
@@ -242,7 +294,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       if (RNG == MSORT_RNG_REPLAY) pa = a.press_choice[i];
       else {
         uint32_t vb = press_mask_bits(c, s);
-        U4 r4 = env_draw(c, gid, kBlkPress, ep, stp);
+        U4 r4 = env_draw(c, gid_lo, gid_hi, kBlkPress, ep, stp);
         int pick = (int)__umulhi(r4.x, (uint32_t)__popc(vb));
         for (int q = 0; q < pick; ++q) vb &= vb - 1;  // drop the `pick` lowest valid actions
         pa = __ffs(vb) - 1;
@@ -252,51 +304,55 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     if (KIND == MSORT_ENV_PRESS && !masking && !press_action_valid(c, s, pa)) { pa = 0; invalid = true; }
 
     // 7: press_action_rules env_super.py:626-640
-    int bales_made = 0;
     if (!skip_press) {
 #pragma unroll
       for (int p = 0; p < 2; ++p) {  // check_press_status :642-659
         if (s.timer[p] > 0) {
           s.timer[p] -= 1;
           if (s.timer[p] == 0) {
-            bales_made += press_bale(c, a.state, c.n_pad, i, s.mat[p], s.pn[p], s.pq[p]);
+            st_bales += (uint32_t)press_bale(c, a.state, c.n_pad, i, s.mat[p], s.pn[p], s.pq[p]);
             s.mat[p] = 0; s.pn[p] = 0; s.pq[p] = 0;
           }
         }
       }
-      if (pa != 0) {  // use_press :722-769
-        int p = pa <= 5 ? 0 : 1, m = pa - 1 - 5 * p;
-        if (s.timer[p] == 0) {
-          int amt = level_of(s, m);
-          s.started = 1; s.last_amt = amt;
-          int qk = 0;
-          if (m < 4 && amt > 0) {
-            int tv = s.tr[0];
+      if (pa != 0) {  // use_press :722-769 (static indexing only: keeps the env in registers)
+        const bool second = pa > 5;
+        const int m = pa - (second ? 6 : 1);
+        if ((second ? s.timer[1] : s.timer[0]) == 0) {
+          int tv = 0, amt = s.e;
 #pragma unroll
-            for (int q = 1; q < 4; ++q) if (m == q) tv = s.tr[q];
-            qk = __double2int_rn(dmul(ddiv((double)tv, (double)amt), 100.0));  // round(true/total, 2) (:754)
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) if (m == q) { s.tr[q] = 0; s.fl[q] = 0; }
+          for (int q = 0; q < 4; ++q) if (m == q) { tv = s.tr[q]; amt = s.tr[q] + s.fl[q]; s.tr[q] = 0; s.fl[q] = 0; }
           if (m == 4) s.e = 0;
-          s.timer[p] = c.press_time[p]; s.mat[p] = m; s.pn[p] = amt; s.pq[p] = qk;
+          s.started = 1; s.last_amt = amt;
+          const int qk = (m < 4 && amt > 0) ? purity_k(tv, amt) : 0;  // round(true/total, 2) (:754)
+          if (!second) { s.timer[0] = c.press_time[0]; s.mat[0] = m; s.pn[0] = amt; s.pq[0] = qk; }
+          else { s.timer[1] = c.press_time[1]; s.mat[1] = m; s.pn[1] = amt; s.pq[1] = qk; }
         }
       }
     }
+
+    // container levels after sorting and pressing
+    int lv[5];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) lv[m] = s.tr[m] + s.fl[m];
+    lv[4] = s.e;
 
     // 8: overflow termination (detect_overflow :900-905)
     int overflow_mat = -1;
     if (c.flags & MSORT_F_CHECK_OVERFLOW) {
 #pragma unroll
-      for (int m = 4; m >= 0; --m) if (level_of(s, m) > c.cap) overflow_mat = m;
+      for (int m = 4; m >= 0; --m) if (lv[m] > c.cap) overflow_mat = m;
     }
     const bool overflow = overflow_mat >= 0;
 
-    // 9: rewards
+    // 9: rewards (float64 sums of exactly-rounded terms; emitted as float32)
+    int kq[4] = {-1, -1, -1, -1};
+    if (KIND != MSORT_ENV_PRESS) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) kq[m] = lv[m] > 0 ? purity_k(s.tr[m], lv[m]) : -1;
+    }
     double reward;
     bool terminated;
-    double pur[4];
-    if (KIND != MSORT_ENV_PRESS) container_purity(c, s, pur);
     if (overflow) {
       reward = c.ovf_pen;
       s.step += 1;
@@ -304,20 +360,22 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     } else {
       double r_sort = 0.0, r_press = 0.0;
       if (KIND != MSORT_ENV_PRESS) {  // calculate_sorting_reward :963-1003
-        double total = 0.0;
+        if (c.fast_pdiff) {
+          int kt = 0;
 #pragma unroll
-        for (int m = 0; m < 4; ++m) total = dadd(total, dsub(pur[m], c.theta));
-        double sb = dmul(ddiv(total, 4.0), c.scaling);
-        r_sort = tanh(ddiv(sb, c.temperature));
+          for (int m = 0; m < 4; ++m) kt += kq[m] >= 0 ? kq[m] : c.qthr100[m];
+          r_sort = s_lut[min(max(kt, 0), kSortLut - 1)];
+        } else {
+          r_sort = sort_reward_f64(c, kq[0], kq[1], kq[2], kq[3]);
+        }
       }
       if (KIND != MSORT_ENV_SORT) {  // calculate_press_reward :1006-1080
-        int mx = s.e, tl = s.e;
-        bool sev = s.e >= c.lvl_sev, mild = s.e >= c.lvl_mild && s.e < c.lvl_sev;
+        int mx = lv[4], tl = lv[4];
+        bool sev = lv[4] >= c.lvl_sev, mild = lv[4] >= c.lvl_mild && lv[4] < c.lvl_sev;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
-          int l = s.tr[m] + s.fl[m];
-          mx = max(mx, l); tl += l;
-          sev |= l >= c.lvl_sev; mild |= l >= c.lvl_mild && l < c.lvl_sev;
+          mx = max(mx, lv[m]); tl += lv[m];
+          sev |= lv[m] >= c.lvl_sev; mild |= lv[m] >= c.lvl_mild && lv[m] < c.lvl_sev;
         }
         double max_pen = 0.0;  // min(0, severe if any fill>0.95, mild if any fill in (0.90,0.95]) (:1024-1027)
         if (sev && c.pen_sev < max_pen) max_pen = c.pen_sev;
@@ -325,28 +383,27 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
         if (mx >= c.lvl_cat) r_press = c.pen_cat;            // :1022-1023
         else if (max_pen < 0.0) r_press = max_pen;           // :1029-1030 (started flag NOT cleared)
         else {
-          double state_reward = dmul(ddiv((double)tl, (double)(5 * c.cap)), c.max_state);
-          double action_reward = 0.0;
-          if (s.started) {
-            int S = c.S, amount = s.last_amt, nb = amount / S, rm = amount - nb * S;
-            int d = min(rm, S - rm);
-            double eff = dmul(dsub(1.0, dmul(4.0, ddiv((double)d, (double)S))), c.bef);
-            double peak = nb == 0 ? 0.0 : (nb == 1 ? 1.0 / 3.0 : (nb == 2 ? 2.0 / 3.0 : 1.0));
-            action_reward = dadd(eff, dsub(peak, c.bef));
+          double rr = (double)tl * c.c_state;                // overall fill ratio * max_state_reward (:1049-1050)
+          if (s.started) {                                   // :1054-1075
+            const int S = c.S, amount = s.last_amt, nb = amount / S, rm = amount - nb * S;
+            const int d = min(rm, S - rm);
+            const double eff = (1.0 - (double)d * c.c_eff) * c.bef;
+            const double peak = (double)min(nb, 3) * (1.0 / 3.0);
+            rr += eff + (peak - c.bef);
             s.started = 0; s.last_amt = 0;
           }
-          r_press = clipd(dadd(state_reward, action_reward), -1.0, 1.0);
+          r_press = clipd(rr, -1.0, 1.0);
         }
       }
-      reward = KIND == MSORT_ENV_SORT ? r_sort : (KIND == MSORT_ENV_PRESS ? r_press : dadd(r_sort, r_press));
+      reward = KIND == MSORT_ENV_SORT ? r_sort : (KIND == MSORT_ENV_PRESS ? r_press : r_sort + r_press);
       s.step += 1;
       terminated = s.step >= (uint32_t)c.max_steps;
     }
     s.ep_ret = dadd(s.ep_ret, reward);
 
-    // 10: observation (private row of the shared tile), outputs, auto-reset
-    float* orow = &s_obs[threadIdx.x * DP];
-    if (KIND != MSORT_ENV_PRESS) sort_obs(c, s, pur, orow);
+    // 10: observation (this env's row of the dense shared tile), outputs, auto-reset
+    float* orow = &s_obs[tid * D];
+    if (KIND != MSORT_ENV_PRESS) sort_obs(c, s, kq, orow);
     if (KIND == MSORT_ENV_PRESS) press_obs(c, s, orow);
     if (KIND == MSORT_ENV_MONO) press_obs(c, s, orow + 13);
 
@@ -358,10 +415,10 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     if (a.info_sort_mode) a.info_sort_mode[i] = (uint8_t)mode;
     if (a.info_press_action) a.info_press_action[i] = (uint8_t)pa;
     if (a.info_invalid) a.info_invalid[i] = invalid ? 1 : 0;
-    acc_stat[3] = 1.0; acc_stat[4] = reward; acc_stat[5] = overflow ? 1.0 : 0.0;
-    acc_stat[6] = (double)bales_made; acc_stat[7] = invalid ? 1.0 : 0.0;
+    st_reward = reward;
+    st_flags += (overflow ? 1u << 8 : 0u) + (invalid ? 1u << 16 : 0u);
     if (terminated) {
-      acc_stat[0] = 1.0; acc_stat[1] = s.ep_ret; acc_stat[2] = (double)s.step;
+      st_flags += 1u; st_return = s.ep_ret; st_len = s.step;
       if (a.episode_return) a.episode_return[i] = s.ep_ret;
       if (a.episode_length) a.episode_length[i] = (int)s.step;
       if (auto_reset) {
@@ -373,33 +430,42 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
         // unseeded reset (env_super.py:365-420): streams run on, generator re-seeded
         reset_env(c, s);
         s.episode = ep + 1;
-        s.gfirst = (int)(env_draw(c, gid, kBlkReset, s.episode, 0u).x & 1u);
+        s.gfirst = (int)(env_draw(c, gid_lo, gid_hi, kBlkReset, s.episode, 0u).x & 1u);
         zero_cold(a.state, c.n_pad, i);
         env_obs<KIND>(c, s, orow);
       }
     }
-    s_bits[threadIdx.x] = (uint16_t)press_mask_bits(c, s);
+    if (a.mask) put_mask_row<A>(s_mask, tid, press_mask_bits(c, s));
     store_env(a.state, c.n_pad, i, s);
   }
 
-  if (a.stats) {  // warp shuffle -> shared -> one atomic per CTA per statistic
-#pragma unroll
-    for (int k = 0; k < kNumAcc; ++k) {
-      double v = acc_stat[k];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if ((threadIdx.x & 31) == 0) s_acc[k][threadIdx.x >> 5] = v;
+  if (a.stats) {  // warp reduce (REDUX for the integer counters) -> shared -> one atomic per CTA per slot
+    const uint32_t f = __reduce_add_sync(0xffffffffu, st_flags);
+    const uint32_t nb = __reduce_add_sync(0xffffffffu, st_bales);
+    const uint32_t nl = __reduce_add_sync(0xffffffffu, st_len);
+    const uint32_t nu = RNG == MSORT_RNG_REPLAY ? __reduce_add_sync(0xffffffffu, st_underrun) : 0u;
+    const uint32_t ns = __popc(__ballot_sync(0xffffffffu, live));
+    const double rw = warp_sum(st_reward);
+    const double rt = (f & 0xffu) ? warp_sum(st_return) : 0.0;  // warp-uniform condition
+    if ((tid & 31) == 0) {
+      if (f & 0xffu) { atomicAdd(&s_stat[ST_EPISODES], (double)(f & 0xffu)); atomicAdd(&s_stat[ST_RETURN], rt);
+                       atomicAdd(&s_stat[ST_LENGTH], (double)nl); }
+      atomicAdd(&s_stat[ST_STEPS], (double)ns);
+      atomicAdd(&s_stat[ST_REWARD], rw);
+      if ((f >> 8) & 0xffu) atomicAdd(&s_stat[ST_OVERFLOW], (double)((f >> 8) & 0xffu));
+      if (nb) atomicAdd(&s_stat[ST_BALES], (double)nb);
+      if ((f >> 16) & 0xffu) atomicAdd(&s_stat[ST_INVALID], (double)((f >> 16) & 0xffu));
+      if (f >> 24) atomicAdd(&s_stat[ST_CLAMPED], (double)(f >> 24));
+      if (nu) atomicAdd(&s_stat[ST_UNDERRUN], (double)nu);
     }
   }
   __syncthreads();
-  if (a.stats && threadIdx.x < kNumAcc) {
-    double v = 0.0;
-#pragma unroll
-    for (int w = 0; w < kTile / 32; ++w) v += s_acc[threadIdx.x][w];
-    if (v != 0.0) atomicAdd(&a.stats[threadIdx.x], v);
+  if (a.stats && tid < ST_COUNT) {
+    const double v = s_stat[tid];
+    if (v != 0.0) atomicAdd(&a.stats[tid], v);
   }
-  flush_obs_tile<D, DP>(s_obs, a.obs, row0, rows);
-  if (a.mask) flush_mask_tile<A>(s_bits, a.mask, row0, rows);
+  flush_tile(s_obs, a.obs + row0 * D, rows * D * (int)sizeof(float));
+  if (a.mask) flush_tile(s_mask, a.mask + row0 * A, rows * A);
 }
 
 // ---------------------------------------------------------------- K2: reset
@@ -421,7 +487,10 @@ reset_kernel(const __grid_constant__ DevConfig c, uint4* __restrict__ state, con
   reset_env(c, s);
   int fp = first_pattern ? first_pattern[i] : 0;
   if (fp == 1 || fp == 2) s.gfirst = fp - 1;
-  else s.gfirst = (int)(env_draw(c, c.gid0 + i, kBlkReset, s.episode, 0u).x & 1u);
+  else {
+    const unsigned long long g = (unsigned long long)(c.gid0 + i);
+    s.gfirst = (int)(env_draw(c, (uint32_t)g, (uint32_t)(g >> 32) & 0xffffu, kBlkReset, s.episode, 0u).x & 1u);
+  }
   zero_cold(state, c.n_pad, i);
   store_env(state, c.n_pad, i, s);
   if (obs) {
@@ -442,21 +511,21 @@ template <int KIND>
 __global__ void __launch_bounds__(kTile)
 observe_kernel(const __grid_constant__ DevConfig c, const uint4* __restrict__ state, float* __restrict__ obs,
                uint8_t* __restrict__ mask) {
-  constexpr int D = Dims<KIND>::D, DP = Dims<KIND>::DP, A = Dims<KIND>::A;
-  __shared__ float s_obs[kTile * DP];
-  __shared__ uint16_t s_bits[kTile];
+  constexpr int D = Dims<KIND>::D, A = Dims<KIND>::A;
+  __shared__ __align__(16) float s_obs[kTile * D];
+  __shared__ __align__(16) uint8_t s_mask[kTile * A];
   const long long row0 = (long long)blockIdx.x * kTile;
   const long long i = row0 + threadIdx.x;
   const int rows = (int)min((long long)kTile, c.n - row0);
   if (i < c.n) {
     Env s;
     load_env(state, c.n_pad, i, s);
-    env_obs<KIND>(c, s, &s_obs[threadIdx.x * DP]);
-    s_bits[threadIdx.x] = (uint16_t)press_mask_bits(c, s);
+    env_obs<KIND>(c, s, &s_obs[threadIdx.x * D]);
+    put_mask_row<A>(s_mask, threadIdx.x, press_mask_bits(c, s));
   }
   __syncthreads();
-  if (obs) flush_obs_tile<D, DP>(s_obs, obs, row0, rows);
-  if (mask) flush_mask_tile<A>(s_bits, mask, row0, rows);
+  if (obs) flush_tile(s_obs, obs + row0 * D, rows * D * (int)sizeof(float));
+  if (mask) flush_tile(s_mask, mask + row0 * A, rows * A);
 }
 
 // ---------------------------------------------------------------- masked-random action source
@@ -559,10 +628,10 @@ stats_kernel(const __grid_constant__ DevConfig c, const uint4* __restrict__ stat
     load_env(state, c.n_pad, i, s);
     v[0] += 1.0;
     double lvl = (double)s.e, pm = 0.0;
-    double pur[4];
-    container_purity(c, s, pur);
+    int kq[4];
+    purity_ks(s, kq);
 #pragma unroll
-    for (int m = 0; m < 4; ++m) { lvl += (double)(s.tr[m] + s.fl[m]); pm += pur[m]; }
+    for (int m = 0; m < 4; ++m) { lvl += (double)(s.tr[m] + s.fl[m]); pm += kq[m] >= 0 ? 0.01 * (double)kq[m] : c.qthr[m]; }
     v[1] += lvl;
 #pragma unroll
     for (int m = 0; m < 5; ++m) {

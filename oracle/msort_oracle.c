@@ -331,23 +331,35 @@ static void step_one(const msort_config_t* cfg, msort_env_state_t* s, int64_t i,
     }
   }
 
-  /* 5: sort_material env_super.py:511-609 */
+  /* 5: sort_material env_super.py:511-609.
+   * The stations are walked as a sequence of "events": event `it` optionally starts the next
+   * station (when the previous one has no draws left) and then optionally performs ONE
+   * redistribution draw.  That is the reference's loop nest (:534-571) flattened; the order of
+   * every operation is unchanged.  In PHILOX mode event `it` owns random word it&3 of block
+   * BLK_REDIS + (it>>2), used or not (the device kernel follows the same rule). */
   {
-    int L[4], T[4], F[4];
+    int L[4], T[4] = {0, 0, 0, 0}, F[4] = {0, 0, 0, 0};
     for (int m = 0; m < 4; ++m) L[m] = s->sorting[m];
-    uint32_t blk = 0; int have = 0;
-    for (int m = 0; m < 4; ++m) {
-      int t = L[m];                                               /* :535 (already reduced) */
-      int tr = (int)rint((double)t * acc_sorter[m]);              /* :539 half-to-even */
-      int f = t - tr;
-      T[m] = tr; F[m] = f; L[m] = f;                              /* :542-546 */
-      for (int k = 0; k < f; ++k) {                               /* :553-571 */
+    int m = 0, rem = 0;
+    for (uint32_t it = 0;; ++it) {
+      if (rem == 0) {
+        if (m == 4) break;
+        int t = L[m];                                             /* :535 (already reduced) */
+        int tr = (int)rint((double)t * acc_sorter[m]);            /* :539 half-to-even */
+        int f = t - tr;
+        T[m] = tr; F[m] = f; L[m] = f;                            /* :542-546 */
+        rem = f; ++m;
+      }
+      if (!replay && (it & 3u) == 0) env_draw(cfg, gid, BLK_REDIS + (it >> 2), ep, stp, r4);
+      if (rem > 0) {                                              /* :553-571 */
         int tot = L[0] + L[1] + L[2] + L[3];
-        if (tot == 0) break;                                      /* :557-559 */
+        if (tot == 0) { rem = 0; continue; }                      /* :557-559 (unreachable: tot >= rem) */
         int j;
         if (replay) {
-          if (s->replay_cursor >= rp->redis_len) { acc->v[9] += 1; j = -1; }
-          else {
+          if (s->replay_cursor >= rp->redis_len) {
+            acc->v[9] += 1;                     /* stream exhausted: defined fallback, reported */
+            j = 0; while (L[j] == 0) ++j;
+          } else {
             double uu = rp->redis_u[i * rp->redis_len + s->replay_cursor];
             s->replay_cursor += 1;
             double cdf[4], c = 0.0;                               /* numpy Generator.choice(4, p=) */
@@ -357,22 +369,19 @@ static void step_one(const msort_config_t* cfg, msort_env_state_t* s, int64_t i,
             while (j < 4 && cdf[j] <= uu) ++j;                    /* searchsorted(u, 'right') */
             if (j > 3) j = 3;
           }
-          if (j < 0) { /* stream exhausted: deterministic fallback so the run stays defined */
-            j = 0; while (L[j] == 0) ++j;
-          }
         } else {
-          if (have == 0) { env_draw(cfg, gid, BLK_REDIS + blk, ep, stp, r4); ++blk; have = 4; }
-          uint32_t x = r4[4 - have]; --have;
+          uint32_t x = r4[it & 3u];
           uint32_t r = (uint32_t)(((uint64_t)x * (uint64_t)(uint32_t)tot) >> 32);
           j = 0;
           uint32_t cum = (uint32_t)L[0];
           while (r >= cum) { ++j; cum += (uint32_t)L[j]; }
         }
         L[j] -= 1;                                                /* :566-568 */
+        rem -= 1;
       }
     }
     s->cont_e += L[0] + L[1] + L[2] + L[3];                       /* :579,597 */
-    for (int m = 0; m < 4; ++m) { s->cont_true[m] += T[m]; s->cont_false[m] += F[m]; } /* :600-602 */
+    for (int q = 0; q < 4; ++q) { s->cont_true[q] += T[q]; s->cont_false[q] += F[q]; } /* :600-602 */
   }
 
   /* 6: Env_1 samples its own press action under the mask (env_super.py:291-300) */
