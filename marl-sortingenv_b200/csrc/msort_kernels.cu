@@ -7,6 +7,10 @@
 #include "msort_device.cuh"
 #include "msort_launch.h"
 
+#ifndef MSORT_STEP_MIN_BLOCKS
+#define MSORT_STEP_MIN_BLOCKS 6  // resident CTAs per SM the step kernel is compiled for (register cap)
+#endif
+
 namespace msort {
 
 template <int KIND> struct Dims;
@@ -97,7 +101,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 template <int KIND, int RNG>
-__global__ void __launch_bounds__(kTile, 5)
+__global__ void __launch_bounds__(kTile, MSORT_STEP_MIN_BLOCKS)
 step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArgs a) {
   constexpr int D = Dims<KIND>::D, A = Dims<KIND>::A;
   __shared__ __align__(16) float s_obs[kTile * D];
@@ -264,21 +268,33 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
           MSORT_REMOVE(j);
         }
       } else {
-        // tot >= rem > 0 whenever a draw happens: the pool always contains this station's own false units
+        // Branch-free events (selects / predication only) so that the four events of a block and the
+        // Philox rounds of the next block form one basic block the scheduler can interleave.
+        // tot >= rem > 0 whenever a draw happens: the pool always contains this station's own false units.
 #define MSORT_EVENT(x)                                                                                 \
         {                                                                                              \
-          MSORT_STATION_START();                                                                       \
-          if (rem > 0) {                                                                               \
-            const uint32_t r = __umulhi((x), (uint32_t)tot);                                           \
-            const uint32_t pre = L * 0x01010101u; /* byte q = L0+..+Lq (tot <= 255: no carries) */     \
-            const uint32_t j = (r >= (pre & 0xffu)) + (r >= __byte_perm(pre, 0, 0x4441)) +             \
-                               (r >= __byte_perm(pre, 0, 0x4442));                                     \
-            MSORT_REMOVE(j);                                                                           \
-          }                                                                                            \
+          const bool ps = (rem == 0) & (m < 4);                    /* start the next station? */       \
+          const int t = (int)(__funnelshift_r(L, 0u, sh) & 0xffu);   /* shift count taken mod 32 */      \
+          const int tv = __double2int_rn(dmul((double)t, s_accs[m & 3][tid])); /* rint(t*acc) (:539) */ \
+          const uint32_t tvs = ps ? __funnelshift_l(0u, (uint32_t)tv, sh) : 0u;                                           \
+          T4 += tvs; L -= tvs;                                     /* leftover[m] = false_val (:546) */ \
+          tot -= ps ? tv : 0;                                                                          \
+          rem = ps ? t - tv : rem;                                                                     \
+          F4 += ps ? __funnelshift_l(0u, (uint32_t)rem, sh) : 0u;                                      \
+          m += ps ? 1 : 0; sh += ps ? 8u : 0u;                                                         \
+          const bool pd = rem > 0;                                 /* one redistribution draw? */      \
+          const uint32_t r = __umulhi((x), (uint32_t)tot);                                             \
+          const uint32_t pre = L * 0x01010101u; /* byte q = L0+..+Lq (tot <= 255: no carries) */       \
+          uint32_t dec = r >= (pre & 0xffu) ? 0x100u : 1u;                                             \
+          dec = r >= __byte_perm(pre, 0, 0x4441) ? 0x10000u : dec;                                     \
+          dec = r >= __byte_perm(pre, 0, 0x4442) ? 0x1000000u : dec;                                   \
+          L -= pd ? dec : 0u; rem -= pd ? 1 : 0; tot -= pd ? 1 : 0;                                    \
         }
-        for (uint32_t blk = 0; !(rem == 0 && m == 4); ++blk) {
-          const U4 r4 = env_draw(c, gid_lo, gid_hi, kBlkRedis + blk, ep, stp);
-          MSORT_EVENT(r4.x); MSORT_EVENT(r4.y); MSORT_EVENT(r4.z); MSORT_EVENT(r4.w);
+        U4 r4 = env_draw(c, gid_lo, gid_hi, kBlkRedis, ep, stp);
+        for (uint32_t blk = 1; !(rem == 0 && m == 4); ++blk) {
+          const U4 cur = r4;
+          r4 = env_draw(c, gid_lo, gid_hi, kBlkRedis + blk, ep, stp);   // next block, overlapped with the events
+          MSORT_EVENT(cur.x); MSORT_EVENT(cur.y); MSORT_EVENT(cur.z); MSORT_EVENT(cur.w);
         }
 #undef MSORT_EVENT
       }
