@@ -32,6 +32,22 @@ __device__ __forceinline__ void flush_tile(const void* __restrict__ tile, void* 
   for (int e = (n16 << 4) + threadIdx.x; e < bytes; e += kTile) db[e] = sb[e];  // partial last tile only
 }
 
+// Full tiles leave through the TMA engine: one elected thread issues a bulk shared->global copy
+// (cp.async.bulk, SASS UBLKCP) of the whole contiguous tile.  Writers must have executed
+// fence.proxy.async + a CTA barrier before; the issuing thread waits until the engine has read
+// the tile so the CTA's shared memory outlives the copy.
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_store(void* __restrict__ dst, const void* __restrict__ tile, uint32_t bytes) {
+  const uint32_t src = (uint32_t)__cvta_generic_to_shared(tile);
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void bulk_commit_and_wait_read() {
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 // bits 0..3 of x -> bytes 0..3 (0/1 each): bit i lands at 8i through the 2^(7i) term
 __device__ __forceinline__ uint32_t spread4(uint32_t x) { return (x * 0x00204081u) & 0x01010101u; }
 
@@ -106,7 +122,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   constexpr int D = Dims<KIND>::D, A = Dims<KIND>::A;
   __shared__ __align__(16) float s_obs[kTile * D];
   __shared__ __align__(16) uint8_t s_mask[kTile * A];
-  __shared__ double s_accs[4][kTile];  // accuracy_sorter (last step's accuracy_belt), per thread
+  __shared__ double s_accs[RNG == MSORT_RNG_REPLAY ? 4 : 1][RNG == MSORT_RNG_REPLAY ? kTile : 1];  // accuracy_sorter (REPLAY)
   __shared__ float s_policy[KIND == MSORT_ENV_PRESS ? MSORT_POLICY_WEIGHTS : 1];
   __shared__ double s_stat[ST_COUNT];
   __shared__ double s_lut[KIND == MSORT_ENV_PRESS ? 1 : kSortLut];
@@ -148,9 +164,11 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     if (act < 0) { act = 0; st_flags += 1u << 24; }
     if (act >= A) { act = A - 1; st_flags += 1u << 24; }
 
-    // accuracy_sorter <- accuracy_belt (env_super.py:457), parked in shared memory for the sort loop
+    // accuracy_sorter <- accuracy_belt (env_super.py:457): registers for the static PHILOX path,
+    // shared memory for REPLAY's dynamically indexed loop
+    double acc_sorter[4];
 #pragma unroll
-    for (int m = 0; m < 4; ++m) s_accs[m][tid] = s.acc[m];
+    for (int m = 0; m < 4; ++m) { acc_sorter[m] = s.acc[m]; if (RNG == MSORT_RNG_REPLAY) s_accs[m][tid] = s.acc[m]; }
 
     // 1: material flow (update_environment env_super.py:440-442)
     s.sort4 = s.belt4; s.belt4 = s.in4;
@@ -224,85 +242,136 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       }
     }
 
-    // 5: sort_material env_super.py:511-609.  One loop over "events"; an event (optionally) starts
-    //    the next station and then (optionally) performs one redistribution draw, so the warp
-    //    iterates max-over-lanes of (stations without draws + total draws).  In PHILOX mode event
-    //    `it` owns random word it&3 of Philox block it>>2 whether or not it draws; the loop is
-    //    unrolled by four so the word selection is static.
-    {
+    // 5: sort_material env_super.py:511-609.
+    if (RNG == MSORT_RNG_REPLAY) {
+      // REPLAY: the reference's loop nest literally (per-class leftovers, numpy's float64 cdf search),
+      // one recorded uniform per draw.
       uint32_t L = s.sort4, T4 = 0, F4 = 0;  // leftover / true / false counts, packed bytes
-      int m = 0, rem = 0, tot = sum4(L);     // tot == sum of the bytes of L, maintained incrementally
+      int m = 0, rem = 0, tot = sum4(L);
       uint32_t sh = 0;
-
-#define MSORT_STATION_START()                                                                          \
-      if (rem == 0 && m < 4) {                                                                         \
-        const int t = (int)((L >> sh) & 0xffu);                                                        \
-        const int tv = __double2int_rn(dmul((double)t, s_accs[m][tid])); /* int(round(t*acc)) (:539) */ \
-        T4 += (uint32_t)tv << sh;                                                                      \
-        L -= (uint32_t)tv << sh; /* leftover[m] = false_val (:546) */                                  \
-        tot -= tv;                                                                                     \
-        rem = t - tv;                                                                                  \
-        F4 += (uint32_t)rem << sh;                                                                     \
-        ++m; sh += 8;                                                                                  \
-      }
-#define MSORT_REMOVE(j)  { L -= 1u << (8 * (j)); --rem; --tot; }
-
-      if (RNG == MSORT_RNG_REPLAY) {
-        while (true) {
-          MSORT_STATION_START();
-          if (rem == 0) { if (m == 4) break; continue; }
-          uint32_t j;
-          if ((long long)s.cursor >= a.redis_len) {
-            st_underrun += 1;
-            j = 0; while (((L >> (8 * j)) & 0xffu) == 0) ++j;  // defined fallback; reported as an under-run
-          } else {
-            const double uu = a.redis_u[i * a.redis_len + s.cursor];
-            s.cursor += 1;
-            double cdf[3], cs = 0.0;  // numpy Generator.choice(4, p=): cumsum, /= last, searchsorted right
+      while (true) {
+        if (rem == 0 && m < 4) {
+          const int t = (int)((L >> sh) & 0xffu);
+          const int tv = __double2int_rn(dmul((double)t, s_accs[m][tid]));  // int(round(t*acc)) (:539)
+          T4 += (uint32_t)tv << sh;
+          L -= (uint32_t)tv << sh;  // leftover[m] = false_val (:546)
+          tot -= tv;
+          rem = t - tv;
+          F4 += (uint32_t)rem << sh;
+          ++m; sh += 8;
+        }
+        if (rem == 0) { if (m == 4) break; continue; }
+        uint32_t j;
+        if ((long long)s.cursor >= a.redis_len) {
+          st_underrun += 1;
+          j = 0; while (((L >> (8 * j)) & 0xffu) == 0) ++j;  // defined fallback; reported as an under-run
+        } else {
+          const double uu = a.redis_u[i * a.redis_len + s.cursor];
+          s.cursor += 1;
+          double cdf[3], cs = 0.0;  // numpy Generator.choice(4, p=): cumsum, /= last, searchsorted right
 #pragma unroll
-            for (int q = 0; q < 4; ++q) { cs = dadd(cs, ddiv((double)b4(L, q), (double)tot)); if (q < 3) cdf[q] = cs; }
-            j = 0;
+          for (int q = 0; q < 4; ++q) { cs = dadd(cs, ddiv((double)b4(L, q), (double)tot)); if (q < 3) cdf[q] = cs; }
+          j = 0;
 #pragma unroll
-            for (int q = 0; q < 3; ++q) j += ddiv(cdf[q], cs) <= uu ? 1u : 0u;
-          }
-          MSORT_REMOVE(j);
+          for (int q = 0; q < 3; ++q) j += ddiv(cdf[q], cs) <= uu ? 1u : 0u;
         }
-      } else {
-        // Branch-free events (selects / predication only) so that the four events of a block and the
-        // Philox rounds of the next block form one basic block the scheduler can interleave.
-        // tot >= rem > 0 whenever a draw happens: the pool always contains this station's own false units.
-#define MSORT_EVENT(x)                                                                                 \
-        {                                                                                              \
-          const bool ps = (rem == 0) & (m < 4);                    /* start the next station? */       \
-          const int t = (int)(__funnelshift_r(L, 0u, sh) & 0xffu);   /* shift count taken mod 32 */      \
-          const int tv = __double2int_rn(dmul((double)t, s_accs[m & 3][tid])); /* rint(t*acc) (:539) */ \
-          const uint32_t tvs = ps ? __funnelshift_l(0u, (uint32_t)tv, sh) : 0u;                                           \
-          T4 += tvs; L -= tvs;                                     /* leftover[m] = false_val (:546) */ \
-          tot -= ps ? tv : 0;                                                                          \
-          rem = ps ? t - tv : rem;                                                                     \
-          F4 += ps ? __funnelshift_l(0u, (uint32_t)rem, sh) : 0u;                                      \
-          m += ps ? 1 : 0; sh += ps ? 8u : 0u;                                                         \
-          const bool pd = rem > 0;                                 /* one redistribution draw? */      \
-          const uint32_t r = __umulhi((x), (uint32_t)tot);                                             \
-          const uint32_t pre = L * 0x01010101u; /* byte q = L0+..+Lq (tot <= 255: no carries) */       \
-          uint32_t dec = r >= (pre & 0xffu) ? 0x100u : 1u;                                             \
-          dec = r >= __byte_perm(pre, 0, 0x4441) ? 0x10000u : dec;                                     \
-          dec = r >= __byte_perm(pre, 0, 0x4442) ? 0x1000000u : dec;                                   \
-          L -= pd ? dec : 0u; rem -= pd ? 1 : 0; tot -= pd ? 1 : 0;                                    \
-        }
-        U4 r4 = env_draw(c, gid_lo, gid_hi, kBlkRedis, ep, stp);
-        for (uint32_t blk = 1; !(rem == 0 && m == 4); ++blk) {
-          const U4 cur = r4;
-          r4 = env_draw(c, gid_lo, gid_hi, kBlkRedis + blk, ep, stp);   // next block, overlapped with the events
-          MSORT_EVENT(cur.x); MSORT_EVENT(cur.y); MSORT_EVENT(cur.z); MSORT_EVENT(cur.w);
-        }
-#undef MSORT_EVENT
+        L -= 1u << (8 * j); --rem; --tot;
       }
-#undef MSORT_REMOVE
-#undef MSORT_STATION_START
       s.e += sum4(L);                                            // :579,597
 #pragma unroll
       for (int q = 0; q < 4; ++q) { s.tr[q] += b4(T4, q); s.fl[q] += b4(F4, q); }  // :600-602
+    } else {
+      // PHILOX: the same random process in the form DESIGN.md §4 "Sorting" derives.
+      // Removing a unit from a station that has already been processed (or from the current
+      // station's own false units) only ever matters through the SUM of those leftovers — it feeds
+      // later selection probabilities and finally container E — so they are kept as one `lump`;
+      // only not-yet-processed stations are tracked individually.  The draws of the last station
+      // cannot influence anything but that sum, which drops by exactly the number of draws, so
+      // they are not simulated.  Draw k of station S uses half (k&1) of word (k>>1)&3 of Philox
+      // block kBlkRedis + 64*S + (k>>3): first half r = hi(x*tot), second half r = hi(lo(x*tot)*tot').
+      // Stations 0 and 1 share one warp loop: a lane whose station 0 has no false units starts
+      // station 1 up front, so lanes drawing for station 0 and lanes drawing for station 1 run
+      // side by side (with the default boosts every env has exactly one of the two to draw for).
+      int X = b4(s.sort4, 1), L2 = b4(s.sort4, 2), L3 = b4(s.sort4, 3);
+      int tot = b4(s.sort4, 0) + X + L2 + L3, lump = 0, rem;
+      uint32_t blk0 = kBlkRedis;          // first Philox block of the station this lane draws for
+      bool started1 = false;
+      {                                   // station 0
+        const int t = b4(s.sort4, 0);
+        const int tv = __double2int_rn(dmul((double)t, acc_sorter[0]));  // int(round(t*acc)) half-to-even (:539)
+        rem = t - tv;
+        s.tr[0] += tv; s.fl[0] += rem;    // :600-602
+        tot -= tv; lump += rem;           // leftover[0] = false_val (:546)
+      }
+#define MSORT_START_STATION1(cond)                                                                    \
+      if (cond) {                                                                                      \
+        const int t = X;                                                                               \
+        const int tv = __double2int_rn(dmul((double)t, acc_sorter[1]));                                \
+        rem = t - tv;                                                                                  \
+        s.tr[1] += tv; s.fl[1] += rem;                                                                 \
+        tot -= tv; lump += rem; X = 0;                                                                 \
+        blk0 = kBlkRedis + 64u; started1 = true;                                                       \
+      }
+      // one draw over the classes (lump, X, L2, L3) in prefix order; `x` is replaced by the low product
+#define MSORT_DRAW4(x)                                                                                 \
+      {                                                                                                \
+        const bool act = rem > 0;                                                                      \
+        const unsigned long long prod = (unsigned long long)(x) * (uint32_t)tot;                       \
+        const int r = (int)(uint32_t)(prod >> 32);                                                     \
+        (x) = (uint32_t)prod;                                                                          \
+        const int c0 = lump, c1 = c0 + X, c2 = c1 + L2;                                                \
+        const bool h0 = r < c0, h1 = r < c1, h2 = r < c2;                                              \
+        lump -= (act && h0) ? 1 : 0;                                                                   \
+        X -= (act && !h0 && h1) ? 1 : 0;                                                               \
+        L2 -= (act && !h1 && h2) ? 1 : 0;                                                              \
+        L3 -= (act && !h2) ? 1 : 0;                                                                    \
+        tot -= act ? 1 : 0; rem -= act ? 1 : 0;                                                        \
+      }
+#define MSORT_DRAW_LOOP4()                                                                             \
+      for (uint32_t b = 0; rem > 0; ++b) {                                                             \
+        U4 r4 = env_draw(c, gid_lo, gid_hi, blk0 + b, ep, stp);                                        \
+        MSORT_DRAW4(r4.x); MSORT_DRAW4(r4.x); MSORT_DRAW4(r4.y); MSORT_DRAW4(r4.y);                    \
+        if (rem <= 0) break;                                                                           \
+        MSORT_DRAW4(r4.z); MSORT_DRAW4(r4.z); MSORT_DRAW4(r4.w); MSORT_DRAW4(r4.w);                    \
+      }
+      MSORT_START_STATION1(rem == 0);
+      MSORT_DRAW_LOOP4();
+      MSORT_START_STATION1(!started1);    // lanes that drew for station 0 move on to station 1 ...
+      MSORT_DRAW_LOOP4();                 // ... whose draws (none with the default boosts) run here
+      {                                   // station 2: classes (lump, L3)
+        const int t = L2;
+        const int tv = __double2int_rn(dmul((double)t, acc_sorter[2]));
+        rem = t - tv;
+        s.tr[2] += tv; s.fl[2] += rem;
+        tot -= tv; lump += rem;
+      }
+#define MSORT_DRAW2(x)                                                                                 \
+      {                                                                                                \
+        const bool act = rem > 0;                                                                      \
+        const unsigned long long prod = (unsigned long long)(x) * (uint32_t)tot;                       \
+        const int r = (int)(uint32_t)(prod >> 32);                                                     \
+        (x) = (uint32_t)prod;                                                                          \
+        const bool h0 = r < lump;                                                                      \
+        lump -= (act && h0) ? 1 : 0;                                                                   \
+        L3 -= (act && !h0) ? 1 : 0;                                                                    \
+        tot -= act ? 1 : 0; rem -= act ? 1 : 0;                                                        \
+      }
+      for (uint32_t b = 0; rem > 0; ++b) {
+        U4 r4 = env_draw(c, gid_lo, gid_hi, kBlkRedis + 128u + b, ep, stp);
+        MSORT_DRAW2(r4.x); MSORT_DRAW2(r4.x); MSORT_DRAW2(r4.y); MSORT_DRAW2(r4.y);
+        if (rem <= 0) break;
+        MSORT_DRAW2(r4.z); MSORT_DRAW2(r4.z); MSORT_DRAW2(r4.w); MSORT_DRAW2(r4.w);
+      }
+      {                                   // station 3: its draws leave `lump` (the sum of all leftovers) unchanged
+        const int t = L3;
+        const int tv = __double2int_rn(dmul((double)t, acc_sorter[3]));
+        s.tr[3] += tv; s.fl[3] += t - tv;
+      }
+#undef MSORT_DRAW2
+#undef MSORT_DRAW_LOOP4
+#undef MSORT_DRAW4
+#undef MSORT_START_STATION1
+      s.e += lump;                                               // :579,597
     }
 
     // 6: Env_1 samples its own press action under the mask (env_super.py:291-300)
@@ -475,13 +544,22 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       if (nu) atomicAdd(&s_stat[ST_UNDERRUN], (double)nu);
     }
   }
+  fence_async_smem();  // order this thread's tile writes before the async-proxy reads below
   __syncthreads();
   if (a.stats && tid < ST_COUNT) {
     const double v = s_stat[tid];
     if (v != 0.0) atomicAdd(&a.stats[tid], v);
   }
-  flush_tile(s_obs, a.obs + row0 * D, rows * D * (int)sizeof(float));
-  if (a.mask) flush_tile(s_mask, a.mask + row0 * A, rows * A);
+  if (rows == kTile) {
+    if (tid == 0) {
+      bulk_store(a.obs + row0 * D, s_obs, kTile * D * (uint32_t)sizeof(float));
+      if (a.mask) bulk_store(a.mask + row0 * A, s_mask, kTile * A);
+      bulk_commit_and_wait_read();
+    }
+  } else {  // partial last tile
+    flush_tile(s_obs, a.obs + row0 * D, rows * D * (int)sizeof(float));
+    if (a.mask) flush_tile(s_mask, a.mask + row0 * A, rows * A);
+  }
 }
 
 // ---------------------------------------------------------------- K2: reset

@@ -331,57 +331,77 @@ static void step_one(const msort_config_t* cfg, msort_env_state_t* s, int64_t i,
     }
   }
 
-  /* 5: sort_material env_super.py:511-609.
-   * The stations are walked as a sequence of "events": event `it` optionally starts the next
-   * station (when the previous one has no draws left) and then optionally performs ONE
-   * redistribution draw.  That is the reference's loop nest (:534-571) flattened; the order of
-   * every operation is unchanged.  In PHILOX mode event `it` owns random word it&3 of block
-   * BLK_REDIS + (it>>2), used or not (the device kernel follows the same rule). */
-  {
+  /* 5: sort_material env_super.py:511-609 */
+  if (replay) {
+    /* REPLAY: the reference's loop nest, one recorded numpy uniform per `choice` call. */
     int L[4], T[4] = {0, 0, 0, 0}, F[4] = {0, 0, 0, 0};
     for (int m = 0; m < 4; ++m) L[m] = s->sorting[m];
-    int m = 0, rem = 0;
-    for (uint32_t it = 0;; ++it) {
-      if (rem == 0) {
-        if (m == 4) break;
-        int t = L[m];                                             /* :535 (already reduced) */
-        int tr = (int)rint((double)t * acc_sorter[m]);            /* :539 half-to-even */
-        int f = t - tr;
-        T[m] = tr; F[m] = f; L[m] = f;                            /* :542-546 */
-        rem = f; ++m;
-      }
-      if (!replay && (it & 3u) == 0) env_draw(cfg, gid, BLK_REDIS + (it >> 2), ep, stp, r4);
-      if (rem > 0) {                                              /* :553-571 */
+    for (int m = 0; m < 4; ++m) {
+      int t = L[m];                                               /* :535 (already reduced) */
+      int tr = (int)rint((double)t * acc_sorter[m]);              /* :539 half-to-even */
+      int f = t - tr;
+      T[m] = tr; F[m] = f; L[m] = f;                              /* :542-546 */
+      for (int k = 0; k < f; ++k) {                               /* :553-571 */
         int tot = L[0] + L[1] + L[2] + L[3];
-        if (tot == 0) { rem = 0; continue; }                      /* :557-559 (unreachable: tot >= rem) */
+        if (tot == 0) break;                                      /* :557-559 (unreachable: tot >= f-k) */
         int j;
-        if (replay) {
-          if (s->replay_cursor >= rp->redis_len) {
-            acc->v[9] += 1;                     /* stream exhausted: defined fallback, reported */
-            j = 0; while (L[j] == 0) ++j;
-          } else {
-            double uu = rp->redis_u[i * rp->redis_len + s->replay_cursor];
-            s->replay_cursor += 1;
-            double cdf[4], c = 0.0;                               /* numpy Generator.choice(4, p=) */
-            for (int q = 0; q < 4; ++q) { c = c + (double)L[q] / (double)tot; cdf[q] = c; }
-            for (int q = 0; q < 4; ++q) cdf[q] = cdf[q] / c;      /* cdf /= cdf[-1] */
-            j = 0;
-            while (j < 4 && cdf[j] <= uu) ++j;                    /* searchsorted(u, 'right') */
-            if (j > 3) j = 3;
-          }
+        if (s->replay_cursor >= rp->redis_len) {
+          acc->v[9] += 1;                       /* stream exhausted: defined fallback, reported */
+          j = 0; while (L[j] == 0) ++j;
         } else {
-          uint32_t x = r4[it & 3u];
-          uint32_t r = (uint32_t)(((uint64_t)x * (uint64_t)(uint32_t)tot) >> 32);
+          double uu = rp->redis_u[i * rp->redis_len + s->replay_cursor];
+          s->replay_cursor += 1;
+          double cdf[4], c = 0.0;                                 /* numpy Generator.choice(4, p=) */
+          for (int q = 0; q < 4; ++q) { c = c + (double)L[q] / (double)tot; cdf[q] = c; }
+          for (int q = 0; q < 4; ++q) cdf[q] = cdf[q] / c;        /* cdf /= cdf[-1] */
           j = 0;
-          uint32_t cum = (uint32_t)L[0];
-          while (r >= cum) { ++j; cum += (uint32_t)L[j]; }
+          while (j < 4 && cdf[j] <= uu) ++j;                      /* searchsorted(u, 'right') */
+          if (j > 3) j = 3;
         }
         L[j] -= 1;                                                /* :566-568 */
-        rem -= 1;
       }
     }
     s->cont_e += L[0] + L[1] + L[2] + L[3];                       /* :579,597 */
     for (int q = 0; q < 4; ++q) { s->cont_true[q] += T[q]; s->cont_false[q] += F[q]; } /* :600-602 */
+  } else {
+    /* PHILOX: the same random process in the form the device kernel evaluates it (DESIGN.md §4
+     * "Sorting").  Each draw removes one unit chosen uniformly from the pool of leftovers
+     * (p_j = leftover_j / total, :562-563).  Units removed from stations that were already
+     * processed (incl. the current station's own false units) matter only through the SUM of those
+     * leftovers (later selection probabilities and finally E), so they are kept as one `lump`;
+     * stations still to be processed are tracked individually.  The last station's draws reduce
+     * only that sum, by exactly their number, so they are not simulated.
+     * Draw i of station S uses half (i&1) of word (i>>1)&3 of block BLK_REDIS + 64*S + (i>>3):
+     * first half r = hi(x*tot), carry = lo(x*tot); second half r = hi(carry*tot'). */
+    int L[4];
+    for (int m = 0; m < 4; ++m) L[m] = s->sorting[m];
+    int tot = L[0] + L[1] + L[2] + L[3], lump = 0;
+    for (int S = 0; S < 4; ++S) {
+      int t = L[S];
+      int tr = (int)rint((double)t * acc_sorter[S]);              /* :539 half-to-even */
+      int f = t - tr;
+      s->cont_true[S] += tr; s->cont_false[S] += f;               /* :600-602 */
+      tot -= tr;
+      if (S == 3) break;                                          /* its f draws leave lump unchanged */
+      lump += f;                                                  /* leftover[S] = false_val joins the lump */
+      uint32_t carry = 0;
+      for (int k = 0; k < f; ++k) {
+        if ((k & 7) == 0) env_draw(cfg, gid, BLK_REDIS + 64u * (uint32_t)S + (uint32_t)(k >> 3), ep, stp, r4);
+        uint32_t x = (k & 1) ? carry : r4[(k >> 1) & 3];
+        uint64_t prod = (uint64_t)x * (uint64_t)(uint32_t)tot;
+        int r = (int)(uint32_t)(prod >> 32);
+        carry = (uint32_t)prod;
+        int c = lump;
+        if (r < c) lump -= 1;
+        else {
+          int q = S + 1;
+          for (; q < 3; ++q) { c += L[q]; if (r < c) break; }
+          L[q] -= 1;
+        }
+        tot -= 1;
+      }
+    }
+    s->cont_e += lump;                                            /* :579,597: sum of all leftovers */
   }
 
   /* 6: Env_1 samples its own press action under the mask (env_super.py:291-300) */
