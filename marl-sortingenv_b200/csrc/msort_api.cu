@@ -131,6 +131,7 @@ static int digest_config(const msort_config_t& c, DevConfig& d) {
   d.kind = c.env_kind;
   d.max_steps = c.max_steps;
   d.flags = c.flags;
+  d.rng_mode = c.rng_mode;
   set_round_keys(d, c.seed);
   d.batch = c.input_batch_size;
   d.spp = c.steps_per_pattern;

@@ -9,7 +9,8 @@
 //     P3  i32 E, n1, n2, last_press_amount
 //     P4  u32 step | q1,q2,gen_counter,0 | u32 episode | i32 replay_cursor
 //     P5  f64 episode_return | 8 B spare
-//     P6  f64 acc_belt[A,B]       P7  f64 acc_belt[C,D]
+//     P6  f64 acc_belt[A,B]       P7  f64 acc_belt[C,D]   (REPLAY mode only: in PHILOX mode the
+//         accuracies are a pure function of (env, episode, step, last mode) and are recomputed)
 //   cold planes (one per material, touched only when a press finishes that material)
 //     P8+m  u32 bale_n[m], bale_sum[m], last_size[m] | last_q[m]<<24, spare
 //
@@ -44,6 +45,7 @@ struct DevConfig {
   long long n, n_pad, gid0;
   int kind, max_steps;
   unsigned flags;
+  int rng_mode;
   unsigned rk[20];  // Philox round keys: rk[2r] = key0 + r*W0, rk[2r+1] = key1 + r*W1
   int batch, spp;
   unsigned pat[2];  // packed u8x4 counts of pattern 1 / 2
@@ -152,16 +154,48 @@ __device__ __forceinline__ void unpack_env(const uint4& p0, const uint4& p1, con
   s.acc[2] = u2d(p7.x, p7.y); s.acc[3] = u2d(p7.z, p7.w);
 }
 
-__device__ __forceinline__ void load_env(const uint4* __restrict__ st, long long n_pad, long long i, Env& s) {
+// update_accuracy (env_super.py:492-509) for one material: clip(base [+ boost] + (low + range*u), 0, 1)
+__device__ __forceinline__ double accuracy_of(const DevConfig& c, int m, int mode, double u) {
+  double base = c.base_acc[m];
+  if ((m & 1) == mode) base = dadd(base, c.boost);
+  return clipd(dadd(base, dadd(c.noise_low, dmul(c.noise_range, u))), 0.0, 1.0);
+}
+
+// PHILOX mode: accuracy_belt after step (episode, step) under `mode`
+__device__ __forceinline__ void philox_accuracy(const DevConfig& c, uint32_t gid_lo, uint32_t gid_hi16, uint32_t episode,
+                                                uint32_t step, int mode, double acc[4]) {
+  const U4 r4 = env_draw(c, gid_lo, gid_hi16, kBlkNoise, episode, step);
+  acc[0] = accuracy_of(c, 0, mode, (double)r4.x * 2.3283064365386963e-10);
+  acc[1] = accuracy_of(c, 1, mode, (double)r4.y * 2.3283064365386963e-10);
+  acc[2] = accuracy_of(c, 2, mode, (double)r4.z * 2.3283064365386963e-10);
+  acc[3] = accuracy_of(c, 3, mode, (double)r4.w * 2.3283064365386963e-10);
+}
+
+// Loads an env.  In PHILOX mode planes P6/P7 are not read: accuracy_belt is recomputed from the
+// previous step's counter and mode (baseline right after a reset, env_super.py:395).
+__device__ __forceinline__ void load_env(const DevConfig& c, const uint4* __restrict__ st, long long i, Env& s) {
+  const long long n_pad = c.n_pad;
   uint4 p0 = st[0 * n_pad + i], p1 = st[1 * n_pad + i], p2 = st[2 * n_pad + i], p3 = st[3 * n_pad + i];
-  uint4 p4 = st[4 * n_pad + i], p5 = st[5 * n_pad + i], p6 = st[6 * n_pad + i], p7 = st[7 * n_pad + i];
+  uint4 p4 = st[4 * n_pad + i], p5 = st[5 * n_pad + i];
+  uint4 p6 = make_uint4(0, 0, 0, 0), p7 = p6;
+  if (c.rng_mode == MSORT_RNG_REPLAY) { p6 = st[6 * n_pad + i]; p7 = st[7 * n_pad + i]; }
   unpack_env(p0, p1, p2, p3, p4, p5, p6, p7, s);
+  if (c.rng_mode != MSORT_RNG_REPLAY) {
+    if (s.step == 0) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) s.acc[m] = c.base_acc[m];
+    } else {
+      const unsigned long long g = (unsigned long long)(c.gid0 + i);
+      philox_accuracy(c, (uint32_t)g, (uint32_t)(g >> 32) & 0xffffu, s.episode, s.step - 1, s.mode, s.acc);
+    }
+  }
 }
 
 __device__ __forceinline__ uint2 d2u(double d) {
   return make_uint2((uint32_t)__double2loint(d), (uint32_t)__double2hiint(d));
 }
 
+template <bool STORE_ACC>
 __device__ __forceinline__ void store_env(uint4* __restrict__ st, long long n_pad, long long i, const Env& s) {
   uint32_t fl = (uint32_t)(s.gfirst | (s.gidx << 1) | (s.started << 2) | ((s.mode & 1) << 3));
   uint32_t w = (uint32_t)s.timer[0] | ((uint32_t)s.timer[1] << 8) | ((uint32_t)s.mat[0] << 16) |
@@ -174,9 +208,11 @@ __device__ __forceinline__ void store_env(uint4* __restrict__ st, long long n_pa
                                  s.episode, (uint32_t)s.cursor);
   uint2 r = d2u(s.ep_ret);
   st[5 * n_pad + i] = make_uint4(r.x, r.y, 0u, 0u);
-  uint2 a0 = d2u(s.acc[0]), a1 = d2u(s.acc[1]), a2 = d2u(s.acc[2]), a3 = d2u(s.acc[3]);
-  st[6 * n_pad + i] = make_uint4(a0.x, a0.y, a1.x, a1.y);
-  st[7 * n_pad + i] = make_uint4(a2.x, a2.y, a3.x, a3.y);
+  if (STORE_ACC) {
+    uint2 a0 = d2u(s.acc[0]), a1 = d2u(s.acc[1]), a2 = d2u(s.acc[2]), a3 = d2u(s.acc[3]);
+    st[6 * n_pad + i] = make_uint4(a0.x, a0.y, a1.x, a1.y);
+    st[7 * n_pad + i] = make_uint4(a2.x, a2.y, a3.x, a3.y);
+  }
 }
 
 __device__ __forceinline__ int level_of(const Env& s, int m) {
@@ -207,17 +243,20 @@ __device__ __forceinline__ bool press_action_valid(const DevConfig& c, const Env
 // k = rint(fl(fl(tr/tot)*100)) as the reference computes round(true/total, 2)*100
 // (env_super.py:754,789).  For tot < 2^22 the float64 pipeline is within 2.3e-14 of the exact
 // value 100*tr/tot while a non-tie is at least 1/(2*tot) away from a rounding boundary, so
-// exact integer rounding gives the same k; on an exact .5 tie (remainder 0) the float64
-// pipeline itself decides (its result depends on how tr/tot rounds).
+// exact integer rounding gives the same k; on an exact .5 tie the float64 pipeline itself
+// decides (its result depends on how tr/tot rounds).  The integer rounding is found with one
+// float32 approximate quotient and an exact integer correction.
 static __device__ __noinline__ int purity_k_f64(int tr, int tot) {
   return __double2int_rn(dmul(ddiv((double)tr, (double)tot), 100.0));
 }
 
 __device__ __forceinline__ int purity_k(int tr, int tot) {  // tot > 0, 0 <= tr <= tot
-  if (tot < (1 << 22)) {
-    unsigned a = 200u * (unsigned)tr + (unsigned)tot, b = 2u * (unsigned)tot;
-    unsigned q = a / b;
-    if (a != q * b) return (int)q;
+  if (tot < (1 << 17)) {                       // 100*tr and tot are exact in float32
+    const int a = 100 * tr;
+    int k = __float2int_rn(__fdividef((float)a, (float)tot));  // within 1 of the exact rounding
+    int d = 2 * (a - k * tot);                 // exact: twice the signed distance to k, in units of 1/tot
+    if (d > tot) { k += 1; d -= 2 * tot; } else if (d < -tot) { k -= 1; d += 2 * tot; }
+    if (d != tot && d != -tot) return k;       // not a .5 tie: exact rounding == float64 pipeline
   }
   return purity_k_f64(tr, tot);
 }

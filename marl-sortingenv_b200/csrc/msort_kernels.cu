@@ -125,7 +125,6 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   __shared__ double s_accs[RNG == MSORT_RNG_REPLAY ? 4 : 1][RNG == MSORT_RNG_REPLAY ? kTile : 1];  // accuracy_sorter (REPLAY)
   __shared__ float s_policy[KIND == MSORT_ENV_PRESS ? MSORT_POLICY_WEIGHTS : 1];
   __shared__ double s_stat[ST_COUNT];
-  __shared__ double s_lut[KIND == MSORT_ENV_PRESS ? 1 : kSortLut];
 
   const bool masking = c.flags & MSORT_F_ACTION_MASKING;
   const bool auto_reset = c.flags & MSORT_F_AUTO_RESET;
@@ -134,9 +133,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   const int tid = threadIdx.x;
   if (use_mlp) for (int k = tid; k < MSORT_POLICY_WEIGHTS; k += kTile) s_policy[k] = c.policy[k];
   if (a.stats && tid < ST_COUNT) s_stat[tid] = 0.0;
-  if (KIND != MSORT_ENV_PRESS && c.fast_pdiff)
-    for (int k = tid; k < kSortLut; k += kTile) s_lut[k] = c.sort_lut[k];
-  __syncthreads();
+  if (use_mlp || a.stats) __syncthreads();
 
   const long long row0 = (long long)blockIdx.x * kTile;
   const long long i = row0 + tid;
@@ -156,7 +153,9 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       const uint4* st = a.state;
       const long long np = c.n_pad;
       uint4 p0 = st[i], p1 = st[np + i], p2 = st[2 * np + i], p3 = st[3 * np + i];
-      uint4 p4 = st[4 * np + i], p5 = st[5 * np + i], p6 = st[6 * np + i], p7 = st[7 * np + i];
+      uint4 p4 = st[4 * np + i], p5 = st[5 * np + i];
+      uint4 p6 = make_uint4(0, 0, 0, 0), p7 = p6;
+      if (RNG == MSORT_RNG_REPLAY) { p6 = st[6 * np + i]; p7 = st[7 * np + i]; }
       unpack_env(p0, p1, p2, p3, p4, p5, p6, p7, s);
     }
     long long act = a.actions[i];
@@ -164,11 +163,27 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     if (act < 0) { act = 0; st_flags += 1u << 24; }
     if (act >= A) { act = A - 1; st_flags += 1u << 24; }
 
-    // accuracy_sorter <- accuracy_belt (env_super.py:457): registers for the static PHILOX path,
-    // shared memory for REPLAY's dynamically indexed loop
+    // accuracy_sorter <- accuracy_belt (env_super.py:457).  REPLAY: stored in planes P6/P7 (and parked in
+    // shared memory for the dynamically indexed loop).  PHILOX: recomputed from the previous step's
+    // counter and mode — 64 B less state traffic per env-step than storing four float64.
     double acc_sorter[4];
+    if (RNG == MSORT_RNG_REPLAY) {
 #pragma unroll
-    for (int m = 0; m < 4; ++m) { acc_sorter[m] = s.acc[m]; if (RNG == MSORT_RNG_REPLAY) s_accs[m][tid] = s.acc[m]; }
+      for (int m = 0; m < 4; ++m) { acc_sorter[m] = s.acc[m]; s_accs[m][tid] = s.acc[m]; }
+    } else if (stp == 0) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) acc_sorter[m] = c.base_acc[m];  // right after reset (env_super.py:395-396)
+    } else {
+      philox_accuracy(c, gid_lo, gid_hi, ep, stp - 1, s.mode, acc_sorter);
+      if (KIND == MSORT_ENV_PRESS) {
+#pragma unroll
+        for (int m = 0; m < 4; ++m) s.acc[m] = acc_sorter[m];  // the embedded policy observes the old accuracies
+      }
+    }
+    if (RNG != MSORT_RNG_REPLAY && KIND == MSORT_ENV_PRESS && stp == 0) {
+#pragma unroll
+      for (int m = 0; m < 4; ++m) s.acc[m] = c.base_acc[m];
+    }
 
     // 1: material flow (update_environment env_super.py:440-442)
     s.sort4 = s.belt4; s.belt4 = s.in4;
@@ -222,24 +237,13 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     s.mode = mode;
 
     // 4: update_accuracy env_super.py:492-509
-    {
-      double u[4];
-      if (RNG == MSORT_RNG_REPLAY) {
-        const double2* nz = reinterpret_cast<const double2*>(a.noise_u) + 2 * i;
-        double2 n0 = nz[0], n1 = nz[1];
-        u[0] = n0.x; u[1] = n0.y; u[2] = n1.x; u[3] = n1.y;
-      } else {
-        U4 r4 = env_draw(c, gid_lo, gid_hi, kBlkNoise, ep, stp);
-        u[0] = (double)r4.x * 2.3283064365386963e-10; u[1] = (double)r4.y * 2.3283064365386963e-10;
-        u[2] = (double)r4.z * 2.3283064365386963e-10; u[3] = (double)r4.w * 2.3283064365386963e-10;
-      }
-#pragma unroll
-      for (int m = 0; m < 4; ++m) {
-        double base = c.base_acc[m];
-        if ((m & 1) == mode) base = dadd(base, c.boost);
-        double nzv = dadd(c.noise_low, dmul(c.noise_range, u[m]));
-        s.acc[m] = clipd(dadd(base, nzv), 0.0, 1.0);
-      }
+    if (RNG == MSORT_RNG_REPLAY) {
+      const double2* nz = reinterpret_cast<const double2*>(a.noise_u) + 2 * i;
+      const double2 n0 = nz[0], n1 = nz[1];
+      s.acc[0] = accuracy_of(c, 0, mode, n0.x); s.acc[1] = accuracy_of(c, 1, mode, n0.y);
+      s.acc[2] = accuracy_of(c, 2, mode, n1.x); s.acc[3] = accuracy_of(c, 3, mode, n1.y);
+    } else {
+      philox_accuracy(c, gid_lo, gid_hi, ep, stp, mode, s.acc);
     }
 
     // 5: sort_material env_super.py:511-609.
@@ -449,7 +453,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
           int kt = 0;
 #pragma unroll
           for (int m = 0; m < 4; ++m) kt += kq[m] >= 0 ? kq[m] : c.qthr100[m];
-          r_sort = s_lut[min(max(kt, 0), kSortLut - 1)];
+          r_sort = __ldg(&c.sort_lut[min(max(kt, 0), kSortLut - 1)]);  // 3.2 KB table, L1-resident
         } else {
           r_sort = sort_reward_f64(c, kq[0], kq[1], kq[2], kq[3]);
         }
@@ -521,7 +525,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       }
     }
     if (a.mask) put_mask_row<A>(s_mask, tid, press_mask_bits(c, s));
-    store_env(a.state, c.n_pad, i, s);
+    store_env<RNG == MSORT_RNG_REPLAY>(a.state, c.n_pad, i, s);
   }
 
   if (a.stats) {  // warp reduce (REDUX for the integer counters) -> shared -> one atomic per CTA per slot
@@ -575,7 +579,7 @@ reset_kernel(const __grid_constant__ DevConfig c, uint4* __restrict__ state, con
   Env s;
   s.episode = 0; s.cursor = 0;
   if (reset_flags & MSORT_RESET_KEEP_STREAMS) {  // reset(seed=None): streams run on (env_super.py:377)
-    load_env(state, c.n_pad, i, s);
+    load_env(c, state, i, s);
     s.episode += 1;
   }
   reset_env(c, s);
@@ -586,7 +590,7 @@ reset_kernel(const __grid_constant__ DevConfig c, uint4* __restrict__ state, con
     s.gfirst = (int)(env_draw(c, (uint32_t)g, (uint32_t)(g >> 32) & 0xffffu, kBlkReset, s.episode, 0u).x & 1u);
   }
   zero_cold(state, c.n_pad, i);
-  store_env(state, c.n_pad, i, s);
+  store_env<true>(state, c.n_pad, i, s);
   if (obs) {
     float o[D];
     env_obs<KIND>(c, s, o);
@@ -613,7 +617,7 @@ observe_kernel(const __grid_constant__ DevConfig c, const uint4* __restrict__ st
   const int rows = (int)min((long long)kTile, c.n - row0);
   if (i < c.n) {
     Env s;
-    load_env(state, c.n_pad, i, s);
+    load_env(c, state, i, s);
     env_obs<KIND>(c, s, &s_obs[threadIdx.x * D]);
     put_mask_row<A>(s_mask, threadIdx.x, press_mask_bits(c, s));
   }
@@ -659,7 +663,7 @@ export_kernel(const __grid_constant__ DevConfig c, const uint4* __restrict__ sta
   const long long i = (long long)blockIdx.x * kTile + threadIdx.x;
   if (i >= c.n) return;
   Env s;
-  load_env(state, c.n_pad, i, s);
+  load_env(c, state, i, s);
   msort_env_state_t o;
   for (int m = 0; m < 4; ++m) {
     o.input[m] = b4(s.in4, m); o.belt[m] = b4(s.belt4, m); o.sorting[m] = b4(s.sort4, m);
@@ -703,7 +707,7 @@ import_kernel(const __grid_constant__ DevConfig c, uint4* __restrict__ state, co
   s.gfirst = o.gen_first == 2 ? 1 : 0; s.gidx = o.gen_idx & 1; s.gcount = o.gen_counter;
   s.step = (uint32_t)o.step; s.episode = (uint32_t)o.episode; s.mode = o.sensor_mode & 1; s.cursor = o.replay_cursor;
   s.ep_ret = o.ep_return;
-  store_env(state, c.n_pad, i, s);
+  store_env<true>(state, c.n_pad, i, s);
   for (int m = 0; m < 5; ++m)
     state[(kHotPlanes + m) * c.n_pad + i] =
         make_uint4((uint32_t)o.bale_n[m], (uint32_t)o.bale_sum[m],
@@ -719,7 +723,7 @@ stats_kernel(const __grid_constant__ DevConfig c, const uint4* __restrict__ stat
   for (int k = 0; k < MSORT_NUM_STATS; ++k) v[k] = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < c.n; i += (long long)gridDim.x * blockDim.x) {
     Env s;
-    load_env(state, c.n_pad, i, s);
+    load_env(c, state, i, s);
     v[0] += 1.0;
     double lvl = (double)s.e, pm = 0.0;
     int kq[4];
