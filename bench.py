@@ -36,7 +36,6 @@ MAX_STEPS = 50
 SEED = 42
 ACTION_SEED = 7
 ALGO_BYTES_PER_STEP = {"sort": 223, "press": 244, "mono": 307}   # SURVEY.md §8d / DESIGN.md
-STATS_EVERY = 32                                                 # rollout length between stat all-reduces
 # dram__bytes_read.sum + dram__bytes_write.sum per step-kernel launch at this workload, from the
 # `ncu --set full` capture summarised in profiles/ (None until a capture exists).
 NCU_TRAFFIC_BYTES_PER_LAUNCH = None
@@ -45,13 +44,15 @@ NCU_TRAFFIC_BYTES_PER_LAUNCH = None
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="msort", choices=["msort", "reference"])
     ap.add_argument("--kind", default="mono", choices=["sort", "press", "mono"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-graph", action="store_true",
+                    help="launch the K timed steps one by one instead of replaying one CUDA graph of them")
     return ap.parse_args()
 
 
@@ -77,7 +78,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -167,7 +168,8 @@ def workload_config(args, world):
             "env": kind_name, "envs_per_gpu": args.envs_per_gpu, "global_envs": args.envs_per_gpu * world,
             "max_steps": MAX_STEPS, "rng": "philox4x32-10", "action_masking": True, "auto_reset": True,
             "l2": "inputs larger than L2 (no flush needed)", "parallelism": f"env-sharded x{world}",
-            "stats_allreduce_every": STATS_EVERY}
+            "launch": "eager" if args.no_graph else "one CUDA graph of the K step kernels",
+            "stats_allreduce": "once per K-step rollout (NCCL, 128 B)"}
 
 
 # ----------------------------------------------------------------------------- CUDA arm
@@ -215,31 +217,44 @@ def run_msort(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- timed region: K fused step() launches back to back
+    # ---- timed region: K fused step() launches back to back (one CUDA graph of K kernel nodes by
+    #      default, so the measurement is not throttled by Python launch overhead)
+    use_graph = not args.no_graph
     env.reset(seed=SEED)
     env.stats.zero_()
-    launches0 = env.launch_count
     for t in range(W):
         env.step(actions[t])
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    graph = None
+    if use_graph:
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for t in range(K):
+                env.step(actions[W + t])
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)] if not use_graph else None
     sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
     if sampler:
         sampler.start(); time.sleep(0.25)
-    launches1 = env.launch_count
     t0 = time.time()
-    ev[0].record()
-    for t in range(K):
-        env.step(actions[W + t])
-        if world > 1 and (t + 1) % STATS_EVERY == 0:
-            allreduce_stats(env.stats.clone())       # the only collective: 128 B of episode stats
-        ev[t + 1].record()
+    ev0.record()
+    if use_graph:
+        graph.replay()
+    else:
+        ev[0].record()
+        for t in range(K):
+            env.step(actions[W + t])
+            ev[t + 1].record()
+    if world > 1:
+        allreduce_stats(env.stats)            # the only collective: 128 B of episode stats per rollout
+    ev1.record()
     barrier()
     t1 = time.time()
-    gpu_launches = env.launch_count - launches1
+    gpu_launches = K
     clocks = sampler.stop(t0, t1) if sampler else None
-    total_ms = ev[0].elapsed_time(ev[K])
-    per_kernel_ms = [ev[t].elapsed_time(ev[t + 1]) for t in range(K)]
+    total_ms = ev0.elapsed_time(ev1)
+    per_kernel_ms = [ev[t].elapsed_time(ev[t + 1]) for t in range(K)] if not use_graph else [total_ms / K]
     assert torch.equal(env.state, final_ref), "timed run diverged from the recorded run (non-determinism)"
     tt = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -247,8 +262,6 @@ def run_msort(args):
     total_ms = float(tt.item())
     value = n * world * K / (total_ms * 1e-3)
     stats = env.stats.clone()
-    if world > 1:
-        stats = allreduce_stats(stats)
     stats = stats.cpu().tolist()
 
     # ---- e2e: the same steps through the host-buffer API (pinned H2D of actions, D2H of results)

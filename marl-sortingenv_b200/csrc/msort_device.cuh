@@ -282,34 +282,58 @@ static __device__ __noinline__ float pdiff_f64(int k, double qthr) {
 }
 
 // ---------------------------------------------------------------- observations (float32 out)
-// ref: get_sort_obs env_super.py:306-325, compute_belt_proportions :199-210.
-// kq[m] = purity k (0..100) of container m, or -1 when the container is empty.
-__device__ __forceinline__ void sort_obs(const DevConfig& c, const Env& s, const int kq[4], float* o) {
-  int bt = sum4(s.belt4);
-  float inv_bt = bt > 0 ? __frcp_rn((float)bt) : 0.f;
+// The observation row is assembled piecewise so the step kernel can write each group as soon as
+// its inputs are final (keeps them out of registers).
+// ref: get_sort_obs env_super.py:306-325 = [belt_occ, belt proportions x4, accuracy_belt x4, purity diffs x4]
+__device__ __forceinline__ void obs_belt(const Env& s, float* o) {  // o[0..4]; compute_belt_proportions :199-210
+  const int bt = sum4(s.belt4);
+  const float inv_bt = bt > 0 ? __frcp_rn((float)bt) : 0.f;
   o[0] = fminf((float)bt * 0.01f, 1.f);
 #pragma unroll
+  for (int m = 0; m < 4; ++m) o[1 + m] = fminf((float)b4(s.belt4, m) * inv_bt, 1.f);
+}
+
+__device__ __forceinline__ void obs_acc(const double acc[4], float* o) {  // o[5..8]; already clipped to [0,1]
+#pragma unroll
+  for (int m = 0; m < 4; ++m) o[5 + m] = (float)acc[m];
+}
+
+// kq[m] = purity k (0..100) of container m, or -1 when the container is empty (purity == threshold)
+__device__ __forceinline__ void obs_pdiff(const DevConfig& c, const int kq[4], float* o) {  // o[9..12]
+#pragma unroll
   for (int m = 0; m < 4; ++m) {
-    o[1 + m] = fminf((float)b4(s.belt4, m) * inv_bt, 1.f);
-    o[5 + m] = (float)s.acc[m];  // already clipped to [0,1]
-    float d = 0.f;               // empty container: purity == threshold -> 0
+    float d = 0.f;
     if (kq[m] >= 0) d = c.fast_pdiff ? (float)(kq[m] - c.qthr100[m]) * 0.01f : pdiff_f64(kq[m], c.qthr[m]);
     o[9 + m] = clipf(d, -1.f, 1.f);
   }
 }
 
-// ref: get_press_obs env_super.py:327-359
-__device__ __forceinline__ void press_obs(const DevConfig& c, const Env& s, float* o) {
+__device__ __forceinline__ void sort_obs(const DevConfig& c, const Env& s, const int kq[4], float* o) {
+  obs_belt(s, o);
+  obs_acc(s.acc, o);
+  obs_pdiff(c, kq, o);
+}
+
+// ref: get_press_obs env_super.py:327-359 = [levels x5, levels x5 again, sorting/stage x4, timers x2]
+__device__ __forceinline__ void obs_levels_timers(const DevConfig& c, const Env& s, float* o) {  // o[0..9], o[14..15]
 #pragma unroll
   for (int m = 0; m < 5; ++m) {
-    int l = m < 4 ? s.tr[m] + s.fl[m] : s.e;
-    float v = fminf((float)l * c.inv_cap, 1.f);
+    const int l = m < 4 ? s.tr[m] + s.fl[m] : s.e;
+    const float v = fminf((float)l * c.inv_cap, 1.f);
     o[m] = v; o[5 + m] = v;
   }
+  o[14] = fminf((float)s.timer[0] * c.inv_pt[0], 1.f);
+  o[15] = fminf((float)s.timer[1] * c.inv_pt[1], 1.f);
+}
+
+__device__ __forceinline__ void obs_sorting(const DevConfig& c, const Env& s, float* o) {  // o[10..13]
 #pragma unroll
   for (int m = 0; m < 4; ++m) o[10 + m] = fminf((float)b4(s.sort4, m) * c.inv_stage, 1.f);
-#pragma unroll
-  for (int p = 0; p < 2; ++p) o[14 + p] = fminf((float)s.timer[p] * c.inv_pt[p], 1.f);
+}
+
+__device__ __forceinline__ void press_obs(const DevConfig& c, const Env& s, float* o) {
+  obs_levels_timers(c, s, o);
+  obs_sorting(c, s, o);
 }
 
 __device__ __forceinline__ void purity_ks(const Env& s, int kq[4]) {

@@ -8,7 +8,7 @@
 #include "msort_launch.h"
 
 #ifndef MSORT_STEP_MIN_BLOCKS
-#define MSORT_STEP_MIN_BLOCKS 6  // resident CTAs per SM the step kernel is compiled for (register cap)
+#define MSORT_STEP_MIN_BLOCKS 7  // resident CTAs per SM the step kernel is compiled for (register cap)
 #endif
 
 namespace msort {
@@ -160,6 +160,8 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     }
     long long act = a.actions[i];
     const uint32_t ep = s.episode, stp = s.step;
+    float* const orow = &s_obs[tid * D];          // this env's row of the dense obs tile
+    float* const prow = orow + (KIND == MSORT_ENV_MONO ? 13 : 0);  // press part of the row
     if (act < 0) { act = 0; st_flags += 1u << 24; }
     if (act >= A) { act = A - 1; st_flags += 1u << 24; }
 
@@ -203,6 +205,8 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       }
       s.gcount += 1;
     }
+    if (KIND != MSORT_ENV_PRESS) obs_belt(s, orow);      // final for this step: write now
+    if (KIND != MSORT_ENV_SORT) obs_sorting(c, s, prow);
 
     // 3: decode the action
     int mode = 0, pa = 0;
@@ -236,14 +240,18 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     }
     s.mode = mode;
 
-    // 4: update_accuracy env_super.py:492-509
+    // 4: update_accuracy env_super.py:492-509.  PHILOX mode does not keep the new accuracies: they go
+    //    straight into the observation and are recomputed next step (Env_2's obs has none at all).
     if (RNG == MSORT_RNG_REPLAY) {
       const double2* nz = reinterpret_cast<const double2*>(a.noise_u) + 2 * i;
       const double2 n0 = nz[0], n1 = nz[1];
       s.acc[0] = accuracy_of(c, 0, mode, n0.x); s.acc[1] = accuracy_of(c, 1, mode, n0.y);
       s.acc[2] = accuracy_of(c, 2, mode, n1.x); s.acc[3] = accuracy_of(c, 3, mode, n1.y);
-    } else {
-      philox_accuracy(c, gid_lo, gid_hi, ep, stp, mode, s.acc);
+      if (KIND != MSORT_ENV_PRESS) obs_acc(s.acc, orow);
+    } else if (KIND != MSORT_ENV_PRESS) {
+      double acc_new[4];
+      philox_accuracy(c, gid_lo, gid_hi, ep, stp, mode, acc_new);
+      obs_acc(acc_new, orow);
     }
 
     // 5: sort_material env_super.py:511-609.
@@ -491,10 +499,8 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     s.ep_ret = dadd(s.ep_ret, reward);
 
     // 10: observation (this env's row of the dense shared tile), outputs, auto-reset
-    float* orow = &s_obs[tid * D];
-    if (KIND != MSORT_ENV_PRESS) sort_obs(c, s, kq, orow);
-    if (KIND == MSORT_ENV_PRESS) press_obs(c, s, orow);
-    if (KIND == MSORT_ENV_MONO) press_obs(c, s, orow + 13);
+    if (KIND != MSORT_ENV_PRESS) obs_pdiff(c, kq, orow);
+    if (KIND != MSORT_ENV_SORT) obs_levels_timers(c, s, prow);
 
     a.reward[i] = (float)reward;
     a.terminated[i] = terminated ? 1 : 0;
