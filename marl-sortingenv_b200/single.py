@@ -1,0 +1,246 @@
+"""Single-environment classes with the reference's exact constructor / reset / step signatures.
+
+`Env_1_Sorting`, `Env_2_Pressing`, `Env_3_Monolith` here are N=1 views of the batched device
+simulator (ref: env_1_sort.py:12-154, env_2_press.py:12-165, env_monolith.py:12-284): numpy
+observations, Python float rewards, bool flags and an `info` dict with the reference's keys.
+They exist so that code written against the reference (testing.py's episode loop, SB3's
+`check_env`, ActionMasker) runs unchanged; for throughput use the batched classes.
+
+Differences that are inherent to the device implementation (documented in DESIGN.md):
+the random plant is the counter-based Philox generator (same distributions, different bits
+than numpy's PCG64 streams), and Python-side logs (`reward_data`, `press_actions_per_timestep`)
+are replaced by counters (`bale_count` holds per-material count / last size / total size).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .batched import ENV_CLASSES
+
+MATERIALS = ["A", "B", "C", "D"]
+ALL5 = MATERIALS + ["E"]
+
+
+class _SingleEnv:
+    kind = "mono"
+
+    def __init__(self, max_steps: int = 50, seed: int = None, noise_sorting: float = 0.05,
+                 balesize: int = 200, simulation=False, config_path=None, device="cuda:0"):
+        self._b = ENV_CLASSES[self.kind](1, device=device, max_steps=max_steps, seed=seed,
+                                         noise_sorting=noise_sorting, balesize=balesize,
+                                         config_path=config_path, auto_reset=False, info_level="full")
+        self.name = self.kind
+        self.max_steps = max_steps
+        self.seed = seed
+        self.material_names = list(MATERIALS)
+        self.observation_space = self._b.observation_space
+        self.action_space = self._b.action_space
+        self.sort_agent = None
+        self.press_agent = None
+        self.mono_agent = None
+        self.bale_standard_size = int(self._b.cfg.bale_size)
+        self.container_global_max = int(self._b.cfg.container_capacity)
+        self._act = torch.zeros(1, dtype=torch.int64, device=self._b.device)
+        self._masking, self._overflow = True, False
+
+    # ------------------------------------------------------------------ gym surface
+    @property
+    def unwrapped(self):
+        return self
+
+    def reset(self, seed=None, options=None):
+        """ref: Env_X.reset(seed) → (obs, {}) (env_super.py:365-420)."""
+        obs, _ = self._b.reset(seed=seed)
+        return obs[0].cpu().numpy().copy(), {}
+
+    def action_masks(self):
+        return self._b.action_masks()[0].cpu().numpy().copy()
+
+    def get_obs(self):
+        return self._b.get_obs()[0].cpu().numpy().copy()
+
+    def close(self):
+        self._b.close()
+
+    def _set_step_flags(self, use_action_masking, check_overflow):
+        if (use_action_masking, check_overflow) != (self._masking, self._overflow):
+            self._b.set_flags(use_action_masking=use_action_masking, check_overflow=check_overflow)
+            self._masking, self._overflow = use_action_masking, check_overflow
+
+    def _do_step(self, action: int, use_action_masking=True, check_overflow=False):
+        self._set_step_flags(bool(use_action_masking), bool(check_overflow))
+        self._act[0] = int(action)
+        obs, rew, term, trunc, info = self._b.step(self._act)
+        out_obs = obs[0].cpu().numpy().copy()
+        reward = float(rew[0].item())
+        terminated = bool(term[0].item())
+        d = {"action": int(info["action"][0].item())}
+        if bool(info["overflow"][0].item()):
+            d = {"overflow": True, "overflow_material": ALL5[int(info["overflow_material"][0].item())],
+                 "action": d["action"]}
+        return out_obs, reward, terminated, False, d
+
+    # ------------------------------------------------------------------ state views (read-only)
+    def _state(self):
+        return self._b.export_state()[0]
+
+    @property
+    def current_step(self):
+        return int(self._state()["step"])
+
+    @property
+    def container_materials(self):
+        s = self._state()
+        d = {m: int(s["cont_true"][i]) for i, m in enumerate(MATERIALS)}
+        d.update({f"{m}_False": int(s["cont_false"][i]) for i, m in enumerate(MATERIALS)})
+        d["E"] = int(s["cont_e"])
+        return d
+
+    @property
+    def press_state(self):
+        s = self._state()
+        out = {}
+        for i in (1, 2):
+            t = int(s["press_timer"][i - 1])
+            out[f"press_{i}"] = t
+            out[f"material_{i}"] = ALL5[int(s["press_mat"][i - 1])] if t > 0 else 0
+            out[f"n_{i}"] = int(s["press_n"][i - 1])
+            out[f"q_{i}"] = int(s["press_q"][i - 1]) / 100.0
+        return out
+
+    @property
+    def bale_count(self):
+        """Per material: dict(count, last_size, last_quality, total_size) — the reference keeps a
+        list of (size, quality) per bale (env_super.py:661-687); the device keeps these counters."""
+        s = self._state()
+        return {m: dict(count=int(s["bale_n"][i]), last_size=int(s["bale_last_size"][i]),
+                        last_quality=int(s["bale_last_q"][i]), total_size=int(s["bale_sum"][i]))
+                for i, m in enumerate(ALL5)}
+
+    @property
+    def current_material_input(self):
+        return [int(x) for x in self._state()["input"]]
+
+    @property
+    def current_material_belt(self):
+        return [int(x) for x in self._state()["belt"]]
+
+    @property
+    def current_material_sorting(self):
+        return [int(x) for x in self._state()["sorting"]]
+
+    @property
+    def accuracy_belt(self):
+        return [float(x) for x in self._state()["acc_belt"]]
+
+    @property
+    def sensor_current_setting(self):
+        return int(self._state()["sensor_mode"])
+
+    # ------------------------------------------------------------------ heuristics (host side, N=1)
+    def sorting_rules(self):
+        """ref: env_super.py:469-482 (float64 proportions, as the reference)."""
+        belt = self.current_material_belt
+        tot = sum(belt)
+        p = [b / tot if tot > 0 else 0 for b in belt]
+        return 0 if p[0] + p[2] > p[1] + p[3] else 1
+
+    def check_container_level(self):
+        """ref: env_super.py:689-720 — fullest container on the first free press."""
+        ps, cm = self.press_state, self.container_materials
+        free = 1 if ps["press_1"] == 0 else (2 if ps["press_2"] == 0 else None)
+        if free is None:
+            return None, None
+        best_idx, best = None, 0
+        for i, m in enumerate(MATERIALS):
+            lvl = cm[m] + cm[f"{m}_False"]
+            if lvl > best:
+                best, best_idx = lvl, i
+        if cm["E"] > best:
+            best, best_idx = cm["E"], 4
+        return (free, best_idx) if best > 0 else (None, None)
+
+    @staticmethod
+    def press_action_to_discrete(press_id, mat_id):
+        return 0 if press_id == 0 else (press_id - 1) * 5 + mat_id + 1
+
+    @staticmethod
+    def press_discrete_to_action(action):
+        if action == 0:
+            return [0, None]
+        return [1 if action <= 5 else 2, (action - 1) % 5]
+
+
+class Env_1_Sorting(_SingleEnv):
+    """ref: env_1_sort.py:12-154 — Box(13) / Discrete(2); the press part acts randomly under the mask."""
+    kind = "sort"
+
+    def set_agents(self, press_agent=None):
+        self.press_agent = press_agent
+
+    def step(self, action=None, use_action_masking=True, check_overflow=False):
+        return self._do_step(action, use_action_masking, check_overflow)
+
+
+class Env_2_Pressing(_SingleEnv):
+    """ref: env_2_press.py:12-165 — Box(16) / Discrete(11); sort mode from the embedded agent or sorting_rules()."""
+    kind = "press"
+
+    def set_agents(self, sort_agent=None):
+        """ref: env_2_press.py:39-40.  The agent's MLP weights are uploaded and evaluated in the kernel."""
+        self.sort_agent = sort_agent
+        self._b.set_sort_policy(sort_agent)
+
+    def step(self, action, use_action_masking=True, check_overflow=False):
+        return self._do_step(action, use_action_masking, check_overflow)
+
+
+class Env_3_Monolith(_SingleEnv):
+    """ref: env_monolith.py:12-284 — Box(29) / Discrete(22); action = 11*sort_mode + press_action."""
+    kind = "mono"
+
+    def set_agents(self, sort_agent=None, press_agent=None, mono_agent=None):
+        self.sort_agent, self.press_agent, self.mono_agent = sort_agent, press_agent, mono_agent
+
+    def step(self, action=None, mode=None, use_action_masking=True, check_overflow=False):
+        """ref: env_monolith.py:109-284.  `action` given → device path.  The other action sources of the
+        reference (`mono_agent`, mode='random' | 'rule_based' | 'model') are resolved on the host
+        from the current obs / mask / state and then stepped on the device."""
+        if action is None:
+            action = self._choose_action(mode, use_action_masking)
+        return self._do_step(int(action), use_action_masking, check_overflow)
+
+    def _choose_action(self, mode, use_action_masking):
+        if self.mono_agent is not None:                                   # :144-150
+            a, _ = self.mono_agent.predict(self.get_obs(), deterministic=True, action_masks=self.action_masks())
+            return int(a)
+        if mode == "random":                                              # :152-164
+            if use_action_masking:
+                return int(self._b.sample_actions(seed=(self.seed or 0) + 0x5EED, t=self.current_step)[0].item())
+            return int(np.random.randint(0, self.action_space.n))
+        if mode == "rule_based":                                          # :166-184
+            sort_mode = self.sorting_rules()
+            job = self.check_container_level()
+            press = self.press_action_to_discrete(job[0] or 0, job[1] or 0) if job != (None, None) else 0
+            return int(sort_mode) * 11 + int(press)
+        if mode == "model":                                               # :186-221
+            obs = self.get_obs()
+            if self.sort_agent is not None:
+                sm, _ = self.sort_agent.predict(obs[:13], deterministic=True)
+                sort_mode = int(sm)
+            else:
+                sort_mode = int(np.random.randint(0, 2))
+            mask = self.action_masks()[:11]
+            if self.press_agent is not None:
+                try:
+                    pa, _ = self.press_agent.predict(obs[13:], deterministic=True, action_masks=mask)
+                except TypeError:
+                    pa, _ = self.press_agent.predict(obs[13:], deterministic=True)
+                press = int(pa)
+            else:
+                valid = np.flatnonzero(mask) if use_action_masking else np.arange(11)
+                press = int(np.random.choice(valid)) if valid.size else 0
+            return sort_mode * 11 + press
+        raise ValueError("Invalid action source: Provide 'action', set 'mode' to 'random', 'rule_based', "
+                         "or 'model', or assign a mono_agent.")   # ref: env_monolith.py:224-225
