@@ -224,6 +224,8 @@ def run_msort(args):
     env.stats.zero_()
     for t in range(W):
         env.step(actions[t])
+    if world > 1:                                  # NCCL communicators are created lazily: do it before timing
+        allreduce_stats(torch.zeros(16, dtype=torch.float64, device=dev))
     graph = None
     if use_graph:
         torch.cuda.synchronize(dev)
@@ -234,9 +236,9 @@ def run_msort(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)] if not use_graph else None
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    barrier()
     if sampler:
         sampler.start(); time.sleep(0.25)
+    barrier()
     t0 = time.time()
     ev0.record()
     if use_graph:
