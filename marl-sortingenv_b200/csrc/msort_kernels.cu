@@ -579,34 +579,41 @@ reset_kernel(const __grid_constant__ DevConfig c, uint4* __restrict__ state, con
              const uint8_t* __restrict__ first_pattern, float* __restrict__ obs, uint8_t* __restrict__ mask,
              uint32_t reset_flags) {
   constexpr int D = Dims<KIND>::D, A = Dims<KIND>::A;
-  const long long i = (long long)blockIdx.x * kTile + threadIdx.x;
-  if (i >= c.n) return;
-  if (which && !which[i]) return;
-  Env s;
-  s.episode = 0; s.cursor = 0;
-  if (reset_flags & MSORT_RESET_KEEP_STREAMS) {  // reset(seed=None): streams run on (env_super.py:377)
-    load_env(c, state, i, s);
-    s.episode += 1;
+  __shared__ __align__(16) float s_obs[kTile * D];
+  __shared__ __align__(16) uint8_t s_mask[kTile * A];
+  const long long row0 = (long long)blockIdx.x * kTile;
+  const long long i = row0 + threadIdx.x;
+  const int rows = (int)min((long long)kTile, c.n - row0);
+  const bool selected = i < c.n && (!which || which[i]);
+  if (selected) {
+    Env s;
+    s.episode = 0; s.cursor = 0;
+    if (reset_flags & MSORT_RESET_KEEP_STREAMS) {  // reset(seed=None): streams run on (env_super.py:377)
+      load_env(c, state, i, s);
+      s.episode += 1;
+    }
+    reset_env(c, s);
+    int fp = first_pattern ? first_pattern[i] : 0;
+    if (fp == 1 || fp == 2) s.gfirst = fp - 1;
+    else {
+      const unsigned long long g = (unsigned long long)(c.gid0 + i);
+      s.gfirst = (int)(env_draw(c, (uint32_t)g, (uint32_t)(g >> 32) & 0xffffu, kBlkReset, s.episode, 0u).x & 1u);
+    }
+    zero_cold(state, c.n_pad, i);
+    store_env<true>(state, c.n_pad, i, s);
+    float* orow = &s_obs[threadIdx.x * D];
+    env_obs<KIND>(c, s, orow);
+    const uint32_t bits = press_mask_bits(c, s);
+    put_mask_row<A>(s_mask, threadIdx.x, bits);
+    if (which) {  // partial reset: only the selected rows may be written
+      if (obs) for (int k = 0; k < D; ++k) obs[i * D + k] = orow[k];
+      if (mask) for (int k = 0; k < A; ++k) mask[i * A + k] = s_mask[threadIdx.x * A + k];
+    }
   }
-  reset_env(c, s);
-  int fp = first_pattern ? first_pattern[i] : 0;
-  if (fp == 1 || fp == 2) s.gfirst = fp - 1;
-  else {
-    const unsigned long long g = (unsigned long long)(c.gid0 + i);
-    s.gfirst = (int)(env_draw(c, (uint32_t)g, (uint32_t)(g >> 32) & 0xffffu, kBlkReset, s.episode, 0u).x & 1u);
-  }
-  zero_cold(state, c.n_pad, i);
-  store_env<true>(state, c.n_pad, i, s);
-  if (obs) {
-    float o[D];
-    env_obs<KIND>(c, s, o);
-#pragma unroll
-    for (int k = 0; k < D; ++k) obs[i * D + k] = o[k];
-  }
-  if (mask) {
-    uint32_t b = press_mask_bits(c, s);
-#pragma unroll
-    for (int k = 0; k < A; ++k) mask[i * A + k] = A == 2 ? 1 : (uint8_t)((b >> (k >= 11 ? k - 11 : k)) & 1u);
+  if (!which) {  // full reset: coalesced flush of the whole tile
+    __syncthreads();
+    if (obs) flush_tile(s_obs, obs + row0 * D, rows * D * (int)sizeof(float));
+    if (mask) flush_tile(s_mask, mask + row0 * A, rows * A);
   }
 }
 
