@@ -389,6 +389,14 @@ static __device__ __noinline__ int press_bale(const DevConfig& c, uint4* __restr
   return made;
 }
 
+// tanh(x) = 1 - 2/(exp(2x)+1) with the hardware ex2/rcp approximations: absolute error ~1e-7
+// (float32 epsilon), i.e. at the level of the fp32 reference's own rounding — the argmax of the
+// policy can only differ from the reference inside its numerical tie band.
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float e = __expf(2.0f * x);
+  return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+
 // fp32 MLP 13->32->32->2 with tanh; weights staged in shared memory by the CTA
 // (ref: sort_agent.predict env_2_press.py:106-109; arch training.py:115)
 __device__ __forceinline__ int mlp_sort_mode(const float* __restrict__ w, const float* x) {
@@ -399,7 +407,7 @@ __device__ __forceinline__ int mlp_sort_mode(const float* __restrict__ w, const 
     float a = b1[j];
 #pragma unroll
     for (int k = 0; k < 13; ++k) a = fmaf(W1[j * 13 + k], x[k], a);
-    h1[j] = tanhf(a);
+    h1[j] = tanh_fast(a);
   }
   float l0 = b3[0], l1 = b3[1];
 #pragma unroll 2
@@ -407,7 +415,7 @@ __device__ __forceinline__ int mlp_sort_mode(const float* __restrict__ w, const 
     float a = b2[j];
 #pragma unroll
     for (int k = 0; k < 32; ++k) a = fmaf(W2[j * 32 + k], h1[k], a);
-    float h = tanhf(a);
+    float h = tanh_fast(a);
     l0 = fmaf(W3[j], h, l0);
     l1 = fmaf(W3[32 + j], h, l1);
   }
