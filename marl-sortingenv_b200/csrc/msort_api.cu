@@ -132,6 +132,11 @@ static int digest_config(const msort_config_t& c, DevConfig& d) {
   d.max_steps = c.max_steps;
   d.flags = c.flags;
   d.rng_mode = c.rng_mode;
+  // State layout (msort_device.cuh): compact 16-bit container counts are safe only when every level
+  // is provably < 2^16: at most input_batch_size units enter per step and auto-reset bounds the episode.
+  d.layout = c.rng_mode == MSORT_RNG_REPLAY ? LAYOUT_REPLAY
+           : ((c.flags & MSORT_F_AUTO_RESET) && (long long)c.input_batch_size * c.max_steps <= 65535ll) ? LAYOUT_COMPACT
+           : LAYOUT_WIDE;
   set_round_keys(d, c.seed);
   d.batch = c.input_batch_size;
   d.spp = c.steps_per_pattern;
@@ -265,6 +270,9 @@ extern "C" int msort_set_seed(msort_t* h, uint64_t seed) {
 
 extern "C" int msort_set_flags(msort_t* h, uint32_t flags) {
   if (!h) return fail(MSORT_E_INVALID, "msort_set_flags: NULL handle");
+  if (h->dev.layout == LAYOUT_COMPACT && !(flags & MSORT_F_AUTO_RESET))
+    return fail(MSORT_E_UNSUPPORTED, "msort_set_flags: this handle was created with auto-reset and uses the compact "
+                "16-bit state layout; create it without MSORT_F_AUTO_RESET to step past max_steps");
   h->cfg.flags = flags;
   h->dev.flags = flags;
   return MSORT_OK;

@@ -46,6 +46,7 @@ struct DevConfig {
   int kind, max_steps;
   unsigned flags;
   int rng_mode;
+  int layout;                      // LAYOUT_* of the state blob (fixed at create)
   unsigned rk[20];  // Philox round keys: rk[2r] = key0 + r*W0, rk[2r+1] = key1 + r*W1
   int batch, spp;
   unsigned pat[2];  // packed u8x4 counts of pattern 1 / 2
@@ -171,16 +172,78 @@ __device__ __forceinline__ void philox_accuracy(const DevConfig& c, uint32_t gid
   acc[3] = accuracy_of(c, 3, mode, (double)r4.w * 2.3283064365386963e-10);
 }
 
-// Loads an env.  In PHILOX mode planes P6/P7 are not read: accuracy_belt is recomputed from the
-// previous step's counter and mode (baseline right after a reset, env_super.py:395).
+// ---------------------------------------------------------------- state layouts
+// LAYOUT_REPLAY : planes P0..P7 (float64 accuracies stored: they come from recorded streams)
+// LAYOUT_WIDE   : planes P0..P5 (PHILOX: accuracies recomputed from the counter)
+// LAYOUT_COMPACT: PHILOX with auto-reset and 100*max_steps <= 65535, so that every container
+//                 level / press amount is provably < 2^16 (at most 100 units enter per step):
+//     C0 = P0
+//     C1 = u16 true[A..D], u16 false[A..D]
+//     C2 = u16 E, n1, n2, last_press_amount | f64 episode_return
+//     C3 = P4
+//   64 B/env instead of 96 B — 64 B less DRAM traffic per env-step.
+enum { LAYOUT_REPLAY = 0, LAYOUT_WIDE = 1, LAYOUT_COMPACT = 2 };
+
+template <int LAYOUT>
+__device__ __forceinline__ void load_planes(const uint4* __restrict__ st, long long n_pad, long long i, Env& s) {
+  if (LAYOUT == LAYOUT_COMPACT) {
+    const uint4 c0 = st[i], c1 = st[n_pad + i], c2 = st[2 * n_pad + i], c3 = st[3 * n_pad + i];
+    const uint4 p1 = make_uint4(c1.x & 0xffffu, c1.x >> 16, c1.y & 0xffffu, c1.y >> 16);
+    const uint4 p2 = make_uint4(c1.z & 0xffffu, c1.z >> 16, c1.w & 0xffffu, c1.w >> 16);
+    const uint4 p3 = make_uint4(c2.x & 0xffffu, c2.x >> 16, c2.y & 0xffffu, c2.y >> 16);
+    const uint4 p5 = make_uint4(c2.z, c2.w, 0u, 0u), z = make_uint4(0u, 0u, 0u, 0u);
+    unpack_env(c0, p1, p2, p3, c3, p5, z, z, s);
+  } else {
+    const uint4 p0 = st[i], p1 = st[n_pad + i], p2 = st[2 * n_pad + i], p3 = st[3 * n_pad + i];
+    const uint4 p4 = st[4 * n_pad + i], p5 = st[5 * n_pad + i];
+    uint4 p6 = make_uint4(0u, 0u, 0u, 0u), p7 = p6;
+    if (LAYOUT == LAYOUT_REPLAY) { p6 = st[6 * n_pad + i]; p7 = st[7 * n_pad + i]; }
+    unpack_env(p0, p1, p2, p3, p4, p5, p6, p7, s);
+  }
+}
+
+__device__ __forceinline__ uint2 d2u(double d) {
+  return make_uint2((uint32_t)__double2loint(d), (uint32_t)__double2hiint(d));
+}
+
+template <int LAYOUT>
+__device__ __forceinline__ void store_planes(uint4* __restrict__ st, long long n_pad, long long i, const Env& s) {
+  const uint32_t fl = (uint32_t)(s.gfirst | (s.gidx << 1) | (s.started << 2) | ((s.mode & 1) << 3));
+  const uint32_t w = (uint32_t)s.timer[0] | ((uint32_t)s.timer[1] << 8) | ((uint32_t)s.mat[0] << 16) |
+                     ((uint32_t)s.mat[1] << 20) | (fl << 24);
+  const uint4 p0 = make_uint4(s.in4, s.belt4, s.sort4, w);
+  const uint4 p4 = make_uint4(s.step, (uint32_t)s.pq[0] | ((uint32_t)s.pq[1] << 8) | ((uint32_t)s.gcount << 16),
+                              s.episode, (uint32_t)s.cursor);
+  const uint2 r = d2u(s.ep_ret);
+  if (LAYOUT == LAYOUT_COMPACT) {
+    st[i] = p0;
+    st[n_pad + i] = make_uint4((uint32_t)s.tr[0] | ((uint32_t)s.tr[1] << 16), (uint32_t)s.tr[2] | ((uint32_t)s.tr[3] << 16),
+                               (uint32_t)s.fl[0] | ((uint32_t)s.fl[1] << 16), (uint32_t)s.fl[2] | ((uint32_t)s.fl[3] << 16));
+    st[2 * n_pad + i] = make_uint4((uint32_t)s.e | ((uint32_t)s.pn[0] << 16), (uint32_t)s.pn[1] | ((uint32_t)s.last_amt << 16),
+                                   r.x, r.y);
+    st[3 * n_pad + i] = p4;
+  } else {
+    st[i] = p0;
+    st[n_pad + i] = make_uint4((uint32_t)s.tr[0], (uint32_t)s.tr[1], (uint32_t)s.tr[2], (uint32_t)s.tr[3]);
+    st[2 * n_pad + i] = make_uint4((uint32_t)s.fl[0], (uint32_t)s.fl[1], (uint32_t)s.fl[2], (uint32_t)s.fl[3]);
+    st[3 * n_pad + i] = make_uint4((uint32_t)s.e, (uint32_t)s.pn[0], (uint32_t)s.pn[1], (uint32_t)s.last_amt);
+    st[4 * n_pad + i] = p4;
+    st[5 * n_pad + i] = make_uint4(r.x, r.y, 0u, 0u);
+    if (LAYOUT == LAYOUT_REPLAY) {
+      const uint2 a0 = d2u(s.acc[0]), a1 = d2u(s.acc[1]), a2 = d2u(s.acc[2]), a3 = d2u(s.acc[3]);
+      st[6 * n_pad + i] = make_uint4(a0.x, a0.y, a1.x, a1.y);
+      st[7 * n_pad + i] = make_uint4(a2.x, a2.y, a3.x, a3.y);
+    }
+  }
+}
+
+// Runtime-dispatched load/store for the kernels off the hot path.  In PHILOX layouts accuracy_belt is
+// recomputed from the previous step's counter and mode (baseline right after a reset, env_super.py:395).
 __device__ __forceinline__ void load_env(const DevConfig& c, const uint4* __restrict__ st, long long i, Env& s) {
-  const long long n_pad = c.n_pad;
-  uint4 p0 = st[0 * n_pad + i], p1 = st[1 * n_pad + i], p2 = st[2 * n_pad + i], p3 = st[3 * n_pad + i];
-  uint4 p4 = st[4 * n_pad + i], p5 = st[5 * n_pad + i];
-  uint4 p6 = make_uint4(0, 0, 0, 0), p7 = p6;
-  if (c.rng_mode == MSORT_RNG_REPLAY) { p6 = st[6 * n_pad + i]; p7 = st[7 * n_pad + i]; }
-  unpack_env(p0, p1, p2, p3, p4, p5, p6, p7, s);
-  if (c.rng_mode != MSORT_RNG_REPLAY) {
+  if (c.layout == LAYOUT_COMPACT) load_planes<LAYOUT_COMPACT>(st, c.n_pad, i, s);
+  else if (c.layout == LAYOUT_WIDE) load_planes<LAYOUT_WIDE>(st, c.n_pad, i, s);
+  else load_planes<LAYOUT_REPLAY>(st, c.n_pad, i, s);
+  if (c.layout != LAYOUT_REPLAY) {
     if (s.step == 0) {
 #pragma unroll
       for (int m = 0; m < 4; ++m) s.acc[m] = c.base_acc[m];
@@ -191,28 +254,10 @@ __device__ __forceinline__ void load_env(const DevConfig& c, const uint4* __rest
   }
 }
 
-__device__ __forceinline__ uint2 d2u(double d) {
-  return make_uint2((uint32_t)__double2loint(d), (uint32_t)__double2hiint(d));
-}
-
-template <bool STORE_ACC>
-__device__ __forceinline__ void store_env(uint4* __restrict__ st, long long n_pad, long long i, const Env& s) {
-  uint32_t fl = (uint32_t)(s.gfirst | (s.gidx << 1) | (s.started << 2) | ((s.mode & 1) << 3));
-  uint32_t w = (uint32_t)s.timer[0] | ((uint32_t)s.timer[1] << 8) | ((uint32_t)s.mat[0] << 16) |
-               ((uint32_t)s.mat[1] << 20) | (fl << 24);
-  st[0 * n_pad + i] = make_uint4(s.in4, s.belt4, s.sort4, w);
-  st[1 * n_pad + i] = make_uint4((uint32_t)s.tr[0], (uint32_t)s.tr[1], (uint32_t)s.tr[2], (uint32_t)s.tr[3]);
-  st[2 * n_pad + i] = make_uint4((uint32_t)s.fl[0], (uint32_t)s.fl[1], (uint32_t)s.fl[2], (uint32_t)s.fl[3]);
-  st[3 * n_pad + i] = make_uint4((uint32_t)s.e, (uint32_t)s.pn[0], (uint32_t)s.pn[1], (uint32_t)s.last_amt);
-  st[4 * n_pad + i] = make_uint4(s.step, (uint32_t)s.pq[0] | ((uint32_t)s.pq[1] << 8) | ((uint32_t)s.gcount << 16),
-                                 s.episode, (uint32_t)s.cursor);
-  uint2 r = d2u(s.ep_ret);
-  st[5 * n_pad + i] = make_uint4(r.x, r.y, 0u, 0u);
-  if (STORE_ACC) {
-    uint2 a0 = d2u(s.acc[0]), a1 = d2u(s.acc[1]), a2 = d2u(s.acc[2]), a3 = d2u(s.acc[3]);
-    st[6 * n_pad + i] = make_uint4(a0.x, a0.y, a1.x, a1.y);
-    st[7 * n_pad + i] = make_uint4(a2.x, a2.y, a3.x, a3.y);
-  }
+__device__ __forceinline__ void store_env(const DevConfig& c, uint4* __restrict__ st, long long i, const Env& s) {
+  if (c.layout == LAYOUT_COMPACT) store_planes<LAYOUT_COMPACT>(st, c.n_pad, i, s);
+  else if (c.layout == LAYOUT_WIDE) store_planes<LAYOUT_WIDE>(st, c.n_pad, i, s);
+  else store_planes<LAYOUT_REPLAY>(st, c.n_pad, i, s);
 }
 
 __device__ __forceinline__ int level_of(const Env& s, int m) {

@@ -116,7 +116,7 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-template <int KIND, int RNG>
+template <int KIND, int RNG, int LAYOUT>
 __global__ void __launch_bounds__(kTile, KIND == MSORT_ENV_PRESS ? 5 : MSORT_STEP_MIN_BLOCKS)  // Env_2 keeps 32 MLP activations in registers
 step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArgs a) {
   constexpr int D = Dims<KIND>::D, A = Dims<KIND>::A;
@@ -149,15 +149,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     const unsigned long long gid = (unsigned long long)(c.gid0 + i);
     const uint32_t gid_lo = (uint32_t)gid, gid_hi = (uint32_t)(gid >> 32) & 0xffffu;
     Env s;
-    {
-      const uint4* st = a.state;
-      const long long np = c.n_pad;
-      uint4 p0 = st[i], p1 = st[np + i], p2 = st[2 * np + i], p3 = st[3 * np + i];
-      uint4 p4 = st[4 * np + i], p5 = st[5 * np + i];
-      uint4 p6 = make_uint4(0, 0, 0, 0), p7 = p6;
-      if (RNG == MSORT_RNG_REPLAY) { p6 = st[6 * np + i]; p7 = st[7 * np + i]; }
-      unpack_env(p0, p1, p2, p3, p4, p5, p6, p7, s);
-    }
+    load_planes<LAYOUT>(a.state, c.n_pad, i, s);
     long long act = a.actions[i];
     const uint32_t ep = s.episode, stp = s.step;
     float* const orow = &s_obs[tid * D];          // this env's row of the dense obs tile
@@ -531,7 +523,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       }
     }
     if (a.mask) put_mask_row<A>(s_mask, tid, press_mask_bits(c, s));
-    store_env<RNG == MSORT_RNG_REPLAY>(a.state, c.n_pad, i, s);
+    store_planes<LAYOUT>(a.state, c.n_pad, i, s);
   }
 
   if (a.stats) {  // warp reduce (REDUX for the integer counters) -> shared -> one atomic per CTA per slot
@@ -600,7 +592,7 @@ reset_kernel(const __grid_constant__ DevConfig c, uint4* __restrict__ state, con
       s.gfirst = (int)(env_draw(c, (uint32_t)g, (uint32_t)(g >> 32) & 0xffffu, kBlkReset, s.episode, 0u).x & 1u);
     }
     zero_cold(state, c.n_pad, i);
-    store_env<true>(state, c.n_pad, i, s);
+    store_env(c, state, i, s);
     float* orow = &s_obs[threadIdx.x * D];
     env_obs<KIND>(c, s, orow);
     const uint32_t bits = press_mask_bits(c, s);
@@ -720,7 +712,7 @@ import_kernel(const __grid_constant__ DevConfig c, uint4* __restrict__ state, co
   s.gfirst = o.gen_first == 2 ? 1 : 0; s.gidx = o.gen_idx & 1; s.gcount = o.gen_counter;
   s.step = (uint32_t)o.step; s.episode = (uint32_t)o.episode; s.mode = o.sensor_mode & 1; s.cursor = o.replay_cursor;
   s.ep_ret = o.ep_return;
-  store_env<true>(state, c.n_pad, i, s);
+  store_env(c, state, i, s);
   for (int m = 0; m < 5; ++m)
     state[(kHotPlanes + m) * c.n_pad + i] =
         make_uint4((uint32_t)o.bale_n[m], (uint32_t)o.bale_sum[m],
@@ -774,8 +766,9 @@ static inline unsigned tiles(long long n) { return (unsigned)((n + kTile - 1) / 
 
 template <int KIND>
 static cudaError_t launch_step_kind(const DevConfig& c, const StepArgs& a, int rng, cudaStream_t st) {
-  if (rng == MSORT_RNG_REPLAY) step_kernel<KIND, MSORT_RNG_REPLAY><<<tiles(c.n), kTile, 0, st>>>(c, a);
-  else step_kernel<KIND, MSORT_RNG_PHILOX><<<tiles(c.n), kTile, 0, st>>>(c, a);
+  if (rng == MSORT_RNG_REPLAY) step_kernel<KIND, MSORT_RNG_REPLAY, LAYOUT_REPLAY><<<tiles(c.n), kTile, 0, st>>>(c, a);
+  else if (c.layout == LAYOUT_COMPACT) step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT><<<tiles(c.n), kTile, 0, st>>>(c, a);
+  else step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_WIDE><<<tiles(c.n), kTile, 0, st>>>(c, a);
   return cudaGetLastError();
 }
 
