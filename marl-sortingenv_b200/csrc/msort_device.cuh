@@ -35,7 +35,10 @@ namespace msort {
 constexpr int kHotPlanes = 8;
 constexpr int kColdPlanes = 5;
 constexpr int kPlanes = kHotPlanes + kColdPlanes;
-constexpr int kTile = 128;  // envs per CTA tile == threads per CTA
+#ifndef MSORT_TILE
+#define MSORT_TILE 128
+#endif
+constexpr int kTile = MSORT_TILE;  // envs per CTA tile == threads per CTA (32, 64 or 128)
 
 // Philox draw blocks (shared with oracle/msort_oracle.c)
 constexpr uint32_t kBlkNoise = 0, kBlkPress = 1, kBlkReset = 2, kBlkInput = 3, kBlkRedis = 16;

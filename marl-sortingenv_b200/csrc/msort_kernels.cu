@@ -117,7 +117,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 template <int KIND, int RNG, int LAYOUT>
-__global__ void __launch_bounds__(kTile, KIND == MSORT_ENV_PRESS ? 5 : MSORT_STEP_MIN_BLOCKS)  // Env_2 keeps 32 MLP activations in registers
+__global__ void __launch_bounds__(kTile, (KIND == MSORT_ENV_PRESS ? 5 : MSORT_STEP_MIN_BLOCKS) * (128 / kTile))  // Env_2 keeps 32 MLP activations in registers
 step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArgs a) {
   constexpr int D = Dims<KIND>::D, A = Dims<KIND>::A;
   __shared__ __align__(16) float s_obs[kTile * D];
