@@ -1,0 +1,163 @@
+"""GPU-resident MaskablePPO-style rollout + update loop (SURVEY.md §8f item 1 — a CALLER of the hot path).
+
+The reference trains with sb3_contrib.MaskablePPO on one CPU env (training.py:118-143:
+`net_arch=dict(pi=[32,32], vf=[32,32])`, `ent_coef=0.05`, SB3 defaults n_epochs=10, clip 0.2,
+gamma 0.99, lambda 0.95, lr 3e-4, vf_coef 0.5, max_grad_norm 0.5).  SB3's collector loops over
+envs in Python, so it cannot drive 1e4..1e6 device envs; this module is the same algorithm with
+every tensor (observations, masks, actions, advantages, minibatches) resident on the GPU and the
+env stepped by the fused CUDA kernel.  Plain PyTorch — plumbing around the product, not the product.
+"""
+from __future__ import annotations
+
+import math
+import time
+
+import torch
+import torch.nn as nn
+
+
+def _mlp(inp: int, out: int, gain: float) -> nn.Sequential:
+    net = nn.Sequential(nn.Linear(inp, 32), nn.Tanh(), nn.Linear(32, 32), nn.Tanh(), nn.Linear(32, out))
+    for i, g in ((0, math.sqrt(2)), (2, math.sqrt(2)), (4, gain)):       # SB3's orthogonal init
+        nn.init.orthogonal_(net[i].weight, gain=g)
+        nn.init.zeros_(net[i].bias)
+    return net
+
+
+class MaskableActorCritic(nn.Module):
+    """Separate 32-32 tanh towers for policy and value (MaskableActorCriticPolicy, training.py:115)."""
+
+    def __init__(self, obs_dim: int, n_actions: int):
+        super().__init__()
+        self.pi = _mlp(obs_dim, n_actions, 0.01)
+        self.vf = _mlp(obs_dim, 1, 1.0)
+
+    def masked_logits(self, obs, mask):
+        return self.pi(obs).masked_fill(~mask, -1e8)                     # sb3_contrib masks logits with -1e8
+
+    def act(self, obs, mask, deterministic=False):
+        logits = self.masked_logits(obs, mask)
+        logp_all = torch.log_softmax(logits, dim=-1)
+        if deterministic:
+            a = logits.argmax(dim=-1)
+        else:
+            a = torch.multinomial(logp_all.exp(), 1).squeeze(1)
+        return a, logp_all.gather(1, a[:, None]).squeeze(1), self.vf(obs).squeeze(1)
+
+    def evaluate(self, obs, mask, actions):
+        logp_all = torch.log_softmax(self.masked_logits(obs, mask), dim=-1)
+        p = logp_all.exp()
+        entropy = -(p * logp_all.masked_fill(~mask, 0.0)).sum(-1)
+        return logp_all.gather(1, actions[:, None]).squeeze(1), entropy, self.vf(obs).squeeze(1)
+
+
+class MaskablePPO:
+    def __init__(self, env, n_steps: int = 64, batch_size: int = 8192, n_epochs: int = 10, gamma: float = 0.99,
+                 gae_lambda: float = 0.95, clip_range: float = 0.2, ent_coef: float = 0.05, vf_coef: float = 0.5,
+                 learning_rate: float = 3e-4, max_grad_norm: float = 0.5, seed: int = 42):
+        self.env = env
+        self.n, self.D, self.A = env.num_envs, env.D, env.A
+        self.dev = env.device
+        torch.manual_seed(seed)
+        self.policy = MaskableActorCritic(self.D, self.A).to(self.dev)
+        self.opt = torch.optim.Adam(self.policy.parameters(), lr=learning_rate, eps=1e-5)
+        self.n_steps, self.batch_size, self.n_epochs = n_steps, batch_size, n_epochs
+        self.gamma, self.lam, self.clip = gamma, gae_lambda, clip_range
+        self.ent_coef, self.vf_coef, self.max_grad_norm = ent_coef, vf_coef, max_grad_norm
+        T, n, dev = n_steps, self.n, self.dev
+        self.buf = dict(obs=torch.zeros((T, n, self.D), device=dev), mask=torch.zeros((T, n, self.A), dtype=torch.bool, device=dev),
+                        act=torch.zeros((T, n), dtype=torch.int64, device=dev), logp=torch.zeros((T, n), device=dev),
+                        val=torch.zeros((T, n), device=dev), rew=torch.zeros((T, n), device=dev),
+                        done=torch.zeros((T, n), dtype=torch.bool, device=dev))
+        self.num_timesteps = 0
+        self._obs = None
+        self.log = []
+
+    # ------------------------------------------------------------------ rollout
+    @torch.no_grad()
+    def collect_rollout(self):
+        env, b = self.env, self.buf
+        if self._obs is None:
+            self._obs, _ = env.reset()
+        for t in range(self.n_steps):
+            b["obs"][t].copy_(self._obs)
+            b["mask"][t].copy_(env.action_masks())
+            a, logp, v = self.policy.act(b["obs"][t], b["mask"][t])
+            b["act"][t], b["logp"][t], b["val"][t] = a, logp, v
+            obs, rew, term, _, _ = env.step(a)                           # fused CUDA step (auto-reset inside)
+            b["rew"][t].copy_(rew); b["done"][t].copy_(term)
+            self._obs = obs
+        last_v = self.policy.vf(self._obs).squeeze(1)
+        adv = torch.zeros_like(b["rew"])
+        gae = torch.zeros(self.n, device=self.dev)
+        for t in reversed(range(self.n_steps)):                          # GAE(lambda); `terminated` ends the episode
+            nonterm = (~b["done"][t]).float()
+            next_v = last_v if t == self.n_steps - 1 else b["val"][t + 1]
+            delta = b["rew"][t] + self.gamma * next_v * nonterm - b["val"][t]
+            gae = delta + self.gamma * self.lam * nonterm * gae
+            adv[t] = gae
+        self.num_timesteps += self.n_steps * self.n
+        return adv, adv + b["val"]
+
+    # ------------------------------------------------------------------ update
+    def update(self, adv, ret):
+        b = self.buf
+        N = self.n_steps * self.n
+        flat = {k: v.reshape(N, *v.shape[2:]) for k, v in b.items()}
+        adv, ret = adv.reshape(N), ret.reshape(N)
+        stats = {}
+        for _ in range(self.n_epochs):
+            perm = torch.randperm(N, device=self.dev)
+            for s in range(0, N, self.batch_size):
+                idx = perm[s:s + self.batch_size]
+                logp, ent, v = self.policy.evaluate(flat["obs"][idx], flat["mask"][idx], flat["act"][idx])
+                a = adv[idx]
+                a = (a - a.mean()) / (a.std() + 1e-8)
+                ratio = (logp - flat["logp"][idx]).exp()
+                pg = -torch.min(a * ratio, a * ratio.clamp(1 - self.clip, 1 + self.clip)).mean()
+                vl = torch.nn.functional.mse_loss(v, ret[idx])
+                loss = pg + self.vf_coef * vl - self.ent_coef * ent.mean()
+                self.opt.zero_grad(set_to_none=True)
+                loss.backward()
+                nn.utils.clip_grad_norm_(self.policy.parameters(), self.max_grad_norm)
+                self.opt.step()
+            stats = dict(pg=float(pg.detach()), vf=float(vl.detach()), ent=float(ent.detach().mean()))
+        return stats
+
+    def learn(self, total_timesteps: int, log_every: int = 10):
+        it, t0 = 0, time.time()
+        while self.num_timesteps < total_timesteps:
+            adv, ret = self.collect_rollout()
+            st = self.update(adv, ret)
+            it += 1
+            if it % log_every == 0:
+                st.update(timesteps=self.num_timesteps, mean_step_reward=float(self.buf["rew"].mean()),
+                          sps=self.num_timesteps / (time.time() - t0))
+                self.log.append(st)
+        return self
+
+    # ------------------------------------------------------------------ SB3-style inference
+    @torch.no_grad()
+    def predict(self, obs, action_masks=None, deterministic=True):
+        o = torch.as_tensor(obs, device=self.dev, dtype=torch.float32)
+        single = o.dim() == 1
+        o = o.reshape(-1, self.D)
+        m = (torch.ones((o.shape[0], self.A), dtype=torch.bool, device=self.dev) if action_masks is None
+             else torch.as_tensor(action_masks, device=self.dev, dtype=torch.bool).reshape(-1, self.A))
+        a, _, _ = self.policy.act(o, m, deterministic=deterministic)
+        return (int(a[0]) if single else a), None
+
+
+@torch.no_grad()
+def evaluate_policy(model, env_cls, n_envs: int = 1024, steps: int = 200, seed: int = 1, **env_kwargs):
+    """Mean / std of the cumulative reward of the deterministic masked policy over `n_envs` fresh episodes
+    (the reference's protocol: 200 steps, noise 0 — main.py:42-52, benchmark_models.py:126-171)."""
+    env = env_cls(n_envs, max_steps=steps, seed=seed, auto_reset=False, device=model.dev, **env_kwargs)
+    obs, _ = env.reset()
+    total = torch.zeros(n_envs, dtype=torch.float64, device=model.dev)
+    for _ in range(steps):
+        a, _ = model.predict(obs, action_masks=env.action_masks(), deterministic=True)
+        obs, r, term, _, _ = env.step(a)
+        total += r.double()
+    env.close()
+    return total.mean().item(), total.std().item()
