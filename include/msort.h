@@ -245,6 +245,14 @@ int msort_observe(msort_t* h, const void* state, float* obs, uint8_t* mask, void
 int msort_sample_actions(msort_t* h, const uint8_t* mask, int64_t* actions, uint64_t seed, uint32_t t,
                          void* stream);
 
+/* Rule-based action source: sort mode from sorting_rules() (env_super.py:469-482), press job from
+ * check_container_level() (env_super.py:689-720: first free press, fullest container with level > 0),
+ * combined as Env_3.step(mode='rule_based') does (env_monolith.py:166-184).  Env_1 gets the sort mode,
+ * Env_2 the press action.  after_shift != 0 evaluates sorting_rules() on the belt as it will be
+ * AFTER this step's material shift (belt <- input), which is where Env_3.step calls it
+ * (env_monolith.py:114-115 then :168); 0 evaluates it on the current belt (an external caller). */
+int msort_rule_based_actions(msort_t* h, const void* state, int after_shift, int64_t* actions, void* stream);
+
 /* SoA device blob <-> plain msort_env_state_t[N] (device memory). */
 int msort_export_state(msort_t* h, const void* state, msort_env_state_t* out, void* stream);
 int msort_import_state(msort_t* h, void* state, const msort_env_state_t* in, void* stream);

@@ -140,6 +140,7 @@ SYMBOLS = {
                              C.POINTER(MsortReplay), _P]),
     "msort_set_policy": (C.c_int, [_P, _P, C.c_int, _P]),
     "msort_sample_actions": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint32, _P]),
+    "msort_rule_based_actions": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "msort_observe": (C.c_int, [_P, _P, _P, _P, _P]),
     "msort_export_state": (C.c_int, [_P, _P, _P, _P]),
     "msort_import_state": (C.c_int, [_P, _P, _P, _P]),

@@ -195,6 +195,18 @@ class BatchedEnv:
         _abi.check(self.lib, rc, "msort_sample_actions")
         return out
 
+    def rule_based_actions(self, after_shift: bool = True, out: torch.Tensor | None = None) -> torch.Tensor:
+        """The reference's heuristic policy for every env (one kernel launch): sorting_rules() +
+        check_container_level() combined as Env_3.step(mode='rule_based') does
+        (env_monolith.py:166-184, env_super.py:469-482, 689-720)."""
+        if out is None:
+            out = torch.empty(self.num_envs, dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.msort_rule_based_actions(self._h, _ptr(self.state), 1 if after_shift else 0, _ptr(out),
+                                                   self._stream())
+        _abi.check(self.lib, rc, "msort_rule_based_actions")
+        return out
+
     # ------------------------------------------------------------------ host-buffer surface
     def _host_buffers(self):
         if getattr(self, "_hb", None) is None:

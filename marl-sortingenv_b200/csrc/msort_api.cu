@@ -347,6 +347,14 @@ extern "C" int msort_sample_actions(msort_t* h, const uint8_t* mask, int64_t* ac
   return MSORT_OK;
 }
 
+extern "C" int msort_rule_based_actions(msort_t* h, const void* state, int after_shift, int64_t* actions, void* stream) {
+  if (!h || !state || !actions) return fail(MSORT_E_INVALID, "msort_rule_based_actions: NULL argument");
+  if (!aligned(state, 16) || !aligned(actions, 8)) return fail(MSORT_E_INVALID, "msort_rule_based_actions: misaligned buffer");
+  MSORT_TRY_CUDA(launch_rule_actions(h->dev, state, after_shift, actions, (cudaStream_t)stream), "rule-based action kernel");
+  h->launches += 1;
+  return MSORT_OK;
+}
+
 extern "C" int msort_export_state(msort_t* h, const void* state, msort_env_state_t* out, void* stream) {
   if (!h || !state || !out) return fail(MSORT_E_INVALID, "msort_export_state: NULL argument");
   if (!aligned(state, 16) || !aligned(out, 8)) return fail(MSORT_E_INVALID, "msort_export_state: misaligned buffer");

@@ -662,6 +662,37 @@ sample_kernel(const __grid_constant__ DevConfig c, const uint8_t* __restrict__ m
   actions[row0 + threadIdx.x] = a;
 }
 
+// ---------------------------------------------------------------- rule-based action source
+// ref: Env_3.step(mode='rule_based') env_monolith.py:166-184
+__global__ void __launch_bounds__(kTile)
+rule_actions_kernel(const __grid_constant__ DevConfig c, const uint4* __restrict__ state, int after_shift,
+                    long long* __restrict__ actions) {
+  const long long i = (long long)blockIdx.x * kTile + threadIdx.x;
+  if (i >= c.n) return;
+  Env s;
+  load_env(c, state, i, s);
+  // sorting_rules env_super.py:469-482: mode 0 iff pA+pC > pB+pD (float64 proportions; empty belt -> 1)
+  const uint32_t belt = after_shift ? s.in4 : s.belt4;
+  const int ac = b4(belt, 0) + b4(belt, 2), bd = b4(belt, 1) + b4(belt, 3), bt = ac + bd;
+  int mode;
+  if (ac != bd) mode = ac > bd ? 0 : 1;
+  else {
+    double p[4];
+    for (int m = 0; m < 4; ++m) p[m] = bt > 0 ? ddiv((double)b4(belt, m), (double)bt) : 0.0;
+    mode = dadd(p[0], p[2]) > dadd(p[1], p[3]) ? 0 : 1;
+  }
+  // check_container_level env_super.py:689-720
+  int press = 0;
+  const int free_press = s.timer[0] == 0 ? 1 : (s.timer[1] == 0 ? 2 : 0);
+  if (free_press) {
+    int best = 0, idx = -1;
+    for (int m = 0; m < 4; ++m) { const int l = s.tr[m] + s.fl[m]; if (l > best) { best = l; idx = m; } }
+    if (s.e > best) { best = s.e; idx = 4; }
+    if (best > 0) press = (free_press - 1) * 5 + idx + 1;   // press_action_to_discrete :864-867
+  }
+  actions[i] = c.kind == MSORT_ENV_SORT ? mode : (c.kind == MSORT_ENV_PRESS ? press : 11 * mode + press);
+}
+
 // ---------------------------------------------------------------- K6: export / import
 __global__ void __launch_bounds__(kTile)
 export_kernel(const __grid_constant__ DevConfig c, const uint4* __restrict__ state, msort_env_state_t* __restrict__ out) {
@@ -825,6 +856,11 @@ cudaError_t launch_sample(const DevConfig& c, const uint8_t* mask, int64_t* acti
     case MSORT_ENV_PRESS: sample_kernel<11><<<tiles(c.n), kTile, 0, st>>>(c, mask, (long long*)actions, k0, k1, t); break;
     default: sample_kernel<22><<<tiles(c.n), kTile, 0, st>>>(c, mask, (long long*)actions, k0, k1, t); break;
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rule_actions(const DevConfig& c, const void* state, int after_shift, int64_t* actions, cudaStream_t st) {
+  rule_actions_kernel<<<tiles(c.n), kTile, 0, st>>>(c, (const uint4*)state, after_shift, (long long*)actions);
   return cudaGetLastError();
 }
 

@@ -211,6 +211,17 @@ class Env_3_Monolith(_SingleEnv):
             action = self._choose_action(mode, use_action_masking)
         return self._do_step(int(action), use_action_masking, check_overflow)
 
+    def _obs_after_shift(self):
+        """Observation as the reference's agents see it inside step(): after update_environment has
+        shifted input -> belt -> sorting (env_monolith.py:114-115), before anything else changed."""
+        obs = self.get_obs()
+        inp, belt = self.current_material_input, self.current_material_belt
+        tot = sum(inp)
+        obs[0] = min(tot / 100.0, 1.0)
+        obs[1:5] = [x / tot if tot > 0 else 0.0 for x in inp]
+        obs[23:27] = [min(x / float(self._b.cfg.stage_capacity), 1.0) for x in belt]
+        return obs
+
     def _choose_action(self, mode, use_action_masking):
         if self.mono_agent is not None:                                   # :144-150
             a, _ = self.mono_agent.predict(self.get_obs(), deterministic=True, action_masks=self.action_masks())
@@ -219,13 +230,11 @@ class Env_3_Monolith(_SingleEnv):
             if use_action_masking:
                 return int(self._b.sample_actions(seed=(self.seed or 0) + 0x5EED, t=self.current_step)[0].item())
             return int(np.random.randint(0, self.action_space.n))
-        if mode == "rule_based":                                          # :166-184
-            sort_mode = self.sorting_rules()
-            job = self.check_container_level()
-            press = self.press_action_to_discrete(job[0] or 0, job[1] or 0) if job != (None, None) else 0
-            return int(sort_mode) * 11 + int(press)
+        if mode == "rule_based":                                          # :166-184 (device kernel)
+            # the reference evaluates sorting_rules() AFTER update_environment has moved input -> belt
+            return int(self._b.rule_based_actions(after_shift=True)[0].item())
         if mode == "model":                                               # :186-221
-            obs = self.get_obs()
+            obs = self._obs_after_shift()
             if self.sort_agent is not None:
                 sm, _ = self.sort_agent.predict(obs[:13], deterministic=True)
                 sort_mode = int(sm)

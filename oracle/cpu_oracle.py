@@ -55,6 +55,8 @@ def lib():
         L.mso_sample_masked_actions.restype = None
         L.mso_sample_masked_actions.argtypes = [C.POINTER(_abi.MsortConfig), C.c_void_p, C.c_int64,
                                                 C.c_uint64, C.c_uint32, C.c_void_p]
+        L.mso_rule_based_actions.restype = None
+        L.mso_rule_based_actions.argtypes = [C.POINTER(_abi.MsortConfig), C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
         L.mso_philox4x32_10.restype = None
         L.mso_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.mso_state_size.restype = C.c_int
@@ -156,6 +158,11 @@ class OracleEnv:
     def sample_masked_actions(self, seed: int, t: int):
         act = np.zeros(self.n, dtype=np.int64)
         self.L.mso_sample_masked_actions(C.byref(self.cfg), _ptr(self.state), self.n, seed, t, _ptr(act))
+        return act
+
+    def rule_based_actions(self, after_shift: bool = True):
+        act = np.zeros(self.n, dtype=np.int64)
+        self.L.mso_rule_based_actions(C.byref(self.cfg), _ptr(self.state), self.n, 1 if after_shift else 0, _ptr(act))
         return act
 
     def rollout(self, T: int, action_seed: int = 1):

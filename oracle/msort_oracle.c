@@ -603,6 +603,30 @@ void mso_sample_masked_actions(const msort_config_t* cfg, const msort_env_state_
   }
 }
 
+/* Rule-based action source (sorting_rules env_super.py:469-482 + check_container_level :689-720, combined as
+ * Env_3.step(mode='rule_based') env_monolith.py:166-184).  after_shift: evaluate sorting_rules on the belt
+ * as it is after this step's material shift (belt <- input), where Env_3.step calls it. */
+void mso_rule_based_actions(const msort_config_t* cfg, const msort_env_state_t* st, int64_t n, int after_shift,
+                            int64_t* actions) {
+  for (int64_t i = 0; i < n; ++i) {
+    const msort_env_state_t* s = &st[i];
+    const int32_t* belt = after_shift ? s->input : s->belt;
+    int tot = belt[0] + belt[1] + belt[2] + belt[3];
+    double p[4];
+    for (int m = 0; m < 4; ++m) p[m] = tot > 0 ? (double)belt[m] / (double)tot : 0.0;
+    int mode = (p[0] + p[2] > p[1] + p[3]) ? 0 : 1;
+    int press = 0;
+    int free_press = s->press_timer[0] == 0 ? 1 : (s->press_timer[1] == 0 ? 2 : 0);
+    if (free_press) {
+      int best = 0, idx = -1;
+      for (int m = 0; m < 4; ++m) { int l = s->cont_true[m] + s->cont_false[m]; if (l > best) { best = l; idx = m; } }
+      if (s->cont_e > best) { best = s->cont_e; idx = 4; }
+      if (best > 0) press = (free_press - 1) * 5 + idx + 1;
+    }
+    actions[i] = cfg->env_kind == MSORT_ENV_SORT ? mode : (cfg->env_kind == MSORT_ENV_PRESS ? press : 11 * mode + press);
+  }
+}
+
 /* CPU-baseline driver: each of `nthreads` workers owns a contiguous slice of the envs and runs
  * T masked-random steps over it with auto-reset, like one SubprocVecEnv worker stepping its
  * envs (no per-step barrier between workers).  Returns env-steps executed.

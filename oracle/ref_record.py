@@ -179,11 +179,17 @@ def record(kind: str, *, seed: int, steps: int, max_steps: int = 50, noise: floa
         elif policy == "second_valid":      # Appendix C, Env_3 row
             v = np.flatnonzero(mask)
             a = int(v[1]) if v.size > 1 else 0
+        elif policy == "mode_rule_based":   # Env_3.step(action=None, mode='rule_based'): chosen inside step()
+            a = None
         else:
             raise ValueError(policy)
         n_before = env.rng.n_choice
         kw = dict(use_action_masking=use_action_masking, check_overflow=check_overflow)
-        obs, reward, term, trunc, info = env.step(a, **kw)
+        if a is None:
+            obs, reward, term, trunc, info = env.step(None, mode="rule_based", **kw)
+            a = int(info["action"])
+        else:
+            obs, reward, term, trunc, info = env.step(a, **kw)
         assert trunc is False
         out["action"].append(a)
         out["noise_u"].append(twin_noise.random(4))

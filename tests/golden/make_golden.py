@@ -66,6 +66,10 @@ def groups():
                                       use_action_masking=True, check_overflow=False,
                                       auto_reset=False, steps=90, seeds=[0, 3, 4, 42],
                                       policy="masked_random")))
+    # --- Env_3.step(mode='rule_based'): the reference's own heuristic picks the action inside step()
+    g.append(("rule_mono", dict(kind="mono", max_steps=200, noise=0.0, balesize=200, use_action_masking=True,
+                                check_overflow=False, auto_reset=False, steps=200, seeds=[1, 2, 3],
+                                policy="mode_rule_based")))
     # --- Env_2 with an embedded sort-policy MLP (both modes occur with action gain 1.0)
     g.append(("mlp_press", dict(kind="press", max_steps=50, noise=0.05, balesize=200,
                                 use_action_masking=True, check_overflow=False, auto_reset=True,

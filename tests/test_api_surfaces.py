@@ -129,3 +129,33 @@ def test_vecenv_adapter_sb3_protocol():
     assert n_done == 2 * n
     assert venv.env_is_wrapped(object) == [False] * n and venv.get_attr("name") == ["mono"] * n
     venv.close()
+
+
+def test_device_rule_based_actions_match_reference_choices():
+    """The device heuristic kernel picks the reference's own rule-based actions on the recorded states."""
+    from cuda_backend import CudaBackend
+    from parity_util import config_for, golden_group, pack_counts
+    meta, batch = golden_group("rule_mono")
+    n = batch["action"].shape[1]
+    gpu = CudaBackend(config_for(meta, n))
+    gpu.reset(first_pattern=batch["first_pattern0"])
+    for t in range(meta["steps"]):
+        a = gpu.env.rule_based_actions(after_shift=True).cpu().numpy()
+        assert np.array_equal(a, batch["action"][t]), f"step {t}"
+        gpu.step(batch["action"][t], noise_u=batch["noise_u"][t], redis_u=batch["redis_u"],
+                 input_counts=pack_counts(batch["input_counts"][t]))
+
+
+def test_published_rule_based_return_batched_on_device():
+    """4096 device envs under the device rule-based policy: 44.03 +- 1.10 published (benchmark_plot_summary.py:14)."""
+    import torch
+    from marl_sortingenv_b200 import BatchedMonolithEnv
+    n = 4096
+    env = BatchedMonolithEnv(n, max_steps=200, seed=77, noise_sorting=0.0, auto_reset=False)
+    env.reset()
+    total = torch.zeros(n, dtype=torch.float64, device="cuda")
+    for t in range(200):
+        _, r, term, _, _ = env.step(env.rule_based_actions())
+        total += r.double()
+    assert bool(term.all())
+    assert abs(total.mean().item() - 44.03) < 3 * 1.10 / np.sqrt(10) + 0.3, (total.mean().item(), total.std().item())

@@ -68,3 +68,18 @@ def test_material_conservation_invariant():
             total = (s["cont_true"].sum(1) + s["cont_false"].sum(1) + s["cont_e"] + s["press_n"].sum(1)
                      + s["bale_sum"].sum(1) + s["input"].sum(1) + s["belt"].sum(1))
             assert np.all(total == 100 * (t + 1))
+
+
+def test_rule_based_action_source_matches_reference_choices():
+    """Env_3.step(mode='rule_based') picks its action inside step() (env_monolith.py:166-184); the
+    restated heuristic must pick the same action from the same state on every recorded step."""
+    from parity_util import pack_counts
+    meta, batch = golden_group("rule_mono")
+    n = batch["action"].shape[1]
+    env = OracleEnv(config_for(meta, n))
+    env.reset(first_pattern=batch["first_pattern0"])
+    for t in range(meta["steps"]):
+        assert np.array_equal(env.rule_based_actions(after_shift=True), batch["action"][t]), f"step {t}"
+        env.step(batch["action"][t], noise_u=batch["noise_u"][t], redis_u=batch["redis_u"],
+                 input_counts=pack_counts(batch["input_counts"][t]))
+    assert abs(batch["reward"].sum(0).mean() - 44.03) < 1.5      # published Rule-Based return 44.03 +- 1.10
