@@ -45,6 +45,18 @@ def flatten_sort_policy(agent) -> torch.Tensor:
     return torch.cat(parts)
 
 
+def load_sb3_zip(path: str) -> torch.Tensor:
+    """Weights of the sorting policy from an SB3 model archive written by `model.save()`
+    (ref: training.py:271-287 saves `./models/{prefix}_{timesteps}.zip`).  The archive holds
+    `policy.pth`, a torch state-dict with the keys listed in SB3_KEYS."""
+    import io
+    import zipfile
+    with zipfile.ZipFile(path) as z:
+        with z.open("policy.pth") as f:
+            sd = torch.load(io.BytesIO(f.read()), map_location="cpu", weights_only=True)
+    return flatten_sort_policy(sd)
+
+
 def sb3_style_init(seed: int = 0, action_gain: float = 0.01) -> torch.Tensor:
     """Random-init weights the way SB3 initialises an MlpPolicy: orthogonal with gains
     (sqrt 2, sqrt 2, action_gain), zero biases."""

@@ -115,3 +115,20 @@ def test_policy_flattening_sb3_layout():
     assert flatten_sort_policy(sb3_style_init(1)).numel() == 1570
     with pytest.raises(ValueError):
         flatten_sort_policy(np.zeros(10, np.float32))
+
+
+def test_load_sb3_zip_layout(tmp_path):
+    import io
+    import zipfile
+    import torch
+    from marl_sortingenv_b200.policy import SB3_KEYS, SHAPES, load_sb3_zip
+    sd = {k: torch.randn(*s) for k, s in zip(SB3_KEYS, SHAPES)}
+    sd["mlp_extractor.value_net.0.weight"] = torch.randn(32, 13)      # extra keys of a real archive are ignored
+    sd["log_std"] = torch.zeros(1)
+    buf = io.BytesIO(); torch.save(sd, buf)
+    path = tmp_path / "sort_100000.zip"
+    with zipfile.ZipFile(path, "w") as z:
+        z.writestr("policy.pth", buf.getvalue())
+        z.writestr("data", "{}")
+    w = load_sb3_zip(str(path))
+    assert w.numel() == 1570 and torch.equal(w[416:448], sd[SB3_KEYS[1]]) and torch.equal(w[1504:1568].reshape(2, 32), sd[SB3_KEYS[4]])
