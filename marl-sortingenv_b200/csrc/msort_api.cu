@@ -188,6 +188,28 @@ static int digest_config(const msort_config_t& c, DevConfig& d) {
       if (std::fabs((double)ref - (double)fast) > 1e-7 + 2e-6 * std::fabs((double)ref)) d.fast_pdiff = 0;
     }
   }
+  // purity ties (purity_k in msort_device.cuh): outcome of the float64 pipeline rint(fl(fl(tr/tot)*100)) when
+  // 100*tr/tot is exactly k + 1/2, i.e. tr/tot == (2k+1)/200 — a function of k alone
+  for (int k = 0; k < 100; ++k) {
+    volatile double q = (double)(2 * k + 1) / 200.0;
+    volatile double y = q * 100.0;
+    if ((int)std::rint(y) == k + 1) d.tie_up[k >> 5] |= 1u << (k & 31);
+  }
+  // FAST step-kernel instantiation (PHILOX mode): legal when, in the kernel's own float64 operation order,
+  //  * a boosted accuracy clip((base+boost) + (low + range*u), 0, 1) is exactly 1.0 for every u in [0,1)
+  //    (the noise term is monotone in u, so u = 0 is the worst case),
+  //  * an unboosted accuracy base + (low + range*u) stays inside [0,1] (the clip is the identity),
+  //  * and a whole batch fits 7 bits (the packed-byte class selection of the redistribution draws).
+  d.fast = c.rng_mode == MSORT_RNG_PHILOX && c.input_batch_size <= 127;
+  for (int m = 0; m < 4 && d.fast; ++m) {
+    volatile double boosted = d.base_acc[m] + d.boost;
+    volatile double lo_b = boosted + d.noise_low;
+    volatile double lo_u = d.base_acc[m] + d.noise_low;
+    volatile double span = d.noise_range * 1.0;
+    volatile double nz_hi = d.noise_low + span;
+    volatile double hi_u = d.base_acc[m] + nz_hi;
+    if (!(lo_b >= 1.0) || !(lo_u >= 0.0) || !(hi_u <= 1.0)) d.fast = 0;
+  }
   d.policy = nullptr;
   return MSORT_OK;
 }

@@ -19,8 +19,8 @@
 //   * rint(t*acc), the accuracy noise: float64 with explicit round-to-nearest intrinsics
 //     (never contracted to FMA; numpy does not fuse);
 //   * 2-decimal purity / bale quality rint(true/total*100): exact integer rounding, which
-//     provably equals the float64 pipeline except on exact .5 ties, where the float64
-//     pipeline itself is evaluated (purity_k);
+//     provably equals the float64 pipeline except on exact .5 ties, whose float64 outcome
+//     depends only on the tie value and comes from a host-built table (purity_k);
 //   * fill-ratio and bale-remainder comparisons: host-precomputed integer thresholds.
 // Observations and rewards are emitted as float32 within 1e-5 relative of the reference
 // (they never feed back into state), so they use float32 / reciprocal arithmetic.
@@ -60,6 +60,10 @@ struct DevConfig {
   int rem_new_bale;                // smallest remainder with rem > S*threshold (f64)
   int qthr100[4];                  // 100*quality_threshold when that is an integer (fast_pdiff)
   int fast_pdiff;                  // 1: obs purity diff == (k - qthr100)/100 within tolerance for all k
+  int fast;                        // 1: the host proved (digest_config) that a boosted accuracy always clips to
+                                   //    exactly 1.0, an unboosted one never clips, and a batch fits 7 bits, so the
+                                   //    step kernel may run its FAST instantiation (same results, fewer instructions)
+  unsigned tie_up[4];              // bit k: the float64 pipeline rounds the exact tie (2k+1)/200 up to k+1 (purity_k)
   float inv_cap, inv_stage, inv_pt[2];
   double base_acc[4], boost, noise_low, noise_range;
   double qthr[4];
@@ -173,6 +177,18 @@ __device__ __forceinline__ void philox_accuracy(const DevConfig& c, uint32_t gid
   acc[1] = accuracy_of(c, 1, mode, (double)r4.y * 2.3283064365386963e-10);
   acc[2] = accuracy_of(c, 2, mode, (double)r4.z * 2.3283064365386963e-10);
   acc[3] = accuracy_of(c, 3, mode, (double)r4.w * 2.3283064365386963e-10);
+}
+
+// FAST form (DevConfig::fast): only the two stations the mode does NOT boost carry noise — a = station 0
+// (mode 1) or 1 (mode 0), b = station 2 (mode 1) or 3 (mode 0); the boosted ones are exactly 1.0 and
+// the clip is the identity for the others.  Same words, same float64 operations as accuracy_of.
+__device__ __forceinline__ void philox_accuracy2(const DevConfig& c, uint32_t gid_lo, uint32_t gid_hi16, uint32_t episode,
+                                                 uint32_t step, int mode, double& a, double& b) {
+  const U4 r4 = env_draw(c, gid_lo, gid_hi16, kBlkNoise, episode, step);
+  const uint32_t ua = mode ? r4.x : r4.y, ub = mode ? r4.z : r4.w;
+  const double ba = mode ? c.base_acc[0] : c.base_acc[1], bb = mode ? c.base_acc[2] : c.base_acc[3];
+  a = dadd(ba, dadd(c.noise_low, dmul(c.noise_range, (double)ua * 2.3283064365386963e-10)));
+  b = dadd(bb, dadd(c.noise_low, dmul(c.noise_range, (double)ub * 2.3283064365386963e-10)));
 }
 
 // ---------------------------------------------------------------- state layouts
@@ -298,13 +314,20 @@ static __device__ __noinline__ int purity_k_f64(int tr, int tot) {
   return __double2int_rn(dmul(ddiv((double)tr, (double)tot), 100.0));
 }
 
-__device__ __forceinline__ int purity_k(int tr, int tot) {  // tot > 0, 0 <= tr <= tot
+// On an exact tie 100*tr/tot = k0 + 1/2 the quotient tr/tot equals (2*k0+1)/200 whatever tr and tot
+// are, so fl(tr/tot), fl(.*100) and the final rint depend on k0 alone: the host evaluates the
+// float64 pipeline once per k0 = 0..99 and hands the outcomes over as the bit table c.tie_up.
+__device__ __forceinline__ int purity_k(const DevConfig& c, int tr, int tot) {  // tot > 0, 0 <= tr <= tot
   if (tot < (1 << 17)) {                       // 100*tr and tot are exact in float32
     const int a = 100 * tr;
     int k = __float2int_rn(__fdividef((float)a, (float)tot));  // within 1 of the exact rounding
     int d = 2 * (a - k * tot);                 // exact: twice the signed distance to k, in units of 1/tot
     if (d > tot) { k += 1; d -= 2 * tot; } else if (d < -tot) { k -= 1; d += 2 * tot; }
-    if (d != tot && d != -tot) return k;       // not a .5 tie: exact rounding == float64 pipeline
+    if (d == tot || d == -tot) {               // .5 tie: k0 = floor of the exact value, outcome from the table
+      const int k0 = d == tot ? k : k - 1;
+      k = k0 + (int)((c.tie_up[(k0 >> 5) & 3] >> (k0 & 31)) & 1u);
+    }
+    return k;                                  // not a tie: exact rounding == float64 pipeline
   }
   return purity_k_f64(tr, tot);
 }
@@ -384,11 +407,11 @@ __device__ __forceinline__ void press_obs(const DevConfig& c, const Env& s, floa
   obs_sorting(c, s, o);
 }
 
-__device__ __forceinline__ void purity_ks(const Env& s, int kq[4]) {
+__device__ __forceinline__ void purity_ks(const DevConfig& c, const Env& s, int kq[4]) {
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
     int tot = s.tr[m] + s.fl[m];
-    kq[m] = tot > 0 ? purity_k(s.tr[m], tot) : -1;
+    kq[m] = tot > 0 ? purity_k(c, s.tr[m], tot) : -1;
   }
 }
 
@@ -396,7 +419,7 @@ template <int KIND>
 __device__ __forceinline__ void env_obs(const DevConfig& c, const Env& s, float* o) {
   if (KIND != MSORT_ENV_PRESS) {
     int kq[4];
-    purity_ks(s, kq);
+    purity_ks(c, s, kq);
     sort_obs(c, s, kq, o);
   }
   if (KIND == MSORT_ENV_PRESS) press_obs(c, s, o);

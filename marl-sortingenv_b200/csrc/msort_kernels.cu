@@ -48,6 +48,14 @@ __device__ __forceinline__ void bulk_commit_and_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// every byte of x -> 0xff if its bit 7 is set, else 0x00 (PRMT with sign-replicating selectors;
+// __byte_perm masks those selector bits away, hence the PTX)
+__device__ __forceinline__ uint32_t byte_sign_mask(uint32_t x) {
+  uint32_t m;
+  asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(m) : "r"(x));
+  return m;
+}
+
 // bits 0..3 of x -> bytes 0..3 (0/1 each): bit i lands at 8i through the 2^(7i) term
 __device__ __forceinline__ uint32_t spread4(uint32_t x) { return (x * 0x00204081u) & 0x01010101u; }
 
@@ -93,6 +101,7 @@ struct StepArgs {
   uint8_t* info_sort_mode;
   uint8_t* info_press_action;
   uint8_t* info_invalid;
+  int any_step_info;  // any of the six per-step info arrays above is present
   float* terminal_obs;
   double* episode_return;
   int* episode_length;
@@ -116,7 +125,10 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-template <int KIND, int RNG, int LAYOUT>
+// FAST (PHILOX only, chosen by the host when DevConfig::fast holds): boosted accuracies are exactly 1.0,
+// unboosted ones need no clip, and the redistribution classes fit one register of packed bytes.
+// Results are identical to the generic instantiation; only the instruction count differs.
+template <int KIND, int RNG, int LAYOUT, bool FAST>
 __global__ void __launch_bounds__(kTile, (KIND == MSORT_ENV_PRESS ? 5 : MSORT_STEP_MIN_BLOCKS) * (128 / kTile))  // Env_2 keeps 32 MLP activations in registers
 step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArgs a) {
   constexpr int D = Dims<KIND>::D, A = Dims<KIND>::A;
@@ -161,9 +173,19 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     // shared memory for the dynamically indexed loop).  PHILOX: recomputed from the previous step's
     // counter and mode — 64 B less state traffic per env-step than storing four float64.
     double acc_sorter[4];
+    double acc_a = 0.0, acc_b = 0.0;              // FAST: accuracies of the two unboosted stations of the previous mode
+    const int pm = s.mode;                        // previous step's sensor mode
     if (RNG == MSORT_RNG_REPLAY) {
 #pragma unroll
       for (int m = 0; m < 4; ++m) { acc_sorter[m] = s.acc[m]; s_accs[m][tid] = s.acc[m]; }
+    } else if (FAST) {
+      // stp == 0: the sorting stage is empty right after a reset, so the values are never multiplied
+      // by anything but 0; only Env_2's embedded policy observes them (set below)
+      if (stp != 0) philox_accuracy2(c, gid_lo, gid_hi, ep, stp - 1, pm, acc_a, acc_b);
+      if (KIND == MSORT_ENV_PRESS) {
+        s.acc[0] = pm ? acc_a : 1.0; s.acc[1] = pm ? 1.0 : acc_a;
+        s.acc[2] = pm ? acc_b : 1.0; s.acc[3] = pm ? 1.0 : acc_b;
+      }
     } else if (stp == 0) {
 #pragma unroll
       for (int m = 0; m < 4; ++m) acc_sorter[m] = c.base_acc[m];  // right after reset (env_super.py:395-396)
@@ -215,7 +237,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       } else if (use_mlp) {
         float so[13];
         int kq[4];
-        purity_ks(s, kq);
+        purity_ks(c, s, kq);
         sort_obs(c, s, kq, so);
         mode = mlp_sort_mode(s_policy, so);
       } else {  // sorting_rules env_super.py:469-482: pA+pC > pB+pD on float64 proportions
@@ -241,9 +263,17 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       s.acc[2] = accuracy_of(c, 2, mode, n1.x); s.acc[3] = accuracy_of(c, 3, mode, n1.y);
       if (KIND != MSORT_ENV_PRESS) obs_acc(s.acc, orow);
     } else if (KIND != MSORT_ENV_PRESS) {
-      double acc_new[4];
-      philox_accuracy(c, gid_lo, gid_hi, ep, stp, mode, acc_new);
-      obs_acc(acc_new, orow);
+      if (FAST) {
+        double na, nb;
+        philox_accuracy2(c, gid_lo, gid_hi, ep, stp, mode, na, nb);
+        const float fa = (float)na, fb = (float)nb;
+        orow[5] = mode ? fa : 1.f; orow[6] = mode ? 1.f : fa;
+        orow[7] = mode ? fb : 1.f; orow[8] = mode ? 1.f : fb;
+      } else {
+        double acc_new[4];
+        philox_accuracy(c, gid_lo, gid_hi, ep, stp, mode, acc_new);
+        obs_acc(acc_new, orow);
+      }
     }
 
     // 5: sort_material env_super.py:511-609.
@@ -284,6 +314,85 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       s.e += sum4(L);                                            // :579,597
 #pragma unroll
       for (int q = 0; q < 4; ++q) { s.tr[q] += b4(T4, q); s.fl[q] += b4(F4, q); }  // :600-602
+    } else if (FAST) {
+      // PHILOX, FAST form of the block below (same draws, same class selection, same results).
+      // The four classes live in one register as bytes  lump | X<<8 | L2<<16 | L3<<24  (every prefix
+      // sum <= batch <= 127).  With P = C*0x01010101 (byte k = prefix sum through class k) and the
+      // draw r replicated as 0x7f-r in every byte, bit 7 of byte k of P + (0x7f-r) is set iff r < P_k;
+      // the hits are monotone in k, H = those bits as 0/1 bytes, and C + 255*H = C - (1 << 8j) for
+      // the first hit j: one multiply-add removes the unit from the selected class.
+      // With the boosted stations exact (accuracy 1.0: all true, no draws) exactly one of stations
+      // 0/1 and at most station 2 draw, as selected by the previous mode pm.
+      uint32_t C = s.sort4 & 0xffffff00u;
+      int tot = sum4(s.sort4), rem;
+      uint32_t T4, F4, blk0 = kBlkRedis;
+      {                                   // station 0 (unboosted iff pm == 1)
+        const int t = b4(s.sort4, 0);
+        const int tv = pm ? __double2int_rn(dmul((double)t, acc_a)) : t;   // int(round(t*acc)) half-to-even (:539)
+        rem = t - tv;
+        T4 = (uint32_t)tv; F4 = (uint32_t)rem;
+        tot -= tv; C += (uint32_t)rem;    // leftover[0] = false_val (:546)
+      }
+      if (!pm) {                          // station 0 had nothing to redistribute: station 1 draws in the same loop
+        const int t = b4(C, 1);
+        const int tv = __double2int_rn(dmul((double)t, acc_a));
+        rem = t - tv;
+        T4 |= (uint32_t)tv << 8; F4 |= (uint32_t)rem << 8;
+        tot -= tv; C = (C & 0xffff00ffu) + (uint32_t)rem;
+        blk0 = kBlkRedis + 64u;
+      }
+#define MSORT_PDRAW(x, k)                                                                              \
+      {                                                                                                \
+        const unsigned long long prod = (unsigned long long)(x) * (uint32_t)(tot - (k));               \
+        const uint32_t r = (uint32_t)(prod >> 32);                                                     \
+        (x) = (uint32_t)prod;                                                                          \
+        const uint32_t Tq = (C - r) * 0x01010101u + 0x7f7f7f7fu;   /* == C*0x01010101 + (0x7f - r) per byte */ \
+        const uint32_t M = byte_sign_mask(Tq);                     /* byte k -> 0xff if its bit 7 is set: 255*H */ \
+        if (rem > (k)) C += M;                                                                         \
+      }
+      // draw k of a block sees tot - k units (every earlier draw of an active lane removed one); an
+      // inactive lane's products are never used
+      for (uint32_t b = 0; rem > 0; ++b, tot -= min(rem, 8), rem -= 8) {
+        U4 r4 = env_draw(c, gid_lo, gid_hi, blk0 + b, ep, stp);
+        MSORT_PDRAW(r4.x, 0); MSORT_PDRAW(r4.x, 1); MSORT_PDRAW(r4.y, 2); MSORT_PDRAW(r4.y, 3);
+        if (rem <= 4) { tot -= rem; break; }
+        MSORT_PDRAW(r4.z, 4); MSORT_PDRAW(r4.z, 5); MSORT_PDRAW(r4.w, 6); MSORT_PDRAW(r4.w, 7);
+      }
+#undef MSORT_PDRAW
+      if (pm) {                           // station 1 after station 0's draws: boosted, everything left is true
+        T4 |= (C & 0xff00u);
+        tot -= b4(C, 1); C &= 0xffff00ffu;
+      }
+      int lump;
+      {                                   // station 2 (unboosted iff pm == 1): classes (lump, L3), tot == lump + L3
+        const int t = b4(C, 2);
+        const int tv = pm ? __double2int_rn(dmul((double)t, acc_b)) : t;
+        rem = t - tv;
+        T4 |= (uint32_t)tv << 16; F4 |= (uint32_t)rem << 16;
+        tot -= tv; lump = b4(C, 0) + rem;
+      }
+#define MSORT_PDRAW2(x, k)                                                                             \
+      {                                                                                                \
+        const unsigned long long prod = (unsigned long long)(x) * (uint32_t)(tot - (k));               \
+        const int r = (int)(uint32_t)(prod >> 32);                                                     \
+        (x) = (uint32_t)prod;                                                                          \
+        if (rem > (k) && r < lump) lump -= 1;                                                          \
+      }
+      for (uint32_t b = 0; rem > 0; ++b, tot -= min(rem, 8), rem -= 8) {
+        U4 r4 = env_draw(c, gid_lo, gid_hi, kBlkRedis + 128u + b, ep, stp);
+        MSORT_PDRAW2(r4.x, 0); MSORT_PDRAW2(r4.x, 1); MSORT_PDRAW2(r4.y, 2); MSORT_PDRAW2(r4.y, 3);
+        if (rem <= 4) { tot -= rem; break; }
+        MSORT_PDRAW2(r4.z, 4); MSORT_PDRAW2(r4.z, 5); MSORT_PDRAW2(r4.w, 6); MSORT_PDRAW2(r4.w, 7);
+      }
+#undef MSORT_PDRAW2
+      {                                   // station 3 (unboosted iff pm == 0); its draws leave the pool sum unchanged
+        const int t = tot - lump;
+        const int tv = pm ? t : __double2int_rn(dmul((double)t, acc_b));
+        T4 |= (uint32_t)tv << 24; F4 |= (uint32_t)(t - tv) << 24;
+      }
+      s.e += lump;                                               // :579,597
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { s.tr[q] += b4(T4, q); s.fl[q] += b4(F4, q); }  // :600-602
     } else {
       // PHILOX: the same random process in the form DESIGN.md §4 "Sorting" derives.
       // Removing a unit from a station that has already been processed (or from the current
@@ -298,13 +407,14 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       // side by side (with the default boosts every env has exactly one of the two to draw for).
       int X = b4(s.sort4, 1), L2 = b4(s.sort4, 2), L3 = b4(s.sort4, 3);
       int tot = b4(s.sort4, 0) + X + L2 + L3, lump = 0, rem;
+      uint32_t T4 = 0, F4 = 0;            // per-station true / false counts (bytes), added to the containers below
       uint32_t blk0 = kBlkRedis;          // first Philox block of the station this lane draws for
       bool started1 = false;
       {                                   // station 0
         const int t = b4(s.sort4, 0);
         const int tv = __double2int_rn(dmul((double)t, acc_sorter[0]));  // int(round(t*acc)) half-to-even (:539)
         rem = t - tv;
-        s.tr[0] += tv; s.fl[0] += rem;    // :600-602
+        T4 = (uint32_t)tv; F4 = (uint32_t)rem;
         tot -= tv; lump += rem;           // leftover[0] = false_val (:546)
       }
 #define MSORT_START_STATION1(cond)                                                                    \
@@ -312,7 +422,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
         const int t = X;                                                                               \
         const int tv = __double2int_rn(dmul((double)t, acc_sorter[1]));                                \
         rem = t - tv;                                                                                  \
-        s.tr[1] += tv; s.fl[1] += rem;                                                                 \
+        T4 |= (uint32_t)tv << 8; F4 |= (uint32_t)rem << 8;                                             \
         tot -= tv; lump += rem; X = 0;                                                                 \
         blk0 = kBlkRedis + 64u; started1 = true;                                                       \
       }
@@ -346,7 +456,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
         const int t = L2;
         const int tv = __double2int_rn(dmul((double)t, acc_sorter[2]));
         rem = t - tv;
-        s.tr[2] += tv; s.fl[2] += rem;
+        T4 |= (uint32_t)tv << 16; F4 |= (uint32_t)rem << 16;
         tot -= tv; lump += rem;
       }
 #define MSORT_DRAW2(x)                                                                                 \
@@ -369,13 +479,15 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       {                                   // station 3: its draws leave `lump` (the sum of all leftovers) unchanged
         const int t = L3;
         const int tv = __double2int_rn(dmul((double)t, acc_sorter[3]));
-        s.tr[3] += tv; s.fl[3] += t - tv;
+        T4 |= (uint32_t)tv << 24; F4 |= (uint32_t)(t - tv) << 24;
       }
 #undef MSORT_DRAW2
 #undef MSORT_DRAW_LOOP4
 #undef MSORT_DRAW4
 #undef MSORT_START_STATION1
       s.e += lump;                                               // :579,597
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { s.tr[q] += b4(T4, q); s.fl[q] += b4(F4, q); }  // :600-602
     }
 
     // 6: Env_1 samples its own press action under the mask (env_super.py:291-300)
@@ -413,7 +525,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
           for (int q = 0; q < 4; ++q) if (m == q) { tv = s.tr[q]; amt = s.tr[q] + s.fl[q]; s.tr[q] = 0; s.fl[q] = 0; }
           if (m == 4) s.e = 0;
           s.started = 1; s.last_amt = amt;
-          const int qk = (m < 4 && amt > 0) ? purity_k(tv, amt) : 0;  // round(true/total, 2) (:754)
+          const int qk = (m < 4 && amt > 0) ? purity_k(c, tv, amt) : 0;  // round(true/total, 2) (:754)
           if (!second) { s.timer[0] = c.press_time[0]; s.mat[0] = m; s.pn[0] = amt; s.pq[0] = qk; }
           else { s.timer[1] = c.press_time[1]; s.mat[1] = m; s.pn[1] = amt; s.pq[1] = qk; }
         }
@@ -438,7 +550,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     int kq[4] = {-1, -1, -1, -1};
     if (KIND != MSORT_ENV_PRESS) {
 #pragma unroll
-      for (int m = 0; m < 4; ++m) kq[m] = lv[m] > 0 ? purity_k(s.tr[m], lv[m]) : -1;
+      for (int m = 0; m < 4; ++m) kq[m] = lv[m] > 0 ? purity_k(c, s.tr[m], lv[m]) : -1;
     }
     double reward;
     bool terminated;
@@ -496,12 +608,14 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
 
     a.reward[i] = (float)reward;
     a.terminated[i] = terminated ? 1 : 0;
-    if (a.info_action) a.info_action[i] = act;
-    if (a.info_overflow) a.info_overflow[i] = overflow ? 1 : 0;
-    if (a.info_overflow_mat) a.info_overflow_mat[i] = (int8_t)overflow_mat;
-    if (a.info_sort_mode) a.info_sort_mode[i] = (uint8_t)mode;
-    if (a.info_press_action) a.info_press_action[i] = (uint8_t)pa;
-    if (a.info_invalid) a.info_invalid[i] = invalid ? 1 : 0;
+    if (a.any_step_info) {
+      if (a.info_action) a.info_action[i] = act;
+      if (a.info_overflow) a.info_overflow[i] = overflow ? 1 : 0;
+      if (a.info_overflow_mat) a.info_overflow_mat[i] = (int8_t)overflow_mat;
+      if (a.info_sort_mode) a.info_sort_mode[i] = (uint8_t)mode;
+      if (a.info_press_action) a.info_press_action[i] = (uint8_t)pa;
+      if (a.info_invalid) a.info_invalid[i] = invalid ? 1 : 0;
+    }
     st_reward = reward;
     st_flags += (overflow ? 1u << 8 : 0u) + (invalid ? 1u << 16 : 0u);
     if (terminated) {
@@ -763,7 +877,7 @@ stats_kernel(const __grid_constant__ DevConfig c, const uint4* __restrict__ stat
     v[0] += 1.0;
     double lvl = (double)s.e, pm = 0.0;
     int kq[4];
-    purity_ks(s, kq);
+    purity_ks(c, s, kq);
 #pragma unroll
     for (int m = 0; m < 4; ++m) { lvl += (double)(s.tr[m] + s.fl[m]); pm += kq[m] >= 0 ? 0.01 * (double)kq[m] : c.qthr[m]; }
     v[1] += lvl;
@@ -797,9 +911,15 @@ static inline unsigned tiles(long long n) { return (unsigned)((n + kTile - 1) / 
 
 template <int KIND>
 static cudaError_t launch_step_kind(const DevConfig& c, const StepArgs& a, int rng, cudaStream_t st) {
-  if (rng == MSORT_RNG_REPLAY) step_kernel<KIND, MSORT_RNG_REPLAY, LAYOUT_REPLAY><<<tiles(c.n), kTile, 0, st>>>(c, a);
-  else if (c.layout == LAYOUT_COMPACT) step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT><<<tiles(c.n), kTile, 0, st>>>(c, a);
-  else step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_WIDE><<<tiles(c.n), kTile, 0, st>>>(c, a);
+  const unsigned g = tiles(c.n);
+  if (rng == MSORT_RNG_REPLAY) step_kernel<KIND, MSORT_RNG_REPLAY, LAYOUT_REPLAY, false><<<g, kTile, 0, st>>>(c, a);
+  else if (c.layout == LAYOUT_COMPACT) {
+    if (c.fast) step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true><<<g, kTile, 0, st>>>(c, a);
+    else step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, false><<<g, kTile, 0, st>>>(c, a);
+  } else {
+    if (c.fast) step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_WIDE, true><<<g, kTile, 0, st>>>(c, a);
+    else step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_WIDE, false><<<g, kTile, 0, st>>>(c, a);
+  }
   return cudaGetLastError();
 }
 
@@ -814,6 +934,8 @@ cudaError_t launch_step(const DevConfig& c, const StepLaunch& l, int rng, cudaSt
   a.info_sort_mode = f ? f->sort_mode : nullptr;
   a.info_press_action = f ? f->press_action : nullptr;
   a.info_invalid = f ? f->invalid_action : nullptr;
+  a.any_step_info = a.info_action || a.info_overflow || a.info_overflow_mat || a.info_sort_mode ||
+                    a.info_press_action || a.info_invalid;
   a.terminal_obs = f ? f->terminal_obs : nullptr;
   a.episode_return = f ? f->episode_return : nullptr;
   a.episode_length = f ? f->episode_length : nullptr;

@@ -43,13 +43,13 @@ def test_cuda_embedded_mlp_matches_reference_argmax(cuda_backend):
 
 
 def _philox_cross_check(cuda_backend, kind, n, T, *, masking=True, overflow=False, noise=0.05,
-                        max_steps=50, balesize=200, seed=42, offset=0, mlp=None):
+                        max_steps=50, balesize=200, seed=42, offset=0, mlp=None, auto_reset=True, config=None):
     """PHILOX mode: CUDA and the oracle share the counter scheme, so everything must agree."""
     from oracle.cpu_oracle import OracleEnv
     meta = dict(kind=kind, max_steps=max_steps, noise=noise, balesize=balesize,
-                use_action_masking=masking, check_overflow=overflow, auto_reset=True, mlp=mlp is not None)
-    cfg_o = config_for(meta, n, rng_mode="philox", seed=seed, global_env_offset=offset)
-    cfg_c = config_for(meta, n, rng_mode="philox", seed=seed, global_env_offset=offset)
+                use_action_masking=masking, check_overflow=overflow, auto_reset=auto_reset, mlp=mlp is not None)
+    cfg_o = config_for(meta, n, rng_mode="philox", seed=seed, global_env_offset=offset, config=config)
+    cfg_c = config_for(meta, n, rng_mode="philox", seed=seed, global_env_offset=offset, config=config)
     ora, gpu = OracleEnv(cfg_o, nthreads=8), cuda_backend(cfg_c)
     if mlp is not None:
         ora.set_policy(mlp); gpu.set_policy(mlp)
@@ -97,6 +97,37 @@ def test_cuda_matches_oracle_philox(cuda_backend, kind, masking):
 def test_cuda_matches_oracle_philox_overflow_and_offsets(cuda_backend):
     _philox_cross_check(cuda_backend, "mono", 1000, 120, masking=False, overflow=True, offset=123456789012)
     _philox_cross_check(cuda_backend, "press", 777, 80, masking=True, overflow=True, noise=0.0, max_steps=33, balesize=150)
+
+
+def _variant_config(changes):
+    """config.yml with some keys replaced: {(section, key): value}."""
+    import copy
+    from marl_sortingenv_b200.config import load_config
+    cfg = copy.deepcopy(load_config(None))
+    for (sec, key), val in changes.items():
+        cfg[sec][key] = val
+    return cfg
+
+
+@pytest.mark.parametrize("kind", ["sort", "press", "mono"])
+def test_cuda_matches_oracle_philox_generic_instantiation(cuda_backend, kind):
+    """The step kernel has a FAST instantiation for configs where the host can prove that boosted
+    accuracies clip to 1.0 (default config.yml) and a generic one.  These configs force the generic
+    one: a boost that does not saturate (boosted stations mis-sort too, accuracies really clip),
+    and a batch larger than the packed-byte class selection allows."""
+    weak = _variant_config({("sorting_station", "boost"): 0.22})
+    done = _philox_cross_check(cuda_backend, kind, 2048 + 5, 70, config=weak, noise=0.08)
+    assert done >= 2048
+    big = _variant_config({("simulation", "input_batch_size"): 200})
+    _philox_cross_check(cuda_backend, kind, 1024 + 3, 60, config=big, masking=False)
+
+
+@pytest.mark.parametrize("config_kind", ["default", "weak_boost"])
+def test_cuda_matches_oracle_philox_wide_layout(cuda_backend, config_kind):
+    """Without auto-reset the state keeps 32-bit container counts (LAYOUT_WIDE): FAST and generic."""
+    cfg = None if config_kind == "default" else _variant_config({("sorting_station", "boost"): 0.22})
+    _philox_cross_check(cuda_backend, "mono", 1500, 90, max_steps=400, auto_reset=False, config=cfg)
+    _philox_cross_check(cuda_backend, "sort", 700, 60, max_steps=400, auto_reset=False, config=cfg, masking=False)
 
 
 def test_cuda_matches_oracle_philox_mlp(cuda_backend):
