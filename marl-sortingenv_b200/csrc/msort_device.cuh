@@ -94,8 +94,11 @@ struct U4 { uint32_t x, y, z, w; };
 // 10 rounds, round keys precomputed on the host (uniform kernel parameters).
 __device__ __forceinline__ U4 philox_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                         const unsigned (&rk)[20]) {
+#ifndef MSORT_PHILOX_ROUNDS
+#define MSORT_PHILOX_ROUNDS 10   // anything else is a timing experiment, never a product build
+#endif
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < MSORT_PHILOX_ROUNDS; ++r) {
     unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
     unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
     c0 = (uint32_t)(p1 >> 32) ^ c1 ^ rk[2 * r];

@@ -136,7 +136,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   __shared__ __align__(16) uint8_t s_mask[kTile * A];
   __shared__ double s_accs[RNG == MSORT_RNG_REPLAY ? 4 : 1][RNG == MSORT_RNG_REPLAY ? kTile : 1];  // accuracy_sorter (REPLAY)
   __shared__ float s_policy[KIND == MSORT_ENV_PRESS ? MSORT_POLICY_WEIGHTS : 1];
-  __shared__ double s_stat[ST_COUNT];
+  __shared__ double s_stat[kTile / 32][ST_COUNT];   // per-warp partial sums (plain stores: no init, no atomics)
 
   const bool masking = c.flags & MSORT_F_ACTION_MASKING;
   const bool auto_reset = c.flags & MSORT_F_AUTO_RESET;
@@ -144,8 +144,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
                        !(RNG == MSORT_RNG_REPLAY && a.sort_mode_in);
   const int tid = threadIdx.x;
   if (use_mlp) for (int k = tid; k < MSORT_POLICY_WEIGHTS; k += kTile) s_policy[k] = c.policy[k];
-  if (a.stats && tid < ST_COUNT) s_stat[tid] = 0.0;
-  if (use_mlp || a.stats) __syncthreads();
+  if (use_mlp) __syncthreads();
 
   const long long row0 = (long long)blockIdx.x * kTile;
   const long long i = row0 + tid;
@@ -179,9 +178,9 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
 #pragma unroll
       for (int m = 0; m < 4; ++m) { acc_sorter[m] = s.acc[m]; s_accs[m][tid] = s.acc[m]; }
     } else if (FAST) {
-      // stp == 0: the sorting stage is empty right after a reset, so the values are never multiplied
-      // by anything but 0; only Env_2's embedded policy observes them (set below)
-      if (stp != 0) philox_accuracy2(c, gid_lo, gid_hi, ep, stp - 1, pm, acc_a, acc_b);
+      // stp == 0 (counter wraps): the sorting stage is empty right after a reset, so the values are never
+      // multiplied by anything but 0; only Env_2's embedded policy observes them (set below)
+      philox_accuracy2(c, gid_lo, gid_hi, ep, stp - 1, pm, acc_a, acc_b);   // unconditional: no branch between the Philox chains
       if (KIND == MSORT_ENV_PRESS) {
         s.acc[0] = pm ? acc_a : 1.0; s.acc[1] = pm ? 1.0 : acc_a;
         s.acc[2] = pm ? acc_b : 1.0; s.acc[3] = pm ? 1.0 : acc_b;
@@ -229,6 +228,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       mode = (int)act;
     } else if (KIND == MSORT_ENV_MONO) {
       mode = (int)act >= 11 ? 1 : 0; pa = (int)act - 11 * mode;
+      // validity is judged on the levels BEFORE this step's sort (env_monolith.py:132-138)
       if (!masking && !press_action_valid(c, s, pa)) { pa = 0; skip_press = true; invalid = true; }
     } else {
       pa = (int)act;
@@ -649,21 +649,19 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     const double rw = warp_sum(st_reward);
     const double rt = (f & 0xffu) ? warp_sum(st_return) : 0.0;  // warp-uniform condition
     if ((tid & 31) == 0) {
-      if (f & 0xffu) { atomicAdd(&s_stat[ST_EPISODES], (double)(f & 0xffu)); atomicAdd(&s_stat[ST_RETURN], rt);
-                       atomicAdd(&s_stat[ST_LENGTH], (double)nl); }
-      atomicAdd(&s_stat[ST_STEPS], (double)ns);
-      atomicAdd(&s_stat[ST_REWARD], rw);
-      if ((f >> 8) & 0xffu) atomicAdd(&s_stat[ST_OVERFLOW], (double)((f >> 8) & 0xffu));
-      if (nb) atomicAdd(&s_stat[ST_BALES], (double)nb);
-      if ((f >> 16) & 0xffu) atomicAdd(&s_stat[ST_INVALID], (double)((f >> 16) & 0xffu));
-      if (f >> 24) atomicAdd(&s_stat[ST_CLAMPED], (double)(f >> 24));
-      if (nu) atomicAdd(&s_stat[ST_UNDERRUN], (double)nu);
+      double* w = s_stat[tid >> 5];
+      w[ST_EPISODES] = (double)(f & 0xffu); w[ST_RETURN] = rt; w[ST_LENGTH] = (double)nl;
+      w[ST_STEPS] = (double)ns; w[ST_REWARD] = rw;
+      w[ST_OVERFLOW] = (double)((f >> 8) & 0xffu); w[ST_BALES] = (double)nb;
+      w[ST_INVALID] = (double)((f >> 16) & 0xffu); w[ST_CLAMPED] = (double)(f >> 24); w[ST_UNDERRUN] = (double)nu;
     }
   }
   fence_async_smem();  // order this thread's tile writes before the async-proxy reads below
   __syncthreads();
   if (a.stats && tid < ST_COUNT) {
-    const double v = s_stat[tid];
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kTile / 32; ++w) v += s_stat[w][tid];
     if (v != 0.0) atomicAdd(&a.stats[tid], v);
   }
   if (rows == kTile) {

@@ -23,6 +23,11 @@ class CudaBackend:
             auto_reset=bool(f & _abi.F_AUTO_RESET),
             rng_mode="replay" if cfg.rng_mode == _abi.RNG_REPLAY else "philox",
             global_env_offset=int(cfg.global_env_offset))
+        # the env is re-created from scalar arguments: make sure it digested the very same msort_config_t
+        import copy
+        want = copy.copy(cfg)
+        want.flags = int(cfg.flags) & ~_abi.F_SORT_POLICY_MLP | (int(self.env.cfg.flags) & _abi.F_SORT_POLICY_MLP)
+        assert bytes(self.env.cfg) == bytes(want), "CudaBackend: the env's config differs from the requested one"
         self.n = int(cfg.num_envs)
         self._redis = None
         if policy is not None:

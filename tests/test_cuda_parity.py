@@ -50,7 +50,7 @@ def _philox_cross_check(cuda_backend, kind, n, T, *, masking=True, overflow=Fals
                 use_action_masking=masking, check_overflow=overflow, auto_reset=auto_reset, mlp=mlp is not None)
     cfg_o = config_for(meta, n, rng_mode="philox", seed=seed, global_env_offset=offset, config=config)
     cfg_c = config_for(meta, n, rng_mode="philox", seed=seed, global_env_offset=offset, config=config)
-    ora, gpu = OracleEnv(cfg_o, nthreads=8), cuda_backend(cfg_c)
+    ora, gpu = OracleEnv(cfg_o, nthreads=8), cuda_backend(cfg_c, config=config)
     if mlp is not None:
         ora.set_policy(mlp); gpu.set_policy(mlp)
     o0, m0 = ora.reset()
