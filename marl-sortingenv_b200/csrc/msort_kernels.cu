@@ -624,9 +624,23 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       if (a.episode_length) a.episode_length[i] = (int)s.step;
       if (auto_reset) {
         if (a.terminal_obs) {
-          float* t = a.terminal_obs + i * D;
+          // Episodes of one warp normally end together: then the warp's 32 rows are one contiguous
+          // range in the tile and in the tensor, copied with coalesced stores.  (All 32 lanes reach
+          // this point in that case, so __activemask() names the whole warp.)
+          const unsigned tm = __activemask();
+          if (tm == 0xffffffffu) {
+            __syncwarp();                 // the rows of all 32 lanes are complete in shared memory
+            const int w0 = tid & ~31, lane = tid & 31;
+            const float* src = &s_obs[w0 * D];
+            float* dst = a.terminal_obs + (row0 + w0) * D;
 #pragma unroll
-          for (int k = 0; k < D; ++k) t[k] = orow[k];
+            for (int k = 0; k < D; ++k) dst[k * 32 + lane] = src[k * 32 + lane];
+            __syncwarp();                 // before any lane overwrites its row with the reset observation
+          } else {
+            float* t = a.terminal_obs + i * D;
+#pragma unroll
+            for (int k = 0; k < D; ++k) t[k] = orow[k];
+          }
         }
         // unseeded reset (env_super.py:365-420): streams run on, generator re-seeded
         reset_env(c, s);
