@@ -2,6 +2,7 @@
 // digestion (host float64 arithmetic identical to the reference's), handle management and
 // kernel launches.  No torch types, no exceptions across the boundary, no CPU fallback.
 #include <cuda_runtime.h>
+#include <algorithm>
 
 #include <cmath>
 #include <cstdarg>
@@ -200,7 +201,32 @@ static int digest_config(const msort_config_t& c, DevConfig& d) {
   //    (the noise term is monotone in u, so u = 0 is the worst case),
   //  * an unboosted accuracy base + (low + range*u) stays inside [0,1] (the clip is the identity),
   //  * and a whole batch fits 7 bits (the packed-byte class selection of the redistribution draws).
-  d.fast = c.rng_mode == MSORT_RNG_PHILOX && c.input_batch_size <= 127;
+  //  * no input remainder (every stage holds one of the two patterns or nothing), whole-percent quality
+  //    thresholds inside [0,1], and overflow penalties ordered severe <= mild, so that the press penalty
+  //    depends on the fullest container alone.
+  d.fast = c.rng_mode == MSORT_RNG_PHILOX && c.input_batch_size <= 127 && d.pat_remainder == 0 && d.fast_pdiff &&
+           c.overflow_penalty_severe <= c.overflow_penalty_mild;
+  for (int m = 0; m < 4; ++m) {
+    if (std::fabs(c.quality_threshold[m] * 100.0 - (double)d.qthr100[m]) > 1e-9 || d.qthr100[m] < 0 || d.qthr100[m] > 100) d.fast = 0;
+  }
+  d.pen_sev0 = std::min(0.0, c.overflow_penalty_severe);
+  d.pen_mild0 = std::min(0.0, c.overflow_penalty_mild);
+  d.small_lv = d.layout == LAYOUT_COMPACT && (long long)c.input_batch_size * c.max_steps <= 8192ll;
+  d.S_magic = (unsigned)((1ull << 32) / (unsigned long long)c.bale_size) + 1u;
+  // observation tables for the three possible stage contents (same float32 operations as obs_belt / obs_sorting)
+  for (int w = 0; w < 3; ++w) {
+    const unsigned v = w < 2 ? d.pat[w] : 0u;
+    int cnt[4], bt = 0;
+    for (int m = 0; m < 4; ++m) { cnt[m] = (int)((v >> (8 * m)) & 0xffu); bt += cnt[m]; }
+    volatile float inv_bt = bt > 0 ? 1.0f / (float)bt : 0.f;
+    volatile float occ = (float)bt * 0.01f;
+    d.obs_belt_tab[w][0] = std::fmin((float)occ, 1.f);
+    for (int m = 0; m < 4; ++m) {
+      volatile float pb = (float)cnt[m] * inv_bt, ps = (float)cnt[m] * d.inv_stage;
+      d.obs_belt_tab[w][1 + m] = std::fmin((float)pb, 1.f);
+      d.obs_sort_tab[w][m] = std::fmin((float)ps, 1.f);
+    }
+  }
   for (int m = 0; m < 4 && d.fast; ++m) {
     volatile double boosted = d.base_acc[m] + d.boost;
     volatile double lo_b = boosted + d.noise_low;

@@ -64,6 +64,12 @@ struct DevConfig {
                                    //    exactly 1.0, an unboosted one never clips, and a batch fits 7 bits, so the
                                    //    step kernel may run its FAST instantiation (same results, fewer instructions)
   unsigned tie_up[4];              // bit k: the float64 pipeline rounds the exact tie (2k+1)/200 up to k+1 (purity_k)
+  int small_lv;                    // 1: every container level is provably <= 8192 (compact layout, batch*max_steps
+                                   //    <= 8192): the float32 quotient in purity_k then rounds to the right integer
+  unsigned S_magic;                // floor(2^32/S)+1: n/S == umulhi(n, S_magic) for n, S < 2^16
+  double pen_sev0, pen_mild0;      // min(0, severe / mild overflow penalty) (FAST press reward)
+  float obs_belt_tab[3][5];        // FAST: belt part of the observation for belt == pattern 1 / pattern 2 / empty
+  float obs_sort_tab[3][4];        // FAST: sorting-stage part of the observation, same three cases
   float inv_cap, inv_stage, inv_pt[2];
   double base_acc[4], boost, noise_low, noise_range;
   double qthr[4];
@@ -322,10 +328,14 @@ static __device__ __noinline__ int purity_k_f64(int tr, int tot) {
 // float64 pipeline once per k0 = 0..99 and hands the outcomes over as the bit table c.tie_up.
 __device__ __forceinline__ int purity_k(const DevConfig& c, int tr, int tot) {  // tot > 0, 0 <= tr <= tot
   if (tot < (1 << 17)) {                       // 100*tr and tot are exact in float32
-    const int a = 100 * tr;
-    int k = __float2int_rn(__fdividef((float)a, (float)tot));  // within 1 of the exact rounding
-    int d = 2 * (a - k * tot);                 // exact: twice the signed distance to k, in units of 1/tot
-    if (d > tot) { k += 1; d -= 2 * tot; } else if (d < -tot) { k -= 1; d += 2 * tot; }
+    const int a2 = 200 * tr, t2 = 2 * tot;
+    int k = __float2int_rn(__fdividef((float)(100 * tr), (float)tot));  // within 1 of the exact rounding
+    int d = a2 - k * t2;                       // exact: twice the signed distance to k, in units of 1/tot
+    // __fdividef is within 2 ulp (2.4e-5 at a quotient of 100) while a non-tie sits at least 1/(2*tot)
+    // from a rounding boundary: for tot <= 8192 (c.small_lv) k is already the exact rounding
+    if (!c.small_lv) {
+      if (d > tot) { k += 1; d -= t2; } else if (d < -tot) { k -= 1; d += t2; }
+    }
     if (d == tot || d == -tot) {               // .5 tie: k0 = floor of the exact value, outcome from the table
       const int k0 = d == tot ? k : k - 1;
       k = k0 + (int)((c.tie_up[(k0 >> 5) & 3] >> (k0 & 31)) & 1u);

@@ -218,8 +218,32 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       }
       s.gcount += 1;
     }
-    if (KIND != MSORT_ENV_PRESS) obs_belt(s, orow);      // final for this step: write now
-    if (KIND != MSORT_ENV_SORT) obs_sorting(c, s, prow);
+    if (FAST) {
+      // without an input remainder every stage holds pattern 1, pattern 2 or nothing (right after a
+      // reset): those parts of the observation come from host-built tables (same float32 operations)
+      // (a stage holding anything else can only come from an imported state: computed directly)
+      if (KIND != MSORT_ENV_PRESS) {
+        const bool b0 = s.belt4 == c.pat[0], b1 = s.belt4 == c.pat[1];
+        if (b0 || b1 || s.belt4 == 0u) {
+#pragma unroll
+          for (int k = 0; k < 5; ++k) orow[k] = b0 ? c.obs_belt_tab[0][k] : (b1 ? c.obs_belt_tab[1][k] : c.obs_belt_tab[2][k]);
+        } else {
+          obs_belt(s, orow);
+        }
+      }
+      if (KIND != MSORT_ENV_SORT) {
+        const bool s0 = s.sort4 == c.pat[0], s1 = s.sort4 == c.pat[1];
+        if (s0 || s1 || s.sort4 == 0u) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) prow[10 + k] = s0 ? c.obs_sort_tab[0][k] : (s1 ? c.obs_sort_tab[1][k] : c.obs_sort_tab[2][k]);
+        } else {
+          obs_sorting(c, s, prow);
+        }
+      }
+    } else {
+      if (KIND != MSORT_ENV_PRESS) obs_belt(s, orow);      // final for this step: write now
+      if (KIND != MSORT_ENV_SORT) obs_sorting(c, s, prow);
+    }
 
     // 3: decode the action
     int mode = 0, pa = 0;
@@ -561,7 +585,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     } else {
       double r_sort = 0.0, r_press = 0.0;
       if (KIND != MSORT_ENV_PRESS) {  // calculate_sorting_reward :963-1003
-        if (c.fast_pdiff) {
+        if (FAST || c.fast_pdiff) {
           int kt = 0;
 #pragma unroll
           for (int m = 0; m < 4; ++m) kt += kq[m] >= 0 ? kq[m] : c.qthr100[m];
@@ -572,21 +596,30 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       }
       if (KIND != MSORT_ENV_SORT) {  // calculate_press_reward :1006-1080
         int mx = lv[4], tl = lv[4];
-        bool sev = lv[4] >= c.lvl_sev, mild = lv[4] >= c.lvl_mild && lv[4] < c.lvl_sev;
+        double max_pen;        // min(0, severe if any fill>0.95, mild if any fill in (0.90,0.95]) (:1024-1027)
+        if (FAST) {            // penalties ordered severe <= mild (host-checked): only the fullest container matters
 #pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          mx = max(mx, lv[m]); tl += lv[m];
-          sev |= lv[m] >= c.lvl_sev; mild |= lv[m] >= c.lvl_mild && lv[m] < c.lvl_sev;
+          for (int m = 0; m < 4; ++m) { mx = max(mx, lv[m]); tl += lv[m]; }
+          max_pen = mx >= c.lvl_sev ? c.pen_sev0 : (mx >= c.lvl_mild ? c.pen_mild0 : 0.0);
+        } else {
+          bool sev = lv[4] >= c.lvl_sev, mild = lv[4] >= c.lvl_mild && lv[4] < c.lvl_sev;
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            mx = max(mx, lv[m]); tl += lv[m];
+            sev |= lv[m] >= c.lvl_sev; mild |= lv[m] >= c.lvl_mild && lv[m] < c.lvl_sev;
+          }
+          max_pen = 0.0;
+          if (sev && c.pen_sev < max_pen) max_pen = c.pen_sev;
+          if (mild && c.pen_mild < max_pen) max_pen = c.pen_mild;
         }
-        double max_pen = 0.0;  // min(0, severe if any fill>0.95, mild if any fill in (0.90,0.95]) (:1024-1027)
-        if (sev && c.pen_sev < max_pen) max_pen = c.pen_sev;
-        if (mild && c.pen_mild < max_pen) max_pen = c.pen_mild;
         if (mx >= c.lvl_cat) r_press = c.pen_cat;            // :1022-1023
         else if (max_pen < 0.0) r_press = max_pen;           // :1029-1030 (started flag NOT cleared)
         else {
           double rr = (double)tl * c.c_state;                // overall fill ratio * max_state_reward (:1049-1050)
           if (s.started) {                                   // :1054-1075
-            const int S = c.S, amount = s.last_amt, nb = amount / S, rm = amount - nb * S;
+            const int S = c.S, amount = s.last_amt;
+            const int nb = LAYOUT == LAYOUT_COMPACT ? (int)__umulhi((uint32_t)amount, c.S_magic) : amount / S;  // amount < 2^16 in the compact layout
+            const int rm = amount - nb * S;
             const int d = min(rm, S - rm);
             const double eff = (1.0 - (double)d * c.c_eff) * c.bef;
             const double peak = (double)min(nb, 3) * (1.0 / 3.0);
@@ -603,7 +636,14 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     s.ep_ret = dadd(s.ep_ret, reward);
 
     // 10: observation (this env's row of the dense shared tile), outputs, auto-reset
-    if (KIND != MSORT_ENV_PRESS) obs_pdiff(c, kq, orow);
+    if (KIND != MSORT_ENV_PRESS) {
+      if (FAST) {   // whole-percent thresholds in [0,1] (host-checked): (k - 100*thr)/100 is already inside [-1,1]
+#pragma unroll
+        for (int m = 0; m < 4; ++m) orow[9 + m] = kq[m] >= 0 ? (float)(kq[m] - c.qthr100[m]) * 0.01f : 0.f;
+      } else {
+        obs_pdiff(c, kq, orow);
+      }
+    }
     if (KIND != MSORT_ENV_SORT) obs_levels_timers(c, s, prow);
 
     a.reward[i] = (float)reward;
