@@ -23,6 +23,7 @@ struct msort_handle {
   float* policy_dev;  // owned device constants (tiny, allocated at create): 1570 policy floats ...
   double* lut_dev;    // ... and the kSortLut-entry float64 sorting-reward table
   bool policy_set;
+  float policy_host[MSORT_POLICY_WEIGHTS];  // host copy: travels to the step kernel as a kernel parameter
   int64_t launches;
 };
 
@@ -362,7 +363,7 @@ extern "C" int msort_step(msort_t* h, void* state, const int64_t* actions, float
   if (h->dev.kind == MSORT_ENV_PRESS && (h->dev.flags & MSORT_F_SORT_POLICY_MLP) && !h->policy_set &&
       !(replay && replay->sort_mode))
     return fail(MSORT_E_INVALID, "msort_step: embedded sort policy requested but msort_set_policy() was never called");
-  StepLaunch l{state, actions, obs, reward, terminated, mask, info, replay};
+  StepLaunch l{state, actions, obs, reward, terminated, mask, info, replay, h->policy_set ? h->policy_host : nullptr};
   MSORT_TRY_CUDA(launch_step(h->dev, l, h->cfg.rng_mode, (cudaStream_t)stream), "step kernel");
   h->launches += 1;
   return MSORT_OK;
@@ -370,8 +371,16 @@ extern "C" int msort_step(msort_t* h, void* state, const int64_t* actions, float
 
 extern "C" int msort_set_policy(msort_t* h, const float* weights, int weights_on_device, void* stream) {
   if (!h || !weights) return fail(MSORT_E_INVALID, "msort_set_policy: NULL argument");
-  MSORT_TRY_CUDA(cudaMemcpyAsync(h->policy_dev, weights, sizeof(float) * MSORT_POLICY_WEIGHTS,
-                                 weights_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+  // The step kernel receives the weights as a kernel parameter, so the library keeps a host copy.  A
+  // device-resident source is copied back once, here (the one place besides msort_sync_check that waits).
+  if (weights_on_device) {
+    MSORT_TRY_CUDA(cudaMemcpyAsync(h->policy_host, weights, sizeof(h->policy_host), cudaMemcpyDeviceToHost,
+                                   (cudaStream_t)stream), "cudaMemcpyAsync(policy)");
+    MSORT_TRY_CUDA(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize(policy)");
+  } else {
+    memcpy(h->policy_host, weights, sizeof(h->policy_host));
+  }
+  MSORT_TRY_CUDA(cudaMemcpyAsync(h->policy_dev, h->policy_host, sizeof(h->policy_host), cudaMemcpyHostToDevice,
                                  (cudaStream_t)stream), "cudaMemcpyAsync(policy)");
   h->policy_set = true;
   return MSORT_OK;

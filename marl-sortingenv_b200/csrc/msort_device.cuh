@@ -481,27 +481,28 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
 
-// fp32 MLP 13->32->32->2 with tanh; weights staged in shared memory by the CTA
+// fp32 MLP 13->32->32->2 with tanh, fully unrolled; `w` is the kernel-parameter copy of the weights, so
+// every weight is a constant-bank operand of its FFMA
 // (ref: sort_agent.predict env_2_press.py:106-109; arch training.py:115)
-__device__ __forceinline__ int mlp_sort_mode(const float* __restrict__ w, const float* x) {
-  const float *W1 = w, *b1 = w + 416, *W2 = w + 448, *b2 = w + 1472, *W3 = w + 1504, *b3 = w + 1568;
+__device__ __forceinline__ int mlp_sort_mode(const float (&w)[MSORT_POLICY_WEIGHTS], const float* x) {
+  constexpr int W1 = 0, b1 = 416, W2 = 448, b2 = 1472, W3 = 1504, b3 = 1568;
   float h1[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
-    float a = b1[j];
+    float a = w[b1 + j];
 #pragma unroll
-    for (int k = 0; k < 13; ++k) a = fmaf(W1[j * 13 + k], x[k], a);
+    for (int k = 0; k < 13; ++k) a = fmaf(w[W1 + j * 13 + k], x[k], a);
     h1[j] = tanh_fast(a);
   }
-  float l0 = b3[0], l1 = b3[1];
-#pragma unroll 2
-  for (int j = 0; j < 32; ++j) {
-    float a = b2[j];
+  float l0 = w[b3], l1 = w[b3 + 1];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) a = fmaf(W2[j * 32 + k], h1[k], a);
-    float h = tanh_fast(a);
-    l0 = fmaf(W3[j], h, l0);
-    l1 = fmaf(W3[32 + j], h, l1);
+  for (int j = 0; j < 32; ++j) {
+    float a = w[b2 + j];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) a = fmaf(w[W2 + j * 32 + k], h1[k], a);
+    const float h = tanh_fast(a);
+    l0 = fmaf(w[W3 + j], h, l0);
+    l1 = fmaf(w[W3 + 32 + j], h, l1);
   }
   return l1 > l0 ? 1 : 0;
 }

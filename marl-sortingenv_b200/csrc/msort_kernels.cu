@@ -4,6 +4,9 @@
 // memory so every global store is a coalesced 4-byte-per-lane (128 B per warp) store.
 #include <cuda_runtime.h>
 
+#include <cstring>
+#include <type_traits>
+
 #include "msort_device.cuh"
 #include "msort_launch.h"
 
@@ -125,17 +128,24 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// Env_2's embedded policy travels as a kernel parameter (6.3 KB of the 32 KB parameter space): the
+// weights then sit in the constant bank and every FFMA of the fully unrolled MLP takes its weight
+// as a constant operand — no load instruction at all.
+struct PolicyW { float w[MSORT_POLICY_WEIGHTS]; };
+struct NoPolicy {};
+template <int KIND> using PolicyParam = typename std::conditional<KIND == MSORT_ENV_PRESS, PolicyW, NoPolicy>::type;
+
 // FAST (PHILOX only, chosen by the host when DevConfig::fast holds): boosted accuracies are exactly 1.0,
 // unboosted ones need no clip, and the redistribution classes fit one register of packed bytes.
 // Results are identical to the generic instantiation; only the instruction count differs.
 template <int KIND, int RNG, int LAYOUT, bool FAST>
 __global__ void __launch_bounds__(kTile, (KIND == MSORT_ENV_PRESS ? 5 : MSORT_STEP_MIN_BLOCKS) * (128 / kTile))  // Env_2 keeps 32 MLP activations in registers
-step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArgs a) {
+step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArgs a,
+            const __grid_constant__ PolicyParam<KIND> pw) {
   constexpr int D = Dims<KIND>::D, A = Dims<KIND>::A;
   __shared__ __align__(16) float s_obs[kTile * D];
   __shared__ __align__(16) uint8_t s_mask[kTile * A];
   __shared__ double s_accs[RNG == MSORT_RNG_REPLAY ? 4 : 1][RNG == MSORT_RNG_REPLAY ? kTile : 1];  // accuracy_sorter (REPLAY)
-  __shared__ float s_policy[KIND == MSORT_ENV_PRESS ? MSORT_POLICY_WEIGHTS : 1];
   __shared__ double s_stat[kTile / 32][ST_COUNT];   // per-warp partial sums (plain stores: no init, no atomics)
 
   const bool masking = c.flags & MSORT_F_ACTION_MASKING;
@@ -143,8 +153,6 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   const bool use_mlp = KIND == MSORT_ENV_PRESS && (c.flags & MSORT_F_SORT_POLICY_MLP) &&
                        !(RNG == MSORT_RNG_REPLAY && a.sort_mode_in);
   const int tid = threadIdx.x;
-  if (use_mlp) for (int k = tid; k < MSORT_POLICY_WEIGHTS; k += kTile) s_policy[k] = c.policy[k];
-  if (use_mlp) __syncthreads();
 
   const long long row0 = (long long)blockIdx.x * kTile;
   const long long i = row0 + tid;
@@ -263,7 +271,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
         int kq[4];
         purity_ks(c, s, kq);
         sort_obs(c, s, kq, so);
-        mode = mlp_sort_mode(s_policy, so);
+        if constexpr (KIND == MSORT_ENV_PRESS) mode = mlp_sort_mode(pw.w, so);
       } else {  // sorting_rules env_super.py:469-482: pA+pC > pB+pD on float64 proportions
         int ac = b4(s.belt4, 0) + b4(s.belt4, 2), bd = b4(s.belt4, 1) + b4(s.belt4, 3);
         if (ac != bd) mode = ac > bd ? 0 : 1;  // strict integer inequality survives the float64 rounding
@@ -962,15 +970,19 @@ stats_kernel(const __grid_constant__ DevConfig c, const uint4* __restrict__ stat
 static inline unsigned tiles(long long n) { return (unsigned)((n + kTile - 1) / kTile); }
 
 template <int KIND>
-static cudaError_t launch_step_kind(const DevConfig& c, const StepArgs& a, int rng, cudaStream_t st) {
+static cudaError_t launch_step_kind(const DevConfig& c, const StepArgs& a, const float* policy_host, int rng, cudaStream_t st) {
   const unsigned g = tiles(c.n);
-  if (rng == MSORT_RNG_REPLAY) step_kernel<KIND, MSORT_RNG_REPLAY, LAYOUT_REPLAY, false><<<g, kTile, 0, st>>>(c, a);
+  PolicyParam<KIND> pw;
+  if constexpr (KIND == MSORT_ENV_PRESS) {
+    if (policy_host) memcpy(pw.w, policy_host, sizeof(pw.w)); else memset(pw.w, 0, sizeof(pw.w));
+  }
+  if (rng == MSORT_RNG_REPLAY) step_kernel<KIND, MSORT_RNG_REPLAY, LAYOUT_REPLAY, false><<<g, kTile, 0, st>>>(c, a, pw);
   else if (c.layout == LAYOUT_COMPACT) {
-    if (c.fast) step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true><<<g, kTile, 0, st>>>(c, a);
-    else step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, false><<<g, kTile, 0, st>>>(c, a);
+    if (c.fast) step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true><<<g, kTile, 0, st>>>(c, a, pw);
+    else step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, false><<<g, kTile, 0, st>>>(c, a, pw);
   } else {
-    if (c.fast) step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_WIDE, true><<<g, kTile, 0, st>>>(c, a);
-    else step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_WIDE, false><<<g, kTile, 0, st>>>(c, a);
+    if (c.fast) step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_WIDE, true><<<g, kTile, 0, st>>>(c, a, pw);
+    else step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_WIDE, false><<<g, kTile, 0, st>>>(c, a, pw);
   }
   return cudaGetLastError();
 }
@@ -997,9 +1009,9 @@ cudaError_t launch_step(const DevConfig& c, const StepLaunch& l, int rng, cudaSt
   a.redis_len = r ? r->redis_len : 0; a.input_counts = r ? r->input_counts : nullptr;
   a.press_choice = r ? r->press_choice : nullptr; a.sort_mode_in = r ? r->sort_mode : nullptr;
   switch (c.kind) {
-    case MSORT_ENV_SORT: return launch_step_kind<MSORT_ENV_SORT>(c, a, rng, st);
-    case MSORT_ENV_PRESS: return launch_step_kind<MSORT_ENV_PRESS>(c, a, rng, st);
-    default: return launch_step_kind<MSORT_ENV_MONO>(c, a, rng, st);
+    case MSORT_ENV_SORT: return launch_step_kind<MSORT_ENV_SORT>(c, a, l.policy_host, rng, st);
+    case MSORT_ENV_PRESS: return launch_step_kind<MSORT_ENV_PRESS>(c, a, l.policy_host, rng, st);
+    default: return launch_step_kind<MSORT_ENV_MONO>(c, a, l.policy_host, rng, st);
   }
 }
 

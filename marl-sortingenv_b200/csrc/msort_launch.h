@@ -19,6 +19,7 @@ struct StepLaunch {
   uint8_t* mask;
   const msort_info_out_t* info;
   const msort_replay_t* replay;
+  const float* policy_host;  // Env_2 embedded policy (host copy, MSORT_POLICY_WEIGHTS floats) or nullptr
 };
 
 cudaError_t launch_step(const DevConfig& c, const StepLaunch& l, int rng, cudaStream_t st);
