@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MSORT_ABI_VERSION 1
+#define MSORT_ABI_VERSION 2
 
 /* ------------------------------------------------------------------ enums */
 typedef enum msort_status {
@@ -182,6 +182,12 @@ typedef struct msort_info_out {
                                    0 episodes finished, 1 sum episode return, 2 sum episode length,
                                    3 env-steps, 4 sum reward, 5 overflows, 6 bales pressed,
                                    7 invalid actions, 8 clamped actions, 9 replay under-runs */
+  float* reward_sort;           /* [N] sorting term of the reward (reward_data['Reward'][t][0],
+                                   env_super.py:933; 0 where the env kind does not compute it)   */
+  float* reward_press;          /* [N] pressing term (reward_data['Reward'][t][1])               */
+  uint32_t* sorted_true;        /* [N] units sorted correctly this step, one byte per station A..D
+                                   (true_arr of sort_material, env_super.py:539; feeds the logged
+                                   mean purity reward_data['Accuracy'], env_super.py:605-607)    */
 } msort_info_out_t;
 
 typedef struct msort_handle msort_t;
@@ -255,6 +261,12 @@ int msort_rule_based_actions(msort_t* h, const void* state, int after_shift, int
 
 /* SoA device blob <-> plain msort_env_state_t[N] (device memory). */
 int msort_export_state(msort_t* h, const void* state, msort_env_state_t* out, void* stream);
+/* The same for a subset: out[j] = plain state of env env_ids[j], j < count (device memory).  The
+ * telemetry recorder's per-step snapshot of the traced envs — the device-side stand-in for the
+ * reference's per-step Python logs (reward_data / press_actions_per_timestep / bale_count,
+ * env_super.py:928-946,631-637,661-687). */
+int msort_gather_state(msort_t* h, const void* state, const int64_t* env_ids, int64_t count,
+                       msort_env_state_t* out, void* stream);
 int msort_import_state(msort_t* h, void* state, const msort_env_state_t* in, void* stream);
 
 /* State-wide sums for the episode-statistics all-reduce (out16: device, f64[16], overwritten):

@@ -18,6 +18,9 @@ def __getattr__(name):  # lazy: the env classes need torch + the CUDA library
     if name in ("Env_1_Sorting", "Env_2_Pressing", "Env_3_Monolith"):
         from . import single
         return getattr(single, name)
+    if name in ("TraceRecorder",):
+        from . import telemetry
+        return telemetry.TraceRecorder
     if name in ("MsortVecEnv",):
         from . import vecenv
         return getattr(vecenv, name)

@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 ENV_SORT, ENV_PRESS, ENV_MONO = 1, 2, 3
 KIND_BY_NAME = {"sort": ENV_SORT, "press": ENV_PRESS, "mono": ENV_MONO}
@@ -119,6 +119,7 @@ class MsortInfoOut(C.Structure):
         ("sort_mode", C.c_void_p), ("press_action", C.c_void_p), ("invalid_action", C.c_void_p),
         ("terminal_obs", C.c_void_p), ("episode_return", C.c_void_p),
         ("episode_length", C.c_void_p), ("stats", C.c_void_p),
+        ("reward_sort", C.c_void_p), ("reward_press", C.c_void_p), ("sorted_true", C.c_void_p),
     ]
 
 
@@ -143,6 +144,7 @@ SYMBOLS = {
     "msort_rule_based_actions": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "msort_observe": (C.c_int, [_P, _P, _P, _P, _P]),
     "msort_export_state": (C.c_int, [_P, _P, _P, _P]),
+    "msort_gather_state": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
     "msort_import_state": (C.c_int, [_P, _P, _P, _P]),
     "msort_reduce_stats": (C.c_int, [_P, _P, _P, _P]),
     "msort_sync_check": (C.c_int, [_P, _P]),

@@ -88,6 +88,11 @@ class BatchedEnv:
             self.info_buffers["sort_mode"] = torch.zeros(n, dtype=torch.uint8, device=dev)
             self.info_buffers["press_action"] = torch.zeros(n, dtype=torch.uint8, device=dev)
             self.info_buffers["invalid_action"] = torch.zeros(n, dtype=torch.bool, device=dev)
+            # the two reward terms the reference logs per step (reward_data['Reward'], env_super.py:933)
+            self.info_buffers["reward_sort"] = torch.zeros(n, dtype=torch.float32, device=dev)
+            self.info_buffers["reward_press"] = torch.zeros(n, dtype=torch.float32, device=dev)
+            # units sorted correctly this step, one byte per station (→ logged mean purity, env_super.py:605)
+            self.info_buffers["sorted_true"] = torch.zeros(n, dtype=torch.int32, device=dev)
         b = self.info_buffers
         self._info.action = _ptr(b.get("action"))
         self._info.overflow = _ptr(b.get("overflow"))
@@ -99,6 +104,10 @@ class BatchedEnv:
         self._info.episode_return = _ptr(b.get("episode_return"))
         self._info.episode_length = _ptr(b.get("episode_length"))
         self._info.stats = _ptr(self.stats)
+        self._info.reward_sort = _ptr(b.get("reward_sort"))
+        self._info.reward_press = _ptr(b.get("reward_press"))
+        self._info.sorted_true = _ptr(b.get("sorted_true"))
+        self._trace = None
         self._has_info = info_level != "none" or track_stats
         self._was_reset = False
         self.sort_agent = None
@@ -155,6 +164,8 @@ class BatchedEnv:
                                       _ptr(self.mask), flags, self._stream())
         _abi.check(self.lib, rc, "msort_reset")
         self._was_reset = True
+        if self._trace is not None and which is None:
+            self._trace.start()
         return self.obs, {}
 
     def step(self, actions, replay: dict | None = None):
@@ -178,7 +189,23 @@ class BatchedEnv:
                                      C.byref(self._info) if self._has_info else None,
                                      C.byref(rp) if rp is not None else None, self._stream())
         _abi.check(self.lib, rc, "msort_step")
+        if self._trace is not None:
+            self._trace.record()
         return self.obs, self.reward, self.terminated, self.truncated, self.info_buffers
+
+    def attach_trace(self, env_ids, capacity: int):
+        """Record per-step telemetry of the listed envs (the device stand-in for the reference's
+        reward_data / press_actions_per_timestep / bale_count logs, env_super.py:928-946): returns a
+        `telemetry.TraceRecorder` that `reset()` restarts and every `step()` appends to.  Needs
+        `info_level='full'`.  `detach_trace()` stops recording."""
+        from .telemetry import TraceRecorder
+        self._trace = TraceRecorder(self, env_ids, capacity)
+        if self._was_reset:
+            self._trace.start()
+        return self._trace
+
+    def detach_trace(self):
+        self._trace = None
 
     def action_masks(self):
         """ref: Env_X.action_masks() (env_super.py:869-898) on the current state: bool [N, A]."""

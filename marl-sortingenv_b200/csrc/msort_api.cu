@@ -420,6 +420,16 @@ extern "C" int msort_export_state(msort_t* h, const void* state, msort_env_state
   return MSORT_OK;
 }
 
+extern "C" int msort_gather_state(msort_t* h, const void* state, const int64_t* env_ids, int64_t count,
+                                  msort_env_state_t* out, void* stream) {
+  if (!h || !state || (count > 0 && (!env_ids || !out))) return fail(MSORT_E_INVALID, "msort_gather_state: NULL argument");
+  if (count < 0) return fail(MSORT_E_INVALID, "msort_gather_state: negative count");
+  if (!aligned(state, 16) || !aligned(out, 8) || !aligned(env_ids, 8)) return fail(MSORT_E_INVALID, "msort_gather_state: misaligned buffer");
+  MSORT_TRY_CUDA(launch_gather(h->dev, state, env_ids, count, out, (cudaStream_t)stream), "gather kernel");
+  h->launches += 1;
+  return MSORT_OK;
+}
+
 extern "C" int msort_import_state(msort_t* h, void* state, const msort_env_state_t* in, void* stream) {
   if (!h || !state || !in) return fail(MSORT_E_INVALID, "msort_import_state: NULL argument");
   if (!aligned(state, 16) || !aligned(in, 8)) return fail(MSORT_E_INVALID, "msort_import_state: misaligned buffer");

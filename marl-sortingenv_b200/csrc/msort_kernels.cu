@@ -104,6 +104,9 @@ struct StepArgs {
   uint8_t* info_sort_mode;
   uint8_t* info_press_action;
   uint8_t* info_invalid;
+  uint32_t* info_sorted_true;
+  float* info_r_sort;
+  float* info_r_press;
   int any_step_info;  // any of the six per-step info arrays above is present
   float* terminal_obs;
   double* episode_return;
@@ -309,6 +312,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     }
 
     // 5: sort_material env_super.py:511-609.
+    uint32_t sorted_true4 = 0;   // correctly sorted units per station this step (bytes A..D); reported only
     if (RNG == MSORT_RNG_REPLAY) {
       // REPLAY: the reference's loop nest literally (per-class leftovers, numpy's float64 cdf search),
       // one recorded uniform per draw.
@@ -346,6 +350,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       s.e += sum4(L);                                            // :579,597
 #pragma unroll
       for (int q = 0; q < 4; ++q) { s.tr[q] += b4(T4, q); s.fl[q] += b4(F4, q); }  // :600-602
+      sorted_true4 = T4;
     } else if (FAST) {
       // PHILOX, FAST form of the block below (same draws, same class selection, same results).
       // The four classes live in one register as bytes  lump | X<<8 | L2<<16 | L3<<24  (every prefix
@@ -425,6 +430,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       s.e += lump;                                               // :579,597
 #pragma unroll
       for (int q = 0; q < 4; ++q) { s.tr[q] += b4(T4, q); s.fl[q] += b4(F4, q); }  // :600-602
+      sorted_true4 = T4;
     } else {
       // PHILOX: the same random process in the form DESIGN.md §4 "Sorting" derives.
       // Removing a unit from a station that has already been processed (or from the current
@@ -520,6 +526,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       s.e += lump;                                               // :579,597
 #pragma unroll
       for (int q = 0; q < 4; ++q) { s.tr[q] += b4(T4, q); s.fl[q] += b4(F4, q); }  // :600-602
+      sorted_true4 = T4;
     }
 
     // 6: Env_1 samples its own press action under the mask (env_super.py:291-300)
@@ -584,10 +591,12 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
 #pragma unroll
       for (int m = 0; m < 4; ++m) kq[m] = lv[m] > 0 ? purity_k(c, s.tr[m], lv[m]) : -1;
     }
-    double reward;
+    double reward, rs_term = 0.0, rp_term = 0.0;   // the two terms are only reported (telemetry)
     bool terminated;
     if (overflow) {
       reward = c.ovf_pen;
+      // logged split of the penalty: Env_3 halves it (env_monolith.py:271), Env_1/2 book it as pressing
+      if (KIND == MSORT_ENV_MONO) { rs_term = rp_term = 0.5 * c.ovf_pen; } else { rp_term = c.ovf_pen; }
       s.step += 1;
       terminated = true;
     } else {
@@ -638,6 +647,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
         }
       }
       reward = KIND == MSORT_ENV_SORT ? r_sort : (KIND == MSORT_ENV_PRESS ? r_press : r_sort + r_press);
+      rs_term = r_sort; rp_term = r_press;
       s.step += 1;
       terminated = s.step >= (uint32_t)c.max_steps;
     }
@@ -663,6 +673,9 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       if (a.info_sort_mode) a.info_sort_mode[i] = (uint8_t)mode;
       if (a.info_press_action) a.info_press_action[i] = (uint8_t)pa;
       if (a.info_invalid) a.info_invalid[i] = invalid ? 1 : 0;
+      if (a.info_sorted_true) a.info_sorted_true[i] = sorted_true4;
+      if (a.info_r_sort) a.info_r_sort[i] = (float)rs_term;
+      if (a.info_r_press) a.info_r_press[i] = (float)rp_term;
     }
     st_reward = reward;
     st_flags += (overflow ? 1u << 8 : 0u) + (invalid ? 1u << 16 : 0u);
@@ -868,10 +881,8 @@ rule_actions_kernel(const __grid_constant__ DevConfig c, const uint4* __restrict
 }
 
 // ---------------------------------------------------------------- K6: export / import
-__global__ void __launch_bounds__(kTile)
-export_kernel(const __grid_constant__ DevConfig c, const uint4* __restrict__ state, msort_env_state_t* __restrict__ out) {
-  const long long i = (long long)blockIdx.x * kTile + threadIdx.x;
-  if (i >= c.n) return;
+__device__ __forceinline__ void export_env(const DevConfig& c, const uint4* __restrict__ state, long long i,
+                                           msort_env_state_t* __restrict__ dst) {
   Env s;
   load_env(c, state, i, s);
   msort_env_state_t o;
@@ -893,7 +904,25 @@ export_kernel(const __grid_constant__ DevConfig c, const uint4* __restrict__ sta
   }
   o.reserved = 0;
   o.ep_return = s.ep_ret;
-  out[i] = o;
+  *dst = o;
+}
+
+__global__ void __launch_bounds__(kTile)
+export_kernel(const __grid_constant__ DevConfig c, const uint4* __restrict__ state, msort_env_state_t* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * kTile + threadIdx.x;
+  if (i >= c.n) return;
+  export_env(c, state, i, &out[i]);
+}
+
+// telemetry snapshot: plain state of the listed envs (ids outside [0, n) give a zeroed record)
+__global__ void __launch_bounds__(kTile)
+gather_kernel(const __grid_constant__ DevConfig c, const uint4* __restrict__ state, const long long* __restrict__ ids,
+              long long count, msort_env_state_t* __restrict__ out) {
+  const long long j = (long long)blockIdx.x * kTile + threadIdx.x;
+  if (j >= count) return;
+  const long long i = ids[j];
+  if (i < 0 || i >= c.n) { memset(&out[j], 0, sizeof(msort_env_state_t)); return; }
+  export_env(c, state, i, &out[j]);
 }
 
 __global__ void __launch_bounds__(kTile)
@@ -998,8 +1027,11 @@ cudaError_t launch_step(const DevConfig& c, const StepLaunch& l, int rng, cudaSt
   a.info_sort_mode = f ? f->sort_mode : nullptr;
   a.info_press_action = f ? f->press_action : nullptr;
   a.info_invalid = f ? f->invalid_action : nullptr;
+  a.info_sorted_true = f ? f->sorted_true : nullptr;
+  a.info_r_sort = f ? f->reward_sort : nullptr;
+  a.info_r_press = f ? f->reward_press : nullptr;
   a.any_step_info = a.info_action || a.info_overflow || a.info_overflow_mat || a.info_sort_mode ||
-                    a.info_press_action || a.info_invalid;
+                    a.info_press_action || a.info_invalid || a.info_r_sort || a.info_r_press || a.info_sorted_true;
   a.terminal_obs = f ? f->terminal_obs : nullptr;
   a.episode_return = f ? f->episode_return : nullptr;
   a.episode_length = f ? f->episode_length : nullptr;
@@ -1052,6 +1084,13 @@ cudaError_t launch_rule_actions(const DevConfig& c, const void* state, int after
 
 cudaError_t launch_export(const DevConfig& c, const void* state, msort_env_state_t* out, cudaStream_t st) {
   export_kernel<<<tiles(c.n), kTile, 0, st>>>(c, (const uint4*)state, out);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather(const DevConfig& c, const void* state, const int64_t* env_ids, long long count,
+                          msort_env_state_t* out, cudaStream_t st) {
+  if (count <= 0) return cudaSuccess;
+  gather_kernel<<<tiles(count), kTile, 0, st>>>(c, (const uint4*)state, (const long long*)env_ids, count, out);
   return cudaGetLastError();
 }
 

@@ -30,6 +30,8 @@ cudaError_t launch_sample(const DevConfig& c, const uint8_t* mask, int64_t* acti
                           cudaStream_t st);
 cudaError_t launch_rule_actions(const DevConfig& c, const void* state, int after_shift, int64_t* actions, cudaStream_t st);
 cudaError_t launch_export(const DevConfig& c, const void* state, msort_env_state_t* out, cudaStream_t st);
+cudaError_t launch_gather(const DevConfig& c, const void* state, const int64_t* env_ids, long long count,
+                          msort_env_state_t* out, cudaStream_t st);
 cudaError_t launch_import(const DevConfig& c, void* state, const msort_env_state_t* in, cudaStream_t st);
 cudaError_t launch_stats(const DevConfig& c, const void* state, double* out16, int sm_count, cudaStream_t st);
 

@@ -122,6 +122,8 @@ class OracleEnv:
             keep = dict(action=np.zeros(n, np.int64), overflow=np.zeros(n, np.uint8),
                         overflow_material=np.full(n, -1, np.int8), sort_mode=np.zeros(n, np.uint8),
                         press_action=np.zeros(n, np.uint8), invalid_action=np.zeros(n, np.uint8),
+                        reward_sort=np.zeros(n, np.float32), reward_press=np.zeros(n, np.float32),
+                        sorted_true=np.zeros(n, np.uint32),
                         terminal_obs=np.zeros((n, D), np.float32),
                         episode_return=np.zeros(n, np.float64),
                         episode_length=np.zeros(n, np.int32))

@@ -332,6 +332,7 @@ static void step_one(const msort_config_t* cfg, msort_env_state_t* s, int64_t i,
   }
 
   /* 5: sort_material env_super.py:511-609 */
+  uint32_t sorted_true4 = 0;   /* true_arr (:539) packed one byte per station; reported for the logged mean purity (:605) */
   if (replay) {
     /* REPLAY: the reference's loop nest, one recorded numpy uniform per `choice` call. */
     int L[4], T[4] = {0, 0, 0, 0}, F[4] = {0, 0, 0, 0};
@@ -363,6 +364,7 @@ static void step_one(const msort_config_t* cfg, msort_env_state_t* s, int64_t i,
     }
     s->cont_e += L[0] + L[1] + L[2] + L[3];                       /* :579,597 */
     for (int q = 0; q < 4; ++q) { s->cont_true[q] += T[q]; s->cont_false[q] += F[q]; } /* :600-602 */
+    for (int q = 0; q < 4; ++q) sorted_true4 |= (uint32_t)T[q] << (8 * q);
   } else {
     /* PHILOX: the same random process in the form the device kernel evaluates it (DESIGN.md §4
      * "Sorting").  Each draw removes one unit chosen uniformly from the pool of leftovers
@@ -381,6 +383,7 @@ static void step_one(const msort_config_t* cfg, msort_env_state_t* s, int64_t i,
       int tr = (int)rint((double)t * acc_sorter[S]);              /* :539 half-to-even */
       int f = t - tr;
       s->cont_true[S] += tr; s->cont_false[S] += f;               /* :600-602 */
+      sorted_true4 |= (uint32_t)tr << (8 * S);
       tot -= tr;
       if (S == 3) break;                                          /* its f draws leave lump unchanged */
       lump += f;                                                  /* leftover[S] = false_val joins the lump */
@@ -454,10 +457,12 @@ static void step_one(const msort_config_t* cfg, msort_env_state_t* s, int64_t i,
       if (level_of(s, m) > cfg->container_capacity) { overflow = 1; overflow_mat = m; break; }
   }
 
-  double reward;
+  double reward, rs_term = 0.0, rp_term = 0.0;   /* the two terms as _log_step_data records them (env_super.py:933) */
   int terminated;
   if (overflow) {
     reward = cfg->overflow_termination_penalty;
+    /* env_monolith.py:271 logs (reward/2, reward/2); env_1_sort.py:141, env_2_press.py:152 log (0, reward) */
+    if (kind == MSORT_ENV_MONO) { rs_term = rp_term = reward / 2; } else { rp_term = reward; }
     s->step += 1;
     terminated = 1;
   } else {
@@ -501,6 +506,7 @@ static void step_one(const msort_config_t* cfg, msort_env_state_t* s, int64_t i,
       }
     }
     reward = kind == MSORT_ENV_SORT ? r_sort : (kind == MSORT_ENV_PRESS ? r_press : r_sort + r_press);
+    rs_term = r_sort; rp_term = r_press;
     s->step += 1;                                                 /* e.g. env_monolith.py:279-280 */
     terminated = s->step >= cfg->max_steps;
   }
@@ -518,6 +524,9 @@ static void step_one(const msort_config_t* cfg, msort_env_state_t* s, int64_t i,
     if (info->sort_mode) info->sort_mode[i] = (uint8_t)mode;
     if (info->press_action) info->press_action[i] = (uint8_t)pa;
     if (info->invalid_action) info->invalid_action[i] = (uint8_t)invalid;
+    if (info->sorted_true) info->sorted_true[i] = sorted_true4;
+    if (info->reward_sort) info->reward_sort[i] = (float)rs_term;
+    if (info->reward_press) info->reward_press[i] = (float)rp_term;
   }
   if (terminated) {
     acc->v[0] += 1; acc->v[1] += s->ep_return; acc->v[2] += s->step;

@@ -135,7 +135,7 @@ def _press_log_to_discrete(entry) -> int:
 def record(kind: str, *, seed: int, steps: int, max_steps: int = 50, noise: float = 0.05,
            balesize: int = 200, policy="masked_random", action_seed: int = 0,
            use_action_masking: bool = True, check_overflow: bool = False,
-           auto_reset: bool = True, mlp_weights=None, actions=None) -> dict:
+           auto_reset: bool = True, mlp_weights=None, actions=None, keep_env: bool = False) -> dict:
     """Run the reference for `steps` env-steps (auto-resetting unseeded like SB3's VecEnv when
     an episode ends, if `auto_reset`) and return everything needed to replay and compare."""
     D, A = KIND_DIMS[kind]
@@ -239,4 +239,6 @@ def record(kind: str, *, seed: int, steps: int, max_steps: int = 50, noise: floa
         "first_pattern": np.asarray(out["first_pattern"], dtype=np.int64),
         "mlp_margin": np.asarray(out["mlp_margin"], dtype=np.float64),
     }
+    if keep_env:
+        res["env"] = env          # the reference env itself (its Python logs; tests/golden/make_log_golden.py)
     return res

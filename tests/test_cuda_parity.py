@@ -74,10 +74,12 @@ def _philox_cross_check(cuda_backend, kind, n, T, *, masking=True, overflow=Fals
             assert np.array_equal(ora.state[f], gpu.export_state()[f]), f
         assert np.array_equal(ot, gt), f"step {t}: terminated"
         assert np.array_equal(om, gm), f"step {t}: mask"
-        for k in ("overflow", "overflow_material", "sort_mode", "press_action", "invalid_action", "action"):
+        for k in ("overflow", "overflow_material", "sort_mode", "press_action", "invalid_action", "action", "sorted_true"):
             assert np.array_equal(np.asarray(oi[k]).astype(np.int64), np.asarray(gi[k]).astype(np.int64)), f"step {t}: {k}"
         assert_float_close(grw, orw, f"step {t}: reward")
         assert_float_close(go, oo, f"step {t}: obs")
+        assert_float_close(gi["reward_sort"], oi["reward_sort"], f"step {t}: reward_sort")
+        assert_float_close(gi["reward_press"], oi["reward_press"], f"step {t}: reward_press")
         if ot.any():
             assert_float_close(gi["terminal_obs"][ot], oi["terminal_obs"][ot], "terminal obs")
             assert_float_close(gi["episode_return"][ot], oi["episode_return"][ot], "episode return")
