@@ -9,6 +9,7 @@ import ctypes as C
 import os
 
 ABI_VERSION = 2
+POLICY_ACT_WEIGHTS = 8352
 
 ENV_SORT, ENV_PRESS, ENV_MONO = 1, 2, 3
 KIND_BY_NAME = {"sort": ENV_SORT, "press": ENV_PRESS, "mono": ENV_MONO}
@@ -143,6 +144,7 @@ SYMBOLS = {
     "msort_sample_actions": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint32, _P]),
     "msort_rule_based_actions": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "msort_observe": (C.c_int, [_P, _P, _P, _P, _P]),
+    "msort_policy_act": (C.c_int, [_P, _P, _P, _P, C.c_uint64, C.c_uint32, C.c_int, _P, _P, _P, _P]),
     "msort_export_state": (C.c_int, [_P, _P, _P, _P]),
     "msort_gather_state": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
     "msort_import_state": (C.c_int, [_P, _P, _P, _P]),

@@ -234,6 +234,31 @@ class BatchedEnv:
         _abi.check(self.lib, rc, "msort_rule_based_actions")
         return out
 
+    def policy_act(self, packed_weights: torch.Tensor, seed: int = 0, t: int = 0, deterministic: bool = False,
+                   obs: torch.Tensor | None = None, mask: torch.Tensor | None = None, out=None):
+        """Fused actor-critic inference + masked categorical draw for every env (one tcgen05 kernel
+        launch; `msort_policy_act`): (actions int64 [N], log-prob f32 [N], value f32 [N]) for the
+        current observation / action mask (or the given ones).  `packed_weights` comes from
+        `ppo.pack_actor_critic`.  ref: MaskablePPO's policy forward during collect_rollouts
+        (training.py:118-143, net_arch pi=[32,32], vf=[32,32])."""
+        obs = self.obs if obs is None else obs
+        mask = self.mask if mask is None else mask
+        if packed_weights.numel() != _abi.POLICY_ACT_WEIGHTS or packed_weights.dtype != torch.float32:
+            raise ValueError(f"packed_weights must hold {_abi.POLICY_ACT_WEIGHTS} float32 values")
+        if not (obs.is_contiguous() and mask.is_contiguous() and packed_weights.is_contiguous()):
+            raise ValueError("policy_act needs contiguous tensors")
+        if out is None:
+            out = (torch.empty(self.num_envs, dtype=torch.int64, device=self.device),
+                   torch.empty(self.num_envs, dtype=torch.float32, device=self.device),
+                   torch.empty(self.num_envs, dtype=torch.float32, device=self.device))
+        a, lp, v = out
+        with torch.cuda.device(self.device):
+            rc = self.lib.msort_policy_act(self._h, _ptr(obs), _ptr(mask), _ptr(packed_weights),
+                                           int(seed) & 0xFFFFFFFFFFFFFFFF, int(t) & 0xFFFFFFFF, 1 if deterministic else 0,
+                                           _ptr(a), _ptr(lp), _ptr(v), self._stream())
+        _abi.check(self.lib, rc, "msort_policy_act")
+        return a, lp, v
+
     # ------------------------------------------------------------------ host-buffer surface
     def _host_buffers(self):
         if getattr(self, "_hb", None) is None:

@@ -6,7 +6,7 @@ import shutil
 import subprocess
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-SOURCES = ["msort_kernels.cu", "msort_api.cu"]
+SOURCES = ["msort_kernels.cu", "msort_policy.cu", "msort_api.cu"]
 HEADERS = ["msort_device.cuh", "msort_launch.h", os.path.join("..", "..", "include", "msort.h")]
 LIB = os.path.join(_CSRC, "libmsort.so")
 

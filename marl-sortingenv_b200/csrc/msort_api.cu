@@ -412,6 +412,20 @@ extern "C" int msort_rule_based_actions(msort_t* h, const void* state, int after
   return MSORT_OK;
 }
 
+extern "C" int msort_policy_act(msort_t* h, const float* obs, const uint8_t* mask, const float* packed_weights,
+                                uint64_t seed, uint32_t t, int deterministic, int64_t* actions, float* logp,
+                                float* value, void* stream) {
+  if (!h || !obs || !mask || !packed_weights || !actions || !logp || !value)
+    return fail(MSORT_E_INVALID, "msort_policy_act: NULL argument");
+  if (!aligned(obs, 4) || !aligned(packed_weights, 16) || !aligned(actions, 8) || !aligned(logp, 4) || !aligned(value, 4))
+    return fail(MSORT_E_INVALID, "msort_policy_act: misaligned buffer");
+  MSORT_TRY_CUDA(launch_policy_act(h->dev, obs, mask, packed_weights, msort_obs_dim(h), msort_num_actions(h), seed, t,
+                                   deterministic, actions, logp, value, h->sm_count, (cudaStream_t)stream),
+                 "policy_act kernel");
+  h->launches += 1;
+  return MSORT_OK;
+}
+
 extern "C" int msort_export_state(msort_t* h, const void* state, msort_env_state_t* out, void* stream) {
   if (!h || !state || !out) return fail(MSORT_E_INVALID, "msort_export_state: NULL argument");
   if (!aligned(state, 16) || !aligned(out, 8)) return fail(MSORT_E_INVALID, "msort_export_state: misaligned buffer");

@@ -29,6 +29,9 @@ cudaError_t launch_observe(const DevConfig& c, const void* state, float* obs, ui
 cudaError_t launch_sample(const DevConfig& c, const uint8_t* mask, int64_t* actions, uint64_t seed, uint32_t t,
                           cudaStream_t st);
 cudaError_t launch_rule_actions(const DevConfig& c, const void* state, int after_shift, int64_t* actions, cudaStream_t st);
+cudaError_t launch_policy_act(const DevConfig& c, const float* obs, const uint8_t* mask, const float* packed,
+                              int D, int A, uint64_t seed, uint32_t t, int deterministic, int64_t* actions,
+                              float* logp, float* value, int sm_count, cudaStream_t st);
 cudaError_t launch_export(const DevConfig& c, const void* state, msort_env_state_t* out, cudaStream_t st);
 cudaError_t launch_gather(const DevConfig& c, const void* state, const int64_t* env_ids, long long count,
                           msort_env_state_t* out, cudaStream_t st);

@@ -1,0 +1,359 @@
+// msort_policy.cu — fused actor-critic inference + masked categorical sampling for the GPU-resident
+// MaskablePPO rollout (ref: MaskablePPO(policy_kwargs=dict(net_arch=dict(pi=[32,32],
+// vf=[32,32]))) training.py:115-131 — two tanh towers obs -> 32 -> 32 -> {A logits | 1 value}; logits
+// masked with -1e8 like sb3_contrib, env_monolith.py:152-158 for the masked draw).
+//
+// Unlike Env_2's embedded 13->32->32->2 policy (argmax parity with an fp32 reference: CUDA cores), this
+// IS a dense contraction with no bit-parity requirement — M = number of envs (1e6), three layers — so it
+// runs on the 5th-generation tensor cores:
+//   * one CTA = one tile of 128 envs = one UMMA M=128 tile; the two towers are evaluated as ONE network
+//     with concatenated / block-diagonal weights:  [128x32]·[32x64] -> tanh -> [128x64]·[64x64] -> tanh
+//     -> [128x64]·[64x32]  (columns 0..A-1 logits, column A value);
+//   * tcgen05.mma.cta_group::1.kind::tf32 issued by one thread, A (activations) and B (weights) in shared
+//     memory in the canonical no-swizzle K-major layout, fp32 accumulators in 64 TMEM columns;
+//   * TMEM lane = tile row = env, so after tcgen05.ld (32x32b) thread r holds row r's outputs: bias + tanh
+//     in registers, written straight back as the next layer's A operand (16-byte chunk kc of row r at
+//     (kc*128 + r)*16 B: consecutive threads -> consecutive 16 B, conflict-free STS.128); two threads per
+//     env, one per tower (accumulator columns 0..31 / 32..63), 256 threads per CTA;
+//   * tcgen05.commit -> mbarrier tells the CTA when a layer's accumulators are complete;
+//   * persistent CTAs (2 per SM): the 33 KB of packed weights are staged into shared memory once; the obs
+//     and mask tiles (contiguous 14.8 KB / 2.8 KB) arrive by TMA bulk copies (cp.async.bulk + mbarrier
+//     complete_tx) into a two-slot ring, the next tile's copy in flight while this tile is computed.
+// Epilogue per env: masked log-softmax over the A logits, inverse-CDF draw with one Philox uniform keyed by
+// (seed, t, global env id) (or argmax), outputs action / log-prob / value with coalesced stores.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "msort_device.cuh"
+#include "msort_launch.h"
+
+namespace msort {
+
+namespace {
+
+constexpr int kRows = 128;                 // envs per tile == UMMA M
+constexpr int kThreads = 256;              // two threads per env: one per tower
+constexpr int kK1 = 32, kN1 = 64;          // layer 1: obs (padded to 32) -> pi hidden | vf hidden
+constexpr int kK2 = 64, kN2 = 64;          // layer 2: block-diagonal
+constexpr int kK3 = 64, kN3 = 32;          // layer 3: A logits | value | padding
+constexpr int kB1 = 0, kB2 = kB1 + kK1 * kN1, kB3 = kB2 + kK2 * kN2;       // float offsets in the packed buffer
+constexpr int kBias1 = kB3 + kK3 * kN3, kBias2 = kBias1 + kN1, kBias3 = kBias2 + kN2;
+constexpr int kPacked = kBias3 + kN3;      // == MSORT_POLICY_ACT_WEIGHTS
+static_assert(kPacked == MSORT_POLICY_ACT_WEIGHTS, "packed actor-critic size");
+constexpr int kTmemCols = 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor, no swizzle, K-major: 8x16B core matrices; SBO = distance between
+// 8-row groups, LBO = distance between the two 16-byte K chunks one instruction consumes
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+
+// instruction descriptor: D fp32, A/B tf32, both K-major, M = 128
+__device__ __forceinline__ constexpr uint32_t umma_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  for (uint32_t spin = 0;; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    if (done) return;
+    if (spin > (1u << 24)) __trap();   // a mis-programmed MMA must fail loudly, never hang the GPU
+  }
+}
+
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+}
+
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+struct __align__(16) PolicySmem {
+  float b[kB3 + kK3 * kN3];        // B1 | B2 | B3 in canonical K-major order (32 KB)
+  float bias[kN1 + kN2 + kN3];
+  float a[kK2 / 4 * kRows * 4];    // A operand: 16 chunks x 128 rows x 16 B (32 KB; layer 1 uses the first 8 chunks)
+  float stage[2][kRows * 32];      // obs tile ring (row-major, D <= 32), filled by TMA bulk copies
+  uint8_t mask[2][kRows * 32];     // mask tile ring (A <= 31)
+  uint64_t bar;                    // MMA completion (tcgen05.commit)
+  uint64_t full[2];                // tile slot filled (TMA complete_tx)
+  uint32_t tmem_base;
+};
+
+// one layer: all threads have written their A chunks; thread 0 issues the K-steps and commits
+template <int K, int N>
+__device__ __forceinline__ void issue_layer(const PolicySmem& sm, int b_off, uint32_t tmem_d, uint64_t* bar) {
+  const uint32_t a0 = smem_u32(sm.a), b0 = smem_u32(sm.b + b_off);
+#pragma unroll
+  for (int s = 0; s < K / 8; ++s) {   // one instruction = K 8 (tf32) = two 16-byte chunks
+    const uint64_t ad = umma_desc(a0 + (uint32_t)(2 * s) * kRows * 16u, kRows * 16u, 128u);
+    const uint64_t bd = umma_desc(b0 + (uint32_t)(2 * s) * N * 16u, N * 16u, 128u);
+    umma_tf32(tmem_d, ad, bd, umma_idesc(N), s > 0 ? 1u : 0u);
+  }
+  umma_commit(bar);
+}
+
+}  // namespace
+
+// tanh for the hidden layers.  Default: the hardware tanh (MUFU.TANH, |error| <~ 5e-4 — the same size as the
+// tf32 rounding of the operands); -DMSORT_POLICY_TANH_APPROX=0 selects 1 - 2/(exp2(c*x)+1) (error ~1e-7).
+#ifndef MSORT_POLICY_TANH_APPROX
+#define MSORT_POLICY_TANH_APPROX 1
+#endif
+__device__ __forceinline__ float policy_tanh(float x) {
+#if MSORT_POLICY_TANH_APPROX
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+#else
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));   // exp(2x)
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return fmaf(-2.0f, r, 1.0f);
+#endif
+}
+
+// 256 threads: thread (row, half) — row = tid & 127 is the env / TMEM lane, half = tid >> 7 the tower:
+// warps 0-3 own accumulator columns 0..31 (policy tower), warps 4-7 columns 32..63 (value tower); both
+// warp groups reach the same TMEM lane quarter (warp % 4).
+template <int D, int A>
+__global__ void __launch_bounds__(kThreads, 2)
+policy_act_kernel(const float* __restrict__ obs, const uint8_t* __restrict__ mask, const float* __restrict__ packed,
+                  long long n, long long gid0, unsigned key0, unsigned key1, unsigned t, int deterministic, int use_tma,
+                  long long* __restrict__ actions, float* __restrict__ logp_out, float* __restrict__ value_out) {
+  static_assert(D <= 32 && A <= 31, "padded layer sizes");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  PolicySmem& sm = *reinterpret_cast<PolicySmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, row = tid & (kRows - 1), half = tid >> 7;
+
+  // ---- one-time setup: TMEM columns, mbarriers, weights
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&sm.tmem_base)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (tid == 0) {
+    mbar_init(&sm.bar, 1);
+    mbar_init(&sm.full[0], 1);
+    mbar_init(&sm.full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {
+    const float4* src = reinterpret_cast<const float4*>(packed);
+    float4* dst = reinterpret_cast<float4*>(sm.b);       // b[] and bias[] are contiguous
+    for (int e = tid; e < kPacked / 4; e += kThreads) dst[e] = src[e];
+  }
+  fence_async_proxy();            // weights were written through the generic proxy, the MMA reads through the async one
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = sm.tmem_base;
+  const uint32_t tcol = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(32 * half);   // this thread's lane, its tower's columns
+  uint32_t phase = 0;
+
+  const long long ntiles = (n + kRows - 1) / kRows;
+  constexpr uint32_t obs_bytes = (uint32_t)(kRows * D) * 4u, mask_bytes = (uint32_t)(kRows * A);
+  static_assert(obs_bytes % 16 == 0 && mask_bytes % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
+  // a full tile is one contiguous, 16-byte-aligned range of each tensor: one TMA bulk copy each
+  auto prefetch = [&](long long tl, int slot) {
+    if (use_tma && tl < ntiles && (tl + 1) * kRows <= n) {
+      mbar_expect_tx(&sm.full[slot], obs_bytes + mask_bytes);
+      bulk_load(sm.stage[slot], obs + tl * kRows * D, obs_bytes, &sm.full[slot]);
+      bulk_load(sm.mask[slot], mask + tl * kRows * A, mask_bytes, &sm.full[slot]);
+    }
+  };
+  if (tid == 0) prefetch(blockIdx.x, 0);
+  uint32_t it = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const long long row0 = tile * kRows;
+    const int rows = (int)min((long long)kRows, n - row0);
+    const int slot = (int)(it & 1u);
+    const float* stage = sm.stage[slot];
+    const uint8_t* mtile = sm.mask[slot];
+    if (tid == 0) {                      // the other slot was released by the barrier that ended the previous tile
+      fence_async_proxy();
+      prefetch(tile + gridDim.x, slot ^ 1);
+    }
+    if (use_tma && rows == kRows) {
+      mbar_wait(&sm.full[slot], (it >> 1) & 1u);
+    } else {                             // ragged last tile (its byte count need not be a multiple of 16) or unaligned tensors: plain loads
+      const float* src = obs + row0 * D;
+      const int tot = rows * D;
+      for (int e = tid; e < kRows * D; e += kThreads) sm.stage[slot][e] = e < tot ? src[e] : 0.f;
+      const uint8_t* ms = mask + row0 * A;
+      const int mt = rows * A;
+      for (int e = tid; e < kRows * A; e += kThreads) sm.mask[slot][e] = e < mt ? ms[e] : (uint8_t)0;
+      __syncthreads();
+    }
+    // ---- layer-1 A operand: obs row zero-padded to 32 columns; each half writes four of the eight chunks
+    {
+      const float* x = stage + row * D;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int kc = 4 * half + q;
+        float4 v;
+        v.x = 4 * kc + 0 < D ? x[4 * kc + 0] : 0.f; v.y = 4 * kc + 1 < D ? x[4 * kc + 1] : 0.f;
+        v.z = 4 * kc + 2 < D ? x[4 * kc + 2] : 0.f; v.w = 4 * kc + 3 < D ? x[4 * kc + 3] : 0.f;
+        *reinterpret_cast<float4*>(sm.a + (kc * kRows + row) * 4) = v;
+      }
+    }
+    fence_async_proxy();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) { fence_after_sync(); issue_layer<kK1, kN1>(sm, kB1, tmem, &sm.bar); }
+    mbar_wait(&sm.bar, phase); phase ^= 1;
+    fence_after_sync();
+
+    // ---- hidden layers: this tower's 32 accumulators -> +bias -> tanh -> its 8 chunks of the next A operand
+#pragma unroll
+    for (int layer = 0; layer < 2; ++layer) {
+      const float* bias = sm.bias + (layer == 0 ? 0 : kN1) + 32 * half;
+      float v[32];
+      tmem_ld32(tcol, v);
+      fence_before_sync();               // this thread's TMEM reads are done: the next MMA may overwrite the columns
+#pragma unroll
+      for (int kc = 0; kc < 8; ++kc) {
+        const float4 bb = *reinterpret_cast<const float4*>(bias + 4 * kc);
+        float4 h;
+        h.x = policy_tanh(v[4 * kc + 0] + bb.x); h.y = policy_tanh(v[4 * kc + 1] + bb.y);
+        h.z = policy_tanh(v[4 * kc + 2] + bb.z); h.w = policy_tanh(v[4 * kc + 3] + bb.w);
+        *reinterpret_cast<float4*>(sm.a + ((8 * half + kc) * kRows + row) * 4) = h;
+      }
+      fence_async_proxy();
+      __syncthreads();
+      if (tid == 0) {
+        fence_after_sync();
+        if (layer == 0) issue_layer<kK2, kN2>(sm, kB2, tmem, &sm.bar);
+        else issue_layer<kK3, kN3>(sm, kB3, tmem, &sm.bar);
+      }
+      mbar_wait(&sm.bar, phase); phase ^= 1;
+      fence_after_sync();
+    }
+
+    // ---- output layer (columns 0..A-1 logits, column A value): the policy-tower threads finish the env
+    if (half == 0) {
+      float o[32];
+      tmem_ld32(tcol, o);
+      const long long i = row0 + row;
+      if (row < rows) {
+        const float* b3 = sm.bias + kN1 + kN2;
+        const uint8_t* mrow = mtile + row * A;
+        float mx = -3.0e38f;
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+          o[a] = mrow[a] ? o[a] + b3[a] : -1e8f;        // sb3_contrib masks logits with -1e8
+          mx = fmaxf(mx, o[a]);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int a = 0; a < A; ++a) { o[a] = __expf(o[a] - mx); sum += o[a]; }   // o[a]: unnormalised probability
+        int act = 0;
+        if (deterministic) {
+          float best = -1.f;
+#pragma unroll
+          for (int a = 0; a < A; ++a) if (o[a] > best) { best = o[a]; act = a; }
+        } else {
+          const unsigned long long g = (unsigned long long)(gid0 + i);
+          const U4 r4 = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), 0xAC70u, t, key0, key1);
+          const float u = ((float)(r4.x >> 8) + 0.5f) * (1.0f / 16777216.0f) * sum;   // uniform in (0, sum)
+          float c = 0.f;
+          int last = 0;
+          bool found = false;
+#pragma unroll
+          for (int a = 0; a < A; ++a) {
+            c += o[a];
+            if (o[a] > 0.f) last = a;
+            if (!found && u < c && o[a] > 0.f) { act = a; found = true; }
+          }
+          if (!found) act = last;
+        }
+        float pa = 0.f;
+#pragma unroll
+        for (int a = 0; a < A; ++a) if (a == act) pa = o[a];
+        actions[i] = act;
+        logp_out[i] = __logf(pa) - __logf(sum);
+        value_out[i] = o[A] + b3[A];
+      }
+    }
+    fence_before_sync();
+    __syncthreads();   // the tile slot, the A buffer and the TMEM columns are reused by the next tile
+  }
+
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "r"(kTmemCols) : "memory");
+  }
+}
+
+template <int D, int A>
+static cudaError_t launch_policy_act_da(const DevConfig& c, const float* obs, const uint8_t* mask, const float* packed,
+                                        uint64_t seed, uint32_t t, int deterministic, int64_t* actions, float* logp,
+                                        float* value, int sm_count, cudaStream_t st) {
+  static_assert(sizeof(PolicySmem) <= 110 * 1024, "two CTAs per SM");
+  const size_t smem = sizeof(PolicySmem);
+  cudaError_t e = cudaFuncSetAttribute(policy_act_kernel<D, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const long long ntiles = (c.n + kRows - 1) / kRows;
+  const unsigned grid = (unsigned)std::min<long long>(ntiles, 2ll * sm_count);
+  // TMA bulk copies need 16-byte aligned tile addresses (tile sizes are multiples of 16 bytes)
+  const int use_tma = ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(mask)) & 15u) == 0;
+  policy_act_kernel<D, A><<<grid, kThreads, smem, st>>>(obs, mask, packed, c.n, c.gid0, (unsigned)(seed & 0xffffffffu),
+                                                        (unsigned)(seed >> 32), t, deterministic, use_tma, (long long*)actions,
+                                                        logp, value);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_policy_act(const DevConfig& c, const float* obs, const uint8_t* mask, const float* packed,
+                              int D, int A, uint64_t seed, uint32_t t, int deterministic, int64_t* actions,
+                              float* logp, float* value, int sm_count, cudaStream_t st) {
+  if (D == 29 && A == 22) return launch_policy_act_da<29, 22>(c, obs, mask, packed, seed, t, deterministic, actions, logp, value, sm_count, st);
+  if (D == 16 && A == 11) return launch_policy_act_da<16, 11>(c, obs, mask, packed, seed, t, deterministic, actions, logp, value, sm_count, st);
+  if (D == 13 && A == 2) return launch_policy_act_da<13, 2>(c, obs, mask, packed, seed, t, deterministic, actions, logp, value, sm_count, st);
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace msort

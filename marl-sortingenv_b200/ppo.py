@@ -51,11 +51,39 @@ class MaskableActorCritic(nn.Module):
         return logp_all.gather(1, actions[:, None]).squeeze(1), entropy, self.vf(obs).squeeze(1)
 
 
+def pack_actor_critic(policy: "MaskableActorCritic", out: torch.Tensor | None = None) -> torch.Tensor:
+    """The two towers as the single 32 -> 64 -> 64 -> 32 network `msort_policy_act` evaluates on the
+    tensor cores (include/msort.h): layer 1 concatenates the towers' first layers, layer 2 is block-
+    diagonal, layer 3 puts the A logits in rows 0..A-1 and the value in row A.  Each weight matrix
+    W[n][k] is stored in the kernel's shared-memory operand order [k/4][n][k%4] (no-swizzle K-major
+    core matrices), followed by the three bias vectors.  Returns MSORT_POLICY_ACT_WEIGHTS floats."""
+    pi, vf = policy.pi, policy.vf
+    dev = pi[0].weight.device
+    D, A = pi[0].weight.shape[1], pi[4].weight.shape[0]
+    assert D <= 32 and A <= 31
+    W1 = torch.zeros((64, 32), device=dev); W1[:32, :D] = pi[0].weight; W1[32:, :D] = vf[0].weight
+    W2 = torch.zeros((64, 64), device=dev); W2[:32, :32] = pi[2].weight; W2[32:, 32:] = vf[2].weight
+    W3 = torch.zeros((32, 64), device=dev); W3[:A, :32] = pi[4].weight; W3[A, 32:] = vf[4].weight[0]
+    b3 = torch.zeros(32, device=dev); b3[:A] = pi[4].bias; b3[A] = vf[4].bias[0]
+
+    def canon(W):                                   # [N, K] -> [K/4][N][4]
+        N, K = W.shape
+        return W.reshape(N, K // 4, 4).permute(1, 0, 2).reshape(-1)
+    packed = torch.cat([canon(W1), canon(W2), canon(W3), pi[0].bias, vf[0].bias, pi[2].bias, vf[2].bias, b3]).float()
+    if out is not None:
+        out.copy_(packed)
+        return out
+    return packed.contiguous()
+
+
 class MaskablePPO:
     def __init__(self, env, n_steps: int = 64, batch_size: int = 8192, n_epochs: int = 10, gamma: float = 0.99,
                  gae_lambda: float = 0.95, clip_range: float = 0.2, ent_coef: float = 0.05, vf_coef: float = 0.5,
-                 learning_rate: float = 3e-4, max_grad_norm: float = 0.5, seed: int = 42):
+                 learning_rate: float = 3e-4, max_grad_norm: float = 0.5, seed: int = 42, fused_act: bool = True):
         self.env = env
+        # rollout inference: one fused tensor-core kernel (msort_policy_act) instead of ~25 torch kernels/step
+        self.fused_act = fused_act and hasattr(env, "policy_act")
+        self.seed = seed
         self.n, self.D, self.A = env.num_envs, env.D, env.A
         self.dev = env.device
         torch.manual_seed(seed)
@@ -79,11 +107,17 @@ class MaskablePPO:
         env, b = self.env, self.buf
         if self._obs is None:
             self._obs, _ = env.reset()
+        packed = pack_actor_critic(self.policy) if self.fused_act else None
         for t in range(self.n_steps):
             b["obs"][t].copy_(self._obs)
             b["mask"][t].copy_(env.action_masks())
-            a, logp, v = self.policy.act(b["obs"][t], b["mask"][t])
-            b["act"][t], b["logp"][t], b["val"][t] = a, logp, v
+            if self.fused_act:                                           # writes straight into the rollout buffers
+                a, _, _ = env.policy_act(packed, seed=self.seed, t=self.num_timesteps // self.n + t,
+                                         obs=b["obs"][t], mask=b["mask"][t],
+                                         out=(b["act"][t], b["logp"][t], b["val"][t]))
+            else:
+                a, logp, v = self.policy.act(b["obs"][t], b["mask"][t])
+                b["act"][t], b["logp"][t], b["val"][t] = a, logp, v
             obs, rew, term, _, _ = env.step(a)                           # fused CUDA step (auto-reset inside)
             b["rew"][t].copy_(rew); b["done"][t].copy_(term)
             self._obs = obs

@@ -1,0 +1,100 @@
+"""msort_policy_act (tcgen05 actor-critic inference + masked categorical draw) against a plain PyTorch
+fp32 reference of the same op: masked log-softmax of the policy tower, value tower.  The kernel feeds
+tf32 operands to the tensor cores (fp32 accumulation), so logits agree to ~1e-3 relative, not bitwise;
+tolerances below are written for that."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(kind, n, seed=0, gain=1.0):
+    import torch
+    import marl_sortingenv_b200 as ms
+    from marl_sortingenv_b200.batched import ENV_CLASSES
+    from marl_sortingenv_b200.ppo import MaskableActorCritic, pack_actor_critic
+    env = ENV_CLASSES[kind](n, max_steps=50, seed=3, info_level="none", track_stats=False)
+    env.reset()
+    for t in range(37):                                  # a state with varied levels / masks
+        env.step(env.sample_actions(5, t))
+    torch.manual_seed(seed)
+    pol = MaskableActorCritic(env.D, env.A).cuda()
+    with torch.no_grad():                                # non-trivial logits and biases
+        pol.pi[4].weight.mul_(gain / 0.01)
+        for net in (pol.pi, pol.vf):
+            for i in (0, 2, 4):
+                net[i].bias.uniform_(-0.3, 0.3)
+    return env, pol, pack_actor_critic(pol)
+
+
+@pytest.mark.parametrize("kind,n", [("mono", 128 * 37 + 5), ("press", 1000), ("sort", 300), ("mono", 77)])
+def test_policy_act_matches_torch_reference(kind, n):
+    import torch
+    env, pol, packed = _setup(kind, n)
+    obs, mask = env.obs.clone(), env.mask.clone()
+    a, lp, v = env.policy_act(packed, seed=11, t=4)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        logp_all = torch.log_softmax(pol.masked_logits(obs, mask), dim=-1)
+        v_ref = pol.vf(obs).squeeze(1)
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    assert a.dtype == torch.int64 and int(a.min()) >= 0 and int(a.max()) < env.A
+    assert bool(mask.gather(1, a[:, None]).all()), "sampled an invalid action"
+    lp_ref = logp_all.gather(1, a[:, None]).squeeze(1)
+    print("max |dlogp|", float((lp - lp_ref).abs().max()), "max |dv|", float((v - v_ref).abs().max()))
+    assert torch.allclose(lp, lp_ref, atol=5e-3, rtol=5e-3), float((lp - lp_ref).abs().max())
+    assert torch.allclose(v, v_ref, atol=5e-3, rtol=5e-3), float((v - v_ref).abs().max())
+    # unaligned views of a larger buffer (rows of a [T, n, D] rollout buffer with odd n): plain-load path
+    big_o = torch.zeros(n * env.D + 1, device="cuda"); big_m = torch.zeros(n * env.A + 1, dtype=torch.bool, device="cuda")
+    o2 = big_o[1:].view(n, env.D); o2.copy_(obs); m2 = big_m[1:].view(n, env.A); m2.copy_(mask)
+    a_u, lp_u, v_u = env.policy_act(packed, seed=11, t=4, obs=o2, mask=m2)
+    assert torch.equal(a_u, a) and torch.equal(lp_u, lp) and torch.equal(v_u, v)
+    # same key -> same draw; another step index -> (mostly) different draws
+    a2, _, _ = env.policy_act(packed, seed=11, t=4)
+    assert torch.equal(a, a2)
+    if n >= 1000 and kind != "sort":
+        a3, _, _ = env.policy_act(packed, seed=11, t=5)
+        assert float((a3 != a).float().mean()) > 0.05
+
+
+def test_policy_act_deterministic_is_argmax_and_draws_follow_the_distribution():
+    import torch
+    env, pol, packed = _setup("mono", 4096, seed=2)
+    obs, mask = env.obs.clone(), env.mask.clone()
+    with torch.no_grad():
+        logits = pol.masked_logits(obs, mask)
+        p = torch.softmax(logits, dim=-1)
+    a, _, _ = env.policy_act(packed, deterministic=True)
+    top2 = logits.topk(2, dim=-1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 2e-2               # away from numerical ties
+    assert torch.equal(a[clear], logits.argmax(-1)[clear])
+    # empirical action frequencies over many keys vs the mean policy distribution
+    counts = torch.zeros(env.A, device="cuda")
+    T = 64
+    for t in range(T):
+        at, _, _ = env.policy_act(packed, seed=1, t=t)
+        counts += torch.bincount(at, minlength=env.A).float()
+    freq = counts / counts.sum()
+    want = p.mean(0)
+    assert float((freq - want).abs().max()) < 4e-3, (freq, want)
+
+
+def test_fused_rollout_matches_torch_rollout_statistics():
+    """collect_rollout with the fused kernel vs the torch path: same policy, same env seed -> the mean
+    step reward of a rollout agrees statistically, and log-probs stored by the kernel agree with
+    evaluate() (what PPO's ratio compares them to)."""
+    import torch
+    import marl_sortingenv_b200 as ms
+    from marl_sortingenv_b200.ppo import MaskablePPO
+    stats = {}
+    for fused in (True, False):
+        env = ms.BatchedMonolithEnv(2048, max_steps=200, seed=42, noise_sorting=0.0, info_level="none", track_stats=False)
+        model = MaskablePPO(env, n_steps=32, seed=0, fused_act=fused)
+        model.collect_rollout()
+        b = model.buf
+        lp_new, _, v_new = model.policy.evaluate(b["obs"].reshape(-1, env.D), b["mask"].reshape(-1, env.A), b["act"].reshape(-1))
+        stats[fused] = (float(b["rew"].mean()), float((lp_new - b["logp"].reshape(-1)).abs().max()),
+                        float((v_new - b["val"].reshape(-1)).abs().max()))
+    assert abs(stats[True][0] - stats[False][0]) < 0.02, stats
+    assert stats[True][1] < 5e-3 and stats[True][2] < 5e-3, stats
