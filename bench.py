@@ -51,6 +51,7 @@ def parse_args():
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-rollout", action="store_true", help="skip the policy-in-the-loop rollout measurement")
     ap.add_argument("--no-graph", action="store_true",
                     help="launch the K timed steps one by one instead of replaying one CUDA graph of them")
     return ap.parse_args()
@@ -289,6 +290,37 @@ def run_msort(args):
                "h2d_bytes_per_step": env.h2d_bytes * world, "d2h_bytes_per_step": env.d2h_bytes * world,
                "steps": Ke, "api": "BatchedEnv.step_host (pinned host actions in; obs, reward, terminated, mask out)"}
 
+    # ---- rollout loop (BASELINE configs[3] "MaskablePPO rollout loop"): every env-step = fused actor-critic
+    #      inference + masked categorical draw (msort_policy_act, tcgen05) followed by the fused step(),
+    #      fresh SB3-style random-init towers 29->32->32->{22|1}; one CUDA graph of Kr such pairs
+    rollout = None
+    if not args.no_rollout:
+        from marl_sortingenv_b200.ppo import MaskableActorCritic, pack_actor_critic
+        torch.manual_seed(0)
+        packed = pack_actor_critic(MaskableActorCritic(env.D, env.A).to(dev))
+        out = (torch.empty(n, dtype=torch.int64, device=dev), torch.empty(n, device=dev), torch.empty(n, device=dev))
+        Kr = 64
+        env.reset(seed=SEED)
+        for t in range(W):
+            env.policy_act(packed, seed=ACTION_SEED, t=t, out=out); env.step(out[0])
+        torch.cuda.synchronize(dev)
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            for t in range(Kr):
+                env.policy_act(packed, seed=ACTION_SEED, t=W + t, out=out); env.step(out[0])
+        gr.replay()
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record(); gr.replay(); r1.record()
+        barrier()
+        tr = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        rollout = {"value": n * world * Kr / (float(tr.item()) * 1e-3), "unit": "env-steps/s", "steps": Kr,
+                   "ms_per_step": float(tr.item()) / Kr, "launches_per_step": 2,
+                   "what": "per env-step: msort_policy_act (actor-critic 29-32-32-{22|1} on tcgen05, masked categorical "
+                           "draw) + fused step(); obs/mask never leave HBM"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -311,6 +343,8 @@ def run_msort(args):
                           "mean_length": stats[2] / max(1.0, stats[0]), "env_steps": stats[3],
                           "bales": stats[6]},
     }
+    if rollout is not None:
+        line["rollout"] = rollout
     if not args.no_cpu_baseline:
         v, cores, sample, _, _ = cpu_rollout(args.kind, budget_s=15.0)
         line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample}
