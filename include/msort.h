@@ -262,16 +262,17 @@ int msort_rule_based_actions(msort_t* h, const void* state, int after_shift, int
 /* Fused actor-critic inference + masked categorical draw for the GPU-resident MaskablePPO rollout
  * (ref: MaskablePPO with net_arch=dict(pi=[32,32], vf=[32,32]), training.py:115-131; SB3 tanh MLPs;
  * logits of invalid actions masked with -1e8 as sb3_contrib does).  One launch evaluates both towers for
- * all N envs on the tensor cores (tcgen05, tf32 inputs, fp32 accumulation) and samples
+ * all N envs on the tensor cores (tcgen05, fp16 operands, fp32 accumulation) and samples
  * action ~ softmax(masked logits) with one Philox uniform keyed by (seed, t, global env id), or takes the
  * argmax when `deterministic`.  All pointers are device memory.
  *  obs [N,D] f32, mask [N,A] u8 (the step() outputs);  actions [N] i64, logp [N] f32, value [N] f32
- *  packed_weights : MSORT_POLICY_ACT_WEIGHTS f32, 16-byte aligned, in the order the kernel stages them
+ *  packed_weights : MSORT_POLICY_ACT_WEIGHTS 32-bit words, 16-byte aligned, in the order the kernel stages them
  *    (see marl-sortingenv_b200/ppo.py pack_actor_critic): for each layer the weight matrix W[n][k]
  *    (n = output unit, k = input unit; towers concatenated / block-diagonal: layer 1 32->64,
  *    layer 2 64->64, layer 3 64->32 with rows 0..A-1 = logits, row A = value) stored as
- *    [k/4][n][k%4], then the three bias vectors (64, 64, 32). */
-#define MSORT_POLICY_ACT_WEIGHTS 8352
+ *    fp16 in the order [k/8][n][k%8] (two values per 32-bit word), then the three fp32 bias vectors
+ *    (64, 64, 32). */
+#define MSORT_POLICY_ACT_WEIGHTS 4256
 int msort_policy_act(msort_t* h, const float* obs, const uint8_t* mask, const float* packed_weights,
                      uint64_t seed, uint32_t t, int deterministic, int64_t* actions, float* logp,
                      float* value, void* stream);

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 ABI_VERSION = 2
-POLICY_ACT_WEIGHTS = 8352
+POLICY_ACT_WEIGHTS = 4256
 
 ENV_SORT, ENV_PRESS, ENV_MONO = 1, 2, 3
 KIND_BY_NAME = {"sort": ENV_SORT, "press": ENV_PRESS, "mono": ENV_MONO}

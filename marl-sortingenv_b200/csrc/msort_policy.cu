@@ -9,18 +9,20 @@
 //   * one CTA = one tile of 128 envs = one UMMA M=128 tile; the two towers are evaluated as ONE network
 //     with concatenated / block-diagonal weights:  [128x32]·[32x64] -> tanh -> [128x64]·[64x64] -> tanh
 //     -> [128x64]·[64x32]  (columns 0..A-1 logits, column A value);
-//   * tcgen05.mma.cta_group::1.kind::tf32 issued by one thread, A (activations) and B (weights) in shared
-//     memory in the canonical no-swizzle K-major layout, fp32 accumulators in 64 TMEM columns;
+//   * tcgen05.mma.cta_group::1.kind::f16 issued by one thread, A (activations) and B (weights) as fp16 in
+//     shared memory in the canonical no-swizzle K-major layout (fp16 keeps the 10 mantissa bits tf32 would;
+//     every operand is O(1)), fp32 accumulators in 64 TMEM columns;
 //   * TMEM lane = tile row = env, so after tcgen05.ld (32x32b) thread r holds row r's outputs: bias + tanh
-//     in registers, written straight back as the next layer's A operand (16-byte chunk kc of row r at
+//     in registers, written straight back as the next layer's A operand (16-byte chunk kc = 8 columns of row r at
 //     (kc*128 + r)*16 B: consecutive threads -> consecutive 16 B, conflict-free STS.128); two threads per
 //     env, one per tower (accumulator columns 0..31 / 32..63), 256 threads per CTA;
 //   * tcgen05.commit -> mbarrier tells the CTA when a layer's accumulators are complete;
-//   * persistent CTAs (2 per SM): the 33 KB of packed weights are staged into shared memory once; the obs
+//   * persistent CTAs (3 per SM): the 17 KB of packed weights are staged into shared memory once; the obs
 //     and mask tiles (contiguous 14.8 KB / 2.8 KB) arrive by TMA bulk copies (cp.async.bulk + mbarrier
 //     complete_tx) into a two-slot ring, the next tile's copy in flight while this tile is computed.
 // Epilogue per env: masked log-softmax over the A logits, inverse-CDF draw with one Philox uniform keyed by
 // (seed, t, global env id) (or argmax), outputs action / log-prob / value with coalesced stores.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -38,9 +40,10 @@ constexpr int kThreads = 256;              // two threads per env: one per tower
 constexpr int kK1 = 32, kN1 = 64;          // layer 1: obs (padded to 32) -> pi hidden | vf hidden
 constexpr int kK2 = 64, kN2 = 64;          // layer 2: block-diagonal
 constexpr int kK3 = 64, kN3 = 32;          // layer 3: A logits | value | padding
-constexpr int kB1 = 0, kB2 = kB1 + kK1 * kN1, kB3 = kB2 + kK2 * kN2;       // float offsets in the packed buffer
-constexpr int kBias1 = kB3 + kK3 * kN3, kBias2 = kBias1 + kN1, kBias3 = kBias2 + kN2;
-constexpr int kPacked = kBias3 + kN3;      // == MSORT_POLICY_ACT_WEIGHTS
+// packed buffer (float32 words): fp16 weights B1 | B2 | B3 (two per word), then the fp32 biases
+constexpr int kB1 = 0, kB2 = kB1 + kK1 * kN1, kB3 = kB2 + kK2 * kN2;       // offsets in fp16 elements
+constexpr int kWeightHalves = kB3 + kK3 * kN3;
+constexpr int kPacked = kWeightHalves / 2 + kN1 + kN2 + kN3;               // == MSORT_POLICY_ACT_WEIGHTS
 static_assert(kPacked == MSORT_POLICY_ACT_WEIGHTS, "packed actor-critic size");
 constexpr int kTmemCols = 64;
 
@@ -53,15 +56,15 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes
          ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
 }
 
-// instruction descriptor: D fp32, A/B tf32, both K-major, M = 128
+// instruction descriptor: D fp32, A/B fp16, both K-major, M = 128
 __device__ __forceinline__ constexpr uint32_t umma_idesc(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
 }
 
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
@@ -114,9 +117,9 @@ __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 struct __align__(16) PolicySmem {
-  float b[kB3 + kK3 * kN3];        // B1 | B2 | B3 in canonical K-major order (32 KB)
+  __half b[kWeightHalves];         // B1 | B2 | B3 in canonical K-major order (16 KB)
   float bias[kN1 + kN2 + kN3];
-  float a[kK2 / 4 * kRows * 4];    // A operand: 16 chunks x 128 rows x 16 B (32 KB; layer 1 uses the first 8 chunks)
+  uint4 a[kK2 / 8 * kRows];        // A operand: 8 chunks (8 fp16 columns each) x 128 rows x 16 B (16 KB; layer 1 uses 4)
   float stage[2][kRows * 32];      // obs tile ring (row-major, D <= 32), filled by TMA bulk copies
   uint8_t mask[2][kRows * 32];     // mask tile ring (A <= 31)
   uint64_t bar;                    // MMA completion (tcgen05.commit)
@@ -129,15 +132,23 @@ template <int K, int N>
 __device__ __forceinline__ void issue_layer(const PolicySmem& sm, int b_off, uint32_t tmem_d, uint64_t* bar) {
   const uint32_t a0 = smem_u32(sm.a), b0 = smem_u32(sm.b + b_off);
 #pragma unroll
-  for (int s = 0; s < K / 8; ++s) {   // one instruction = K 8 (tf32) = two 16-byte chunks
+  for (int s = 0; s < K / 16; ++s) {   // one instruction = K 16 (fp16) = two 16-byte chunks
     const uint64_t ad = umma_desc(a0 + (uint32_t)(2 * s) * kRows * 16u, kRows * 16u, 128u);
     const uint64_t bd = umma_desc(b0 + (uint32_t)(2 * s) * N * 16u, N * 16u, 128u);
-    umma_tf32(tmem_d, ad, bd, umma_idesc(N), s > 0 ? 1u : 0u);
+    umma_f16(tmem_d, ad, bd, umma_idesc(N), s > 0 ? 1u : 0u);
   }
   umma_commit(bar);
 }
 
 }  // namespace
+
+// eight fp32 values -> one 16-byte chunk of fp16 (the K-major core-matrix row)
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+  const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+  const __half2 c = __floats2half2_rn(v[4], v[5]), d = __floats2half2_rn(v[6], v[7]);
+  return make_uint4(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b),
+                    *reinterpret_cast<const uint32_t*>(&c), *reinterpret_cast<const uint32_t*>(&d));
+}
 
 // tanh for the hidden layers.  Default: the hardware tanh (MUFU.TANH, |error| <~ 5e-4 — the same size as the
 // tf32 rounding of the operands); -DMSORT_POLICY_TANH_APPROX=0 selects 1 - 2/(exp2(c*x)+1) (error ~1e-7).
@@ -161,7 +172,7 @@ __device__ __forceinline__ float policy_tanh(float x) {
 // warps 0-3 own accumulator columns 0..31 (policy tower), warps 4-7 columns 32..63 (value tower); both
 // warp groups reach the same TMEM lane quarter (warp % 4).
 template <int D, int A>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
 policy_act_kernel(const float* __restrict__ obs, const uint8_t* __restrict__ mask, const float* __restrict__ packed,
                   long long n, long long gid0, unsigned key0, unsigned key1, unsigned t, int deterministic, int use_tma,
                   long long* __restrict__ actions, float* __restrict__ logp_out, float* __restrict__ value_out) {
@@ -228,16 +239,16 @@ policy_act_kernel(const float* __restrict__ obs, const uint8_t* __restrict__ mas
       for (int e = tid; e < kRows * A; e += kThreads) sm.mask[slot][e] = e < mt ? ms[e] : (uint8_t)0;
       __syncthreads();
     }
-    // ---- layer-1 A operand: obs row zero-padded to 32 columns; each half writes four of the eight chunks
+    // ---- layer-1 A operand: obs row zero-padded to 32 columns; each half writes two of the four chunks
     {
       const float* x = stage + row * D;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int kc = 4 * half + q;
-        float4 v;
-        v.x = 4 * kc + 0 < D ? x[4 * kc + 0] : 0.f; v.y = 4 * kc + 1 < D ? x[4 * kc + 1] : 0.f;
-        v.z = 4 * kc + 2 < D ? x[4 * kc + 2] : 0.f; v.w = 4 * kc + 3 < D ? x[4 * kc + 3] : 0.f;
-        *reinterpret_cast<float4*>(sm.a + (kc * kRows + row) * 4) = v;
+      for (int q = 0; q < 2; ++q) {
+        const int kc = 2 * half + q;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 8 * kc + j < D ? x[8 * kc + j] : 0.f;
+        sm.a[kc * kRows + row] = pack8(v);
       }
     }
     fence_async_proxy();
@@ -255,12 +266,11 @@ policy_act_kernel(const float* __restrict__ obs, const uint8_t* __restrict__ mas
       tmem_ld32(tcol, v);
       fence_before_sync();               // this thread's TMEM reads are done: the next MMA may overwrite the columns
 #pragma unroll
-      for (int kc = 0; kc < 8; ++kc) {
-        const float4 bb = *reinterpret_cast<const float4*>(bias + 4 * kc);
-        float4 h;
-        h.x = policy_tanh(v[4 * kc + 0] + bb.x); h.y = policy_tanh(v[4 * kc + 1] + bb.y);
-        h.z = policy_tanh(v[4 * kc + 2] + bb.z); h.w = policy_tanh(v[4 * kc + 3] + bb.w);
-        *reinterpret_cast<float4*>(sm.a + ((8 * half + kc) * kRows + row) * 4) = h;
+      for (int kc = 0; kc < 4; ++kc) {
+        float h[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) h[j] = policy_tanh(v[8 * kc + j] + bias[8 * kc + j]);
+        sm.a[(4 * half + kc) * kRows + row] = pack8(h);
       }
       fence_async_proxy();
       __syncthreads();
@@ -333,12 +343,12 @@ template <int D, int A>
 static cudaError_t launch_policy_act_da(const DevConfig& c, const float* obs, const uint8_t* mask, const float* packed,
                                         uint64_t seed, uint32_t t, int deterministic, int64_t* actions, float* logp,
                                         float* value, int sm_count, cudaStream_t st) {
-  static_assert(sizeof(PolicySmem) <= 110 * 1024, "two CTAs per SM");
+  static_assert(sizeof(PolicySmem) <= 74 * 1024, "three CTAs per SM");
   const size_t smem = sizeof(PolicySmem);
   cudaError_t e = cudaFuncSetAttribute(policy_act_kernel<D, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long long ntiles = (c.n + kRows - 1) / kRows;
-  const unsigned grid = (unsigned)std::min<long long>(ntiles, 2ll * sm_count);
+  const unsigned grid = (unsigned)std::min<long long>(ntiles, 3ll * sm_count);
   // TMA bulk copies need 16-byte aligned tile addresses (tile sizes are multiples of 16 bytes)
   const int use_tma = ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(mask)) & 15u) == 0;
   policy_act_kernel<D, A><<<grid, kThreads, smem, st>>>(obs, mask, packed, c.n, c.gid0, (unsigned)(seed & 0xffffffffu),

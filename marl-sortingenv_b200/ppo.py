@@ -55,8 +55,9 @@ def pack_actor_critic(policy: "MaskableActorCritic", out: torch.Tensor | None = 
     """The two towers as the single 32 -> 64 -> 64 -> 32 network `msort_policy_act` evaluates on the
     tensor cores (include/msort.h): layer 1 concatenates the towers' first layers, layer 2 is block-
     diagonal, layer 3 puts the A logits in rows 0..A-1 and the value in row A.  Each weight matrix
-    W[n][k] is stored in the kernel's shared-memory operand order [k/4][n][k%4] (no-swizzle K-major
-    core matrices), followed by the three bias vectors.  Returns MSORT_POLICY_ACT_WEIGHTS floats."""
+    W[n][k] is stored as fp16 in the kernel's shared-memory operand order [k/8][n][k%8] (no-swizzle
+    K-major core matrices; two values per 32-bit word), followed by the three fp32 bias vectors.
+    Returns MSORT_POLICY_ACT_WEIGHTS 32-bit words as a float32 tensor."""
     pi, vf = policy.pi, policy.vf
     dev = pi[0].weight.device
     D, A = pi[0].weight.shape[1], pi[4].weight.shape[0]
@@ -66,10 +67,11 @@ def pack_actor_critic(policy: "MaskableActorCritic", out: torch.Tensor | None = 
     W3 = torch.zeros((32, 64), device=dev); W3[:A, :32] = pi[4].weight; W3[A, 32:] = vf[4].weight[0]
     b3 = torch.zeros(32, device=dev); b3[:A] = pi[4].bias; b3[A] = vf[4].bias[0]
 
-    def canon(W):                                   # [N, K] -> [K/4][N][4]
+    def canon(W):                                   # [N, K] fp32 -> [K/8][N][8] fp16, viewed as 32-bit words
         N, K = W.shape
-        return W.reshape(N, K // 4, 4).permute(1, 0, 2).reshape(-1)
-    packed = torch.cat([canon(W1), canon(W2), canon(W3), pi[0].bias, vf[0].bias, pi[2].bias, vf[2].bias, b3]).float()
+        return W.reshape(N, K // 8, 8).permute(1, 0, 2).reshape(-1).half().view(torch.float32)
+    packed = torch.cat([canon(W1), canon(W2), canon(W3),
+                        torch.cat([pi[0].bias, vf[0].bias, pi[2].bias, vf[2].bias, b3]).float()])
     if out is not None:
         out.copy_(packed)
         return out

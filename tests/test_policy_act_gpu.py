@@ -1,7 +1,7 @@
 """msort_policy_act (tcgen05 actor-critic inference + masked categorical draw) against a plain PyTorch
 fp32 reference of the same op: masked log-softmax of the policy tower, value tower.  The kernel feeds
-tf32 operands to the tensor cores (fp32 accumulation), so logits agree to ~1e-3 relative, not bitwise;
-tolerances below are written for that."""
+fp16 operands to the tensor cores (fp32 accumulation) and uses the hardware tanh, so log-probs and
+values agree to ~1e-3 absolute (measured 1.1e-3 / 7e-4), not bitwise; the tolerance below is 5e-3."""
 import pytest
 
 pytestmark = pytest.mark.gpu
