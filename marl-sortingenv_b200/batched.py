@@ -168,10 +168,14 @@ class BatchedEnv:
             self._trace.start()
         return self.obs, {}
 
-    def step(self, actions, replay: dict | None = None):
+    def step(self, actions, replay: dict | None = None, out_obs: torch.Tensor | None = None,
+             out_mask: torch.Tensor | None = None):
         """ref: Env_X.step(action) → (obs, reward, terminated, truncated, info), batched.
         `actions`: int64 CUDA tensor [N].  Returned tensors are views of internal buffers that
-        the next step() overwrites."""
+        the next step() overwrites.  `out_obs` [N,D] f32 / `out_mask` [N,A] bool (contiguous CUDA
+        tensors, e.g. slot t+1 of a rollout buffer) receive the new observation / action mask instead
+        of the internal buffers — the kernel writes them in place, nothing is copied; `env.obs` /
+        `env.mask` / `action_masks()` then refer to those tensors."""
         if not self._was_reset:
             # the reference raises AttributeError on step() before reset() (env_super.py:394,402)
             raise AttributeError("step() called before reset()")
@@ -183,6 +187,15 @@ class BatchedEnv:
         rp = None
         if self.rng_mode == "replay":
             rp, _keep = self._make_replay(replay or {})
+        for name, t, shape, dt in (("out_obs", out_obs, (self.num_envs, self.D), torch.float32),
+                                   ("out_mask", out_mask, (self.num_envs, self.A), torch.bool)):
+            if t is not None and not (t.is_cuda and t.is_contiguous() and tuple(t.shape) == shape and t.dtype == dt
+                                      and t.data_ptr() % 16 == 0):
+                raise ValueError(f"{name} must be a contiguous, 16-byte aligned CUDA tensor of shape {shape}, dtype {dt}")
+        if out_obs is not None:
+            self.obs = out_obs
+        if out_mask is not None:
+            self.mask = out_mask
         with torch.cuda.device(self.device):
             rc = self.lib.msort_step(self._h, _ptr(self.state), _ptr(actions), _ptr(self.obs),
                                      _ptr(self.reward), _ptr(self.terminated), _ptr(self.mask),

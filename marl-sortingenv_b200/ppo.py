@@ -110,9 +110,14 @@ class MaskablePPO:
         if self._obs is None:
             self._obs, _ = env.reset()
         packed = pack_actor_critic(self.policy) if self.fused_act else None
+        # zero-copy rollout: step t writes its observation / mask straight into slot t+1 of the buffers
+        # (the last step into a spare pair), so nothing but the first slot is ever copied
+        direct = self.fused_act and (self.n * self.D * 4) % 16 == 0 and (self.n * self.A) % 16 == 0
+        if direct and not hasattr(self, "_tail"):
+            self._tail = (torch.zeros((self.n, self.D), device=self.dev), torch.zeros((self.n, self.A), dtype=torch.bool, device=self.dev))
+        b["obs"][0].copy_(self._obs)
+        b["mask"][0].copy_(env.action_masks())
         for t in range(self.n_steps):
-            b["obs"][t].copy_(self._obs)
-            b["mask"][t].copy_(env.action_masks())
             if self.fused_act:                                           # writes straight into the rollout buffers
                 a, _, _ = env.policy_act(packed, seed=self.seed, t=self.num_timesteps // self.n + t,
                                          obs=b["obs"][t], mask=b["mask"][t],
@@ -120,7 +125,14 @@ class MaskablePPO:
             else:
                 a, logp, v = self.policy.act(b["obs"][t], b["mask"][t])
                 b["act"][t], b["logp"][t], b["val"][t] = a, logp, v
-            obs, rew, term, _, _ = env.step(a)                           # fused CUDA step (auto-reset inside)
+            last = t + 1 == self.n_steps
+            if direct:
+                oo, om = (self._tail if last else (b["obs"][t + 1], b["mask"][t + 1]))
+                obs, rew, term, _, _ = env.step(a, out_obs=oo, out_mask=om)   # fused CUDA step (auto-reset inside)
+            else:
+                obs, rew, term, _, _ = env.step(a)
+                if not last:
+                    b["obs"][t + 1].copy_(obs); b["mask"][t + 1].copy_(env.action_masks())
             b["rew"][t].copy_(rew); b["done"][t].copy_(term)
             self._obs = obs
         last_v = self.policy.vf(self._obs).squeeze(1)

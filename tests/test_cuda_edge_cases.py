@@ -157,3 +157,26 @@ def test_replay_mode_requires_streams_and_reports_underrun():
     total = (st["cont_true"].sum(1) + st["cont_false"].sum(1) + st["cont_e"] + st["press_n"].sum(1)
              + st["bale_sum"].sum(1) + st["input"].sum(1) + st["belt"].sum(1))
     assert np.all(total == 600)
+
+
+def test_step_writes_into_caller_buffers():
+    """step(out_obs=, out_mask=) writes the new observation / mask in place into caller tensors (zero-copy
+    rollout buffers) and leaves everything else identical to the default call."""
+    import torch
+    import marl_sortingenv_b200 as ms
+    n = 1000
+    e1 = ms.BatchedMonolithEnv(n, max_steps=20, seed=5)
+    e2 = ms.BatchedMonolithEnv(n, max_steps=20, seed=5)
+    e1.reset(); e2.reset()
+    buf_o = torch.zeros((8, n, e2.D), device="cuda")
+    buf_m = torch.zeros((8, n, e2.A), dtype=torch.bool, device="cuda")
+    for t in range(30):
+        a = e1.sample_actions(3, t)
+        o1, r1, d1, _, _ = e1.step(a)
+        o2, r2, d2, _, _ = e2.step(a, out_obs=buf_o[t % 8], out_mask=buf_m[t % 8])
+        assert o2.data_ptr() == buf_o[t % 8].data_ptr() and e2.action_masks().data_ptr() == buf_m[t % 8].data_ptr()
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)
+        assert torch.equal(e1.action_masks(), e2.action_masks())
+    assert torch.equal(e1.state, e2.state)
+    with pytest.raises(ValueError):
+        e2.step(a, out_obs=torch.zeros((n, e2.D + 1), device="cuda"))
