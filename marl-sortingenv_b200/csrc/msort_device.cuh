@@ -134,6 +134,17 @@ __device__ __forceinline__ U4 env_draw(const DevConfig& c, uint32_t gid_lo, uint
   return philox_rk(gid_lo, gid_hi16 | (block << 16), episode, step, c.rk);
 }
 
+// One redistribution draw from a 64-bit lane (xh:xl) of a Philox block: r = floor(lane * tot / 2^64) is
+// uniform on [0, tot) up to tot/2^64; the low 64 bits of the product are the lane for the next draw
+// (they are uniform on a progression of 2^64/tot points, so draw j of a lane is biased by <= tot^j / 2^64:
+// six draws per lane with tot <= 100 stay below 6e-8).  Shared with oracle/msort_oracle.c.
+__device__ __forceinline__ uint32_t draw64(uint32_t& xl, uint32_t& xh, uint32_t tot) {
+  const unsigned long long p0 = (unsigned long long)xl * tot;
+  const unsigned long long p1 = (unsigned long long)xh * tot + (p0 >> 32);
+  xl = (uint32_t)p0; xh = (uint32_t)p1;
+  return (uint32_t)(p1 >> 32);
+}
+
 // ---------------------------------------------------------------- env registers
 struct Env {
   uint32_t in4, belt4, sort4;  // packed u8x4 stage counts (A | B<<8 | C<<16 | D<<24)

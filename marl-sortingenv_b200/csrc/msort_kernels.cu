@@ -378,22 +378,22 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
         tot -= tv; C = (C & 0xffff00ffu) + (uint32_t)rem;
         blk0 = kBlkRedis + 64u;
       }
-#define MSORT_PDRAW(x, k)                                                                              \
+#define MSORT_PDRAW(xl, xh, k)                                                                         \
       {                                                                                                \
-        const unsigned long long prod = (unsigned long long)(x) * (uint32_t)(tot - (k));               \
-        const uint32_t r = (uint32_t)(prod >> 32);                                                     \
-        (x) = (uint32_t)prod;                                                                          \
+        const uint32_t r = draw64(xl, xh, (uint32_t)(tot - (k)));                                      \
         const uint32_t Tq = (C - r) * 0x01010101u + 0x7f7f7f7fu;   /* == C*0x01010101 + (0x7f - r) per byte */ \
         const uint32_t M = byte_sign_mask(Tq);                     /* byte k -> 0xff if its bit 7 is set: 255*H */ \
         if (rem > (k)) C += M;                                                                         \
       }
       // draw k of a block sees tot - k units (every earlier draw of an active lane removed one); an
       // inactive lane's products are never used
-      for (uint32_t b = 0; rem > 0; ++b, tot -= min(rem, 8), rem -= 8) {
+      for (uint32_t b = 0; rem > 0; ++b, tot -= min(rem, 12), rem -= 12) {
         U4 r4 = env_draw(c, gid_lo, gid_hi, blk0 + b, ep, stp);
-        MSORT_PDRAW(r4.x, 0); MSORT_PDRAW(r4.x, 1); MSORT_PDRAW(r4.y, 2); MSORT_PDRAW(r4.y, 3);
-        if (rem <= 4) { tot -= rem; break; }
-        MSORT_PDRAW(r4.z, 4); MSORT_PDRAW(r4.z, 5); MSORT_PDRAW(r4.w, 6); MSORT_PDRAW(r4.w, 7);
+        MSORT_PDRAW(r4.x, r4.y, 0); MSORT_PDRAW(r4.x, r4.y, 1); MSORT_PDRAW(r4.x, r4.y, 2);
+        MSORT_PDRAW(r4.x, r4.y, 3); MSORT_PDRAW(r4.x, r4.y, 4); MSORT_PDRAW(r4.x, r4.y, 5);
+        if (rem <= 6) { tot -= rem; break; }
+        MSORT_PDRAW(r4.z, r4.w, 6); MSORT_PDRAW(r4.z, r4.w, 7); MSORT_PDRAW(r4.z, r4.w, 8);
+        MSORT_PDRAW(r4.z, r4.w, 9); MSORT_PDRAW(r4.z, r4.w, 10); MSORT_PDRAW(r4.z, r4.w, 11);
       }
 #undef MSORT_PDRAW
       if (pm) {                           // station 1 after station 0's draws: boosted, everything left is true
@@ -408,18 +408,18 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
         T4 |= (uint32_t)tv << 16; F4 |= (uint32_t)rem << 16;
         tot -= tv; lump = b4(C, 0) + rem;
       }
-#define MSORT_PDRAW2(x, k)                                                                             \
+#define MSORT_PDRAW2(xl, xh, k)                                                                        \
       {                                                                                                \
-        const unsigned long long prod = (unsigned long long)(x) * (uint32_t)(tot - (k));               \
-        const int r = (int)(uint32_t)(prod >> 32);                                                     \
-        (x) = (uint32_t)prod;                                                                          \
+        const int r = (int)draw64(xl, xh, (uint32_t)(tot - (k)));                                      \
         if (rem > (k) && r < lump) lump -= 1;                                                          \
       }
-      for (uint32_t b = 0; rem > 0; ++b, tot -= min(rem, 8), rem -= 8) {
+      for (uint32_t b = 0; rem > 0; ++b, tot -= min(rem, 12), rem -= 12) {
         U4 r4 = env_draw(c, gid_lo, gid_hi, kBlkRedis + 128u + b, ep, stp);
-        MSORT_PDRAW2(r4.x, 0); MSORT_PDRAW2(r4.x, 1); MSORT_PDRAW2(r4.y, 2); MSORT_PDRAW2(r4.y, 3);
-        if (rem <= 4) { tot -= rem; break; }
-        MSORT_PDRAW2(r4.z, 4); MSORT_PDRAW2(r4.z, 5); MSORT_PDRAW2(r4.w, 6); MSORT_PDRAW2(r4.w, 7);
+        MSORT_PDRAW2(r4.x, r4.y, 0); MSORT_PDRAW2(r4.x, r4.y, 1); MSORT_PDRAW2(r4.x, r4.y, 2);
+        MSORT_PDRAW2(r4.x, r4.y, 3); MSORT_PDRAW2(r4.x, r4.y, 4); MSORT_PDRAW2(r4.x, r4.y, 5);
+        if (rem <= 6) { tot -= rem; break; }
+        MSORT_PDRAW2(r4.z, r4.w, 6); MSORT_PDRAW2(r4.z, r4.w, 7); MSORT_PDRAW2(r4.z, r4.w, 8);
+        MSORT_PDRAW2(r4.z, r4.w, 9); MSORT_PDRAW2(r4.z, r4.w, 10); MSORT_PDRAW2(r4.z, r4.w, 11);
       }
 #undef MSORT_PDRAW2
       {                                   // station 3 (unboosted iff pm == 0); its draws leave the pool sum unchanged
@@ -438,8 +438,10 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       // later selection probabilities and finally container E — so they are kept as one `lump`;
       // only not-yet-processed stations are tracked individually.  The draws of the last station
       // cannot influence anything but that sum, which drops by exactly the number of draws, so
-      // they are not simulated.  Draw k of station S uses half (k&1) of word (k>>1)&3 of Philox
-      // block kBlkRedis + 64*S + (k>>3): first half r = hi(x*tot), second half r = hi(lo(x*tot)*tot').
+      // they are not simulated.  Draw k of station S uses Philox block kBlkRedis + 64*S + k/12: the block's
+      // words form two 64-bit lanes (y:x) and (w:z); draws k%12 = 0..5 come from the first, 6..11 from the
+      // second, each as r = hi64(lane*tot), lane = lo64(lane*tot) (draw64; the j-th draw of a lane is
+      // biased by at most tot^j / 2^64 <= 6e-8).
       // Stations 0 and 1 share one warp loop: a lane whose station 0 has no false units starts
       // station 1 up front, so lanes drawing for station 0 and lanes drawing for station 1 run
       // side by side (with the default boosts every env has exactly one of the two to draw for).
@@ -465,12 +467,10 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
         blk0 = kBlkRedis + 64u; started1 = true;                                                       \
       }
       // one draw over the classes (lump, X, L2, L3) in prefix order; `x` is replaced by the low product
-#define MSORT_DRAW4(x)                                                                                 \
+#define MSORT_DRAW4(xl, xh)                                                                            \
       {                                                                                                \
         const bool act = rem > 0;                                                                      \
-        const unsigned long long prod = (unsigned long long)(x) * (uint32_t)tot;                       \
-        const int r = (int)(uint32_t)(prod >> 32);                                                     \
-        (x) = (uint32_t)prod;                                                                          \
+        const int r = (int)draw64(xl, xh, (uint32_t)tot);                                              \
         const int c0 = lump, c1 = c0 + X, c2 = c1 + L2;                                                \
         const bool h0 = r < c0, h1 = r < c1, h2 = r < c2;                                              \
         lump -= (act && h0) ? 1 : 0;                                                                   \
@@ -482,9 +482,11 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
 #define MSORT_DRAW_LOOP4()                                                                             \
       for (uint32_t b = 0; rem > 0; ++b) {                                                             \
         U4 r4 = env_draw(c, gid_lo, gid_hi, blk0 + b, ep, stp);                                        \
-        MSORT_DRAW4(r4.x); MSORT_DRAW4(r4.x); MSORT_DRAW4(r4.y); MSORT_DRAW4(r4.y);                    \
+        MSORT_DRAW4(r4.x, r4.y); MSORT_DRAW4(r4.x, r4.y); MSORT_DRAW4(r4.x, r4.y);                     \
+        MSORT_DRAW4(r4.x, r4.y); MSORT_DRAW4(r4.x, r4.y); MSORT_DRAW4(r4.x, r4.y);                     \
         if (rem <= 0) break;                                                                           \
-        MSORT_DRAW4(r4.z); MSORT_DRAW4(r4.z); MSORT_DRAW4(r4.w); MSORT_DRAW4(r4.w);                    \
+        MSORT_DRAW4(r4.z, r4.w); MSORT_DRAW4(r4.z, r4.w); MSORT_DRAW4(r4.z, r4.w);                     \
+        MSORT_DRAW4(r4.z, r4.w); MSORT_DRAW4(r4.z, r4.w); MSORT_DRAW4(r4.z, r4.w);                     \
       }
       MSORT_START_STATION1(rem == 0);
       MSORT_DRAW_LOOP4();
@@ -497,12 +499,10 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
         T4 |= (uint32_t)tv << 16; F4 |= (uint32_t)rem << 16;
         tot -= tv; lump += rem;
       }
-#define MSORT_DRAW2(x)                                                                                 \
+#define MSORT_DRAW2(xl, xh)                                                                            \
       {                                                                                                \
         const bool act = rem > 0;                                                                      \
-        const unsigned long long prod = (unsigned long long)(x) * (uint32_t)tot;                       \
-        const int r = (int)(uint32_t)(prod >> 32);                                                     \
-        (x) = (uint32_t)prod;                                                                          \
+        const int r = (int)draw64(xl, xh, (uint32_t)tot);                                              \
         const bool h0 = r < lump;                                                                      \
         lump -= (act && h0) ? 1 : 0;                                                                   \
         L3 -= (act && !h0) ? 1 : 0;                                                                    \
@@ -510,9 +510,11 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       }
       for (uint32_t b = 0; rem > 0; ++b) {
         U4 r4 = env_draw(c, gid_lo, gid_hi, kBlkRedis + 128u + b, ep, stp);
-        MSORT_DRAW2(r4.x); MSORT_DRAW2(r4.x); MSORT_DRAW2(r4.y); MSORT_DRAW2(r4.y);
+        MSORT_DRAW2(r4.x, r4.y); MSORT_DRAW2(r4.x, r4.y); MSORT_DRAW2(r4.x, r4.y);
+        MSORT_DRAW2(r4.x, r4.y); MSORT_DRAW2(r4.x, r4.y); MSORT_DRAW2(r4.x, r4.y);
         if (rem <= 0) break;
-        MSORT_DRAW2(r4.z); MSORT_DRAW2(r4.z); MSORT_DRAW2(r4.w); MSORT_DRAW2(r4.w);
+        MSORT_DRAW2(r4.z, r4.w); MSORT_DRAW2(r4.z, r4.w); MSORT_DRAW2(r4.z, r4.w);
+        MSORT_DRAW2(r4.z, r4.w); MSORT_DRAW2(r4.z, r4.w); MSORT_DRAW2(r4.z, r4.w);
       }
       {                                   // station 3: its draws leave `lump` (the sum of all leftovers) unchanged
         const int t = L3;

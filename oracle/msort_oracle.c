@@ -373,8 +373,9 @@ static void step_one(const msort_config_t* cfg, msort_env_state_t* s, int64_t i,
      * leftovers (later selection probabilities and finally E), so they are kept as one `lump`;
      * stations still to be processed are tracked individually.  The last station's draws reduce
      * only that sum, by exactly their number, so they are not simulated.
-     * Draw i of station S uses half (i&1) of word (i>>1)&3 of block BLK_REDIS + 64*S + (i>>3):
-     * first half r = hi(x*tot), carry = lo(x*tot); second half r = hi(carry*tot'). */
+     * Draw i of station S uses block BLK_REDIS + 64*S + i/12, whose words form two 64-bit lanes (w1:w0)
+     * and (w3:w2): draws i%12 = 0..5 come from the first, 6..11 from the second, each as
+     * r = hi64(lane*tot), lane = lo64(lane*tot). */
     int L[4];
     for (int m = 0; m < 4; ++m) L[m] = s->sorting[m];
     int tot = L[0] + L[1] + L[2] + L[3], lump = 0;
@@ -387,13 +388,13 @@ static void step_one(const msort_config_t* cfg, msort_env_state_t* s, int64_t i,
       tot -= tr;
       if (S == 3) break;                                          /* its f draws leave lump unchanged */
       lump += f;                                                  /* leftover[S] = false_val joins the lump */
-      uint32_t carry = 0;
+      uint64_t lane = 0;
       for (int k = 0; k < f; ++k) {
-        if ((k & 7) == 0) env_draw(cfg, gid, BLK_REDIS + 64u * (uint32_t)S + (uint32_t)(k >> 3), ep, stp, r4);
-        uint32_t x = (k & 1) ? carry : r4[(k >> 1) & 3];
-        uint64_t prod = (uint64_t)x * (uint64_t)(uint32_t)tot;
-        int r = (int)(uint32_t)(prod >> 32);
-        carry = (uint32_t)prod;
+        if (k % 12 == 0) env_draw(cfg, gid, BLK_REDIS + 64u * (uint32_t)S + (uint32_t)(k / 12), ep, stp, r4);
+        if (k % 6 == 0) lane = (k % 12 == 0) ? (((uint64_t)r4[1] << 32) | r4[0]) : (((uint64_t)r4[3] << 32) | r4[2]);
+        unsigned __int128 prod = (unsigned __int128)lane * (uint64_t)(uint32_t)tot;
+        int r = (int)(uint32_t)(prod >> 64);
+        lane = (uint64_t)prod;
         int c = lump;
         if (r < c) lump -= 1;
         else {
