@@ -17,9 +17,10 @@
 //     (kc*128 + r)*16 B: consecutive threads -> consecutive 16 B, conflict-free STS.128); two threads per
 //     env, one per tower (accumulator columns 0..31 / 32..63), 256 threads per CTA;
 //   * tcgen05.commit -> mbarrier tells the CTA when a layer's accumulators are complete;
-//   * persistent CTAs (3 per SM): the 17 KB of packed weights are staged into shared memory once; the obs
+//   * persistent CTAs (4 per SM): the 17 KB of packed weights are staged into shared memory once; the obs
 //     and mask tiles (contiguous 14.8 KB / 2.8 KB) arrive by TMA bulk copies (cp.async.bulk + mbarrier
-//     complete_tx) into a two-slot ring, the next tile's copy in flight while this tile is computed.
+//     complete_tx); the next tile's copies are issued as soon as layer 1 has consumed the obs tile and
+//     land behind the three layers of the current one.
 // Epilogue per env: masked log-softmax over the A logits, inverse-CDF draw with one Philox uniform keyed by
 // (seed, t, global env id) (or argmax), outputs action / log-prob / value with coalesced stores.
 #include <cuda_fp16.h>
@@ -116,20 +117,22 @@ __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fenc
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+template <int D, int A>
 struct __align__(16) PolicySmem {
   __half b[kWeightHalves];         // B1 | B2 | B3 in canonical K-major order (16 KB)
   float bias[kN1 + kN2 + kN3];
   uint4 a[kK2 / 8 * kRows];        // A operand: 8 chunks (8 fp16 columns each) x 128 rows x 16 B (16 KB; layer 1 uses 4)
-  float stage[2][kRows * 32];      // obs tile ring (row-major, D <= 32), filled by TMA bulk copies
-  uint8_t mask[2][kRows * 32];     // mask tile ring (A <= 31)
+  float stage[kRows * D];          // obs tile (row-major), filled by a TMA bulk copy; free again once layer 1's A operand is built
+  uint8_t mask[2][kRows * A];      // mask tile ring (needed until the end of the tile)
   uint64_t bar;                    // MMA completion (tcgen05.commit)
-  uint64_t full[2];                // tile slot filled (TMA complete_tx)
+  uint64_t full_obs;               // obs tile landed (TMA complete_tx)
+  uint64_t full_mask[2];           // mask tile landed
   uint32_t tmem_base;
 };
 
 // one layer: all threads have written their A chunks; thread 0 issues the K-steps and commits
-template <int K, int N>
-__device__ __forceinline__ void issue_layer(const PolicySmem& sm, int b_off, uint32_t tmem_d, uint64_t* bar) {
+template <int K, int N, class Smem>
+__device__ __forceinline__ void issue_layer(const Smem& sm, int b_off, uint32_t tmem_d, uint64_t* bar) {
   const uint32_t a0 = smem_u32(sm.a), b0 = smem_u32(sm.b + b_off);
 #pragma unroll
   for (int s = 0; s < K / 16; ++s) {   // one instruction = K 16 (fp16) = two 16-byte chunks
@@ -172,13 +175,14 @@ __device__ __forceinline__ float policy_tanh(float x) {
 // warps 0-3 own accumulator columns 0..31 (policy tower), warps 4-7 columns 32..63 (value tower); both
 // warp groups reach the same TMEM lane quarter (warp % 4).
 template <int D, int A>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 4)
 policy_act_kernel(const float* __restrict__ obs, const uint8_t* __restrict__ mask, const float* __restrict__ packed,
                   long long n, long long gid0, unsigned key0, unsigned key1, unsigned t, int deterministic, int use_tma,
                   long long* __restrict__ actions, float* __restrict__ logp_out, float* __restrict__ value_out) {
   static_assert(D <= 32 && A <= 31, "padded layer sizes");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  PolicySmem& sm = *reinterpret_cast<PolicySmem*>(smem_raw);
+  using Smem = PolicySmem<D, A>;
+  Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, row = tid & (kRows - 1), half = tid >> 7;
 
   // ---- one-time setup: TMEM columns, mbarriers, weights
@@ -188,8 +192,9 @@ policy_act_kernel(const float* __restrict__ obs, const uint8_t* __restrict__ mas
   }
   if (tid == 0) {
     mbar_init(&sm.bar, 1);
-    mbar_init(&sm.full[0], 1);
-    mbar_init(&sm.full[1], 1);
+    mbar_init(&sm.full_obs, 1);
+    mbar_init(&sm.full_mask[0], 1);
+    mbar_init(&sm.full_mask[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   {
@@ -211,50 +216,63 @@ policy_act_kernel(const float* __restrict__ obs, const uint8_t* __restrict__ mas
   // a full tile is one contiguous, 16-byte-aligned range of each tensor: one TMA bulk copy each
   auto prefetch = [&](long long tl, int slot) {
     if (use_tma && tl < ntiles && (tl + 1) * kRows <= n) {
-      mbar_expect_tx(&sm.full[slot], obs_bytes + mask_bytes);
-      bulk_load(sm.stage[slot], obs + tl * kRows * D, obs_bytes, &sm.full[slot]);
-      bulk_load(sm.mask[slot], mask + tl * kRows * A, mask_bytes, &sm.full[slot]);
+      mbar_expect_tx(&sm.full_obs, obs_bytes);
+      bulk_load(sm.stage, obs + tl * kRows * D, obs_bytes, &sm.full_obs);
+      mbar_expect_tx(&sm.full_mask[slot], mask_bytes);
+      bulk_load(sm.mask[slot], mask + tl * kRows * A, mask_bytes, &sm.full_mask[slot]);
     }
   };
-  if (tid == 0) prefetch(blockIdx.x, 0);
-  uint32_t it = 0;
-  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-    const long long row0 = tile * kRows;
-    const int rows = (int)min((long long)kRows, n - row0);
-    const int slot = (int)(it & 1u);
-    const float* stage = sm.stage[slot];
-    const uint8_t* mtile = sm.mask[slot];
-    if (tid == 0) {                      // the other slot was released by the barrier that ended the previous tile
-      fence_async_proxy();
-      prefetch(tile + gridDim.x, slot ^ 1);
-    }
-    if (use_tma && rows == kRows) {
-      mbar_wait(&sm.full[slot], (it >> 1) & 1u);
-    } else {                             // ragged last tile (its byte count need not be a multiple of 16) or unaligned tensors: plain loads
-      const float* src = obs + row0 * D;
-      const int tot = rows * D;
-      for (int e = tid; e < kRows * D; e += kThreads) sm.stage[slot][e] = e < tot ? src[e] : 0.f;
-      const uint8_t* ms = mask + row0 * A;
-      const int mt = rows * A;
-      for (int e = tid; e < kRows * A; e += kThreads) sm.mask[slot][e] = e < mt ? ms[e] : (uint8_t)0;
-      __syncthreads();
-    }
-    // ---- layer-1 A operand: obs row zero-padded to 32 columns; each half writes two of the four chunks
-    {
-      const float* x = stage + row * D;
+  // plain-load fallback for a tile TMA cannot fetch (ragged last tile: its byte count need not be a multiple
+  // of 16; or unaligned tensors), executed by `nthr` threads numbered `t0`
+  auto plain_load = [&](long long tl, int slot, int t0, int nthr) {
+    const long long r0 = tl * kRows;
+    const int rws = (int)min((long long)kRows, n - r0);
+    const float* src = obs + r0 * D;
+    for (int e = t0; e < kRows * D; e += nthr) sm.stage[e] = e < rws * D ? src[e] : 0.f;
+    const uint8_t* ms = mask + r0 * A;
+    for (int e = t0; e < kRows * A; e += nthr) sm.mask[slot][e] = e < rws * A ? ms[e] : (uint8_t)0;
+  };
+  // layer-1 A operand of this thread's row: obs zero-padded to 32 columns, chunks [kc0, kc0 + nkc)
+  auto build_a1 = [&](int kc0, int nkc) {
+    const float* x = sm.stage + row * D;
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int kc = 2 * half + q;
+    for (int q = 0; q < 4; ++q) {
+      if (q < nkc) {
+        const int kc = kc0 + q;
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = 8 * kc + j < D ? x[8 * kc + j] : 0.f;
         sm.a[kc * kRows + row] = pack8(v);
       }
     }
+  };
+  auto tile_by_tma = [&](long long tl) { return use_tma && (tl + 1) * kRows <= n; };
+
+  // ---- prologue: the first tile's layer-1 operand (afterwards the value-tower warps build the next tile's
+  //      operand while the policy-tower warps run the softmax epilogue)
+  if (tid == 0) prefetch(blockIdx.x, 0);
+  if ((long long)blockIdx.x < ntiles) {
+    if (tile_by_tma(blockIdx.x)) mbar_wait(&sm.full_obs, 0u);
+    else { plain_load(blockIdx.x, 0, tid, kThreads); __syncthreads(); }
+    build_a1(2 * half, 2);
+  }
+  uint32_t it = 0;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    const long long row0 = tile * kRows;
+    const int rows = (int)min((long long)kRows, n - row0);
+    const int slot = (int)(it & 1u);
+    const uint8_t* mtile = sm.mask[slot];
+    const bool by_tma = tile_by_tma(tile);
     fence_async_proxy();
     fence_before_sync();
-    __syncthreads();
-    if (tid == 0) { fence_after_sync(); issue_layer<kK1, kN1>(sm, kB1, tmem, &sm.bar); }
+    __syncthreads();                     // this tile's layer-1 operand is complete; the previous tile is finished
+    if (tid == 0) {
+      fence_after_sync();
+      issue_layer<kK1, kN1>(sm, kB1, tmem, &sm.bar);
+      // the obs tile has been consumed (the A chunks were built before the barrier) and the other mask slot was
+      // released when the previous tile ended: fetch the next tile behind the three layers
+      prefetch(tile + gridDim.x, slot ^ 1);
+    }
     mbar_wait(&sm.bar, phase); phase ^= 1;
     fence_after_sync();
 
@@ -287,6 +305,7 @@ policy_act_kernel(const float* __restrict__ obs, const uint8_t* __restrict__ mas
     if (half == 0) {
       float o[32];
       tmem_ld32(tcol, o);
+      if (by_tma) mbar_wait(&sm.full_mask[slot], (it >> 1) & 1u);
       const long long i = row0 + row;
       if (row < rows) {
         const float* b3 = sm.bias + kN1 + kN2;
@@ -328,8 +347,19 @@ policy_act_kernel(const float* __restrict__ obs, const uint8_t* __restrict__ mas
         value_out[i] = o[A] + b3[A];
       }
     }
-    fence_before_sync();
-    __syncthreads();   // the tile slot, the A buffer and the TMEM columns are reused by the next tile
+    else {
+      // value-tower warps: layer 3 has consumed the A buffer, so build the NEXT tile's layer-1 operand now
+      const long long next = tile + gridDim.x;
+      if (next < ntiles) {
+        if (tile_by_tma(next)) mbar_wait(&sm.full_obs, (it + 1) & 1u);
+        else {
+          plain_load(next, slot ^ 1, row, kRows);
+          asm volatile("bar.sync 1, %0;" :: "n"(kRows) : "memory");   // the 128 value-tower threads only
+        }
+        build_a1(0, 4);
+      }
+    }
+    // (the barrier at the top of the next iteration ends this tile)
   }
 
   fence_before_sync();
@@ -343,12 +373,12 @@ template <int D, int A>
 static cudaError_t launch_policy_act_da(const DevConfig& c, const float* obs, const uint8_t* mask, const float* packed,
                                         uint64_t seed, uint32_t t, int deterministic, int64_t* actions, float* logp,
                                         float* value, int sm_count, cudaStream_t st) {
-  static_assert(sizeof(PolicySmem) <= 74 * 1024, "three CTAs per SM");
-  const size_t smem = sizeof(PolicySmem);
+  static_assert(sizeof(PolicySmem<D, A>) <= 55 * 1024, "four CTAs per SM");
+  const size_t smem = sizeof(PolicySmem<D, A>);
   cudaError_t e = cudaFuncSetAttribute(policy_act_kernel<D, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long long ntiles = (c.n + kRows - 1) / kRows;
-  const unsigned grid = (unsigned)std::min<long long>(ntiles, 3ll * sm_count);
+  const unsigned grid = (unsigned)std::min<long long>(ntiles, 4ll * sm_count);
   // TMA bulk copies need 16-byte aligned tile addresses (tile sizes are multiples of 16 bytes)
   const int use_tma = ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(mask)) & 15u) == 0;
   policy_act_kernel<D, A><<<grid, kThreads, smem, st>>>(obs, mask, packed, c.n, c.gid0, (unsigned)(seed & 0xffffffffu),
