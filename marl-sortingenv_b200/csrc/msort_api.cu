@@ -264,6 +264,7 @@ extern "C" int msort_create(const msort_config_t* cfg, int device, msort_t** out
   h->dev = d;
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
+  h->dev.sm_count = prop.multiProcessorCount;
   h->policy_dev = nullptr;
   h->lut_dev = nullptr;
   h->policy_set = false;

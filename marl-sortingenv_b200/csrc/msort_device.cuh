@@ -47,6 +47,7 @@ constexpr uint32_t kBlkNoise = 0, kBlkPress = 1, kBlkReset = 2, kBlkInput = 3, k
 struct DevConfig {
   long long n, n_pad, gid0;
   int kind, max_steps;
+  int sm_count;                    // multiprocessors of the handle's device
   unsigned flags;
   int rng_mode;
   int layout;                      // LAYOUT_* of the state blob (fixed at create)

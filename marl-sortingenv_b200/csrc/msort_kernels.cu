@@ -4,6 +4,7 @@
 // memory so every global store is a coalesced 4-byte-per-lane (128 B per warp) store.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstring>
 #include <type_traits>
 
@@ -173,6 +174,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     Env s;
     load_planes<LAYOUT>(a.state, c.n_pad, i, s);
     long long act = a.actions[i];
+
     const uint32_t ep = s.episode, stp = s.step;
     float* const orow = &s_obs[tid * D];          // this env's row of the dense obs tile
     float* const prow = orow + (KIND == MSORT_ENV_MONO ? 13 : 0);  // press part of the row
