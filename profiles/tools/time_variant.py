@@ -1,0 +1,34 @@
+"""Variant timer: python profiles/tools/time_variant.py <libmsort.so> [kind] — state/obs checksums and us/step of one
+build of the library (MSORT_LIB), used to A/B kernel variants on the same box."""
+import os, sys, hashlib
+lib = sys.argv[1]; kind = sys.argv[2] if len(sys.argv) > 2 else "mono"
+os.environ["MSORT_LIB"] = lib
+sys.path.insert(0, "/root/repo")
+import torch
+import marl_sortingenv_b200 as ms
+n = 1 << 20
+cls = {"mono": ms.BatchedMonolithEnv, "sort": ms.BatchedSortingEnv, "press": ms.BatchedPressingEnv}[kind]
+env = cls(n, max_steps=50, seed=42, info_level=os.environ.get("INFO", "episode"))
+if kind == 'press':
+    from marl_sortingenv_b200.policy import sb3_style_init
+    env.set_sort_policy(sb3_style_init(0))
+env.reset()
+T = 128
+acts = torch.zeros((T, n), dtype=torch.int64, device="cuda")
+rsum = torch.zeros((), dtype=torch.float64, device="cuda")
+for t in range(T):
+    env.sample_actions(7, t, out=acts[t]); env.step(acts[t]); rsum += env.reward.double().sum()
+torch.cuda.synchronize()
+h = hashlib.sha1(env.state.cpu().numpy().tobytes()).hexdigest()[:12]
+ho = hashlib.sha1(env.obs.cpu().numpy().tobytes()).hexdigest()[:12]
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    for t in range(512):
+        env.step(acts[t % T])
+g.replay(); torch.cuda.synchronize()
+best = 1e9
+for rep in range(3):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+    best = min(best, e0.elapsed_time(e1) / 512 * 1e3)
+print(f"{os.path.basename(lib):28s} {kind:5s} state {h} obs {ho} rsum {rsum.item():.6f}  us/step {best:.2f}  G/s {n/best/1e3:.2f}", flush=True)
