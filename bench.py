@@ -156,7 +156,8 @@ def run_reference(args):
         "gpu_launches": 0,
         "note": ("CPU arm = oracle/msort_oracle.c (C port of the reference's step/reset, pinned to recorded "
                  "reference trajectories) on all host cores; the Python reference itself cannot travel to the box "
-                 "(measured in the build container at 1.5e3 steps/s/core, BASELINE.md §2)"),
+                 "(measured in the build container under a SubprocVecEnv-style pool: 18.9e3 env-steps/s on 8 cores, "
+                 "profiles/cpu_reference_subproc_r01.json)"),
     }
     print(json.dumps(line), flush=True)
 
