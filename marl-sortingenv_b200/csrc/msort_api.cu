@@ -20,8 +20,7 @@ struct msort_handle {
   DevConfig dev;
   int device;
   int sm_count;
-  float* policy_dev;  // owned device constants (tiny, allocated at create): 1570 policy floats ...
-  double* lut_dev;    // ... and the kSortLut-entry float64 sorting-reward table
+  double* lut_dev;    // owned device constant (tiny, allocated at create): the kSortLut-entry float64 sorting-reward table
   bool policy_set;
   float policy_host[MSORT_POLICY_WEIGHTS];  // host copy: travels to the step kernel as a kernel parameter
   int64_t launches;
@@ -237,7 +236,6 @@ static int digest_config(const msort_config_t& c, DevConfig& d) {
     volatile double hi_u = d.base_acc[m] + nz_hi;
     if (!(lo_b >= 1.0) || !(lo_u >= 0.0) || !(hi_u <= 1.0)) d.fast = 0;
   }
-  d.policy = nullptr;
   return MSORT_OK;
 }
 
@@ -265,15 +263,10 @@ extern "C" int msort_create(const msort_config_t* cfg, int device, msort_t** out
   h->device = device;
   h->sm_count = prop.multiProcessorCount;
   h->dev.sm_count = prop.multiProcessorCount;
-  h->policy_dev = nullptr;
   h->lut_dev = nullptr;
   h->policy_set = false;
   h->launches = 0;
-  e = cudaMalloc(&h->policy_dev, sizeof(float) * MSORT_POLICY_WEIGHTS);
-  if (e != cudaSuccess) { delete h; cudaSetDevice(prev_device); return cuda_fail(e, "cudaMalloc(policy)"); }
-  cudaMemset(h->policy_dev, 0, sizeof(float) * MSORT_POLICY_WEIGHTS);
   cudaSetDevice(prev_device);  // launches run on the caller's current device, which must be `device`
-  h->dev.policy = h->policy_dev;
   // sorting-reward table (see sort_reward_f64 in msort_device.cuh): same formula, host float64
   {
     double lut[kSortLut];
@@ -282,7 +275,7 @@ extern "C" int msort_create(const msort_config_t* cfg, int device, msort_t** out
     e = cudaMalloc(&h->lut_dev, sizeof(lut));
     if (e == cudaSuccess) e = cudaMemcpy(h->lut_dev, lut, sizeof(lut), cudaMemcpyHostToDevice);
     cudaSetDevice(prev_device);
-    if (e != cudaSuccess) { cudaFree(h->policy_dev); delete h; return cuda_fail(e, "cudaMalloc(sort lut)"); }
+    if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaMalloc(sort lut)"); }
     h->dev.sort_lut = h->lut_dev;
     // the table is exact only when every threshold is a whole percent; otherwise the kernel evaluates float64
     for (int m = 0; m < 4; ++m)
@@ -294,7 +287,6 @@ extern "C" int msort_create(const msort_config_t* cfg, int device, msort_t** out
 
 extern "C" int msort_destroy(msort_t* h) {
   if (!h) return MSORT_OK;
-  if (h->policy_dev) cudaFree(h->policy_dev);
   if (h->lut_dev) cudaFree(h->lut_dev);
   delete h;
   return MSORT_OK;
@@ -381,8 +373,6 @@ extern "C" int msort_set_policy(msort_t* h, const float* weights, int weights_on
   } else {
     memcpy(h->policy_host, weights, sizeof(h->policy_host));
   }
-  MSORT_TRY_CUDA(cudaMemcpyAsync(h->policy_dev, h->policy_host, sizeof(h->policy_host), cudaMemcpyHostToDevice,
-                                 (cudaStream_t)stream), "cudaMemcpyAsync(policy)");
   h->policy_set = true;
   return MSORT_OK;
 }

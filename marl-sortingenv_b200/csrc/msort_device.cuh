@@ -77,7 +77,6 @@ struct DevConfig {
   double theta4, c_sort;           // sum of 4 thetas; (scaling/4)/temperature
   double c_state, c_eff;           // max_state/(5*cap); 4/S
   double pen_cat, pen_sev, pen_mild, bef, ovf_pen;
-  const float* policy;             // 1570 fp32 weights in device memory (Env_2 embedded MLP)
   const double* sort_lut;          // kSortLut float64 sorting rewards indexed by the purity sum (see sort_reward)
 };
 

@@ -93,7 +93,8 @@ def test_fused_rollout_matches_torch_rollout_statistics():
         model = MaskablePPO(env, n_steps=32, seed=0, fused_act=fused)
         model.collect_rollout()
         b = model.buf
-        lp_new, _, v_new = model.policy.evaluate(b["obs"].reshape(-1, env.D), b["mask"].reshape(-1, env.A), b["act"].reshape(-1))
+        with torch.no_grad():
+            lp_new, _, v_new = model.policy.evaluate(b["obs"].reshape(-1, env.D), b["mask"].reshape(-1, env.A), b["act"].reshape(-1))
         stats[fused] = (float(b["rew"].mean()), float((lp_new - b["logp"].reshape(-1)).abs().max()),
                         float((v_new - b["val"].reshape(-1)).abs().max()))
     assert abs(stats[True][0] - stats[False][0]) < 0.02, stats
