@@ -6,10 +6,13 @@ observations, Python float rewards, bool flags and an `info` dict with the refer
 They exist so that code written against the reference (testing.py's episode loop, SB3's
 `check_env`, ActionMasker) runs unchanged; for throughput use the batched classes.
 
-Differences that are inherent to the device implementation (documented in DESIGN.md):
-the random plant is the counter-based Philox generator (same distributions, different bits
-than numpy's PCG64 streams), and Python-side logs (`reward_data`, `press_actions_per_timestep`)
-are replaced by counters (`bale_count` holds per-material count / last size / total size).
+The reference's Python-side logs — `reward_data`, `press_actions_per_timestep`, `bale_count` (the
+lists `testing.test_env` sums and `utils/plotting.plot_env` renders; env_super.py:928-946, 631-637,
+661-687) — are available under the same names: a telemetry recorder (telemetry.py) snapshots the env
+on the device after every step and the lists are rebuilt from the snapshots on access.
+
+Inherent difference (documented in DESIGN.md): the random plant is the counter-based Philox generator
+(same distributions, different bits than numpy's PCG64 streams).
 """
 from __future__ import annotations
 
@@ -43,6 +46,8 @@ class _SingleEnv:
         self.container_global_max = int(self._b.cfg.container_capacity)
         self._act = torch.zeros(1, dtype=torch.int64, device=self._b.device)
         self._masking, self._overflow = True, False
+        from .telemetry import TraceRecorder
+        self._b._trace = TraceRecorder(self._b, [0], capacity=max(int(max_steps), 1), growable=True)
 
     # ------------------------------------------------------------------ gym surface
     @property
@@ -109,10 +114,32 @@ class _SingleEnv:
             out[f"q_{i}"] = int(s["press_q"][i - 1]) / 100.0
         return out
 
+    # ---- the reference's per-step logs, rebuilt from the device snapshots of this episode
+    def _logs(self):
+        if not self._b._trace.started:
+            raise AttributeError("reward_data / press_actions_per_timestep / bale_count exist after reset()")  # as in the reference
+        return self._b._trace.reference_logs(0)
+
+    @property
+    def reward_data(self):
+        """ref: env_super.py:402-408, 928-946 — dict of per-step lists ('Reward' = (r_sort, r_press), 'Total',
+        'Setting', 'Belt_Occupancy', 'Belt_Proportions', 'Accuracy', '<M>_True', '<M>_False')."""
+        return self._logs()["reward_data"]
+
+    @property
+    def press_actions_per_timestep(self):
+        """ref: env_super.py:631-637, 729-736 — (press, material) per step, (0, None) for the no-op, 111/222 codes."""
+        return self._logs()["press_actions_per_timestep"]
+
     @property
     def bale_count(self):
-        """Per material: dict(count, last_size, last_quality, total_size) — the reference keeps a
-        list of (size, quality) per bale (env_super.py:661-687); the device keeps these counters."""
+        """ref: env_super.py:661-687 — per material the list of (size, quality) of every bale pressed this episode."""
+        return self._logs()["bale_count"]
+
+    @property
+    def bale_counters(self):
+        """Per material: dict(count, last_size, last_quality, total_size) — the counters the device keeps
+        instead of the reference's per-bale lists."""
         s = self._state()
         return {m: dict(count=int(s["bale_n"][i]), last_size=int(s["bale_last_size"][i]),
                         last_quality=int(s["bale_last_q"][i]), total_size=int(s["bale_sum"][i]))
@@ -209,6 +236,11 @@ class Env_3_Monolith(_SingleEnv):
         from the current obs / mask / state and then stepped on the device."""
         if action is None:
             action = self._choose_action(mode, use_action_masking)
+            # Only an external action and mode='random' without masking are sanitised (env_monolith.py:132-138,
+            # 246-257); a mono_agent's, rule-based, modular or masked-random choice goes straight to
+            # press_action_rules (:258-262) whatever `use_action_masking` says.
+            if not (mode == "random" and self.mono_agent is None):
+                return self._do_step(int(action), True, check_overflow)
         return self._do_step(int(action), use_action_masking, check_overflow)
 
     def _obs_after_shift(self):

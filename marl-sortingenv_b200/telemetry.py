@@ -175,8 +175,9 @@ class TraceRecorder:
     """Per-step snapshots of `env_ids` of a BatchedEnv, taken on the device (one small gather
     launch per step) into buffers preallocated for `capacity` steps."""
 
-    def __init__(self, env, env_ids, capacity: int):
+    def __init__(self, env, env_ids, capacity: int, growable: bool = False):
         import torch
+        self.growable = growable
         missing = [k for k in _INFO_KEYS if k not in env.info_buffers]
         if missing:
             raise ValueError(f"TraceRecorder needs an env created with info_level='full' (missing {missing})")
@@ -216,7 +217,9 @@ class TraceRecorder:
         if not self.started:
             raise RuntimeError("TraceRecorder.record() before start()")
         if self.t >= self.capacity:
-            raise RuntimeError(f"TraceRecorder capacity ({self.capacity} steps) exhausted")
+            if not self.growable:
+                raise RuntimeError(f"TraceRecorder capacity ({self.capacity} steps) exhausted")
+            self._grow()
         env = self.env
         self._gather(self.snaps[self.t + 1])
         for k in _INFO_KEYS:
@@ -224,6 +227,18 @@ class TraceRecorder:
         torch.index_select(env.reward, 0, self.ids, out=self.info["reward"][self.t])
         torch.index_select(env.terminated, 0, self.ids, out=self.info["terminated"][self.t])
         self.t += 1
+
+    def _grow(self):
+        import torch
+        new_cap = 2 * self.capacity
+        snaps = torch.zeros((new_cap + 1, self.K, self._dt.itemsize), dtype=torch.uint8, device=self.snaps.device)
+        snaps[: self.capacity + 1] = self.snaps
+        self.snaps = snaps
+        for k, v in self.info.items():
+            nv = torch.zeros((new_cap, self.K), dtype=v.dtype, device=v.device)
+            nv[: self.capacity] = v
+            self.info[k] = nv
+        self.capacity = new_cap
 
     # ---- host side
     def arrays(self, j: int):

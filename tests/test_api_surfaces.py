@@ -44,7 +44,13 @@ def test_single_env_matches_oracle(kind):
     cm = env.container_materials
     assert cm["A"] == int(ora.state["cont_true"][0][0]) and cm["E"] == int(ora.state["cont_e"][0])
     assert env.current_step == 40
-    assert sum(b["total_size"] for b in env.bale_count.values()) == int(ora.state["bale_sum"][0].sum())
+    assert sum(b["total_size"] for b in env.bale_counters.values()) == int(ora.state["bale_sum"][0].sum())
+    # the reference-format logs rebuilt from the device snapshots
+    assert sum(size for bales in env.bale_count.values() for size, _ in bales) == int(ora.state["bale_sum"][0].sum())
+    assert {m: len(b) for m, b in env.bale_count.items()} == {m: int(ora.state["bale_n"][0][i]) for i, m in enumerate("ABCDE")}
+    rd = env.reward_data
+    assert len(rd["Reward"]) == len(env.press_actions_per_timestep) == env.current_step
+    assert abs(sum(rd["Total"]) - total) < 1e-3
 
 
 def test_overflow_info_and_unmasked_sanitising():
@@ -79,6 +85,24 @@ def test_published_rule_based_return():
         env.close()
     assert abs(np.mean(returns) - 44.03) < 1.5, returns
     assert np.std(returns) < 3.0
+
+
+def test_rule_based_mode_is_never_sanitised():
+    """Env_3.step(mode='rule_based') runs the same code with and without action masking: the heuristic's
+    choice is applied directly (env_monolith.py:166-184, 258-262), even when it presses a container below
+    the bale size — the published 44.03 / 43.20 rows differ only by seeds."""
+    from marl_sortingenv_b200 import Env_3_Monolith
+    tot = {}
+    for masking in (True, False):
+        env = Env_3_Monolith(max_steps=120, seed=3, noise_sorting=0.0, balesize=200)
+        env.reset(seed=3)
+        total, done = 0.0, False
+        while not done:
+            _, r, done, _, _ = env.step(action=None, mode="rule_based", use_action_masking=masking)
+            total += r
+        tot[masking] = (total, env.container_materials, env.press_state)
+        env.close()
+    assert tot[True] == tot[False]
 
 
 def test_published_random_masked_return():
