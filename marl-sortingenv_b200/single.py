@@ -136,6 +136,20 @@ class _SingleEnv:
         """ref: env_super.py:661-687 — per material the list of (size, quality) of every bale pressed this episode."""
         return self._logs()["bale_count"]
 
+    def render(self, mode="human", save=False, show=True, log_dir="./img/log", filename="plot", title="", format="svg",
+               checksum=True, steps_test=None):
+        """ref: Env_Super.render (env_super.py:229-233) — hands the env to the reference's dashboard
+        `utils.plotting.plot_env`.  The dashboard itself is not part of this package (plotting is out of
+        scope): it is imported from the reference checkout on `sys.path`, and it receives an object carrying
+        exactly the attributes it unpacks (plotting.py:32-48), rebuilt from the device snapshots."""
+        try:
+            from utils.plotting import plot_env
+        except ImportError as e:
+            raise RuntimeError("render() uses the reference's own utils/plotting.py (matplotlib, seaborn): put the "
+                               "MARL-SortingEnv checkout on sys.path") from e
+        return plot_env(env=self._b._trace.reference_view(0), save=save, show=show, log_dir=log_dir, filename=filename,
+                        title=title, format=format, checksum=checksum, steps_test=steps_test)
+
     @property
     def bale_counters(self):
         """Per material: dict(count, last_size, last_quality, total_size) — the counters the device keeps
