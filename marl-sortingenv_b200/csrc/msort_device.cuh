@@ -337,14 +337,15 @@ static __device__ __noinline__ int purity_k_f64(int tr, int tot) {
 // On an exact tie 100*tr/tot = k0 + 1/2 the quotient tr/tot equals (2*k0+1)/200 whatever tr and tot
 // are, so fl(tr/tot), fl(.*100) and the final rint depend on k0 alone: the host evaluates the
 // float64 pipeline once per k0 = 0..99 and hands the outcomes over as the bit table c.tie_up.
+template <bool SMALL = false>   // SMALL: the caller knows c.small_lv holds (compile-time copy of the flag)
 __device__ __forceinline__ int purity_k(const DevConfig& c, int tr, int tot) {  // tot > 0, 0 <= tr <= tot
-  if (tot < (1 << 17)) {                       // 100*tr and tot are exact in float32
+  if (SMALL || tot < (1 << 17)) {              // 100*tr and tot are exact in float32
     const int a2 = 200 * tr, t2 = 2 * tot;
     int k = __float2int_rn(__fdividef((float)(100 * tr), (float)tot));  // within 1 of the exact rounding
     int d = a2 - k * t2;                       // exact: twice the signed distance to k, in units of 1/tot
     // __fdividef is within 2 ulp (2.4e-5 at a quotient of 100) while a non-tie sits at least 1/(2*tot)
     // from a rounding boundary: for tot <= 8192 (c.small_lv) k is already the exact rounding
-    if (!c.small_lv) {
+    if (!SMALL && !c.small_lv) {
       if (d > tot) { k += 1; d -= t2; } else if (d < -tot) { k -= 1; d += t2; }
     }
     if (d == tot || d == -tot) {               // .5 tie: k0 = floor of the exact value, outcome from the table

@@ -142,7 +142,11 @@ template <int KIND> using PolicyParam = typename std::conditional<KIND == MSORT_
 // FAST (PHILOX only, chosen by the host when DevConfig::fast holds): boosted accuracies are exactly 1.0,
 // unboosted ones need no clip, and the redistribution classes fit one register of packed bytes.
 // Results are identical to the generic instantiation; only the instruction count differs.
-template <int KIND, int RNG, int LAYOUT, bool FAST>
+// HOT (FAST + compact layout only): the per-call switches are the training configuration — action masking
+// and auto-reset on, no overflow check, mask output wanted, no per-step info arrays, small levels — and are
+// compiled in, which removes ~20 uniform branches (and the basic-block boundaries they put in the
+// scheduler's way).  Chosen per launch by launch_step_kind.
+template <int KIND, int RNG, int LAYOUT, bool FAST, bool HOT = false>
 __global__ void __launch_bounds__(kTile, (KIND == MSORT_ENV_PRESS ? 5 : MSORT_STEP_MIN_BLOCKS) * (128 / kTile))  // Env_2 keeps 32 MLP activations in registers
 step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArgs a,
             const __grid_constant__ PolicyParam<KIND> pw) {
@@ -152,8 +156,10 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   __shared__ double s_accs[RNG == MSORT_RNG_REPLAY ? 4 : 1][RNG == MSORT_RNG_REPLAY ? kTile : 1];  // accuracy_sorter (REPLAY)
   __shared__ double s_stat[kTile / 32][ST_COUNT];   // per-warp partial sums (plain stores: no init, no atomics)
 
-  const bool masking = c.flags & MSORT_F_ACTION_MASKING;
-  const bool auto_reset = c.flags & MSORT_F_AUTO_RESET;
+  static_assert(!HOT || (FAST && LAYOUT == LAYOUT_COMPACT), "HOT specialises the FAST compact kernel");
+  const bool masking = HOT || (c.flags & MSORT_F_ACTION_MASKING);
+  const bool auto_reset = HOT || (c.flags & MSORT_F_AUTO_RESET);
+  const bool want_mask = HOT || a.mask != nullptr;
   const bool use_mlp = KIND == MSORT_ENV_PRESS && (c.flags & MSORT_F_SORT_POLICY_MLP) &&
                        !(RNG == MSORT_RNG_REPLAY && a.sort_mode_in);
   const int tid = threadIdx.x;
@@ -221,7 +227,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     } else {
       if (s.gcount >= c.spp) { s.gidx ^= 1; s.gcount = 0; }
       s.in4 = c.pat[s.gidx ^ s.gfirst];
-      if (c.pat_remainder > 0) {
+      if (!FAST && c.pat_remainder > 0) {   // FAST implies no remainder
         U4 r4 = {0, 0, 0, 0};
         for (int k = 0; k < c.pat_remainder; ++k) {
           if ((k & 3) == 0) r4 = env_draw(c, gid_lo, gid_hi, kBlkInput + 0x100u * (uint32_t)(k >> 2), ep, stp);
@@ -568,7 +574,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
           for (int q = 0; q < 4; ++q) if (m == q) { tv = s.tr[q]; amt = s.tr[q] + s.fl[q]; s.tr[q] = 0; s.fl[q] = 0; }
           if (m == 4) s.e = 0;
           s.started = 1; s.last_amt = amt;
-          const int qk = (m < 4 && amt > 0) ? purity_k(c, tv, amt) : 0;  // round(true/total, 2) (:754)
+          const int qk = (m < 4 && amt > 0) ? purity_k<HOT>(c, tv, amt) : 0;  // round(true/total, 2) (:754)
           if (!second) { s.timer[0] = c.press_time[0]; s.mat[0] = m; s.pn[0] = amt; s.pq[0] = qk; }
           else { s.timer[1] = c.press_time[1]; s.mat[1] = m; s.pn[1] = amt; s.pq[1] = qk; }
         }
@@ -583,7 +589,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
 
     // 8: overflow termination (detect_overflow :900-905)
     int overflow_mat = -1;
-    if (c.flags & MSORT_F_CHECK_OVERFLOW) {
+    if (!HOT && (c.flags & MSORT_F_CHECK_OVERFLOW)) {
 #pragma unroll
       for (int m = 4; m >= 0; --m) if (lv[m] > c.cap) overflow_mat = m;
     }
@@ -593,7 +599,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     int kq[4] = {-1, -1, -1, -1};
     if (KIND != MSORT_ENV_PRESS) {
 #pragma unroll
-      for (int m = 0; m < 4; ++m) kq[m] = lv[m] > 0 ? purity_k(c, s.tr[m], lv[m]) : -1;
+      for (int m = 0; m < 4; ++m) kq[m] = lv[m] > 0 ? purity_k<HOT>(c, s.tr[m], lv[m]) : -1;
     }
     double reward, rs_term = 0.0, rp_term = 0.0;   // the two terms are only reported (telemetry)
     bool terminated;
@@ -670,7 +676,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
 
     a.reward[i] = (float)reward;
     a.terminated[i] = terminated ? 1 : 0;
-    if (a.any_step_info) {
+    if (!HOT && a.any_step_info) {
       if (a.info_action) a.info_action[i] = act;
       if (a.info_overflow) a.info_overflow[i] = overflow ? 1 : 0;
       if (a.info_overflow_mat) a.info_overflow_mat[i] = (int8_t)overflow_mat;
@@ -715,7 +721,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
         env_obs<KIND>(c, s, orow);
       }
     }
-    if (a.mask) put_mask_row<A>(s_mask, tid, press_mask_bits(c, s));
+    if (want_mask) put_mask_row<A>(s_mask, tid, press_mask_bits(c, s));
     store_planes<LAYOUT>(a.state, c.n_pad, i, s);
   }
 
@@ -746,12 +752,12 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   if (rows == kTile) {
     if (tid == 0) {
       bulk_store(a.obs + row0 * D, s_obs, kTile * D * (uint32_t)sizeof(float));
-      if (a.mask) bulk_store(a.mask + row0 * A, s_mask, kTile * A);
+      if (want_mask) bulk_store(a.mask + row0 * A, s_mask, kTile * A);
       bulk_commit_and_wait_read();
     }
   } else {  // partial last tile
     flush_tile(s_obs, a.obs + row0 * D, rows * D * (int)sizeof(float));
-    if (a.mask) flush_tile(s_mask, a.mask + row0 * A, rows * A);
+    if (want_mask) flush_tile(s_mask, a.mask + row0 * A, rows * A);
   }
 }
 
@@ -1011,7 +1017,10 @@ static cudaError_t launch_step_kind(const DevConfig& c, const StepArgs& a, const
   }
   if (rng == MSORT_RNG_REPLAY) step_kernel<KIND, MSORT_RNG_REPLAY, LAYOUT_REPLAY, false><<<g, kTile, 0, st>>>(c, a, pw);
   else if (c.layout == LAYOUT_COMPACT) {
-    if (c.fast) step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true><<<g, kTile, 0, st>>>(c, a, pw);
+    const unsigned want = MSORT_F_ACTION_MASKING | MSORT_F_AUTO_RESET, never = MSORT_F_CHECK_OVERFLOW;
+    const bool hot = c.fast && c.small_lv && (c.flags & want) == want && !(c.flags & never) && a.mask && !a.any_step_info;
+    if (hot) step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true><<<g, kTile, 0, st>>>(c, a, pw);
+    else if (c.fast) step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true><<<g, kTile, 0, st>>>(c, a, pw);
     else step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, false><<<g, kTile, 0, st>>>(c, a, pw);
   } else {
     if (c.fast) step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_WIDE, true><<<g, kTile, 0, st>>>(c, a, pw);
