@@ -212,6 +212,18 @@ static int digest_config(const msort_config_t& c, DevConfig& d) {
   d.pen_sev0 = std::min(0.0, c.overflow_penalty_severe);
   d.pen_mild0 = std::min(0.0, c.overflow_penalty_mild);
   d.small_lv = d.layout == LAYOUT_COMPACT && (long long)c.input_batch_size * c.max_steps <= 8192ll;
+  // at most twelve mis-sorted units per station: false(t) = t - rint(t*acc) with acc >= base + noise_low (rounding is
+  // monotone), for every stage count t a station can see (0 .. largest pattern count; draws only lower it)
+  d.one_block = 1;
+  for (int m = 0; m < 4 && d.one_block; ++m) {
+    int tmax = std::max(c.pattern_counts[0][m], c.pattern_counts[1][m]);
+    volatile double amin = d.base_acc[m] + d.noise_low;
+    if (amin < 0.0) amin = 0.0;
+    for (int t = 0; t <= tmax; ++t) {
+      volatile double prod = (double)t * amin;
+      if (t - (int)std::rint(prod) > 12) { d.one_block = 0; break; }
+    }
+  }
   d.S_magic = (unsigned)((1ull << 32) / (unsigned long long)c.bale_size) + 1u;
   // observation tables for the three possible stage contents (same float32 operations as obs_belt / obs_sorting)
   for (int w = 0; w < 3; ++w) {

@@ -67,6 +67,7 @@ struct DevConfig {
   unsigned tie_up[4];              // bit k: the float64 pipeline rounds the exact tie (2k+1)/200 up to k+1 (purity_k)
   int small_lv;                    // 1: every container level is provably <= 8192 (compact layout, batch*max_steps
                                    //    <= 8192): the float32 quotient in purity_k then rounds to the right integer
+  int one_block;                   // 1: no station can ever have more than 12 mis-sorted units (one Philox block of draws)
   unsigned S_magic;                // floor(2^32/S)+1: n/S == umulhi(n, S_magic) for n, S < 2^16
   double pen_sev0, pen_mild0;      // min(0, severe / mild overflow penalty) (FAST press reward)
   float obs_belt_tab[3][5];        // FAST: belt part of the observation for belt == pattern 1 / pattern 2 / empty

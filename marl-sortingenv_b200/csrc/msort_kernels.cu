@@ -143,7 +143,8 @@ template <int KIND> using PolicyParam = typename std::conditional<KIND == MSORT_
 // unboosted ones need no clip, and the redistribution classes fit one register of packed bytes.
 // Results are identical to the generic instantiation; only the instruction count differs.
 // HOT (FAST + compact layout only): the per-call switches are the training configuration — action masking
-// and auto-reset on, no overflow check, mask output wanted, no per-step info arrays, small levels — and are
+// and auto-reset on, no overflow check, mask output wanted, no per-step info arrays, small levels, at most
+// twelve redistribution draws per station (DevConfig::one_block) — and are
 // compiled in, which removes ~20 uniform branches (and the basic-block boundaries they put in the
 // scheduler's way).  Chosen per launch by launch_step_kind.
 template <int KIND, int RNG, int LAYOUT, bool FAST, bool HOT = false>
@@ -192,6 +193,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     // counter and mode — 64 B less state traffic per env-step than storing four float64.
     double acc_sorter[4];
     double acc_a = 0.0, acc_b = 0.0;              // FAST: accuracies of the two unboosted stations of the previous mode
+    U4 hotA = {0, 0, 0, 0}, hotB = {0, 0, 0, 0};  // HOT: the two redistribution blocks
     const int pm = s.mode;                        // previous step's sensor mode
     if (RNG == MSORT_RNG_REPLAY) {
 #pragma unroll
@@ -200,6 +202,10 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       // stp == 0 (counter wraps): the sorting stage is empty right after a reset, so the values are never
       // multiplied by anything but 0; only Env_2's embedded policy observes them (set below)
       philox_accuracy2(c, gid_lo, gid_hi, ep, stp - 1, pm, acc_a, acc_b);   // unconditional: no branch between the Philox chains
+      if (HOT) {   // one block per station is enough (c.one_block): start both redistribution blocks now, next to the accuracy chains
+        hotA = env_draw(c, gid_lo, gid_hi, kBlkRedis + (pm ? 0u : 64u), ep, stp);
+        hotB = env_draw(c, gid_lo, gid_hi, kBlkRedis + 128u, ep, stp);
+      }
       if (KIND == MSORT_ENV_PRESS) {
         s.acc[0] = pm ? acc_a : 1.0; s.acc[1] = pm ? 1.0 : acc_a;
         s.acc[2] = pm ? acc_b : 1.0; s.acc[3] = pm ? 1.0 : acc_b;
@@ -395,6 +401,16 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       }
       // draw k of a block sees tot - k units (every earlier draw of an active lane removed one); an
       // inactive lane's products are never used
+      if (HOT) {                          // at most twelve draws (host-proved): one straight, predicated block
+        if (rem > 0) {
+          U4 r4 = hotA;
+          MSORT_PDRAW(r4.x, r4.y, 0); MSORT_PDRAW(r4.x, r4.y, 1); MSORT_PDRAW(r4.x, r4.y, 2);
+          MSORT_PDRAW(r4.x, r4.y, 3); MSORT_PDRAW(r4.x, r4.y, 4); MSORT_PDRAW(r4.x, r4.y, 5);
+          MSORT_PDRAW(r4.z, r4.w, 6); MSORT_PDRAW(r4.z, r4.w, 7); MSORT_PDRAW(r4.z, r4.w, 8);
+          MSORT_PDRAW(r4.z, r4.w, 9); MSORT_PDRAW(r4.z, r4.w, 10); MSORT_PDRAW(r4.z, r4.w, 11);
+          tot -= rem;
+        }
+      } else
       for (uint32_t b = 0; rem > 0; ++b, tot -= min(rem, 12), rem -= 12) {
         U4 r4 = env_draw(c, gid_lo, gid_hi, blk0 + b, ep, stp);
         MSORT_PDRAW(r4.x, r4.y, 0); MSORT_PDRAW(r4.x, r4.y, 1); MSORT_PDRAW(r4.x, r4.y, 2);
@@ -421,6 +437,16 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
         const int r = (int)draw64(xl, xh, (uint32_t)(tot - (k)));                                      \
         if (rem > (k) && r < lump) lump -= 1;                                                          \
       }
+      if (HOT) {
+        if (rem > 0) {
+          U4 r4 = hotB;
+          MSORT_PDRAW2(r4.x, r4.y, 0); MSORT_PDRAW2(r4.x, r4.y, 1); MSORT_PDRAW2(r4.x, r4.y, 2);
+          MSORT_PDRAW2(r4.x, r4.y, 3); MSORT_PDRAW2(r4.x, r4.y, 4); MSORT_PDRAW2(r4.x, r4.y, 5);
+          MSORT_PDRAW2(r4.z, r4.w, 6); MSORT_PDRAW2(r4.z, r4.w, 7); MSORT_PDRAW2(r4.z, r4.w, 8);
+          MSORT_PDRAW2(r4.z, r4.w, 9); MSORT_PDRAW2(r4.z, r4.w, 10); MSORT_PDRAW2(r4.z, r4.w, 11);
+          tot -= rem;
+        }
+      } else
       for (uint32_t b = 0; rem > 0; ++b, tot -= min(rem, 12), rem -= 12) {
         U4 r4 = env_draw(c, gid_lo, gid_hi, kBlkRedis + 128u + b, ep, stp);
         MSORT_PDRAW2(r4.x, r4.y, 0); MSORT_PDRAW2(r4.x, r4.y, 1); MSORT_PDRAW2(r4.x, r4.y, 2);
@@ -1018,7 +1044,7 @@ static cudaError_t launch_step_kind(const DevConfig& c, const StepArgs& a, const
   if (rng == MSORT_RNG_REPLAY) step_kernel<KIND, MSORT_RNG_REPLAY, LAYOUT_REPLAY, false><<<g, kTile, 0, st>>>(c, a, pw);
   else if (c.layout == LAYOUT_COMPACT) {
     const unsigned want = MSORT_F_ACTION_MASKING | MSORT_F_AUTO_RESET, never = MSORT_F_CHECK_OVERFLOW;
-    const bool hot = c.fast && c.small_lv && (c.flags & want) == want && !(c.flags & never) && a.mask && !a.any_step_info;
+    const bool hot = c.fast && c.small_lv && c.one_block && (c.flags & want) == want && !(c.flags & never) && a.mask && !a.any_step_info;
     if (hot) step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true><<<g, kTile, 0, st>>>(c, a, pw);
     else if (c.fast) step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true><<<g, kTile, 0, st>>>(c, a, pw);
     else step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, false><<<g, kTile, 0, st>>>(c, a, pw);
