@@ -250,8 +250,9 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       if (KIND != MSORT_ENV_PRESS) {
         const bool b0 = s.belt4 == c.pat[0], b1 = s.belt4 == c.pat[1];
         if (b0 || b1 || s.belt4 == 0u) {
+          const float* tb = c.obs_belt_tab[b0 ? 0 : (b1 ? 1 : 2)];   // one indexed constant load per entry
 #pragma unroll
-          for (int k = 0; k < 5; ++k) orow[k] = b0 ? c.obs_belt_tab[0][k] : (b1 ? c.obs_belt_tab[1][k] : c.obs_belt_tab[2][k]);
+          for (int k = 0; k < 5; ++k) orow[k] = tb[k];
         } else {
           obs_belt(s, orow);
         }
@@ -259,8 +260,9 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       if (KIND != MSORT_ENV_SORT) {
         const bool s0 = s.sort4 == c.pat[0], s1 = s.sort4 == c.pat[1];
         if (s0 || s1 || s.sort4 == 0u) {
+          const float* ts = c.obs_sort_tab[s0 ? 0 : (s1 ? 1 : 2)];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) prow[10 + k] = s0 ? c.obs_sort_tab[0][k] : (s1 ? c.obs_sort_tab[1][k] : c.obs_sort_tab[2][k]);
+          for (int k = 0; k < 4; ++k) prow[10 + k] = ts[k];
         } else {
           obs_sorting(c, s, prow);
         }
