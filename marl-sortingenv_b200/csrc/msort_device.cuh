@@ -207,7 +207,7 @@ __device__ __forceinline__ void philox_accuracy2(const DevConfig& c, uint32_t gi
                                                  uint32_t step, int mode, double& a, double& b) {
   const U4 r4 = env_draw(c, gid_lo, gid_hi16, kBlkNoise, episode, step);
   const uint32_t ua = mode ? r4.x : r4.y, ub = mode ? r4.z : r4.w;
-  const double ba = mode ? c.base_acc[0] : c.base_acc[1], bb = mode ? c.base_acc[2] : c.base_acc[3];
+  const double ba = c.base_acc[1 - mode], bb = c.base_acc[3 - mode];   // mode 1 -> stations 0 and 2, mode 0 -> 1 and 3
   a = dadd(ba, dadd(c.noise_low, dmul(c.noise_range, (double)ua * 2.3283064365386963e-10)));
   b = dadd(bb, dadd(c.noise_low, dmul(c.noise_range, (double)ub * 2.3283064365386963e-10)));
 }
@@ -349,9 +349,9 @@ __device__ __forceinline__ int purity_k(const DevConfig& c, int tr, int tot) {  
     if (!SMALL && !c.small_lv) {
       if (d > tot) { k += 1; d -= t2; } else if (d < -tot) { k -= 1; d += t2; }
     }
-    if (d == tot || d == -tot) {               // .5 tie: k0 = floor of the exact value, outcome from the table
-      const int k0 = d == tot ? k : k - 1;
-      k = k0 + (int)((c.tie_up[(k0 >> 5) & 3] >> (k0 & 31)) & 1u);
+    if (abs(d) == tot) {                       // .5 tie: k0 = floor of the exact value (0..99), outcome from the table
+      const int k0 = k - (d < 0 ? 1 : 0);
+      k = k0 + (int)((c.tie_up[k0 >> 5] >> (k0 & 31)) & 1u);
     }
     return k;                                  // not a tie: exact rounding == float64 pipeline
   }

@@ -185,8 +185,9 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     const uint32_t ep = s.episode, stp = s.step;
     float* const orow = &s_obs[tid * D];          // this env's row of the dense obs tile
     float* const prow = orow + (KIND == MSORT_ENV_MONO ? 13 : 0);  // press part of the row
-    if (act < 0) { act = 0; st_flags += 1u << 24; }
-    if (act >= A) { act = A - 1; st_flags += 1u << 24; }
+    if ((unsigned long long)act >= (unsigned long long)A) {   // outside Discrete(A): clamp and count (one unsigned compare)
+      act = act < 0 ? 0 : A - 1; st_flags += 1u << 24;
+    }
 
     // accuracy_sorter <- accuracy_belt (env_super.py:457).  REPLAY: stored in planes P6/P7 (and parked in
     // shared memory for the dynamically indexed loop).  PHILOX: recomputed from the previous step's
