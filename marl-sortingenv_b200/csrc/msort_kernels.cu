@@ -404,15 +404,13 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       }
       // draw k of a block sees tot - k units (every earlier draw of an active lane removed one); an
       // inactive lane's products are never used
-      if (HOT) {                          // at most twelve draws (host-proved): one straight, predicated block
-        if (rem > 0) {
-          U4 r4 = hotA;
-          MSORT_PDRAW(r4.x, r4.y, 0); MSORT_PDRAW(r4.x, r4.y, 1); MSORT_PDRAW(r4.x, r4.y, 2);
-          MSORT_PDRAW(r4.x, r4.y, 3); MSORT_PDRAW(r4.x, r4.y, 4); MSORT_PDRAW(r4.x, r4.y, 5);
-          MSORT_PDRAW(r4.z, r4.w, 6); MSORT_PDRAW(r4.z, r4.w, 7); MSORT_PDRAW(r4.z, r4.w, 8);
-          MSORT_PDRAW(r4.z, r4.w, 9); MSORT_PDRAW(r4.z, r4.w, 10); MSORT_PDRAW(r4.z, r4.w, 11);
-          tot -= rem;
-        }
+      if (HOT) {                          // at most twelve draws (host-proved): one straight, predicated block —
+        U4 r4 = hotA;                     // unconditional: the unboosted station almost always mis-sorts something
+        MSORT_PDRAW(r4.x, r4.y, 0); MSORT_PDRAW(r4.x, r4.y, 1); MSORT_PDRAW(r4.x, r4.y, 2);
+        MSORT_PDRAW(r4.x, r4.y, 3); MSORT_PDRAW(r4.x, r4.y, 4); MSORT_PDRAW(r4.x, r4.y, 5);
+        MSORT_PDRAW(r4.z, r4.w, 6); MSORT_PDRAW(r4.z, r4.w, 7); MSORT_PDRAW(r4.z, r4.w, 8);
+        MSORT_PDRAW(r4.z, r4.w, 9); MSORT_PDRAW(r4.z, r4.w, 10); MSORT_PDRAW(r4.z, r4.w, 11);
+        tot -= rem;
       } else
       for (uint32_t b = 0; rem > 0; ++b, tot -= min(rem, 12), rem -= 12) {
         U4 r4 = env_draw(c, gid_lo, gid_hi, blk0 + b, ep, stp);
