@@ -22,7 +22,7 @@ struct msort_handle {
   int sm_count;
   double* lut_dev;    // owned device constant (tiny, allocated at create): the kSortLut-entry float64 sorting-reward table
   bool policy_set;
-  float policy_host[MSORT_POLICY_WEIGHTS];  // host copy: travels to the step kernel as a kernel parameter
+  float policy_host[MSORT_POLICY_WEIGHTS];  // host copy in the kernel's paired layout (pack_policy_pairs): travels to the step kernel as a kernel parameter
   int64_t launches;
 };
 
@@ -378,13 +378,15 @@ extern "C" int msort_set_policy(msort_t* h, const float* weights, int weights_on
   if (!h || !weights) return fail(MSORT_E_INVALID, "msort_set_policy: NULL argument");
   // The step kernel receives the weights as a kernel parameter, so the library keeps a host copy.  A
   // device-resident source is copied back once, here (the one place besides msort_sync_check that waits).
+  float sb3[MSORT_POLICY_WEIGHTS];   // SB3 order, as include/msort.h documents
   if (weights_on_device) {
-    MSORT_TRY_CUDA(cudaMemcpyAsync(h->policy_host, weights, sizeof(h->policy_host), cudaMemcpyDeviceToHost,
-                                   (cudaStream_t)stream), "cudaMemcpyAsync(policy)");
+    MSORT_TRY_CUDA(cudaMemcpyAsync(sb3, weights, sizeof(sb3), cudaMemcpyDeviceToHost, (cudaStream_t)stream),
+                   "cudaMemcpyAsync(policy)");
     MSORT_TRY_CUDA(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize(policy)");
   } else {
-    memcpy(h->policy_host, weights, sizeof(h->policy_host));
+    memcpy(sb3, weights, sizeof(sb3));
   }
+  pack_policy_pairs(sb3, h->policy_host);
   h->policy_set = true;
   return MSORT_OK;
 }

@@ -494,29 +494,54 @@ __device__ __forceinline__ float tanh_fast(float x) {
   return 1.0f - __fdividef(2.0f, e + 1.0f);
 }
 
-// fp32 MLP 13->32->32->2 with tanh, fully unrolled; `w` is the kernel-parameter copy of the weights, so
-// every weight is a constant-bank operand of its FFMA
-// (ref: sort_agent.predict env_2_press.py:106-109; arch training.py:115)
-__device__ __forceinline__ int mlp_sort_mode(const float (&w)[MSORT_POLICY_WEIGHTS], const float* x) {
+// fp32 MLP 13->32->32->2 with tanh, fully unrolled (ref: sort_agent.predict env_2_press.py:106-109; arch
+// training.py:115).  `w` is the kernel-parameter copy of the weights in the PAIRED layout pack_policy_pairs()
+// builds (msort_kernels.cu): the weights of output neurons 2p and 2p+1 for the same input sit side by side, so
+// one Blackwell packed FMA (`fma.rn.f32x2`, SASS FFMA2: two independent IEEE fp32 FMAs per lane and issue
+// slot — the 3-register FFMA only reaches half of the fp32 pipe) advances both neurons.  Its weight pair is a
+// uniform-register operand straight from the constant bank (LDCU.128 feeds two FFMA2), its input the scalar
+// register broadcast to both halves.  Every neuron still sums bias + w_0 x_0 + w_1 x_1 + ... in the same
+// order with the same roundings as the scalar loop, so the logits are bit-identical to it.
+__device__ __forceinline__ unsigned long long f2pack(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2unpack(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+// `w2` = the paired weights as 64-bit words (pair p = floats 2p, 2p+1) of the kernel parameter.
+__device__ __forceinline__ int mlp_sort_mode(const unsigned long long* __restrict__ w2, const float* x) {
   constexpr int W1 = 0, b1 = 416, W2 = 448, b2 = 1472, W3 = 1504, b3 = 1568;
   float h1[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    float a = w[b1 + j];
+  for (int jp = 0; jp < 16; ++jp) {
+    unsigned long long a = w2[b1 / 2 + jp];
 #pragma unroll
-    for (int k = 0; k < 13; ++k) a = fmaf(w[W1 + j * 13 + k], x[k], a);
-    h1[j] = tanh_fast(a);
+    for (int k = 0; k < 13; ++k) a = ffma2(w2[W1 / 2 + jp * 13 + k], f2pack(x[k], x[k]), a);
+    float lo, hi;
+    f2unpack(a, lo, hi);
+    h1[2 * jp] = tanh_fast(lo); h1[2 * jp + 1] = tanh_fast(hi);
   }
-  float l0 = w[b3], l1 = w[b3 + 1];
+  unsigned long long l = w2[b3 / 2];   // (logit 0, logit 1)
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    float a = w[b2 + j];
+  for (int jp = 0; jp < 16; ++jp) {
+    unsigned long long a = w2[b2 / 2 + jp];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) a = fmaf(w[W2 + j * 32 + k], h1[k], a);
-    const float h = tanh_fast(a);
-    l0 = fmaf(w[W3 + j], h, l0);
-    l1 = fmaf(w[W3 + 32 + j], h, l1);
+    for (int k = 0; k < 32; ++k) a = ffma2(w2[W2 / 2 + jp * 32 + k], f2pack(h1[k], h1[k]), a);
+    float lo, hi;
+    f2unpack(a, lo, hi);
+    const float h0 = tanh_fast(lo), hh = tanh_fast(hi);
+    l = ffma2(w2[W3 / 2 + 2 * jp], f2pack(h0, h0), l);
+    l = ffma2(w2[W3 / 2 + 2 * jp + 1], f2pack(hh, hh), l);
   }
+  float l0, l1;
+  f2unpack(l, l0, l1);
   return l1 > l0 ? 1 : 0;
 }
 

@@ -11,6 +11,12 @@
 #include "msort_device.cuh"
 #include "msort_launch.h"
 
+#ifndef MSORT_PREFETCH_TILES
+#define MSORT_PREFETCH_TILES 296  // L2 prefetch distance of the step kernel in tiles (2 per SM; 0 = off): 148..518 measured alike, +3.4 %
+#endif
+#ifndef MSORT_PRESS_MIN_BLOCKS
+#define MSORT_PRESS_MIN_BLOCKS 5  // Env_2 (embedded MLP: 32 activations + FFMA2 accumulator pairs in registers)
+#endif
 #ifndef MSORT_STEP_MIN_BLOCKS
 #define MSORT_STEP_MIN_BLOCKS 7  // resident CTAs per SM the step kernel is compiled for (register cap)
 #endif
@@ -135,7 +141,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // Env_2's embedded policy travels as a kernel parameter (6.3 KB of the 32 KB parameter space): the
 // weights then sit in the constant bank and every FFMA of the fully unrolled MLP takes its weight
 // as a constant operand — no load instruction at all.
-struct PolicyW { float w[MSORT_POLICY_WEIGHTS]; };
+struct alignas(16) PolicyW { float w[(MSORT_POLICY_WEIGHTS + 3) / 4 * 4]; };   // paired layout (pack_policy_pairs), padded to whole LDCU.128s
 struct NoPolicy {};
 template <int KIND> using PolicyParam = typename std::conditional<KIND == MSORT_ENV_PRESS, PolicyW, NoPolicy>::type;
 
@@ -148,7 +154,7 @@ template <int KIND> using PolicyParam = typename std::conditional<KIND == MSORT_
 // compiled in, which removes ~20 uniform branches (and the basic-block boundaries they put in the
 // scheduler's way).  Chosen per launch by launch_step_kind.
 template <int KIND, int RNG, int LAYOUT, bool FAST, bool HOT = false>
-__global__ void __launch_bounds__(kTile, (KIND == MSORT_ENV_PRESS ? 5 : MSORT_STEP_MIN_BLOCKS) * (128 / kTile))  // Env_2 keeps 32 MLP activations in registers
+__global__ void __launch_bounds__(kTile, (KIND == MSORT_ENV_PRESS ? MSORT_PRESS_MIN_BLOCKS : MSORT_STEP_MIN_BLOCKS) * (128 / kTile))  // Env_2 keeps 32 MLP activations in registers
 step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArgs a,
             const __grid_constant__ PolicyParam<KIND> pw) {
   constexpr int D = Dims<KIND>::D, A = Dims<KIND>::A;
@@ -175,6 +181,19 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   uint32_t st_bales = 0, st_len = 0, st_underrun = 0;
   double st_reward = 0.0, st_return = 0.0;
 
+#if MSORT_PREFETCH_TILES > 0
+  // Pull the state planes and actions of the tile that runs MSORT_PREFETCH_TILES CTAs later (about one wave of
+  // resident CTAs) into L2, so that its initial loads — the largest single stall of the kernel — see L2
+  // latency instead of DRAM latency.  64 state lines + 8 action lines of 128 B per tile.
+  if (LAYOUT == LAYOUT_COMPACT) {
+    const long long pt = (long long)blockIdx.x + MSORT_PREFETCH_TILES;
+    if (pt < (long long)gridDim.x && tid < 72) {
+      const char* p = tid < 64 ? reinterpret_cast<const char*>(a.state + (tid >> 4) * c.n_pad + pt * kTile) + (tid & 15) * 128
+                               : reinterpret_cast<const char*>(a.actions + pt * kTile) + (tid - 64) * 128;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
+  }
+#endif
   if (live) {
     const unsigned long long gid = (unsigned long long)(c.gid0 + i);
     const uint32_t gid_lo = (uint32_t)gid, gid_hi = (uint32_t)(gid >> 32) & 0xffffu;
@@ -291,7 +310,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
         int kq[4];
         purity_ks(c, s, kq);
         sort_obs(c, s, kq, so);
-        if constexpr (KIND == MSORT_ENV_PRESS) mode = mlp_sort_mode(pw.w, so);
+        if constexpr (KIND == MSORT_ENV_PRESS) mode = mlp_sort_mode(reinterpret_cast<const unsigned long long*>(pw.w), so);
       } else {  // sorting_rules env_super.py:469-482: pA+pC > pB+pD on float64 proportions
         int ac = b4(s.belt4, 0) + b4(s.belt4, 2), bd = b4(s.belt4, 1) + b4(s.belt4, 3);
         if (ac != bd) mode = ac > bd ? 0 : 1;  // strict integer inequality survives the float64 rounding
@@ -1033,6 +1052,27 @@ stats_kernel(const __grid_constant__ DevConfig c, const uint4* __restrict__ stat
 }
 
 // ---------------------------------------------------------------- launch wrappers
+// Embedded-policy weights: SB3 order (include/msort.h: W1[32][13] b1[32] W2[32][32] b2[32] W3[2][32] b3[2]) ->
+// the paired layout mlp_sort_mode() consumes: for every pair of output neurons (2p, 2p+1) and every input k
+// the two weights side by side (one FFMA2 operand); the last layer pairs the two logits.  Section offsets
+// and the bias sections are unchanged.
+void pack_policy_pairs(const float* sb3, float* paired) {
+  constexpr int W1 = 0, b1 = 416, W2 = 448, b2 = 1472, W3 = 1504, b3 = 1568;
+  for (int jp = 0; jp < 16; ++jp)
+    for (int k = 0; k < 13; ++k) {
+      paired[W1 + (jp * 13 + k) * 2] = sb3[W1 + (2 * jp) * 13 + k];
+      paired[W1 + (jp * 13 + k) * 2 + 1] = sb3[W1 + (2 * jp + 1) * 13 + k];
+    }
+  for (int jp = 0; jp < 16; ++jp)
+    for (int k = 0; k < 32; ++k) {
+      paired[W2 + (jp * 32 + k) * 2] = sb3[W2 + (2 * jp) * 32 + k];
+      paired[W2 + (jp * 32 + k) * 2 + 1] = sb3[W2 + (2 * jp + 1) * 32 + k];
+    }
+  for (int j = 0; j < 32; ++j) { paired[W3 + 2 * j] = sb3[W3 + j]; paired[W3 + 2 * j + 1] = sb3[W3 + 32 + j]; }
+  for (int j = 0; j < 32; ++j) { paired[b1 + j] = sb3[b1 + j]; paired[b2 + j] = sb3[b2 + j]; }
+  paired[b3] = sb3[b3]; paired[b3 + 1] = sb3[b3 + 1];
+}
+
 static inline unsigned tiles(long long n) { return (unsigned)((n + kTile - 1) / kTile); }
 
 template <int KIND>
@@ -1040,7 +1080,8 @@ static cudaError_t launch_step_kind(const DevConfig& c, const StepArgs& a, const
   const unsigned g = tiles(c.n);
   PolicyParam<KIND> pw;
   if constexpr (KIND == MSORT_ENV_PRESS) {
-    if (policy_host) memcpy(pw.w, policy_host, sizeof(pw.w)); else memset(pw.w, 0, sizeof(pw.w));
+    memset(pw.w, 0, sizeof(pw.w));
+    if (policy_host) memcpy(pw.w, policy_host, MSORT_POLICY_WEIGHTS * sizeof(float));
   }
   if (rng == MSORT_RNG_REPLAY) step_kernel<KIND, MSORT_RNG_REPLAY, LAYOUT_REPLAY, false><<<g, kTile, 0, st>>>(c, a, pw);
   else if (c.layout == LAYOUT_COMPACT) {

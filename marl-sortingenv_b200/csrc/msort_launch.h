@@ -19,9 +19,10 @@ struct StepLaunch {
   uint8_t* mask;
   const msort_info_out_t* info;
   const msort_replay_t* replay;
-  const float* policy_host;  // Env_2 embedded policy (host copy, MSORT_POLICY_WEIGHTS floats) or nullptr
+  const float* policy_host;  // Env_2 embedded policy (host copy in the paired layout, MSORT_POLICY_WEIGHTS floats) or nullptr
 };
 
+void pack_policy_pairs(const float* sb3, float* paired);   // SB3 weight order -> the step kernel's FFMA2 operand order
 cudaError_t launch_step(const DevConfig& c, const StepLaunch& l, int rng, cudaStream_t st);
 cudaError_t launch_reset(const DevConfig& c, void* state, const uint8_t* which, const uint8_t* first_pattern,
                          float* obs, uint8_t* mask, uint32_t reset_flags, cudaStream_t st);
