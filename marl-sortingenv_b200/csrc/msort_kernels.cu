@@ -14,6 +14,9 @@
 #ifndef MSORT_PREFETCH_TILES
 #define MSORT_PREFETCH_TILES 296  // L2 prefetch distance of the step kernel in tiles (2 per SM; 0 = off): 148..518 measured alike, +3.4 %
 #endif
+#ifndef MSORT_HOT_PERSIST
+#define MSORT_HOT_PERSIST 1       // Env_2's HOT step kernel: 1 = resident CTAs loop over tiles, next tile's state staged by TMA
+#endif
 #ifndef MSORT_PRESS_MIN_BLOCKS
 #define MSORT_PRESS_MIN_BLOCKS 5  // Env_2 (embedded MLP: 32 activations + FFMA2 accumulator pairs in registers)
 #endif
@@ -115,6 +118,7 @@ struct StepArgs {
   float* info_r_sort;
   float* info_r_press;
   int any_step_info;  // any of the six per-step info arrays above is present
+  int act_tma;        // actions are 16-byte aligned: the persistent kernel may fetch a tile's actions by TMA
   float* terminal_obs;
   double* episode_return;
   int* episode_length;
@@ -171,7 +175,40 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
                        !(RNG == MSORT_RNG_REPLAY && a.sort_mode_in);
   const int tid = threadIdx.x;
 
-  const long long row0 = (long long)blockIdx.x * kTile;
+  // PERSIST (Env_2's HOT instantiation): the grid is one wave of resident CTAs, each looping over tiles
+  // blockIdx.x, blockIdx.x + gridDim.x, ...  While a tile is computed the TMA engine already copies the next
+  // tile's four state planes (and its actions) into shared memory — issued by one thread, completion counted
+  // on an mbarrier — so no warp waits for DRAM at the top of a tile.  Measured: Env_2 (long, MLP-heavy tiles)
+  // +7 %; Env_1 / Env_3 10-17 % SLOWER than one CTA per tile with the hardware scheduler refilling the SM
+  // (second barrier per tile, ~50 more instructions per warp), so they keep that form plus the L2 prefetch.
+  constexpr bool PERSIST = HOT && MSORT_HOT_PERSIST && KIND == MSORT_ENV_PRESS;
+  __shared__ __align__(16) uint4 s_in[PERSIST ? 4 * kTile : 1];        // staged state planes C0..C3 of the next tile
+  __shared__ __align__(16) long long s_act[PERSIST ? kTile : 2];       // ... and its actions
+  __shared__ __align__(8) uint64_t s_full;                             // "staged tile has landed"
+  const long long ntiles = (c.n + kTile - 1) / kTile;
+  auto stage_tile = [&](long long t) {                                  // one thread: start the copies of tile t
+    const bool whole = (t + 1) * kTile <= c.n && a.act_tma;
+    mbar_expect_tx(&s_full, 4u * kTile * 16u + (whole ? kTile * 8u : 0u));
+#pragma unroll
+    for (int p = 0; p < 4; ++p) bulk_load(&s_in[p * kTile], a.state + p * c.n_pad + t * kTile, kTile * 16u, &s_full);
+    if (whole) bulk_load(s_act, a.actions + t * kTile, kTile * 8u, &s_full);
+  };
+  // The once-per-tile serial jobs go to three different warps so that no warp is the CTA's straggler at the
+  // two barriers: lane 0 of warp 1 stages the next tile, warp 2 adds the statistics, lane 0 of warp 3 issues
+  // (and later waits for) the bulk stores.  Without PERSIST everything stays with warp 0: the other warps exit.
+  constexpr int kStageTid = 32 % kTile, kStatTid = PERSIST ? 64 % kTile : 0, kStoreTid = PERSIST ? 96 % kTile : 0;
+  uint32_t phase = 0;
+  if (PERSIST) {
+    if (tid == kStageTid) {
+      mbar_init(&s_full, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      stage_tile(blockIdx.x);
+    }
+    __syncthreads();
+  }
+  long long tile = blockIdx.x;
+  do {   // one pass unless PERSIST
+  const long long row0 = tile * kTile;
   const long long i = row0 + tid;
   const bool live = i < c.n;
   const int rows = (int)min((long long)kTile, c.n - row0);
@@ -185,7 +222,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   // Pull the state planes and actions of the tile that runs MSORT_PREFETCH_TILES CTAs later (about one wave of
   // resident CTAs) into L2, so that its initial loads — the largest single stall of the kernel — see L2
   // latency instead of DRAM latency.  64 state lines + 8 action lines of 128 B per tile.
-  if (LAYOUT == LAYOUT_COMPACT) {
+  if (LAYOUT == LAYOUT_COMPACT && !PERSIST) {
     const long long pt = (long long)blockIdx.x + MSORT_PREFETCH_TILES;
     if (pt < (long long)gridDim.x && tid < 72) {
       const char* p = tid < 64 ? reinterpret_cast<const char*>(a.state + (tid >> 4) * c.n_pad + pt * kTile) + (tid & 15) * 128
@@ -194,12 +231,24 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     }
   }
 #endif
+  Env s;
+  long long act = 0;
+  if (PERSIST) {
+    mbar_wait(&s_full, phase); phase ^= 1u;
+    if (live) {
+      load_planes<LAYOUT>(s_in, kTile, tid, s);
+      act = (a.act_tma && rows == kTile) ? s_act[tid] : a.actions[i];
+    }
+    if (tid == kStoreTid) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous tile's obs / mask have left shared memory
+    __syncthreads();                                                                       // every thread has taken its env out of the staging buffer
+    if (tid == kStageTid && tile + gridDim.x < ntiles) stage_tile(tile + gridDim.x);
+  } else if (live) {
+    load_planes<LAYOUT>(a.state, c.n_pad, i, s);
+    act = a.actions[i];
+  }
   if (live) {
     const unsigned long long gid = (unsigned long long)(c.gid0 + i);
     const uint32_t gid_lo = (uint32_t)gid, gid_hi = (uint32_t)(gid >> 32) & 0xffffu;
-    Env s;
-    load_planes<LAYOUT>(a.state, c.n_pad, i, s);
-    long long act = a.actions[i];
 
     const uint32_t ep = s.episode, stp = s.step;
     float* const orow = &s_obs[tid * D];          // this env's row of the dense obs tile
@@ -789,22 +838,26 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   }
   fence_async_smem();  // order this thread's tile writes before the async-proxy reads below
   __syncthreads();
-  if (a.stats && tid < ST_COUNT) {
+  if (a.stats && tid >= kStatTid && tid < kStatTid + ST_COUNT) {
     double v = 0.0;
 #pragma unroll
-    for (int w = 0; w < kTile / 32; ++w) v += s_stat[w][tid];
-    if (v != 0.0) atomicAdd(&a.stats[tid], v);
+    for (int w = 0; w < kTile / 32; ++w) v += s_stat[w][tid - kStatTid];
+    if (v != 0.0) atomicAdd(&a.stats[tid - kStatTid], v);
   }
   if (rows == kTile) {
-    if (tid == 0) {
+    if (tid == kStoreTid) {
       bulk_store(a.obs + row0 * D, s_obs, kTile * D * (uint32_t)sizeof(float));
       if (want_mask) bulk_store(a.mask + row0 * A, s_mask, kTile * A);
-      bulk_commit_and_wait_read();
+      if (PERSIST) asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // waited for before the tile is written again
+      else bulk_commit_and_wait_read();
     }
   } else {  // partial last tile
     flush_tile(s_obs, a.obs + row0 * D, rows * D * (int)sizeof(float));
     if (want_mask) flush_tile(s_mask, a.mask + row0 * A, rows * A);
   }
+  tile += gridDim.x;
+  } while (PERSIST && tile < ntiles);
+  if (PERSIST && tid == kStoreTid) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory outlives the last copies
 }
 
 // ---------------------------------------------------------------- K2: reset
@@ -1087,7 +1140,19 @@ static cudaError_t launch_step_kind(const DevConfig& c, const StepArgs& a, const
   else if (c.layout == LAYOUT_COMPACT) {
     const unsigned want = MSORT_F_ACTION_MASKING | MSORT_F_AUTO_RESET, never = MSORT_F_CHECK_OVERFLOW;
     const bool hot = c.fast && c.small_lv && c.one_block && (c.flags & want) == want && !(c.flags & never) && a.mask && !a.any_step_info;
-    if (hot) step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true><<<g, kTile, 0, st>>>(c, a, pw);
+    if (hot) {
+      auto kern = step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true>;
+      unsigned gp = g;
+      if (MSORT_HOT_PERSIST && KIND == MSORT_ENV_PRESS) {   // persistent: exactly one wave of resident CTAs (asked from the occupancy calculator once)
+        static int per_sm = 0;
+        if (per_sm == 0) {
+          cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTile, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+        }
+        gp = std::min(g, (unsigned)(c.sm_count * per_sm));
+      }
+      kern<<<gp, kTile, 0, st>>>(c, a, pw);
+    }
     else if (c.fast) step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true><<<g, kTile, 0, st>>>(c, a, pw);
     else step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, false><<<g, kTile, 0, st>>>(c, a, pw);
   } else {
@@ -1113,6 +1178,7 @@ cudaError_t launch_step(const DevConfig& c, const StepLaunch& l, int rng, cudaSt
   a.info_r_press = f ? f->reward_press : nullptr;
   a.any_step_info = a.info_action || a.info_overflow || a.info_overflow_mat || a.info_sort_mode ||
                     a.info_press_action || a.info_invalid || a.info_r_sort || a.info_r_press || a.info_sorted_true;
+  a.act_tma = ((uintptr_t)l.actions & 15u) == 0;
   a.terminal_obs = f ? f->terminal_obs : nullptr;
   a.episode_return = f ? f->episode_return : nullptr;
   a.episode_length = f ? f->episode_length : nullptr;

@@ -6,7 +6,7 @@ os.environ["MSORT_LIB"] = lib
 sys.path.insert(0, "/root/repo")
 import torch
 import marl_sortingenv_b200 as ms
-n = 1 << 20
+n = int(os.environ.get("N", 1 << 20))
 cls = {"mono": ms.BatchedMonolithEnv, "sort": ms.BatchedSortingEnv, "press": ms.BatchedPressingEnv}[kind]
 env = cls(n, max_steps=50, seed=42, info_level=os.environ.get("INFO", "episode"))
 if kind == 'press':
