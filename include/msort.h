@@ -298,6 +298,17 @@ int msort_sync_check(msort_t* h, void* stream);
 /* Number of kernels this handle has launched (bench.py's gpu_launches). */
 int64_t msort_launch_count(const msort_t* h);
 
+/* Which instantiation of the step kernel the handle's last msort_step launched (diagnostics / tests):
+ * 0 none yet, 1 REPLAY, 2 generic, 3 FAST (host-proved config facts compiled in),
+ * 4 HOT (FAST + the training-loop switches compiled in), 5 HOT persistent (Env_2: TMA-staged tiles). */
+#define MSORT_STEP_NONE 0
+#define MSORT_STEP_REPLAY 1
+#define MSORT_STEP_GENERIC 2
+#define MSORT_STEP_FAST 3
+#define MSORT_STEP_HOT 4
+#define MSORT_STEP_HOT_PERSISTENT 5
+int msort_step_variant(const msort_t* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -151,6 +151,7 @@ SYMBOLS = {
     "msort_reduce_stats": (C.c_int, [_P, _P, _P, _P]),
     "msort_sync_check": (C.c_int, [_P, _P]),
     "msort_launch_count": (C.c_int64, [_P]),
+    "msort_step_variant": (C.c_int, [_P]),
 }
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))

@@ -137,6 +137,11 @@ class BatchedEnv:
     def launch_count(self) -> int:
         return int(self.lib.msort_launch_count(self._h))
 
+    @property
+    def step_variant(self) -> str:
+        """Which instantiation of the step kernel the last step() launched (include/msort.h MSORT_STEP_*)."""
+        return ("none", "replay", "generic", "fast", "hot", "hot_persistent")[int(self.lib.msort_step_variant(self._h))]
+
     def set_flags(self, *, use_action_masking=None, check_overflow=None, auto_reset=None):
         f = int(self.cfg.flags)
         for val, bit in ((use_action_masking, _abi.F_ACTION_MASKING), (check_overflow, _abi.F_CHECK_OVERFLOW),

@@ -22,6 +22,7 @@ struct msort_handle {
   int sm_count;
   double* lut_dev;    // owned device constant (tiny, allocated at create): the kSortLut-entry float64 sorting-reward table
   bool policy_set;
+  int step_variant = MSORT_STEP_NONE;       // instantiation of the last step launch (msort_step_variant)
   float policy_host[MSORT_POLICY_WEIGHTS];  // host copy in the kernel's paired layout (pack_policy_pairs): travels to the step kernel as a kernel parameter
   int64_t launches;
 };
@@ -314,6 +315,7 @@ extern "C" int msort_num_actions(const msort_t* h) {
   return h->dev.kind == MSORT_ENV_SORT ? MSORT_NUM_ACTIONS_SORT : (h->dev.kind == MSORT_ENV_PRESS ? MSORT_NUM_ACTIONS_PRESS : MSORT_NUM_ACTIONS_MONO);
 }
 extern "C" int64_t msort_launch_count(const msort_t* h) { return h ? h->launches : 0; }
+extern "C" int msort_step_variant(const msort_t* h) { return h ? h->step_variant : MSORT_STEP_NONE; }
 
 extern "C" int msort_set_seed(msort_t* h, uint64_t seed) {
   if (!h) return fail(MSORT_E_INVALID, "msort_set_seed: NULL handle");
@@ -368,7 +370,7 @@ extern "C" int msort_step(msort_t* h, void* state, const int64_t* actions, float
   if (h->dev.kind == MSORT_ENV_PRESS && (h->dev.flags & MSORT_F_SORT_POLICY_MLP) && !h->policy_set &&
       !(replay && replay->sort_mode))
     return fail(MSORT_E_INVALID, "msort_step: embedded sort policy requested but msort_set_policy() was never called");
-  StepLaunch l{state, actions, obs, reward, terminated, mask, info, replay, h->policy_set ? h->policy_host : nullptr};
+  StepLaunch l{state, actions, obs, reward, terminated, mask, info, replay, &h->step_variant, h->policy_set ? h->policy_host : nullptr};
   MSORT_TRY_CUDA(launch_step(h->dev, l, h->cfg.rng_mode, (cudaStream_t)stream), "step kernel");
   h->launches += 1;
   return MSORT_OK;

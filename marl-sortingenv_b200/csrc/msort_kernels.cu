@@ -1129,13 +1129,16 @@ void pack_policy_pairs(const float* sb3, float* paired) {
 static inline unsigned tiles(long long n) { return (unsigned)((n + kTile - 1) / kTile); }
 
 template <int KIND>
-static cudaError_t launch_step_kind(const DevConfig& c, const StepArgs& a, const float* policy_host, int rng, cudaStream_t st) {
+static cudaError_t launch_step_kind(const DevConfig& c, const StepArgs& a, const float* policy_host, int rng, cudaStream_t st, int* variant) {
   const unsigned g = tiles(c.n);
+  int dummy;
+  int& var = variant ? *variant : dummy;
   PolicyParam<KIND> pw;
   if constexpr (KIND == MSORT_ENV_PRESS) {
     memset(pw.w, 0, sizeof(pw.w));
     if (policy_host) memcpy(pw.w, policy_host, MSORT_POLICY_WEIGHTS * sizeof(float));
   }
+  var = rng == MSORT_RNG_REPLAY ? MSORT_STEP_REPLAY : (c.fast ? MSORT_STEP_FAST : MSORT_STEP_GENERIC);
   if (rng == MSORT_RNG_REPLAY) step_kernel<KIND, MSORT_RNG_REPLAY, LAYOUT_REPLAY, false><<<g, kTile, 0, st>>>(c, a, pw);
   else if (c.layout == LAYOUT_COMPACT) {
     const unsigned want = MSORT_F_ACTION_MASKING | MSORT_F_AUTO_RESET, never = MSORT_F_CHECK_OVERFLOW;
@@ -1143,7 +1146,9 @@ static cudaError_t launch_step_kind(const DevConfig& c, const StepArgs& a, const
     if (hot) {
       auto kern = step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true>;
       unsigned gp = g;
-      if (MSORT_HOT_PERSIST && KIND == MSORT_ENV_PRESS) {   // persistent: exactly one wave of resident CTAs (asked from the occupancy calculator once)
+      var = MSORT_STEP_HOT;
+      if (MSORT_HOT_PERSIST && KIND == MSORT_ENV_PRESS) {
+        var = MSORT_STEP_HOT_PERSISTENT;   // persistent: exactly one wave of resident CTAs (asked from the occupancy calculator once)
         static int per_sm = 0;
         if (per_sm == 0) {
           cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1188,9 +1193,9 @@ cudaError_t launch_step(const DevConfig& c, const StepLaunch& l, int rng, cudaSt
   a.redis_len = r ? r->redis_len : 0; a.input_counts = r ? r->input_counts : nullptr;
   a.press_choice = r ? r->press_choice : nullptr; a.sort_mode_in = r ? r->sort_mode : nullptr;
   switch (c.kind) {
-    case MSORT_ENV_SORT: return launch_step_kind<MSORT_ENV_SORT>(c, a, l.policy_host, rng, st);
-    case MSORT_ENV_PRESS: return launch_step_kind<MSORT_ENV_PRESS>(c, a, l.policy_host, rng, st);
-    default: return launch_step_kind<MSORT_ENV_MONO>(c, a, l.policy_host, rng, st);
+    case MSORT_ENV_SORT: return launch_step_kind<MSORT_ENV_SORT>(c, a, l.policy_host, rng, st, l.variant);
+    case MSORT_ENV_PRESS: return launch_step_kind<MSORT_ENV_PRESS>(c, a, l.policy_host, rng, st, l.variant);
+    default: return launch_step_kind<MSORT_ENV_MONO>(c, a, l.policy_host, rng, st, l.variant);
   }
 }
 

@@ -19,6 +19,7 @@ struct StepLaunch {
   uint8_t* mask;
   const msort_info_out_t* info;
   const msort_replay_t* replay;
+  int* variant;              // out (nullable): MSORT_STEP_* of the instantiation launched
   const float* policy_host;  // Env_2 embedded policy (host copy in the paired layout, MSORT_POLICY_WEIGHTS floats) or nullptr
 };
 

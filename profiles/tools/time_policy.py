@@ -1,4 +1,5 @@
-import sys, torch, time
+import os, sys, torch, time
+if len(sys.argv) > 1: os.environ["MSORT_LIB"] = sys.argv[1]
 sys.path.insert(0, "/root/repo")
 import marl_sortingenv_b200 as ms
 from marl_sortingenv_b200.ppo import MaskablePPO, MaskableActorCritic, pack_actor_critic
@@ -10,6 +11,11 @@ packed = pack_actor_critic(pol)
 for t in range(20):
     a, lp, v = env.policy_act(packed, seed=1, t=t); env.step(a)
 torch.cuda.synchronize()
+with torch.no_grad():
+    a, lp, v = env.policy_act(packed, seed=1, t=99)
+    ref = torch.log_softmax(pol.masked_logits(env.obs, env.mask), dim=-1).gather(1, a[:, None]).squeeze(1)
+    print("max |logp - torch fp32|:", float((lp - ref).abs().max()), " max |value - torch fp32|:", float((v - pol.vf(env.obs).squeeze(1)).abs().max()),
+          " mean |dlogp|:", float((lp - ref).abs().mean()))
 def timeit(f, k=50):
     f(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -13,7 +13,7 @@ _KIND = {_abi.ENV_SORT: "sort", _abi.ENV_PRESS: "press", _abi.ENV_MONO: "mono"}
 
 
 class CudaBackend:
-    def __init__(self, cfg: _abi.MsortConfig, device="cuda:0", config=None, policy=None):
+    def __init__(self, cfg: _abi.MsortConfig, device="cuda:0", config=None, policy=None, info_level="full"):
         kind = _KIND[cfg.env_kind]
         f = int(cfg.flags)
         self.env = ENV_CLASSES[kind](
@@ -22,7 +22,7 @@ class CudaBackend:
             use_action_masking=bool(f & _abi.F_ACTION_MASKING), check_overflow=bool(f & _abi.F_CHECK_OVERFLOW),
             auto_reset=bool(f & _abi.F_AUTO_RESET),
             rng_mode="replay" if cfg.rng_mode == _abi.RNG_REPLAY else "philox",
-            global_env_offset=int(cfg.global_env_offset))
+            global_env_offset=int(cfg.global_env_offset), info_level=info_level)
         # the env is re-created from scalar arguments: make sure it digested the very same msort_config_t
         import copy
         want = copy.copy(cfg)
@@ -55,7 +55,8 @@ class CudaBackend:
         self.env.sync_check()
         assert not bool(trunc.any())
         out = {k: v.cpu().numpy().copy() for k, v in info.items()}
-        out["terminal_obs"] = out.pop("terminal_observation")
+        if "terminal_observation" in out:
+            out["terminal_obs"] = out.pop("terminal_observation")
         return (obs.cpu().numpy().copy(), rew.cpu().numpy().astype(np.float64), term.cpu().numpy().copy(),
                 self.env.action_masks().cpu().numpy().copy(), out)
 
