@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MSORT_ABI_VERSION 2
+#define MSORT_ABI_VERSION 3
 
 /* ------------------------------------------------------------------ enums */
 typedef enum msort_status {
@@ -243,6 +243,12 @@ int msort_set_policy(msort_t* h, const float* weights, int weights_on_device, vo
 
 /* ref: Env_X.get_obs() / action_masks() on the current state, no transition. */
 int msort_observe(msort_t* h, const void* state, float* obs, uint8_t* mask, void* stream);
+
+/* The observation the agents of Env_3_Monolith.step(mode='model') are shown (env_monolith.py:114-115,
+ * 186-221: get_sort_obs / get_press_obs are read after update_environment has moved input -> belt ->
+ * sorting and before anything else of the step): same as msort_observe on that shifted plant.  The mask
+ * is the current one (container levels and press timers do not change in the shift).  No transition. */
+int msort_observe_after_shift(msort_t* h, const void* state, float* obs, uint8_t* mask, void* stream);
 
 /* Masked-random action source: actions[i] = uniform choice among the valid entries of
  * mask[i, :] (all-zero row -> 0), Philox-keyed by (seed, t, global env id).

@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 POLICY_ACT_WEIGHTS = 4256
 
 ENV_SORT, ENV_PRESS, ENV_MONO = 1, 2, 3
@@ -144,6 +144,7 @@ SYMBOLS = {
     "msort_sample_actions": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint32, _P]),
     "msort_rule_based_actions": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "msort_observe": (C.c_int, [_P, _P, _P, _P, _P]),
+    "msort_observe_after_shift": (C.c_int, [_P, _P, _P, _P, _P]),
     "msort_policy_act": (C.c_int, [_P, _P, _P, _P, C.c_uint64, C.c_uint32, C.c_int, _P, _P, _P, _P]),
     "msort_export_state": (C.c_int, [_P, _P, _P, _P]),
     "msort_gather_state": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),

@@ -321,6 +321,20 @@ class BatchedEnv:
         _abi.check(self.lib, rc, "msort_observe")
         return self.obs
 
+    def observe_after_shift(self, out: torch.Tensor | None = None) -> torch.Tensor:
+        """The observation the agents of `Env_3_Monolith.step(mode='model')` are shown (env_monolith.py:114-115,
+        186-221): the plant after update_environment has moved input -> belt -> sorting, before anything else
+        of the coming step.  Returns a float32 [N, D] tensor of its own (`out` or a cached buffer); `env.obs`
+        and the state are untouched."""
+        if out is None:
+            if getattr(self, "_obs_shift", None) is None:
+                self._obs_shift = torch.empty((self.num_envs, self.D), dtype=torch.float32, device=self.device)
+            out = self._obs_shift
+        with torch.cuda.device(self.device):
+            rc = self.lib.msort_observe_after_shift(self._h, _ptr(self.state), _ptr(out), None, self._stream())
+        _abi.check(self.lib, rc, "msort_observe_after_shift")
+        return out
+
     # ------------------------------------------------------------------ embedded sort agent (Env_2)
     def set_agents(self, sort_agent=None, **_):
         """ref: Env_2_Pressing.set_agents(sort_agent) (env_2_press.py:39-40).  Accepts a flat

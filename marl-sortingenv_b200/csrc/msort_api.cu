@@ -393,13 +393,21 @@ extern "C" int msort_set_policy(msort_t* h, const float* weights, int weights_on
   return MSORT_OK;
 }
 
-extern "C" int msort_observe(msort_t* h, const void* state, float* obs, uint8_t* mask, void* stream) {
-  if (!h || !state) return fail(MSORT_E_INVALID, "msort_observe: NULL handle/state");
+static int observe_impl(msort_t* h, const void* state, float* obs, uint8_t* mask, int after_shift, void* stream, const char* who) {
+  if (!h || !state) return fail(MSORT_E_INVALID, "%s: NULL handle/state", who);
   if (!aligned(state, 16) || (obs && !aligned(obs, 4)) || (mask && !aligned(mask, 4)))
-    return fail(MSORT_E_INVALID, "msort_observe: misaligned buffer");
-  MSORT_TRY_CUDA(launch_observe(h->dev, state, obs, mask, (cudaStream_t)stream), "observe kernel");
+    return fail(MSORT_E_INVALID, "%s: misaligned buffer", who);
+  MSORT_TRY_CUDA(launch_observe(h->dev, state, obs, mask, after_shift, (cudaStream_t)stream), "observe kernel");
   h->launches += 1;
   return MSORT_OK;
+}
+
+extern "C" int msort_observe(msort_t* h, const void* state, float* obs, uint8_t* mask, void* stream) {
+  return observe_impl(h, state, obs, mask, 0, stream, "msort_observe");
+}
+
+extern "C" int msort_observe_after_shift(msort_t* h, const void* state, float* obs, uint8_t* mask, void* stream) {
+  return observe_impl(h, state, obs, mask, 1, stream, "msort_observe_after_shift");
 }
 
 extern "C" int msort_sample_actions(msort_t* h, const uint8_t* mask, int64_t* actions, uint64_t seed, uint32_t t,

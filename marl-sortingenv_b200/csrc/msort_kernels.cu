@@ -909,7 +909,7 @@ reset_kernel(const __grid_constant__ DevConfig c, uint4* __restrict__ state, con
 template <int KIND>
 __global__ void __launch_bounds__(kTile)
 observe_kernel(const __grid_constant__ DevConfig c, const uint4* __restrict__ state, float* __restrict__ obs,
-               uint8_t* __restrict__ mask) {
+               uint8_t* __restrict__ mask, int after_shift) {
   constexpr int D = Dims<KIND>::D, A = Dims<KIND>::A;
   __shared__ __align__(16) float s_obs[kTile * D];
   __shared__ __align__(16) uint8_t s_mask[kTile * A];
@@ -919,6 +919,9 @@ observe_kernel(const __grid_constant__ DevConfig c, const uint4* __restrict__ st
   if (i < c.n) {
     Env s;
     load_env(c, state, i, s);
+    // what the agents of Env_3.step(mode='model') see (env_monolith.py:114-115,186-221): the plant after
+    // update_environment has moved input -> belt -> sorting, before anything else of the step happened
+    if (after_shift) { s.sort4 = s.belt4; s.belt4 = s.in4; }
     env_obs<KIND>(c, s, &s_obs[threadIdx.x * D]);
     put_mask_row<A>(s_mask, threadIdx.x, press_mask_bits(c, s));
   }
@@ -1209,11 +1212,11 @@ cudaError_t launch_reset(const DevConfig& c, void* state, const uint8_t* which, 
   return cudaGetLastError();
 }
 
-cudaError_t launch_observe(const DevConfig& c, const void* state, float* obs, uint8_t* mask, cudaStream_t st) {
+cudaError_t launch_observe(const DevConfig& c, const void* state, float* obs, uint8_t* mask, int after_shift, cudaStream_t st) {
   switch (c.kind) {
-    case MSORT_ENV_SORT: observe_kernel<MSORT_ENV_SORT><<<tiles(c.n), kTile, 0, st>>>(c, (const uint4*)state, obs, mask); break;
-    case MSORT_ENV_PRESS: observe_kernel<MSORT_ENV_PRESS><<<tiles(c.n), kTile, 0, st>>>(c, (const uint4*)state, obs, mask); break;
-    default: observe_kernel<MSORT_ENV_MONO><<<tiles(c.n), kTile, 0, st>>>(c, (const uint4*)state, obs, mask); break;
+    case MSORT_ENV_SORT: observe_kernel<MSORT_ENV_SORT><<<tiles(c.n), kTile, 0, st>>>(c, (const uint4*)state, obs, mask, after_shift); break;
+    case MSORT_ENV_PRESS: observe_kernel<MSORT_ENV_PRESS><<<tiles(c.n), kTile, 0, st>>>(c, (const uint4*)state, obs, mask, after_shift); break;
+    default: observe_kernel<MSORT_ENV_MONO><<<tiles(c.n), kTile, 0, st>>>(c, (const uint4*)state, obs, mask, after_shift); break;
   }
   return cudaGetLastError();
 }

@@ -27,7 +27,7 @@ void pack_policy_pairs(const float* sb3, float* paired);   // SB3 weight order -
 cudaError_t launch_step(const DevConfig& c, const StepLaunch& l, int rng, cudaStream_t st);
 cudaError_t launch_reset(const DevConfig& c, void* state, const uint8_t* which, const uint8_t* first_pattern,
                          float* obs, uint8_t* mask, uint32_t reset_flags, cudaStream_t st);
-cudaError_t launch_observe(const DevConfig& c, const void* state, float* obs, uint8_t* mask, cudaStream_t st);
+cudaError_t launch_observe(const DevConfig& c, const void* state, float* obs, uint8_t* mask, int after_shift, cudaStream_t st);
 cudaError_t launch_sample(const DevConfig& c, const uint8_t* mask, int64_t* actions, uint64_t seed, uint32_t t,
                           cudaStream_t st);
 cudaError_t launch_rule_actions(const DevConfig& c, const void* state, int after_shift, int64_t* actions, cudaStream_t st);

@@ -20,7 +20,8 @@ SHAPES = [(32, 13), (32,), (32, 32), (32,), (2, 32), (2,)]
 
 def flatten_sort_policy(agent) -> torch.Tensor:
     """Accepts: flat array/tensor of 1570 floats; a state_dict with SB3's key names; an object
-    with `.policy.state_dict()` (an SB3 PPO model) or `.state_dict()` (an SB3 policy)."""
+    with `.policy.state_dict()` (an SB3 PPO model) or `.state_dict()` (an SB3 policy); this package's MaskablePPO / MaskableActorCritic
+    trained on BatchedSortingEnv (its policy tower)."""
     if isinstance(agent, (np.ndarray, list, tuple)):
         agent = torch.as_tensor(np.asarray(agent, dtype=np.float32))
     if isinstance(agent, torch.Tensor):
@@ -29,6 +30,10 @@ def flatten_sort_policy(agent) -> torch.Tensor:
             raise ValueError(f"sort policy needs {POLICY_WEIGHTS} weights, got {w.numel()}")
         return w
     sd = agent
+    pol = getattr(agent, "policy", agent)
+    if hasattr(pol, "pi") and hasattr(pol, "vf") and not isinstance(agent, dict):   # this package's MaskablePPO / MaskableActorCritic
+        from .ppo import sort_policy_weights
+        return flatten_sort_policy(sort_policy_weights(pol))
     if not isinstance(sd, dict):
         if hasattr(agent, "policy") and hasattr(agent.policy, "state_dict"):
             sd = agent.policy.state_dict()

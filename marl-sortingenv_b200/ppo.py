@@ -197,6 +197,40 @@ class MaskablePPO:
 
 
 @torch.no_grad()
+def modular_actions(env, sort_agent=None, press_agent=None, use_action_masking: bool = True, seed: int = 0, t: int = 0):
+    """Batched action source of `Env_3_Monolith.step(mode='model')` (env_monolith.py:186-221): the sort agent
+    picks the sensor mode from the sorting part of the observation, the press agent the press action from the
+    pressing part (under the press mask when masking is on), both shown the plant AFTER update_environment's
+    shift (env_monolith.py:114-115) and both deterministic; a missing agent falls back to a uniform draw — over
+    the valid press actions when masking is on (:213-219).  action = 11 * sort_mode + press_action.
+    `sort_agent` / `press_agent`: objects with SB3's `predict(obs, deterministic=True[, action_masks=])` that
+    accept batched CUDA tensors (this module's MaskablePPO), or None."""
+    n, dev = env.num_envs, env.device
+    obs = env.observe_after_shift()
+    g = torch.Generator(device=dev).manual_seed(int(seed) * 1_000_003 + int(t))
+    if sort_agent is not None:
+        mode, _ = sort_agent.predict(obs[:, :13], deterministic=True)
+    else:
+        mode = torch.randint(0, 2, (n,), device=dev, generator=g)
+    pmask = env.action_masks()[:, :11]
+    if press_agent is not None:
+        press, _ = press_agent.predict(obs[:, 13:], deterministic=True, action_masks=pmask if use_action_masking else None)
+    elif use_action_masking:
+        press = torch.multinomial(pmask.float(), 1, generator=g).squeeze(1)
+    else:
+        press = torch.randint(0, 11, (n,), device=dev, generator=g)
+    return mode.to(torch.int64) * 11 + press.to(torch.int64)
+
+
+def sort_policy_weights(model) -> torch.Tensor:
+    """The policy tower of a sort agent trained here (MaskablePPO on BatchedSortingEnv) as the flat 1570-float
+    vector Env_2's embedded policy takes (`BatchedPressingEnv.set_agents(sort_agent=...)`, env_2_press.py:39-40)."""
+    pi = model.policy.pi if hasattr(model, "policy") else model.pi
+    return torch.cat([pi[0].weight.reshape(-1), pi[0].bias, pi[2].weight.reshape(-1), pi[2].bias,
+                      pi[4].weight.reshape(-1), pi[4].bias]).detach().float().cpu()
+
+
+@torch.no_grad()
 def evaluate_policy(model, env_cls, n_envs: int = 1024, steps: int = 200, seed: int = 1, **env_kwargs):
     """Mean / std of the cumulative reward of the deterministic masked policy over `n_envs` fresh episodes
     (the reference's protocol: 200 steps, noise 0 — main.py:42-52, benchmark_models.py:126-171)."""

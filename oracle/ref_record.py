@@ -132,6 +132,43 @@ def _press_log_to_discrete(entry) -> int:
     return (p - 1) * 5 + int(m) + 1
 
 
+class SortStubAgent:
+    """Deterministic stand-in for a trained sort agent in Env_3.step(mode='model') (env_monolith.py:189-193):
+    remembers the observation the reference hands it and answers with a fixed rule on it (belt share of
+    A+C against B+D, observation entries 1..4)."""
+
+    def __init__(self):
+        self.seen = None
+
+    def predict(self, obs, deterministic=True, **_):
+        x = np.asarray(obs, dtype=np.float32)
+        self.seen = x.copy()
+        return (0 if float(x[1]) + float(x[3]) > float(x[2]) + float(x[4]) else 1), None
+
+
+class MaskablePressStubAgent:
+    """Deterministic stand-in for a MaskablePPO press agent (the reference passes `action_masks` when the
+    type name contains 'Maskable' and the object has `.policy`, env_monolith.py:199-206): the valid press
+    action whose container is fullest by the observation (entries 0..4; ties -> lowest action), no-op when
+    only the no-op is valid."""
+    policy = object()
+
+    def __init__(self):
+        self.seen = None
+        self.seen_mask = None
+
+    def predict(self, obs, deterministic=True, action_masks=None, **_):
+        x = np.asarray(obs, dtype=np.float32)
+        self.seen = x.copy()
+        m = np.ones(11, dtype=bool) if action_masks is None else np.asarray(action_masks, dtype=bool)
+        self.seen_mask = m.copy()
+        best, best_level = 0, -1.0
+        for a in range(1, 11):
+            if m[a] and float(x[(a - 1) % 5]) > best_level:
+                best, best_level = a, float(x[(a - 1) % 5])
+        return best, None
+
+
 def record(kind: str, *, seed: int, steps: int, max_steps: int = 50, noise: float = 0.05,
            balesize: int = 200, policy="masked_random", action_seed: int = 0,
            use_action_masking: bool = True, check_overflow: bool = False,
@@ -145,6 +182,10 @@ def record(kind: str, *, seed: int, steps: int, max_steps: int = 50, noise: floa
     if kind == "press" and mlp_weights is not None:
         agent = NumpyMlpSortAgent(mlp_weights)
         env.set_agents(sort_agent=agent)
+    stubs = None
+    if policy == "mode_model":          # Env_3.step(action=None, mode='model') with both agents assigned
+        stubs = (SortStubAgent(), MaskablePressStubAgent())
+        env.set_agents(sort_agent=stubs[0], press_agent=stubs[1])
     obs0, _ = env.reset(seed=seed)
     env.rng = _CountingRng(env.rng)
     twin_noise = np.random.default_rng(seed + 4)
@@ -154,7 +195,7 @@ def record(kind: str, *, seed: int, steps: int, max_steps: int = 50, noise: floa
     out = {k: [] for k in ("action", "noise_u", "n_draws", "input_counts", "press_choice",
                            "sort_mode", "obs", "reward", "terminated", "overflow",
                            "overflow_material", "mask", "state", "acc_belt", "reset_before",
-                           "first_pattern", "mlp_margin")}
+                           "first_pattern", "mlp_margin", "agent_obs")}
     first_pattern0 = int(env.input_generator.pattern_sequence[0])
     reset_next = False
     for t in range(steps):
@@ -179,15 +220,17 @@ def record(kind: str, *, seed: int, steps: int, max_steps: int = 50, noise: floa
         elif policy == "second_valid":      # Appendix C, Env_3 row
             v = np.flatnonzero(mask)
             a = int(v[1]) if v.size > 1 else 0
-        elif policy == "mode_rule_based":   # Env_3.step(action=None, mode='rule_based'): chosen inside step()
+        elif policy in ("mode_rule_based", "mode_model"):   # Env_3.step(action=None, mode=...): chosen inside step()
             a = None
         else:
             raise ValueError(policy)
         n_before = env.rng.n_choice
         kw = dict(use_action_masking=use_action_masking, check_overflow=check_overflow)
         if a is None:
-            obs, reward, term, trunc, info = env.step(None, mode="rule_based", **kw)
+            obs, reward, term, trunc, info = env.step(None, mode="model" if stubs else "rule_based", **kw)
             a = int(info["action"])
+            if stubs:                   # what the two agents were shown inside step(): sort obs (13) | press obs (16)
+                out["agent_obs"].append(np.concatenate([stubs[0].seen, stubs[1].seen]))
         else:
             obs, reward, term, trunc, info = env.step(a, **kw)
         assert trunc is False
@@ -239,6 +282,8 @@ def record(kind: str, *, seed: int, steps: int, max_steps: int = 50, noise: floa
         "first_pattern": np.asarray(out["first_pattern"], dtype=np.int64),
         "mlp_margin": np.asarray(out["mlp_margin"], dtype=np.float64),
     }
+    if stubs:
+        res["agent_obs"] = np.asarray(out["agent_obs"], dtype=np.float32).reshape(steps, D)
     if keep_env:
         res["env"] = env          # the reference env itself (its Python logs; tests/golden/make_log_golden.py)
     return res

@@ -182,3 +182,38 @@ def golden_group(name):
             batch[kk] = v.astype(wide[kk]) if kk in wide else v
     batch["T"] = meta["steps"]
     return meta, batch
+
+
+# ---------------------------------------------------------------- Env_3 mode='model' fixture and stand-in agents
+def model_mode_golden():
+    """tests/golden/reference_model_mode.npz (tests/golden/make_model_mode_golden.py): the reference's
+    Env_3.step(mode='model') with deterministic stand-in agents -> (meta, batch [T,R,...])."""
+    d = np.load(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden", "reference_model_mode.npz"),
+                allow_pickle=False)
+    meta = _json.loads(str(d["model_mono/meta"]))
+    batch = {k[len("model_mono/"):]: np.asarray(d[k]) for k in d.files if k.startswith("model_mono/") and not k.endswith("/meta")}
+    for k in ("action", "input_counts", "sort_mode", "state", "n_draws"):
+        batch[k] = batch[k].astype(np.int64)
+    batch["T"] = meta["steps"]
+    return meta, batch
+
+
+class TorchSortStub:
+    """Batched twin of oracle/ref_record.py SortStubAgent (same rule, torch tensors)."""
+
+    def predict(self, obs, deterministic=True, **_):
+        import torch
+        return torch.where(obs[:, 1] + obs[:, 3] > obs[:, 2] + obs[:, 4], 0, 1), None
+
+
+class TorchPressStub:
+    """Batched twin of oracle/ref_record.py MaskablePressStubAgent."""
+
+    def predict(self, obs, deterministic=True, action_masks=None, **_):
+        import torch
+        n = obs.shape[0]
+        m = torch.ones((n, 11), dtype=torch.bool, device=obs.device) if action_masks is None else action_masks
+        level = obs[:, :5].repeat(1, 2)                                   # level of action a's container, a = 1..10
+        score = torch.where(m[:, 1:], level, torch.full_like(level, -1.0))
+        best = score.argmax(dim=1) + 1                                    # first maximum = lowest action on ties
+        return torch.where(m[:, 1:].any(dim=1), best, torch.zeros_like(best)), None

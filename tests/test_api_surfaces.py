@@ -170,6 +170,31 @@ def test_device_rule_based_actions_match_reference_choices():
                  input_counts=pack_counts(batch["input_counts"][t]))
 
 
+def test_device_modular_action_source_matches_reference_mode_model():
+    """Env_3.step(mode='model') (env_monolith.py:186-221) on the device: the observation the two agents are
+    shown (msort_observe_after_shift) equals what the reference handed its agents, and modular_actions()
+    composes the reference's own action from the same agents' answers — on every recorded step."""
+    import torch
+    from cuda_backend import CudaBackend
+    from marl_sortingenv_b200.ppo import modular_actions
+    from parity_util import TorchPressStub, TorchSortStub, assert_float_close, config_for, model_mode_golden, pack_counts
+    meta, batch = model_mode_golden()
+    n = batch["action"].shape[1]
+    gpu = CudaBackend(config_for(meta, n))
+    gpu.reset(first_pattern=batch["first_pattern0"])
+    before = gpu.env.obs.clone()
+    for t in range(meta["steps"]):
+        seen = gpu.env.observe_after_shift()
+        assert_float_close(seen.cpu().numpy(), batch["agent_obs"][t], f"step {t}: agents' observation")
+        a = modular_actions(gpu.env, TorchSortStub(), TorchPressStub(), use_action_masking=True)
+        assert np.array_equal(a.cpu().numpy(), batch["action"][t]), f"step {t}"
+        assert torch.equal(gpu.env.obs, before)                           # no transition, env.obs untouched
+        gpu.step(batch["action"][t], noise_u=batch["noise_u"][t], redis_u=batch["redis_u"],
+                 input_counts=pack_counts(batch["input_counts"][t]))
+        before = gpu.env.obs.clone()
+    assert len(np.unique(batch["action"])) > 10                           # both sort modes and most press actions occur
+
+
 def test_published_rule_based_return_batched_on_device():
     """4096 device envs under the device rule-based policy: 44.03 +- 1.10 published (benchmark_plot_summary.py:14)."""
     import torch
