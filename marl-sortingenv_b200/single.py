@@ -259,14 +259,9 @@ class Env_3_Monolith(_SingleEnv):
 
     def _obs_after_shift(self):
         """Observation as the reference's agents see it inside step(): after update_environment has
-        shifted input -> belt -> sorting (env_monolith.py:114-115), before anything else changed."""
-        obs = self.get_obs()
-        inp, belt = self.current_material_input, self.current_material_belt
-        tot = sum(inp)
-        obs[0] = min(tot / 100.0, 1.0)
-        obs[1:5] = [x / tot if tot > 0 else 0.0 for x in inp]
-        obs[23:27] = [min(x / float(self._b.cfg.stage_capacity), 1.0) for x in belt]
-        return obs
+        shifted input -> belt -> sorting (env_monolith.py:114-115), before anything else changed
+        (msort_observe_after_shift)."""
+        return self._b.observe_after_shift()[0].cpu().numpy()
 
     def _choose_action(self, mode, use_action_masking):
         if self.mono_agent is not None:                                   # :144-150
@@ -288,9 +283,11 @@ class Env_3_Monolith(_SingleEnv):
                 sort_mode = int(np.random.randint(0, 2))
             mask = self.action_masks()[:11]
             if self.press_agent is not None:
-                try:
+                # masks go to the agent only with masking on and a MaskablePPO-like agent (env_monolith.py:199-210)
+                maskable = hasattr(self.press_agent, "policy") and "Maskable" in str(type(self.press_agent))
+                if use_action_masking and maskable:
                     pa, _ = self.press_agent.predict(obs[13:], deterministic=True, action_masks=mask)
-                except TypeError:
+                else:
                     pa, _ = self.press_agent.predict(obs[13:], deterministic=True)
                 press = int(pa)
             else:

@@ -195,6 +195,31 @@ def test_device_modular_action_source_matches_reference_mode_model():
     assert len(np.unique(batch["action"])) > 10                           # both sort modes and most press actions occur
 
 
+def test_single_env_mode_model_uses_the_agents_like_the_reference():
+    """Env_3_Monolith.step(mode='model') of the single-env class with the stand-in agents the fixture was recorded
+    with: each agent is shown its part of the shifted observation, the press agent gets the 11-entry press mask
+    only when masking is on, and the action is 11 * sort_mode + press_action (env_monolith.py:186-221)."""
+    from marl_sortingenv_b200 import Env_3_Monolith
+    from oracle.ref_record import MaskablePressStubAgent, SortStubAgent
+    env = Env_3_Monolith(max_steps=60, seed=9, noise_sorting=0.05)
+    sort_agent, press_agent = SortStubAgent(), MaskablePressStubAgent()
+    env.set_agents(sort_agent=sort_agent, press_agent=press_agent)
+    env.reset(seed=9)
+    pressed = 0
+    for t in range(60):
+        masking = t % 3 != 0
+        want_obs = env._b.observe_after_shift()[0].cpu().numpy()
+        mask = np.asarray(env.action_masks())[:11].copy()
+        _, _, term, _, info = env.step(None, mode="model", use_action_masking=masking)
+        assert np.array_equal(sort_agent.seen, want_obs[:13]) and np.array_equal(press_agent.seen, want_obs[13:])
+        assert np.array_equal(press_agent.seen_mask, mask if masking else np.ones(11, dtype=bool))
+        sm = 0 if want_obs[1] + want_obs[3] > want_obs[2] + want_obs[4] else 1
+        pa, _ = MaskablePressStubAgent().predict(want_obs[13:], action_masks=mask if masking else None)
+        assert int(info["action"]) == 11 * sm + pa
+        pressed += int(pa != 0)
+    assert term and pressed > 3
+
+
 def test_published_rule_based_return_batched_on_device():
     """4096 device envs under the device rule-based policy: 44.03 +- 1.10 published (benchmark_plot_summary.py:14)."""
     import torch
