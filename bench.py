@@ -159,7 +159,7 @@ def run_reference(args):
                  "(measured in the build container under a SubprocVecEnv-style pool: 18.9e3 env-steps/s on 8 cores, "
                  "profiles/cpu_reference_subproc_r01.json)"),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world):
@@ -172,6 +172,26 @@ def workload_config(args, world):
             "l2": "inputs larger than L2 (no flush needed)", "parallelism": f"env-sharded x{world}",
             "launch": "eager" if args.no_graph else "one CUDA graph of the K step kernels",
             "stats_allreduce": "once per K-step rollout (NCCL, 128 B)"}
+
+
+# ----------------------------------------------------------------------------- the one JSON line
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Native libraries print banners on fd 1 (NCCL's "NCCL version ..." at communicator creation): point fd 1
+    at stderr for the rest of the process and keep the real stdout for the ONE JSON line the driver parses."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 # ----------------------------------------------------------------------------- CUDA arm
@@ -187,6 +207,7 @@ def run_msort(args):
         os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                                    f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                                    "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:])
+    claim_stdout()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -349,7 +370,7 @@ def run_msort(args):
     if not args.no_cpu_baseline:
         v, cores, sample, _, _ = cpu_rollout(args.kind, budget_s=15.0)
         line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -232,7 +232,9 @@ int msort_set_seed(msort_t* h, uint64_t seed);
  * env_2_press.py:88-165, env_monolith.py:109-284) followed by Env_X.action_masks()
  * (env_super.py:869-898) on the new state.  One fused kernel launch.
  *  actions    : i64[N]    obs : f32[N,D]   reward : f32[N]   terminated : u8[N]
- *  mask       : u8[N,A] (nullable)   info / replay : nullable */
+ *  mask       : u8[N,A] (nullable)   info / replay : nullable
+ * state, obs and mask must be 16-byte aligned (whole tiles of 128 envs leave as 16-byte vectors / TMA bulk
+ * copies), actions 8-byte (16-byte lets Env_2's persistent kernel fetch them by TMA), reward 4-byte. */
 int msort_step(msort_t* h, void* state, const int64_t* actions, float* obs, float* reward,
                uint8_t* terminated, uint8_t* mask, const msort_info_out_t* info,
                const msort_replay_t* replay, void* stream);

@@ -338,7 +338,8 @@ extern "C" int msort_reset(msort_t* h, void* state, const uint8_t* which, const 
                            uint8_t* mask, uint32_t reset_flags, void* stream) {
   if (!h || !state) return fail(MSORT_E_INVALID, "msort_reset: NULL handle/state");
   if (!aligned(state, 16)) return fail(MSORT_E_INVALID, "msort_reset: state must be 16-byte aligned");
-  if (obs && !aligned(obs, 4)) return fail(MSORT_E_INVALID, "msort_reset: obs misaligned");
+  if ((obs && !aligned(obs, 16)) || (mask && !aligned(mask, 16)))
+    return fail(MSORT_E_INVALID, "msort_reset: obs / mask must be 16-byte aligned (tiles leave as 16-byte vectors)");
   MSORT_TRY_CUDA(launch_reset(h->dev, state, which, first_pattern, obs, mask, reset_flags, (cudaStream_t)stream), "reset kernel");
   h->launches += 1;
   return MSORT_OK;
@@ -350,8 +351,9 @@ extern "C" int msort_step(msort_t* h, void* state, const int64_t* actions, float
     return fail(MSORT_E_INVALID, "msort_step: NULL required argument");
   if (!aligned(state, 16)) return fail(MSORT_E_INVALID, "msort_step: state must be 16-byte aligned");
   if (!aligned(actions, 8)) return fail(MSORT_E_INVALID, "msort_step: actions must be int64-aligned");
-  if (!aligned(obs, 4) || !aligned(reward, 4)) return fail(MSORT_E_INVALID, "msort_step: obs/reward must be float-aligned");
-  if (mask && !aligned(mask, 4)) return fail(MSORT_E_INVALID, "msort_step: mask must be 4-byte aligned");
+  if (!aligned(obs, 16)) return fail(MSORT_E_INVALID, "msort_step: obs must be 16-byte aligned (tiles leave by TMA bulk copies)");
+  if (!aligned(reward, 4)) return fail(MSORT_E_INVALID, "msort_step: reward must be float-aligned");
+  if (mask && !aligned(mask, 16)) return fail(MSORT_E_INVALID, "msort_step: mask must be 16-byte aligned (tiles leave by TMA bulk copies)");
   if (info && info->struct_size != sizeof(msort_info_out_t)) return fail(MSORT_E_INVALID, "msort_step: bad info struct_size");
   if (info && info->stats && !aligned(info->stats, 8)) return fail(MSORT_E_INVALID, "msort_step: stats misaligned");
   if (h->cfg.rng_mode == MSORT_RNG_REPLAY) {
@@ -395,8 +397,8 @@ extern "C" int msort_set_policy(msort_t* h, const float* weights, int weights_on
 
 static int observe_impl(msort_t* h, const void* state, float* obs, uint8_t* mask, int after_shift, void* stream, const char* who) {
   if (!h || !state) return fail(MSORT_E_INVALID, "%s: NULL handle/state", who);
-  if (!aligned(state, 16) || (obs && !aligned(obs, 4)) || (mask && !aligned(mask, 4)))
-    return fail(MSORT_E_INVALID, "%s: misaligned buffer", who);
+  if (!aligned(state, 16) || (obs && !aligned(obs, 16)) || (mask && !aligned(mask, 16)))
+    return fail(MSORT_E_INVALID, "%s: state / obs / mask must be 16-byte aligned", who);
   MSORT_TRY_CUDA(launch_observe(h->dev, state, obs, mask, after_shift, (cudaStream_t)stream), "observe kernel");
   h->launches += 1;
   return MSORT_OK;

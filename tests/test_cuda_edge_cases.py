@@ -128,6 +128,12 @@ def test_argument_errors_are_reported_not_crashed():
     rc = lib.msort_step(h, C.c_void_p(env.state.data_ptr() + 4), p(a), p(env.obs), p(env.reward), p(env.terminated),
                         p(env.mask), None, None, None)
     assert rc == _abi.E_INVALID and b"aligned" in lib.msort_last_error()
+    rc = lib.msort_step(h, p(env.state), p(a), C.c_void_p(env.obs.data_ptr() + 4), p(env.reward), p(env.terminated),
+                        p(env.mask), None, None, None)
+    assert rc == _abi.E_INVALID and b"16-byte" in lib.msort_last_error()       # obs tiles leave by TMA bulk copies
+    rc = lib.msort_step(h, p(env.state), p(a), p(env.obs), p(env.reward), p(env.terminated),
+                        C.c_void_p(env.mask.data_ptr() + 4), None, None, None)
+    assert rc == _abi.E_INVALID and b"16-byte" in lib.msort_last_error()
     rp = _abi.MsortReplay(); rp.struct_size = C.sizeof(rp)
     rc = lib.msort_step(h, p(env.state), p(a), p(env.obs), p(env.reward), p(env.terminated), p(env.mask), None,
                         C.byref(rp), None)
@@ -180,3 +186,27 @@ def test_step_writes_into_caller_buffers():
     assert torch.equal(e1.state, e2.state)
     with pytest.raises(ValueError):
         e2.step(a, out_obs=torch.zeros((n, e2.D + 1), device="cuda"))
+
+
+def test_persistent_env2_kernel_with_unaligned_actions_and_kernel_variants():
+    """Env_2's persistent HOT kernel fetches a tile's actions by TMA only when the action tensor is 16-byte
+    aligned; an 8-byte-aligned view takes the plain-load path.  Both, and the FAST kernel that runs when a
+    per-step info array is requested, must leave the same state behind.  More tiles than resident CTAs, ragged."""
+    import torch
+    from marl_sortingenv_b200 import BatchedPressingEnv
+    from marl_sortingenv_b200.policy import sb3_style_init
+    n = 128 * 148 * 6 + 77
+    envs = [BatchedPressingEnv(n, max_steps=20, seed=21, info_level=lvl) for lvl in ("episode", "episode", "full")]
+    for e in envs:
+        e.set_sort_policy(sb3_style_init(4, action_gain=1.0))
+        e.reset()
+    buf = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
+    for t in range(45):
+        a = envs[0].sample_actions(seed=2, t=t)
+        buf[1:].copy_(a)
+        assert buf[1:].data_ptr() % 16 == 8
+        envs[0].step(a); envs[1].step(buf[1:]); envs[2].step(a)
+    assert envs[0].step_variant == "hot_persistent" and envs[1].step_variant == "hot_persistent" and envs[2].step_variant == "fast"
+    assert torch.equal(envs[0].state, envs[1].state) and torch.equal(envs[0].state, envs[2].state)
+    assert torch.equal(envs[0].obs, envs[1].obs) and torch.equal(envs[0].obs, envs[2].obs)
+    assert torch.equal(envs[0].mask, envs[2].mask) and torch.equal(envs[0].reward, envs[1].reward)
