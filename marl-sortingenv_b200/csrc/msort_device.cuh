@@ -366,15 +366,17 @@ static __device__ __noinline__ int purity_k_f64(int tr, int tot) {
 // On an exact tie 100*tr/tot = k0 + 1/2 the quotient tr/tot equals (2*k0+1)/200 whatever tr and tot
 // are, so fl(tr/tot), fl(.*100) and the final rint depend on k0 alone: the host evaluates the
 // float64 pipeline once per k0 = 0..99 and hands the outcomes over as the bit table c.tie_up.
-template <bool SMALL = false>   // SMALL: the caller knows c.small_lv holds (compile-time copy of the flag)
+// SMALL: the caller knows c.small_lv holds (compile-time copy of the flag).  LARGE16: the caller knows it does
+// NOT hold but tot < 2^16 (compact layout): the correction step is taken without asking.
+template <bool SMALL = false, bool LARGE16 = false>
 __device__ __forceinline__ int purity_k(const DevConfig& c, int tr, int tot) {  // tot > 0, 0 <= tr <= tot
-  if (SMALL || tot < (1 << 17)) {              // 100*tr and tot are exact in float32
+  if (SMALL || LARGE16 || tot < (1 << 17)) {   // 100*tr and tot are exact in float32
     const int a2 = 200 * tr, t2 = 2 * tot;
     int k = __float2int_rn(__fdividef((float)(100 * tr), (float)tot));  // within 1 of the exact rounding
     int d = a2 - k * t2;                       // exact: twice the signed distance to k, in units of 1/tot
     // __fdividef is within 2 ulp (2.4e-5 at a quotient of 100) while a non-tie sits at least 1/(2*tot)
     // from a rounding boundary: for tot <= 8192 (c.small_lv) k is already the exact rounding
-    if (!SMALL && !c.small_lv) {
+    if (!SMALL && (LARGE16 || !c.small_lv)) {
       if (d > tot) { k += 1; d -= t2; } else if (d < -tot) { k -= 1; d += t2; }
     }
     if (abs(d) == tot) {                       // .5 tie: k0 = floor of the exact value (0..99), outcome from the table
@@ -530,46 +532,69 @@ __device__ __forceinline__ float tanh_fast(float x) {
 // uniform-register operand straight from the constant bank (LDCU.128 feeds two FFMA2), its input the scalar
 // register broadcast to both halves.  Every neuron still sums bias + w_0 x_0 + w_1 x_1 + ... in the same
 // order with the same roundings as the scalar loop, so the logits are bit-identical to it.
-__device__ __forceinline__ unsigned long long f2pack(float lo, float hi) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
+// acc + w * (x, x) on both halves; one asm statement per FFMA2 (the pair (x, x) is folded into the instruction's
+// scalar-broadcast operand form by ptxas).  Inline PTX rather than the `__ffma2_rn` builtin on purpose: with the
+// builtin the compiler interleaves all sixteen accumulator chains and spills (measured 199 us vs 154 us per
+// 1 048 576 envs); the opaque statements keep the chains in program order.
+__device__ __forceinline__ unsigned long long ffma2_bcast(unsigned long long w, float x, unsigned long long acc) {
+  unsigned long long d;
+  asm("{\n\t.reg .b64 xx;\n\tmov.b64 xx, {%2, %2};\n\tfma.rn.f32x2 %0, %1, xx, %3;\n\t}" : "=l"(d) : "l"(w), "f"(x), "l"(acc));
+  return d;
 }
 __device__ __forceinline__ void f2unpack(unsigned long long v, float& lo, float& hi) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
-__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-// `w2` = the paired weights as 64-bit words (pair p = floats 2p, 2p+1) of the kernel parameter.
-__device__ __forceinline__ int mlp_sort_mode(const unsigned long long* __restrict__ w2, const float* x) {
+
+// PACKED = the FFMA2 form (used by the HOT instantiation); otherwise the same sums with scalar FFMA — identical
+// roundings, identical logits — which keeps the seven colder Env_2 instantiations cheap to compile (cicc spends
+// ~20 s per kernel on the ~800 asm statements of the packed form).
+template <bool PACKED>
+__device__ __forceinline__ int mlp_sort_mode(const float (&w)[(MSORT_POLICY_WEIGHTS + 3) / 4 * 4], const float* x) {
   constexpr int W1 = 0, b1 = 416, W2 = 448, b2 = 1472, W3 = 1504, b3 = 1568;
   float h1[32];
+  if (PACKED) {
+    const unsigned long long* const w2 = reinterpret_cast<const unsigned long long*>(w);   // pair p = floats 2p, 2p+1
 #pragma unroll
-  for (int jp = 0; jp < 16; ++jp) {
-    unsigned long long a = w2[b1 / 2 + jp];
+    for (int jp = 0; jp < 16; ++jp) {
+      unsigned long long a = w2[b1 / 2 + jp];
 #pragma unroll
-    for (int k = 0; k < 13; ++k) a = ffma2(w2[W1 / 2 + jp * 13 + k], f2pack(x[k], x[k]), a);
-    float lo, hi;
-    f2unpack(a, lo, hi);
-    h1[2 * jp] = tanh_fast(lo); h1[2 * jp + 1] = tanh_fast(hi);
+      for (int k = 0; k < 13; ++k) a = ffma2_bcast(w2[W1 / 2 + jp * 13 + k], x[k], a);
+      float lo, hi;
+      f2unpack(a, lo, hi);
+      h1[2 * jp] = tanh_fast(lo); h1[2 * jp + 1] = tanh_fast(hi);
+    }
+    unsigned long long l = w2[b3 / 2];   // (logit 0, logit 1)
+#pragma unroll
+    for (int jp = 0; jp < 16; ++jp) {
+      unsigned long long a = w2[b2 / 2 + jp];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) a = ffma2_bcast(w2[W2 / 2 + jp * 32 + k], h1[k], a);
+      float lo, hi;
+      f2unpack(a, lo, hi);
+      l = ffma2_bcast(w2[W3 / 2 + 2 * jp], tanh_fast(lo), l);
+      l = ffma2_bcast(w2[W3 / 2 + 2 * jp + 1], tanh_fast(hi), l);
+    }
+    float l0, l1;
+    f2unpack(l, l0, l1);
+    return l1 > l0 ? 1 : 0;
   }
-  unsigned long long l = w2[b3 / 2];   // (logit 0, logit 1)
 #pragma unroll
-  for (int jp = 0; jp < 16; ++jp) {
-    unsigned long long a = w2[b2 / 2 + jp];
+  for (int j = 0; j < 32; ++j) {       // neuron j = half (j & 1) of pair j / 2
+    float a = w[b1 + j];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) a = ffma2(w2[W2 / 2 + jp * 32 + k], f2pack(h1[k], h1[k]), a);
-    float lo, hi;
-    f2unpack(a, lo, hi);
-    const float h0 = tanh_fast(lo), hh = tanh_fast(hi);
-    l = ffma2(w2[W3 / 2 + 2 * jp], f2pack(h0, h0), l);
-    l = ffma2(w2[W3 / 2 + 2 * jp + 1], f2pack(hh, hh), l);
+    for (int k = 0; k < 13; ++k) a = fmaf(w[W1 + ((j >> 1) * 13 + k) * 2 + (j & 1)], x[k], a);
+    h1[j] = tanh_fast(a);
   }
-  float l0, l1;
-  f2unpack(l, l0, l1);
+  float l0 = w[b3], l1 = w[b3 + 1];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float a = w[b2 + j];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) a = fmaf(w[W2 + ((j >> 1) * 32 + k) * 2 + (j & 1)], h1[k], a);
+    const float h = tanh_fast(a);
+    l0 = fmaf(w[W3 + 2 * j], h, l0);
+    l1 = fmaf(w[W3 + 2 * j + 1], h, l1);
+  }
   return l1 > l0 ? 1 : 0;
 }
 

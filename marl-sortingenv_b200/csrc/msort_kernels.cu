@@ -153,11 +153,12 @@ template <int KIND> using PolicyParam = typename std::conditional<KIND == MSORT_
 // unboosted ones need no clip, and the redistribution classes fit one register of packed bytes.
 // Results are identical to the generic instantiation; only the instruction count differs.
 // HOT (FAST + compact layout only): the per-call switches are the training configuration — action masking
-// and auto-reset on, no overflow check, mask output wanted, no per-step info arrays, small levels, at most
-// twelve redistribution draws per station (DevConfig::one_block) — and are
+// and auto-reset on, no overflow check, mask output wanted, no per-step info arrays, at most twelve
+// redistribution draws per station (DevConfig::one_block); SMALL = levels <= 8192 (DevConfig::small_lv, e.g.
+// max_steps 50), otherwise < 2^16 (compact layout, e.g. the reference's 200-step episodes) — and are
 // compiled in, which removes ~20 uniform branches (and the basic-block boundaries they put in the
 // scheduler's way).  Chosen per launch by launch_step_kind.
-template <int KIND, int RNG, int LAYOUT, bool FAST, bool HOT = false>
+template <int KIND, int RNG, int LAYOUT, bool FAST, bool HOT = false, bool SMALL = HOT>
 __global__ void __launch_bounds__(kTile, (KIND == MSORT_ENV_PRESS ? MSORT_PRESS_MIN_BLOCKS : MSORT_STEP_MIN_BLOCKS) * (128 / kTile))  // Env_2 keeps 32 MLP activations in registers
 step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArgs a,
             const __grid_constant__ PolicyParam<KIND> pw) {
@@ -359,7 +360,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
         int kq[4];
         purity_ks(c, s, kq);
         sort_obs(c, s, kq, so);
-        if constexpr (KIND == MSORT_ENV_PRESS) mode = mlp_sort_mode(reinterpret_cast<const unsigned long long*>(pw.w), so);
+        if constexpr (KIND == MSORT_ENV_PRESS) mode = mlp_sort_mode<HOT>(pw.w, so);
       } else {  // sorting_rules env_super.py:469-482: pA+pC > pB+pD on float64 proportions
         int ac = b4(s.belt4, 0) + b4(s.belt4, 2), bd = b4(s.belt4, 1) + b4(s.belt4, 3);
         if (ac != bd) mode = ac > bd ? 0 : 1;  // strict integer inequality survives the float64 rounding
@@ -669,7 +670,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
           for (int q = 0; q < 4; ++q) if (m == q) { tv = s.tr[q]; amt = s.tr[q] + s.fl[q]; s.tr[q] = 0; s.fl[q] = 0; }
           if (m == 4) s.e = 0;
           s.started = 1; s.last_amt = amt;
-          const int qk = (m < 4 && amt > 0) ? purity_k<HOT>(c, tv, amt) : 0;  // round(true/total, 2) (:754)
+          const int qk = (m < 4 && amt > 0) ? purity_k<SMALL, HOT && !SMALL>(c, tv, amt) : 0;  // round(true/total, 2) (:754)
           if (!second) { s.timer[0] = c.press_time[0]; s.mat[0] = m; s.pn[0] = amt; s.pq[0] = qk; }
           else { s.timer[1] = c.press_time[1]; s.mat[1] = m; s.pn[1] = amt; s.pq[1] = qk; }
         }
@@ -694,7 +695,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     int kq[4] = {-1, -1, -1, -1};
     if (KIND != MSORT_ENV_PRESS) {
 #pragma unroll
-      for (int m = 0; m < 4; ++m) kq[m] = lv[m] > 0 ? purity_k<HOT>(c, s.tr[m], lv[m]) : -1;
+      for (int m = 0; m < 4; ++m) kq[m] = lv[m] > 0 ? purity_k<SMALL, HOT && !SMALL>(c, s.tr[m], lv[m]) : -1;
     }
     double reward, rs_term = 0.0, rp_term = 0.0;   // the two terms are only reported (telemetry)
     bool terminated;
@@ -1145,14 +1146,16 @@ static cudaError_t launch_step_kind(const DevConfig& c, const StepArgs& a, const
   if (rng == MSORT_RNG_REPLAY) step_kernel<KIND, MSORT_RNG_REPLAY, LAYOUT_REPLAY, false><<<g, kTile, 0, st>>>(c, a, pw);
   else if (c.layout == LAYOUT_COMPACT) {
     const unsigned want = MSORT_F_ACTION_MASKING | MSORT_F_AUTO_RESET, never = MSORT_F_CHECK_OVERFLOW;
-    const bool hot = c.fast && c.small_lv && c.one_block && (c.flags & want) == want && !(c.flags & never) && a.mask && !a.any_step_info;
+    const bool hot = c.fast && c.one_block && (c.flags & want) == want && !(c.flags & never) && a.mask && !a.any_step_info;
     if (hot) {
-      auto kern = step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true>;
+      auto kern = c.small_lv ? step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true, true>
+                             : step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true, false>;
       unsigned gp = g;
       var = MSORT_STEP_HOT;
       if (MSORT_HOT_PERSIST && KIND == MSORT_ENV_PRESS) {
         var = MSORT_STEP_HOT_PERSISTENT;   // persistent: exactly one wave of resident CTAs (asked from the occupancy calculator once)
-        static int per_sm = 0;
+        static int per_sm_of[2] = {0, 0};
+        int& per_sm = per_sm_of[c.small_lv ? 1 : 0];
         if (per_sm == 0) {
           cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
           if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTile, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
