@@ -177,6 +177,13 @@ def test_cuda_hot_kernel_matches_oracle(cuda_backend, kind):
     assert _hot_cross_check(cuda_backend, kind, 4096 + 37, 60) >= 2 * 4096
 
 
+@pytest.mark.parametrize("kind", ["sort", "press", "mono"])
+def test_cuda_hot_kernel_matches_oracle_long_episodes(cuda_backend, kind):
+    """batch * max_steps > 8192: the HOT instantiation without the small-level shortcut (container levels up to
+    12 000 here; the reference's benchmark episodes are 200 steps long)."""
+    assert _hot_cross_check(cuda_backend, kind, 1024 + 9, 125, max_steps=120) >= 1024
+
+
 def test_cuda_hot_kernel_matches_oracle_more_than_one_wave(cuda_backend):
     """More tiles than resident CTAs, so Env_2's persistent kernel really loops (its second and later tiles come
     from the TMA-staged buffer) and Env_3's L2 prefetch reaches real tiles; ragged last tile; Env_2 with the
