@@ -246,12 +246,13 @@ def _masked_press_choice(ora, t):
     return a.astype(np.uint8)
 
 
-def test_full_size_properties_config4(cuda_backend):
-    """BASELINE config 4 size (1 048 576 Monolith envs, masked): size-independent properties —
-    material conservation, mask consistency, step counters, reward bounds, determinism."""
+@pytest.mark.parametrize("n", [1 << 20, 1 << 23])
+def test_full_size_properties_config4(cuda_backend, n):
+    """BASELINE config 4 size (1 048 576 Monolith envs, masked) and config 5's total size on one GPU (8 388 608
+    envs, 1.7 GB of state): size-independent properties — material conservation, mask consistency, step
+    counters, reward bounds, determinism."""
     import torch
     from marl_sortingenv_b200 import BatchedMonolithEnv
-    n = 1 << 20
     env = BatchedMonolithEnv(n, max_steps=50, seed=7)
     env.reset()
     g = torch.Generator(device="cuda").manual_seed(5)
