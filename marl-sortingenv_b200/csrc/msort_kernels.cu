@@ -225,7 +225,11 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   // latency instead of DRAM latency.  64 state lines + 8 action lines of 128 B per tile.
   if (LAYOUT == LAYOUT_COMPACT && !PERSIST) {
     const long long pt = (long long)blockIdx.x + MSORT_PREFETCH_TILES;
+#if MSORT_PREFETCH_TRIM
+    if (tid < 96 && pt < (long long)gridDim.x && tid < 72) {   // warp-uniform first test: warp 3 skips the address arithmetic
+#else
     if (pt < (long long)gridDim.x && tid < 72) {
+#endif
       const char* p = tid < 64 ? reinterpret_cast<const char*>(a.state + (tid >> 4) * c.n_pad + pt * kTile) + (tid & 15) * 128
                                : reinterpret_cast<const char*>(a.actions + pt * kTile) + (tid - 64) * 128;
       asm volatile("prefetch.global.L2 [%0];" ::"l"(p));

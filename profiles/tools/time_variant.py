@@ -13,6 +13,19 @@ if kind == 'press':
     from marl_sortingenv_b200.policy import sb3_style_init
     env.set_sort_policy(sb3_style_init(0))
 env.reset()
+if os.environ.get("L2PERSIST"):
+    # experiment: pin the hot state planes in L2 with an access-policy window on the stream (captured into the graph's kernel nodes)
+    import ctypes as C
+    rt = C.CDLL("libcudart.so.12")
+    class Win(C.Structure):
+        _fields_ = [("base_ptr", C.c_void_p), ("num_bytes", C.c_size_t), ("hitRatio", C.c_float), ("hitProp", C.c_int), ("missProp", C.c_int)]
+    class Attr(C.Union):
+        _fields_ = [("win", Win), ("pad", C.c_char * 64)]
+    hot = 64 * ((n + 127) // 128 * 128)
+    print("set limit rc", rt.cudaDeviceSetLimit(C.c_int(6), C.c_size_t(min(hot, 96 << 20))))
+    a = Attr(); a.win = Win(env.state.data_ptr(), hot, float(os.environ["L2PERSIST"]), 2, 1)   # hit: persisting, miss: streaming
+    st = torch.cuda.Stream(); torch.cuda.set_stream(st)
+    print("set attr rc", rt.cudaStreamSetAttribute(C.c_void_p(st.cuda_stream), C.c_int(1), C.byref(a)))
 T = 128
 acts = torch.zeros((T, n), dtype=torch.int64, device="cuda")
 rsum = torch.zeros((), dtype=torch.float64, device="cuda")
