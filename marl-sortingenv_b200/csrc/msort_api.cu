@@ -23,6 +23,8 @@ struct msort_handle {
   double* lut_dev;    // owned device constant (tiny, allocated at create): the kSortLut-entry float64 sorting-reward table
   bool policy_set;
   int step_variant = MSORT_STEP_NONE;       // instantiation of the last step launch (msort_step_variant)
+  bool imported = false;                    // msort_import_state since the last full reset: stage contents are arbitrary, so the
+                                            // HOT kernel's host-proved bound of twelve draws per station does not hold
   float policy_host[MSORT_POLICY_WEIGHTS];  // host copy in the kernel's paired layout (pack_policy_pairs): travels to the step kernel as a kernel parameter
   int64_t launches;
 };
@@ -341,6 +343,7 @@ extern "C" int msort_reset(msort_t* h, void* state, const uint8_t* which, const 
   if ((obs && !aligned(obs, 16)) || (mask && !aligned(mask, 16)))
     return fail(MSORT_E_INVALID, "msort_reset: obs / mask must be 16-byte aligned (tiles leave as 16-byte vectors)");
   MSORT_TRY_CUDA(launch_reset(h->dev, state, which, first_pattern, obs, mask, reset_flags, (cudaStream_t)stream), "reset kernel");
+  if (!which) h->imported = false;          // every env holds a fresh plant again
   h->launches += 1;
   return MSORT_OK;
 }
@@ -372,7 +375,7 @@ extern "C" int msort_step(msort_t* h, void* state, const int64_t* actions, float
   if (h->dev.kind == MSORT_ENV_PRESS && (h->dev.flags & MSORT_F_SORT_POLICY_MLP) && !h->policy_set &&
       !(replay && replay->sort_mode))
     return fail(MSORT_E_INVALID, "msort_step: embedded sort policy requested but msort_set_policy() was never called");
-  StepLaunch l{state, actions, obs, reward, terminated, mask, info, replay, &h->step_variant, h->policy_set ? h->policy_host : nullptr};
+  StepLaunch l{state, actions, obs, reward, terminated, mask, info, replay, &h->step_variant, h->imported ? 0 : 1, h->policy_set ? h->policy_host : nullptr};
   MSORT_TRY_CUDA(launch_step(h->dev, l, h->cfg.rng_mode, (cudaStream_t)stream), "step kernel");
   h->launches += 1;
   return MSORT_OK;
@@ -465,6 +468,7 @@ extern "C" int msort_import_state(msort_t* h, void* state, const msort_env_state
   if (!h || !state || !in) return fail(MSORT_E_INVALID, "msort_import_state: NULL argument");
   if (!aligned(state, 16) || !aligned(in, 8)) return fail(MSORT_E_INVALID, "msort_import_state: misaligned buffer");
   MSORT_TRY_CUDA(launch_import(h->dev, state, in, (cudaStream_t)stream), "import kernel");
+  h->imported = true;
   h->launches += 1;
   return MSORT_OK;
 }

@@ -225,11 +225,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   // latency instead of DRAM latency.  64 state lines + 8 action lines of 128 B per tile.
   if (LAYOUT == LAYOUT_COMPACT && !PERSIST) {
     const long long pt = (long long)blockIdx.x + MSORT_PREFETCH_TILES;
-#if MSORT_PREFETCH_TRIM
-    if (tid < 96 && pt < (long long)gridDim.x && tid < 72) {   // warp-uniform first test: warp 3 skips the address arithmetic
-#else
     if (pt < (long long)gridDim.x && tid < 72) {
-#endif
       const char* p = tid < 64 ? reinterpret_cast<const char*>(a.state + (tid >> 4) * c.n_pad + pt * kTile) + (tid & 15) * 128
                                : reinterpret_cast<const char*>(a.actions + pt * kTile) + (tid - 64) * 128;
       asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -1137,7 +1133,8 @@ void pack_policy_pairs(const float* sb3, float* paired) {
 static inline unsigned tiles(long long n) { return (unsigned)((n + kTile - 1) / kTile); }
 
 template <int KIND>
-static cudaError_t launch_step_kind(const DevConfig& c, const StepArgs& a, const float* policy_host, int rng, cudaStream_t st, int* variant) {
+static cudaError_t launch_step_kind(const DevConfig& c, const StepArgs& a, const float* policy_host, int rng, cudaStream_t st, int* variant,
+                                    int allow_hot) {
   const unsigned g = tiles(c.n);
   int dummy;
   int& var = variant ? *variant : dummy;
@@ -1150,7 +1147,7 @@ static cudaError_t launch_step_kind(const DevConfig& c, const StepArgs& a, const
   if (rng == MSORT_RNG_REPLAY) step_kernel<KIND, MSORT_RNG_REPLAY, LAYOUT_REPLAY, false><<<g, kTile, 0, st>>>(c, a, pw);
   else if (c.layout == LAYOUT_COMPACT) {
     const unsigned want = MSORT_F_ACTION_MASKING | MSORT_F_AUTO_RESET, never = MSORT_F_CHECK_OVERFLOW;
-    const bool hot = c.fast && c.one_block && (c.flags & want) == want && !(c.flags & never) && a.mask && !a.any_step_info;
+    const bool hot = allow_hot && c.fast && c.one_block && (c.flags & want) == want && !(c.flags & never) && a.mask && !a.any_step_info;
     if (hot) {
       auto kern = c.small_lv ? step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true, true>
                              : step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true, false>;
@@ -1203,9 +1200,9 @@ cudaError_t launch_step(const DevConfig& c, const StepLaunch& l, int rng, cudaSt
   a.redis_len = r ? r->redis_len : 0; a.input_counts = r ? r->input_counts : nullptr;
   a.press_choice = r ? r->press_choice : nullptr; a.sort_mode_in = r ? r->sort_mode : nullptr;
   switch (c.kind) {
-    case MSORT_ENV_SORT: return launch_step_kind<MSORT_ENV_SORT>(c, a, l.policy_host, rng, st, l.variant);
-    case MSORT_ENV_PRESS: return launch_step_kind<MSORT_ENV_PRESS>(c, a, l.policy_host, rng, st, l.variant);
-    default: return launch_step_kind<MSORT_ENV_MONO>(c, a, l.policy_host, rng, st, l.variant);
+    case MSORT_ENV_SORT: return launch_step_kind<MSORT_ENV_SORT>(c, a, l.policy_host, rng, st, l.variant, l.allow_hot);
+    case MSORT_ENV_PRESS: return launch_step_kind<MSORT_ENV_PRESS>(c, a, l.policy_host, rng, st, l.variant, l.allow_hot);
+    default: return launch_step_kind<MSORT_ENV_MONO>(c, a, l.policy_host, rng, st, l.variant, l.allow_hot);
   }
 }
 

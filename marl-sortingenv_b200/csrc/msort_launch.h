@@ -20,6 +20,7 @@ struct StepLaunch {
   const msort_info_out_t* info;
   const msort_replay_t* replay;
   int* variant;              // out (nullable): MSORT_STEP_* of the instantiation launched
+  int allow_hot;             // 0: the state may hold stage contents no reset/step produces (imported): no HOT kernel
   const float* policy_host;  // Env_2 embedded policy (host copy in the paired layout, MSORT_POLICY_WEIGHTS floats) or nullptr
 };
 

@@ -210,3 +210,37 @@ def test_persistent_env2_kernel_with_unaligned_actions_and_kernel_variants():
     assert torch.equal(envs[0].state, envs[1].state) and torch.equal(envs[0].state, envs[2].state)
     assert torch.equal(envs[0].obs, envs[1].obs) and torch.equal(envs[0].obs, envs[2].obs)
     assert torch.equal(envs[0].mask, envs[2].mask) and torch.equal(envs[0].reward, envs[1].reward)
+
+
+def test_imported_state_with_unusual_stages_is_stepped_exactly():
+    """The HOT kernel relies on host-proved facts about what a stage can hold (a pattern batch or nothing: at most
+    twelve mis-sorted units per station).  An imported state may hold anything — here a sorting stage of
+    60/0/40/0 and 0/55/0/45 units — so the handle falls back to the FAST kernel (general draw loop) until the
+    next full reset; the step must still match the oracle exactly."""
+    from cuda_backend import CudaBackend
+    from oracle.cpu_oracle import OracleEnv
+    n = 600
+    meta = dict(META, kind="mono", max_steps=30)
+    ora = OracleEnv(config_for(meta, n, rng_mode="philox", seed=8))
+    gpu = CudaBackend(config_for(meta, n, rng_mode="philox", seed=8), info_level="episode")
+    ora.reset(); gpu.reset()
+    for t in range(7):
+        a = ora.sample_masked_actions(4, t)
+        ora.step(a); gpu.step(a)
+    assert gpu.env.step_variant == "hot"
+    st = ora.state.copy()
+    st["sorting"][0::2] = (60, 0, 40, 0)
+    st["sorting"][1::2] = (0, 55, 0, 45)
+    ora.state[:] = st
+    gpu.env.import_state(st)
+    for t in range(7, 20):
+        a = ora.sample_masked_actions(4, t)
+        oo, orw, ot, om, _ = ora.step(a)
+        go, grw, gt, gm, _ = gpu.step(a)
+        assert gpu.env.step_variant == "fast"
+        assert np.array_equal(state_rows(ora.state), state_rows(gpu.export_state())), t
+        assert np.array_equal(om, gm) and np.array_equal(ot, gt)
+        assert_float_close(grw, orw, f"step {t} reward"); assert_float_close(go, oo, f"step {t} obs")
+    gpu.reset()
+    gpu.step(np.zeros(n, dtype=np.int64))
+    assert gpu.env.step_variant == "hot"           # a full reset restores the proved facts
