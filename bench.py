@@ -38,7 +38,7 @@ ACTION_SEED = 7
 ALGO_BYTES_PER_STEP = {"sort": 223, "press": 244, "mono": 307}   # SURVEY.md §8d / DESIGN.md
 # dram__bytes_read.sum + dram__bytes_write.sum per step-kernel launch at this workload, from the
 # `ncu --set full` capture summarised in profiles/ (None until a capture exists).
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {("mono", 1 << 20): 233.2e6}   # profiles/ncu_r01_step_kernel.md (kernel v14)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {("mono", 1 << 20): 232.7e6}   # profiles/ncu_r01_step_kernel.md (kernel v16: 75.6 MB read + 157.1 MB written)
 
 
 def parse_args():
@@ -358,7 +358,7 @@ def run_msort(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get((args.kind, n)), "kernel": f"msort::step_kernel<{args.kind.upper()},PHILOX>",
+                     "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get((args.kind, n)), "kernel": f"msort::step_kernel<{args.kind.upper()},PHILOX> [{env.step_variant} instantiation]",
                      "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo_bytes,
                      "bytes_per_env_step": ALGO_BYTES_PER_STEP[args.kind], "peak_source": peak_src},
         "episode_stats": {"episodes": stats[0], "mean_return": stats[1] / max(1.0, stats[0]),

@@ -225,7 +225,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   // latency instead of DRAM latency.  64 state lines + 8 action lines of 128 B per tile.
   if (LAYOUT == LAYOUT_COMPACT && !PERSIST) {
     const long long pt = (long long)blockIdx.x + MSORT_PREFETCH_TILES;
-    if (pt < (long long)gridDim.x && tid < 72) {
+    if (pt < (long long)gridDim.x && (tid < 64 || (tid < 72 && (pt + 1) * kTile <= c.n))) {   // actions are not padded: whole tiles only
       const char* p = tid < 64 ? reinterpret_cast<const char*>(a.state + (tid >> 4) * c.n_pad + pt * kTile) + (tid & 15) * 128
                                : reinterpret_cast<const char*>(a.actions + pt * kTile) + (tid - 64) * 128;
       asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
