@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MSORT_ABI_VERSION 3
+#define MSORT_ABI_VERSION 4
 
 /* ------------------------------------------------------------------ enums */
 typedef enum msort_status {
@@ -305,6 +305,20 @@ int msort_sync_check(msort_t* h, void* stream);
 
 /* Number of kernels this handle has launched (bench.py's gpu_launches). */
 int64_t msort_launch_count(const msort_t* h);
+
+/* msort_step / msort_policy_act on the env range [first_env, first_env + num_envs) only (first_env a multiple of
+ * 128; PHILOX mode).  Every pointer is the WHOLE-batch base, exactly as passed to msort_step / msort_policy_act;
+ * the library takes the range's slice.  Trajectories do not depend on how the batch is cut (counters use global
+ * env ids), so a caller can put disjoint ranges on different CUDA streams: the rollout loop runs
+ * policy_act -> step of one half beside step / policy_act of the other (marl-sortingenv_b200/ppo.py), which lets
+ * the latency-bound tensor-core policy kernel and the ALU-bound step kernel share the SMs.  The handle's
+ * statistics accumulators (atomics) and launch counter are shared; the handle itself is still not thread-safe. */
+int msort_step_range(msort_t* h, int64_t first_env, int64_t num_envs, void* state, const int64_t* actions,
+                     float* obs, float* reward, uint8_t* terminated, uint8_t* mask,
+                     const msort_info_out_t* info, void* stream);
+int msort_policy_act_range(msort_t* h, int64_t first_env, int64_t num_envs, const float* obs, const uint8_t* mask,
+                           const float* packed_weights, uint64_t seed, uint32_t t, int deterministic,
+                           int64_t* actions, float* logp, float* value, void* stream);
 
 /* Which instantiation of the step kernel the handle's last msort_step launched (diagnostics / tests):
  * 0 none yet, 1 REPLAY, 2 generic, 3 FAST (host-proved config facts compiled in),

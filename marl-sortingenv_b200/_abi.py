@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 POLICY_ACT_WEIGHTS = 4256
 
 ENV_SORT, ENV_PRESS, ENV_MONO = 1, 2, 3
@@ -140,12 +140,14 @@ SYMBOLS = {
     "msort_set_seed": (C.c_int, [_P, C.c_uint64]),
     "msort_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.POINTER(MsortInfoOut),
                              C.POINTER(MsortReplay), _P]),
+    "msort_step_range": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P, C.POINTER(MsortInfoOut), _P]),
     "msort_set_policy": (C.c_int, [_P, _P, C.c_int, _P]),
     "msort_sample_actions": (C.c_int, [_P, _P, _P, C.c_uint64, C.c_uint32, _P]),
     "msort_rule_based_actions": (C.c_int, [_P, _P, C.c_int, _P, _P]),
     "msort_observe": (C.c_int, [_P, _P, _P, _P, _P]),
     "msort_observe_after_shift": (C.c_int, [_P, _P, _P, _P, _P]),
     "msort_policy_act": (C.c_int, [_P, _P, _P, _P, C.c_uint64, C.c_uint32, C.c_int, _P, _P, _P, _P]),
+    "msort_policy_act_range": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, C.c_uint64, C.c_uint32, C.c_int, _P, _P, _P, _P]),
     "msort_export_state": (C.c_int, [_P, _P, _P, _P]),
     "msort_gather_state": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P]),
     "msort_import_state": (C.c_int, [_P, _P, _P, _P]),

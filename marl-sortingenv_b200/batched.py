@@ -174,13 +174,15 @@ class BatchedEnv:
         return self.obs, {}
 
     def step(self, actions, replay: dict | None = None, out_obs: torch.Tensor | None = None,
-             out_mask: torch.Tensor | None = None):
+             out_mask: torch.Tensor | None = None, env_range: tuple[int, int] | None = None):
         """ref: Env_X.step(action) → (obs, reward, terminated, truncated, info), batched.
         `actions`: int64 CUDA tensor [N].  Returned tensors are views of internal buffers that
         the next step() overwrites.  `out_obs` [N,D] f32 / `out_mask` [N,A] bool (contiguous CUDA
         tensors, e.g. slot t+1 of a rollout buffer) receive the new observation / action mask instead
         of the internal buffers — the kernel writes them in place, nothing is copied; `env.obs` /
-        `env.mask` / `action_masks()` then refer to those tensors."""
+        `env.mask` / `action_masks()` then refer to those tensors.  `env_range=(first, stop)` steps only the
+        envs [first, stop) (`first` a multiple of 128; `msort_step_range`): every tensor is still the whole-batch
+        one and only that slice of it is read / written, so disjoint ranges may run on different CUDA streams."""
         if not self._was_reset:
             # the reference raises AttributeError on step() before reset() (env_super.py:394,402)
             raise AttributeError("step() called before reset()")
@@ -202,10 +204,16 @@ class BatchedEnv:
         if out_mask is not None:
             self.mask = out_mask
         with torch.cuda.device(self.device):
-            rc = self.lib.msort_step(self._h, _ptr(self.state), _ptr(actions), _ptr(self.obs),
-                                     _ptr(self.reward), _ptr(self.terminated), _ptr(self.mask),
-                                     C.byref(self._info) if self._has_info else None,
-                                     C.byref(rp) if rp is not None else None, self._stream())
+            if env_range is None:
+                rc = self.lib.msort_step(self._h, _ptr(self.state), _ptr(actions), _ptr(self.obs),
+                                         _ptr(self.reward), _ptr(self.terminated), _ptr(self.mask),
+                                         C.byref(self._info) if self._has_info else None,
+                                         C.byref(rp) if rp is not None else None, self._stream())
+            else:
+                first, stop = int(env_range[0]), int(env_range[1])
+                rc = self.lib.msort_step_range(self._h, first, stop - first, _ptr(self.state), _ptr(actions), _ptr(self.obs),
+                                               _ptr(self.reward), _ptr(self.terminated), _ptr(self.mask),
+                                               C.byref(self._info) if self._has_info else None, self._stream())
         _abi.check(self.lib, rc, "msort_step")
         if self._trace is not None:
             self._trace.record()
@@ -253,12 +261,14 @@ class BatchedEnv:
         return out
 
     def policy_act(self, packed_weights: torch.Tensor, seed: int = 0, t: int = 0, deterministic: bool = False,
-                   obs: torch.Tensor | None = None, mask: torch.Tensor | None = None, out=None):
+                   obs: torch.Tensor | None = None, mask: torch.Tensor | None = None, out=None,
+                   env_range: tuple[int, int] | None = None):
         """Fused actor-critic inference + masked categorical draw for every env (one tcgen05 kernel
         launch; `msort_policy_act`): (actions int64 [N], log-prob f32 [N], value f32 [N]) for the
         current observation / action mask (or the given ones).  `packed_weights` comes from
         `ppo.pack_actor_critic`.  ref: MaskablePPO's policy forward during collect_rollouts
-        (training.py:118-143, net_arch pi=[32,32], vf=[32,32])."""
+        (training.py:118-143, net_arch pi=[32,32], vf=[32,32]).  `env_range=(first, stop)`: only those envs
+        (whole-batch tensors, that slice read / written; the draw is keyed by the global env id)."""
         obs = self.obs if obs is None else obs
         mask = self.mask if mask is None else mask
         if packed_weights.numel() != _abi.POLICY_ACT_WEIGHTS or packed_weights.dtype != torch.float32:
@@ -271,9 +281,15 @@ class BatchedEnv:
                    torch.empty(self.num_envs, dtype=torch.float32, device=self.device))
         a, lp, v = out
         with torch.cuda.device(self.device):
-            rc = self.lib.msort_policy_act(self._h, _ptr(obs), _ptr(mask), _ptr(packed_weights),
-                                           int(seed) & 0xFFFFFFFFFFFFFFFF, int(t) & 0xFFFFFFFF, 1 if deterministic else 0,
-                                           _ptr(a), _ptr(lp), _ptr(v), self._stream())
+            if env_range is None:
+                rc = self.lib.msort_policy_act(self._h, _ptr(obs), _ptr(mask), _ptr(packed_weights),
+                                               int(seed) & 0xFFFFFFFFFFFFFFFF, int(t) & 0xFFFFFFFF, 1 if deterministic else 0,
+                                               _ptr(a), _ptr(lp), _ptr(v), self._stream())
+            else:
+                first, stop = int(env_range[0]), int(env_range[1])
+                rc = self.lib.msort_policy_act_range(self._h, first, stop - first, _ptr(obs), _ptr(mask), _ptr(packed_weights),
+                                                     int(seed) & 0xFFFFFFFFFFFFFFFF, int(t) & 0xFFFFFFFF,
+                                                     1 if deterministic else 0, _ptr(a), _ptr(lp), _ptr(v), self._stream())
         _abi.check(self.lib, rc, "msort_policy_act")
         return a, lp, v
 

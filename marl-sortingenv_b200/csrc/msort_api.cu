@@ -348,8 +348,10 @@ extern "C" int msort_reset(msort_t* h, void* state, const uint8_t* which, const 
   return MSORT_OK;
 }
 
-extern "C" int msort_step(msort_t* h, void* state, const int64_t* actions, float* obs, float* reward, uint8_t* terminated,
-                          uint8_t* mask, const msort_info_out_t* info, const msort_replay_t* replay, void* stream) {
+// `first` / `count`: the env range [first, first + count) the launch covers (whole batch: 0 / N).  Every pointer is the
+// whole-batch base; the range's slice of each buffer is taken here.
+static int step_impl(msort_t* h, long long first, long long count, void* state, const int64_t* actions, float* obs, float* reward,
+                     uint8_t* terminated, uint8_t* mask, const msort_info_out_t* info, const msort_replay_t* replay, void* stream) {
   if (!h || !state || !actions || !obs || !reward || !terminated)
     return fail(MSORT_E_INVALID, "msort_step: NULL required argument");
   if (!aligned(state, 16)) return fail(MSORT_E_INVALID, "msort_step: state must be 16-byte aligned");
@@ -375,10 +377,49 @@ extern "C" int msort_step(msort_t* h, void* state, const int64_t* actions, float
   if (h->dev.kind == MSORT_ENV_PRESS && (h->dev.flags & MSORT_F_SORT_POLICY_MLP) && !h->policy_set &&
       !(replay && replay->sort_mode))
     return fail(MSORT_E_INVALID, "msort_step: embedded sort policy requested but msort_set_policy() was never called");
+  const int D = msort_obs_dim(h), A = msort_num_actions(h);
+  DevConfig d = h->dev;
+  msort_info_out_t sub;
+  if (first != 0 || count != h->dev.n) {            // a sub-range: same plane stride, shifted bases, global ids continue
+    d.n = count; d.gid0 += first;
+    state = (uint4*)state + first; actions += first; obs += first * D; reward += first; terminated += first;
+    if (mask) mask += first * A;
+    if (info) {
+      sub = *info;
+      if (sub.action) sub.action += first;
+      if (sub.overflow) sub.overflow += first;
+      if (sub.overflow_material) sub.overflow_material += first;
+      if (sub.sort_mode) sub.sort_mode += first;
+      if (sub.press_action) sub.press_action += first;
+      if (sub.invalid_action) sub.invalid_action += first;
+      if (sub.terminal_obs) sub.terminal_obs += first * D;
+      if (sub.episode_return) sub.episode_return += first;
+      if (sub.episode_length) sub.episode_length += first;
+      if (sub.reward_sort) sub.reward_sort += first;
+      if (sub.reward_press) sub.reward_press += first;
+      if (sub.sorted_true) sub.sorted_true += first;
+      info = &sub;
+    }
+  }
   StepLaunch l{state, actions, obs, reward, terminated, mask, info, replay, &h->step_variant, h->imported ? 0 : 1, h->policy_set ? h->policy_host : nullptr};
-  MSORT_TRY_CUDA(launch_step(h->dev, l, h->cfg.rng_mode, (cudaStream_t)stream), "step kernel");
+  MSORT_TRY_CUDA(launch_step(d, l, h->cfg.rng_mode, (cudaStream_t)stream), "step kernel");
   h->launches += 1;
   return MSORT_OK;
+}
+
+extern "C" int msort_step(msort_t* h, void* state, const int64_t* actions, float* obs, float* reward, uint8_t* terminated,
+                          uint8_t* mask, const msort_info_out_t* info, const msort_replay_t* replay, void* stream) {
+  if (!h) return fail(MSORT_E_INVALID, "msort_step: NULL required argument");
+  return step_impl(h, 0, h->dev.n, state, actions, obs, reward, terminated, mask, info, replay, stream);
+}
+
+extern "C" int msort_step_range(msort_t* h, int64_t first_env, int64_t num_envs, void* state, const int64_t* actions, float* obs,
+                                float* reward, uint8_t* terminated, uint8_t* mask, const msort_info_out_t* info, void* stream) {
+  if (!h) return fail(MSORT_E_INVALID, "msort_step_range: NULL handle");
+  if (h->cfg.rng_mode != MSORT_RNG_PHILOX) return fail(MSORT_E_INVALID, "msort_step_range: PHILOX mode only");
+  if (first_env < 0 || num_envs <= 0 || first_env + num_envs > h->dev.n || first_env % kTile != 0)
+    return fail(MSORT_E_INVALID, "msort_step_range: range must lie inside the batch and start on a multiple of %d envs", kTile);
+  return step_impl(h, first_env, num_envs, state, actions, obs, reward, terminated, mask, info, nullptr, stream);
 }
 
 extern "C" int msort_set_policy(msort_t* h, const float* weights, int weights_on_device, void* stream) {
@@ -432,18 +473,37 @@ extern "C" int msort_rule_based_actions(msort_t* h, const void* state, int after
   return MSORT_OK;
 }
 
-extern "C" int msort_policy_act(msort_t* h, const float* obs, const uint8_t* mask, const float* packed_weights,
-                                uint64_t seed, uint32_t t, int deterministic, int64_t* actions, float* logp,
-                                float* value, void* stream) {
+static int policy_act_impl(msort_t* h, long long first, long long count, const float* obs, const uint8_t* mask,
+                           const float* packed_weights, uint64_t seed, uint32_t t, int deterministic, int64_t* actions,
+                           float* logp, float* value, void* stream) {
   if (!h || !obs || !mask || !packed_weights || !actions || !logp || !value)
     return fail(MSORT_E_INVALID, "msort_policy_act: NULL argument");
   if (!aligned(obs, 4) || !aligned(packed_weights, 16) || !aligned(actions, 8) || !aligned(logp, 4) || !aligned(value, 4))
     return fail(MSORT_E_INVALID, "msort_policy_act: misaligned buffer");
-  MSORT_TRY_CUDA(launch_policy_act(h->dev, obs, mask, packed_weights, msort_obs_dim(h), msort_num_actions(h), seed, t,
-                                   deterministic, actions, logp, value, h->sm_count, (cudaStream_t)stream),
+  const int D = msort_obs_dim(h), A = msort_num_actions(h);
+  DevConfig d = h->dev;
+  d.n = count; d.gid0 += first;                     // the draw is keyed by the global env id: ranges compose to the whole
+  MSORT_TRY_CUDA(launch_policy_act(d, obs + first * D, mask + first * A, packed_weights, D, A, seed, t, deterministic,
+                                   actions + first, logp + first, value + first, h->sm_count, (cudaStream_t)stream),
                  "policy_act kernel");
   h->launches += 1;
   return MSORT_OK;
+}
+
+extern "C" int msort_policy_act(msort_t* h, const float* obs, const uint8_t* mask, const float* packed_weights,
+                                uint64_t seed, uint32_t t, int deterministic, int64_t* actions, float* logp,
+                                float* value, void* stream) {
+  if (!h) return fail(MSORT_E_INVALID, "msort_policy_act: NULL argument");
+  return policy_act_impl(h, 0, h->dev.n, obs, mask, packed_weights, seed, t, deterministic, actions, logp, value, stream);
+}
+
+extern "C" int msort_policy_act_range(msort_t* h, int64_t first_env, int64_t num_envs, const float* obs, const uint8_t* mask,
+                                      const float* packed_weights, uint64_t seed, uint32_t t, int deterministic,
+                                      int64_t* actions, float* logp, float* value, void* stream) {
+  if (!h) return fail(MSORT_E_INVALID, "msort_policy_act_range: NULL handle");
+  if (first_env < 0 || num_envs <= 0 || first_env + num_envs > h->dev.n || first_env % kTile != 0)
+    return fail(MSORT_E_INVALID, "msort_policy_act_range: range must lie inside the batch and start on a multiple of %d envs", kTile);
+  return policy_act_impl(h, first_env, num_envs, obs, mask, packed_weights, seed, t, deterministic, actions, logp, value, stream);
 }
 
 extern "C" int msort_export_state(msort_t* h, const void* state, msort_env_state_t* out, void* stream) {

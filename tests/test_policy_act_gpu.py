@@ -99,3 +99,40 @@ def test_fused_rollout_matches_torch_rollout_statistics():
                         float((v_new - b["val"].reshape(-1)).abs().max()))
     assert abs(stats[True][0] - stats[False][0]) < 0.02, stats
     assert stats[True][1] < 5e-3 and stats[True][2] < 5e-3, stats
+
+
+def test_env_ranges_on_two_streams_compose_to_the_whole_batch():
+    """msort_step_range / msort_policy_act_range: two disjoint env ranges (ragged second one), each on its own CUDA
+    stream, leave exactly what the whole-batch calls leave — state, obs, mask, reward, done, actions, log-probs,
+    values, statistics.  Range starts must be multiples of 128."""
+    import torch
+    import marl_sortingenv_b200 as ms
+    from marl_sortingenv_b200.ppo import MaskableActorCritic, pack_actor_critic
+    n, cut = 128 * 37 + 51, 128 * 20
+    whole = ms.BatchedMonolithEnv(n, max_steps=20, seed=5, info_level="episode")
+    parts = ms.BatchedMonolithEnv(n, max_steps=20, seed=5, info_level="episode")
+    whole.reset(); parts.reset()
+    torch.manual_seed(1)
+    packed = pack_actor_critic(MaskableActorCritic(whole.D, whole.A).cuda())
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    out_p = (torch.empty(n, dtype=torch.int64, device="cuda"), torch.empty(n, device="cuda"), torch.empty(n, device="cuda"))
+    for t in range(45):
+        a, lp, v = whole.policy_act(packed, seed=9, t=t)
+        whole.step(a)
+        cur = torch.cuda.current_stream()
+        for s, r in zip(streams, ((0, cut), (cut, n))):
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                parts.policy_act(packed, seed=9, t=t, out=out_p, env_range=r)
+                parts.step(out_p[0], env_range=r)
+        for s in streams:
+            cur.wait_stream(s)
+        assert torch.equal(out_p[0], a) and torch.equal(out_p[1], lp) and torch.equal(out_p[2], v), t
+        assert torch.equal(parts.state, whole.state) and torch.equal(parts.obs, whole.obs), t
+        assert torch.equal(parts.mask, whole.mask) and torch.equal(parts.reward, whole.reward), t
+        assert torch.equal(parts.terminated, whole.terminated)
+    for k in ("episode_return", "episode_length", "terminal_observation"):
+        assert torch.equal(parts.info_buffers[k], whole.info_buffers[k]), k
+    assert torch.allclose(parts.stats, whole.stats, rtol=1e-12, atol=0)      # atomics: order differs, sums agree
+    with pytest.raises(Exception):
+        parts.step(out_p[0], env_range=(64, 256))                             # not on a tile boundary
