@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="msort", choices=["msort", "reference"])
+    ap.add_argument("--rollout-streams", type=int, default=2, help="env ranges / CUDA streams of the rollout-loop measurement")
     ap.add_argument("--kind", default="mono", choices=["sort", "press", "mono"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -326,10 +327,22 @@ def run_msort(args):
         for t in range(W):
             env.policy_act(packed, seed=ACTION_SEED, t=t, out=out); env.step(out[0])
         torch.cuda.synchronize(dev)
+        # two env ranges of the one handle on two streams (msort_*_range), as ppo.MaskablePPO's rollout does: the
+        # latency-bound policy kernel of one range shares the SMs with the step kernel of the other
+        half = (n // 2 + 127) // 128 * 128
+        ranges = [(0, n)] if args.rollout_streams < 2 or half >= n else [(0, half), (half, n)]
+        streams = [torch.cuda.Stream(device=dev) for _ in ranges]
         gr = torch.cuda.CUDAGraph()
         with torch.cuda.graph(gr):
+            cur = torch.cuda.current_stream(dev)
+            for s in streams:
+                s.wait_stream(cur)
             for t in range(Kr):
-                env.policy_act(packed, seed=ACTION_SEED, t=W + t, out=out); env.step(out[0])
+                for s, r in zip(streams, ranges):
+                    with torch.cuda.stream(s):
+                        env.policy_act(packed, seed=ACTION_SEED, t=W + t, out=out, env_range=r); env.step(out[0], env_range=r)
+            for s in streams:
+                cur.wait_stream(s)
         gr.replay()
         barrier()
         r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -339,9 +352,9 @@ def run_msort(args):
         if world > 1:
             dist.all_reduce(tr, op=dist.ReduceOp.MAX)
         rollout = {"value": n * world * Kr / (float(tr.item()) * 1e-3), "unit": "env-steps/s", "steps": Kr,
-                   "ms_per_step": float(tr.item()) / Kr, "launches_per_step": 2,
+                   "ms_per_step": float(tr.item()) / Kr, "launches_per_step": 2 * len(ranges), "streams": len(ranges),
                    "what": "per env-step: msort_policy_act (actor-critic 29-32-32-{22|1} on tcgen05, masked categorical "
-                           "draw) + fused step(); obs/mask never leave HBM"}
+                           "draw) + fused step(), env ranges on separate streams; obs/mask never leave HBM"}
 
     if rank != 0:
         if world > 1:
