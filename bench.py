@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="msort", choices=["msort", "reference"])
+    ap.add_argument("--step-streams", type=int, default=2, help="env ranges / CUDA streams each timed step is launched as (1 = one whole-batch launch)")
     ap.add_argument("--rollout-streams", type=int, default=2, help="env ranges / CUDA streams of the rollout-loop measurement")
     ap.add_argument("--kind", default="mono", choices=["sort", "press", "mono"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
@@ -171,7 +172,9 @@ def workload_config(args, world):
             "env": kind_name, "envs_per_gpu": args.envs_per_gpu, "global_envs": args.envs_per_gpu * world,
             "max_steps": MAX_STEPS, "rng": "philox4x32-10", "action_masking": True, "auto_reset": True,
             "l2": "inputs larger than L2 (no flush needed)", "parallelism": f"env-sharded x{world}",
-            "launch": "eager" if args.no_graph else "one CUDA graph of the K step kernels",
+            "launch": ("eager, one whole-batch step kernel per step" if args.no_graph else
+                       "one CUDA graph of the K steps" + (", each step = 2 env-range launches of the step kernel on 2 streams"
+                                                          if args.step_streams >= 2 else ", one step kernel per step")),
             "stats_allreduce": "once per K-step rollout (NCCL, 128 B)"}
 
 
@@ -250,13 +253,31 @@ def run_msort(args):
         env.step(actions[t])
     if world > 1:                                  # NCCL communicators are created lazily: do it before timing
         allreduce_stats(torch.zeros(16, dtype=torch.float64, device=dev))
+    # Each step is launched as `step_streams` env ranges of the one handle on as many CUDA streams (msort_step_range;
+    # ranges are independent, the result is bit-identical — asserted below): the tail of one range's kernel overlaps
+    # the head of the other's, which at 1 M envs recovers the ramp / tail a single 8192-CTA launch pays (62 -> 58 us).
+    # --no-graph keeps one whole-batch launch per step (per-launch events, the ncu launch list).
+    half = (n // 2 + 127) // 128 * 128
+    ranges = [(0, n)] if (args.step_streams < 2 or half >= n or not use_graph) else [(0, half), (half, n)]
+    streams = [torch.cuda.Stream(device=dev) for _ in ranges] if len(ranges) > 1 else []
     graph = None
     if use_graph:
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            for t in range(K):
-                env.step(actions[W + t])
+            if not streams:
+                for t in range(K):
+                    env.step(actions[W + t])
+            else:
+                cur = torch.cuda.current_stream(dev)
+                for st_ in streams:
+                    st_.wait_stream(cur)
+                for t in range(K):
+                    for st_, r in zip(streams, ranges):
+                        with torch.cuda.stream(st_):
+                            env.step(actions[W + t], env_range=r)
+                for st_ in streams:
+                    cur.wait_stream(st_)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)] if not use_graph else None
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -277,7 +298,7 @@ def run_msort(args):
     ev1.record()
     barrier()
     t1 = time.time()
-    gpu_launches = K
+    gpu_launches = K * len(ranges)
     clocks = sampler.stop(t0, t1) if sampler else None
     total_ms = ev0.elapsed_time(ev1)
     per_kernel_ms = [ev[t].elapsed_time(ev[t + 1]) for t in range(K)] if not use_graph else [total_ms / K]
@@ -372,7 +393,7 @@ def run_msort(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(gpu_launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH.get((args.kind, n)), "kernel": f"msort::step_kernel<{args.kind.upper()},PHILOX> [{env.step_variant} instantiation]",
-                     "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo_bytes,
+                     "kernel_ms": kern_ms, "launches_per_step": len(ranges), "algorithmic_bytes_per_launch": algo_bytes,
                      "bytes_per_env_step": ALGO_BYTES_PER_STEP[args.kind], "peak_source": peak_src},
         "episode_stats": {"episodes": stats[0], "mean_return": stats[1] / max(1.0, stats[0]),
                           "mean_length": stats[2] / max(1.0, stats[0]), "env_steps": stats[3],
