@@ -79,6 +79,8 @@ def pack_actor_critic(policy: "MaskableActorCritic", out: torch.Tensor | None = 
 
 
 class MaskablePPO:
+    MIN_ENVS_PER_STREAM = 65536      # below this a second stream only adds launches to the eager rollout loop
+
     def __init__(self, env, n_steps: int = 64, batch_size: int = 8192, n_epochs: int = 10, gamma: float = 0.99,
                  gae_lambda: float = 0.95, clip_range: float = 0.2, ent_coef: float = 0.05, vf_coef: float = 0.5,
                  learning_rate: float = 3e-4, max_grad_norm: float = 0.5, seed: int = 42, fused_act: bool = True,
@@ -106,6 +108,9 @@ class MaskablePPO:
         # The rollout runs on `rollout_streams` CUDA streams over disjoint env ranges (msort_*_range): while the
         # tensor-core policy kernel of one range waits on its MMA round trips, the step kernel of another range uses
         # the SMs (and the tail of every kernel overlaps the head of the next): 134 -> 124 us per env-step at 1 M envs.
+        # (only when a range is big enough for its kernels to outlast their launch overhead: the loop is eager)
+        if self.n < rollout_streams * self.MIN_ENVS_PER_STREAM:
+            rollout_streams = 1
         per = -(-self.n // max(1, rollout_streams)) if rollout_streams > 1 else self.n
         per = -(-per // 128) * 128                                       # ranges start on whole 128-env tiles
         self._ranges = [(lo, min(self.n, lo + per)) for lo in range(0, self.n, per)] if self.fused_act else [(0, self.n)]
