@@ -101,16 +101,22 @@ def test_fused_rollout_matches_torch_rollout_statistics():
     assert stats[True][1] < 5e-3 and stats[True][2] < 5e-3, stats
 
 
-def test_env_ranges_on_two_streams_compose_to_the_whole_batch():
+@pytest.mark.parametrize("kind", ["mono", "press", "sort"])
+def test_env_ranges_on_two_streams_compose_to_the_whole_batch(kind):
     """msort_step_range / msort_policy_act_range: two disjoint env ranges (ragged second one), each on its own CUDA
     stream, leave exactly what the whole-batch calls leave — state, obs, mask, reward, done, actions, log-probs,
     values, statistics.  Range starts must be multiples of 128."""
     import torch
     import marl_sortingenv_b200 as ms
     from marl_sortingenv_b200.ppo import MaskableActorCritic, pack_actor_critic
-    n, cut = 128 * 37 + 51, 128 * 20
-    whole = ms.BatchedMonolithEnv(n, max_steps=20, seed=5, info_level="episode")
-    parts = ms.BatchedMonolithEnv(n, max_steps=20, seed=5, info_level="episode")
+    from marl_sortingenv_b200.batched import ENV_CLASSES
+    from marl_sortingenv_b200.policy import sb3_style_init
+    # Env_2: more tiles per range than resident CTAs, so its persistent kernel loops inside each range
+    n, cut = (128 * 1500 + 51, 128 * 800) if kind == "press" else (128 * 37 + 51, 128 * 20)
+    whole = ENV_CLASSES[kind](n, max_steps=20, seed=5, info_level="episode")
+    parts = ENV_CLASSES[kind](n, max_steps=20, seed=5, info_level="episode")
+    if kind == "press":
+        whole.set_sort_policy(sb3_style_init(2, action_gain=1.0)); parts.set_sort_policy(sb3_style_init(2, action_gain=1.0))
     whole.reset(); parts.reset()
     torch.manual_seed(1)
     packed = pack_actor_critic(MaskableActorCritic(whole.D, whole.A).cuda())
