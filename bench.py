@@ -38,7 +38,7 @@ ACTION_SEED = 7
 ALGO_BYTES_PER_STEP = {"sort": 223, "press": 244, "mono": 307}   # SURVEY.md §8d / DESIGN.md
 # dram__bytes_read.sum + dram__bytes_write.sum per step-kernel launch at this workload, from the
 # `ncu --set full` capture summarised in profiles/ (None until a capture exists).
-NCU_TRAFFIC_BYTES_PER_LAUNCH = {("mono", 1 << 20): 232.7e6}   # profiles/ncu_r01_step_kernel.md (kernel v16: 75.6 MB read + 157.1 MB written)
+NCU_TRAFFIC_BYTES_PER_LAUNCH = {("mono", 1 << 20): 232.4e6}   # profiles/ncu_r01_step_kernel.md (kernel v17: 75.5 MB read + 156.8 MB written)
 
 
 def parse_args():

@@ -20,6 +20,9 @@
 #ifndef MSORT_PRESS_MIN_BLOCKS
 #define MSORT_PRESS_MIN_BLOCKS 5  // Env_2 (embedded MLP: 32 activations + FFMA2 accumulator pairs in registers)
 #endif
+#ifndef MSORT_HOT_MONO_MIN_BLOCKS
+#define MSORT_HOT_MONO_MIN_BLOCKS 8  // Env_3's HOT kernel fits 64 registers without a spill: 8 CTAs (32 warps) per SM, +3..5 %
+#endif
 #ifndef MSORT_STEP_MIN_BLOCKS
 #define MSORT_STEP_MIN_BLOCKS 7  // resident CTAs per SM the step kernel is compiled for (register cap)
 #endif
@@ -159,7 +162,8 @@ template <int KIND> using PolicyParam = typename std::conditional<KIND == MSORT_
 // compiled in, which removes ~20 uniform branches (and the basic-block boundaries they put in the
 // scheduler's way).  Chosen per launch by launch_step_kind.
 template <int KIND, int RNG, int LAYOUT, bool FAST, bool HOT = false, bool SMALL = HOT>
-__global__ void __launch_bounds__(kTile, (KIND == MSORT_ENV_PRESS ? MSORT_PRESS_MIN_BLOCKS : MSORT_STEP_MIN_BLOCKS) * (128 / kTile))  // Env_2 keeps 32 MLP activations in registers
+__global__ void __launch_bounds__(kTile, (KIND == MSORT_ENV_PRESS ? MSORT_PRESS_MIN_BLOCKS   // Env_2 keeps 32 MLP activations in registers
+                                           : (KIND == MSORT_ENV_MONO && HOT) ? MSORT_HOT_MONO_MIN_BLOCKS : MSORT_STEP_MIN_BLOCKS) * (128 / kTile))
 step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArgs a,
             const __grid_constant__ PolicyParam<KIND> pw) {
   constexpr int D = Dims<KIND>::D, A = Dims<KIND>::A;
