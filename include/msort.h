@@ -31,6 +31,8 @@
 extern "C" {
 #endif
 
+/* ABI history: 2 telemetry (msort_gather_state, reward terms) and msort_policy_act; 3 msort_observe_after_shift,
+ * msort_step_variant, obs / mask must be 16-byte aligned; 4 msort_step_range, msort_policy_act_range. */
 #define MSORT_ABI_VERSION 4
 
 /* ------------------------------------------------------------------ enums */
