@@ -28,7 +28,6 @@
 #include <stdint.h>
 
 #include <algorithm>
-#include <cstdlib>
 
 #include "msort_device.cuh"
 #include "msort_launch.h"
@@ -353,8 +352,7 @@ static cudaError_t launch_policy_act_da(const DevConfig& c, const float* obs, co
   cudaError_t e = cudaFuncSetAttribute(policy_act_kernel<D, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const long long ntiles = (c.n + kRows - 1) / kRows;
-  static const int ctas_per_sm = [] { const char* e = getenv("MSORT_POLICY_CTAS_PER_SM"); int v = e ? atoi(e) : 4; return v >= 1 && v <= 4 ? v : 4; }();
-  const unsigned grid = (unsigned)std::min<long long>(ntiles, (long long)ctas_per_sm * sm_count);
+  const unsigned grid = (unsigned)std::min<long long>(ntiles, 4ll * sm_count);
   // TMA bulk copies need 16-byte aligned tile addresses (tile sizes are multiples of 16 bytes)
   const int use_tma = ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(mask)) & 15u) == 0;
   policy_act_kernel<D, A><<<grid, kThreads, smem, st>>>(obs, mask, packed, c.n, c.gid0, (unsigned)(seed & 0xffffffffu),

@@ -1,6 +1,6 @@
 """Experiment: the rollout loop (policy_act + step per env-step) on TWO streams over two half-batches, so that the
 latency-bound tcgen05 policy kernel of one half shares the SMs with the ALU-bound step kernel of the other.
-MSORT_POLICY_CTAS_PER_SM limits the persistent policy grid so that step CTAs fit beside it.
+(A build with the persistent policy grid limited to 1..3 CTAs per SM, so that step CTAs fit beside it, was not faster.)
 python profiles/tools/time_rollout_2stream.py"""
 import os, sys
 sys.path.insert(0, "/root/repo")
