@@ -32,8 +32,9 @@ extern "C" {
 #endif
 
 /* ABI history: 2 telemetry (msort_gather_state, reward terms) and msort_policy_act; 3 msort_observe_after_shift,
- * msort_step_variant, obs / mask must be 16-byte aligned; 4 msort_step_range, msort_policy_act_range. */
-#define MSORT_ABI_VERSION 4
+ * msort_step_variant, obs / mask must be 16-byte aligned; 4 msort_step_range, msort_policy_act_range;
+ * 5 msort_set_option, MSORT_STEP_HOT_TENSOR. */
+#define MSORT_ABI_VERSION 5
 
 /* ------------------------------------------------------------------ enums */
 typedef enum msort_status {
@@ -227,7 +228,10 @@ int msort_reset(msort_t* h, void* state, const uint8_t* which, const uint8_t* fi
  * keyword arguments (env_monolith.py:109). */
 int msort_set_flags(msort_t* h, uint32_t flags);
 
-/* Re-key the Philox generator and restart episode numbering (reset(seed=s) with a new seed). */
+/* Re-key the Philox generator of the WHOLE handle (reset(seed=s) with a new seed).  Call it only together with a
+ * full msort_reset (which == NULL, reset_flags == 0 — that is what restarts episode numbering): the PHILOX layouts
+ * do not store accuracy_belt but recompute it from (key, env, episode, step - 1, mode), so re-keying while some
+ * envs are mid-episode changes their current accuracies and every later draw. */
 int msort_set_seed(msort_t* h, uint64_t seed);
 
 /* ref: Env_X.step(action, use_action_masking, check_overflow) (env_1_sort.py:97-154,
@@ -331,7 +335,21 @@ int msort_policy_act_range(msort_t* h, int64_t first_env, int64_t num_envs, cons
 #define MSORT_STEP_FAST 3
 #define MSORT_STEP_HOT 4
 #define MSORT_STEP_HOT_PERSISTENT 5
+#define MSORT_STEP_HOT_TENSOR 6 /* HOT persistent with Env_2's embedded policy on the tensor cores (tcgen05, fp16-split operands) */
 int msort_step_variant(const msort_t* h);
+
+/* Handle options (diagnostics / experiments; defaults are the production choice).
+ *  MSORT_OPT_TENSOR_POLICY (default 1): Env_2's embedded sort policy (ref: sort_agent.predict, env_2_press.py:106-109)
+ *    is evaluated on the tensor cores when the HOT persistent kernel runs and the weights fit the fp16 split;
+ *    0 = always the per-thread fp32 FFMA2 form. */
+#define MSORT_OPT_TENSOR_POLICY 1
+int msort_set_option(msort_t* h, int option, int64_t value);
+
+/* Diagnostics: the tensor-core form of Env_2's embedded policy alone.  sort_obs [count,13] f32 (device) -> logits
+ * [count,2] f32 (device), evaluated exactly as the HOT_TENSOR step kernel evaluates it (fp16-split operands, fp32
+ * accumulation in TMEM), so a test can bound its error against the fp32 network of the reference
+ * (sort_agent.predict, env_2_press.py:106-109).  MSORT_E_UNSUPPORTED when the policy does not fit the split. */
+int msort_debug_policy_logits(msort_t* h, const float* sort_obs, int64_t count, float* logits, void* stream);
 
 #ifdef __cplusplus
 }

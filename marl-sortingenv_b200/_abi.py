@@ -8,7 +8,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 POLICY_ACT_WEIGHTS = 4256
 
 ENV_SORT, ENV_PRESS, ENV_MONO = 1, 2, 3
@@ -155,7 +155,10 @@ SYMBOLS = {
     "msort_sync_check": (C.c_int, [_P, _P]),
     "msort_launch_count": (C.c_int64, [_P]),
     "msort_step_variant": (C.c_int, [_P]),
+    "msort_set_option": (C.c_int, [_P, C.c_int, C.c_int64]),
+    "msort_debug_policy_logits": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
 }
+OPT_TENSOR_POLICY = 1
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "csrc", "libmsort.so")

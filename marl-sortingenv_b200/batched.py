@@ -140,7 +140,11 @@ class BatchedEnv:
     @property
     def step_variant(self) -> str:
         """Which instantiation of the step kernel the last step() launched (include/msort.h MSORT_STEP_*)."""
-        return ("none", "replay", "generic", "fast", "hot", "hot_persistent")[int(self.lib.msort_step_variant(self._h))]
+        return ("none", "replay", "generic", "fast", "hot", "hot_persistent", "hot_tensor")[int(self.lib.msort_step_variant(self._h))]
+
+    def set_option(self, option: int, value: int):
+        """Handle options of include/msort.h (MSORT_OPT_*), e.g. `_abi.OPT_TENSOR_POLICY`."""
+        _abi.check(self.lib, self.lib.msort_set_option(self._h, int(option), int(value)), "msort_set_option")
 
     def set_flags(self, *, use_action_masking=None, check_overflow=None, auto_reset=None):
         f = int(self.cfg.flags)
@@ -157,6 +161,11 @@ class BatchedEnv:
         episode numbering; `seed=None` after the first reset keeps the streams running
         (env_super.py:377-378)."""
         flags = 0
+        if seed is not None and which is not None:
+            # the Philox key belongs to the whole handle and the PHILOX layouts recompute every env's sorter accuracies
+            # from (key, env, episode, step): re-keying under a partial reset would change the envs that are NOT reset
+            raise ValueError("reset(seed=..., which=...): a new seed re-keys every env of the batch; "
+                             "reset the whole batch with the seed, or the subset without one")
         if seed is not None:
             self.seed = seed
             _abi.check(self.lib, self.lib.msort_set_seed(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF), "msort_set_seed")
@@ -369,6 +378,16 @@ class BatchedEnv:
         _abi.check(self.lib, rc, "msort_set_policy")
         torch.cuda.current_stream(self.device).synchronize()   # `w` may be freed after return
         self.set_flags_mlp(True)
+
+    def policy_logits_tensor(self, sort_obs: torch.Tensor) -> torch.Tensor:
+        """Diagnostics: the two logits of the embedded sort policy for `sort_obs` [K,13] f32 (CUDA), computed by the
+        tensor-core form the HOT_TENSOR step kernel uses (`msort_debug_policy_logits`)."""
+        o = sort_obs.to(device=self.device, dtype=torch.float32).contiguous()
+        out = torch.empty((o.shape[0], 2), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self.lib.msort_debug_policy_logits(self._h, _ptr(o), o.shape[0], _ptr(out), self._stream())
+        _abi.check(self.lib, rc, "msort_debug_policy_logits")
+        return out
 
     def set_flags_mlp(self, on: bool):
         f = int(self.cfg.flags)

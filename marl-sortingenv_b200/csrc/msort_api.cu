@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -26,6 +27,11 @@ struct msort_handle {
   bool imported = false;                    // msort_import_state since the last full reset: stage contents are arbitrary, so the
                                             // HOT kernel's host-proved bound of twelve draws per station does not hold
   float policy_host[MSORT_POLICY_WEIGHTS];  // host copy in the kernel's paired layout (pack_policy_pairs): travels to the step kernel as a kernel parameter
+  uint32_t policy_tc_host[kTcWords];        // the same policy packed for the tensor-core path (pack_policy_tc); source of the upload
+  uint32_t* policy_tc_dev = nullptr;        // owned device copy (11 KB, allocated by the first msort_set_policy)
+  bool policy_tc_ok = false;                // the policy fits the fp16 split (else the FFMA2 kernel evaluates it)
+  bool policy_tc_enabled = true;            // msort_set_option(MSORT_OPT_TENSOR_POLICY)
+  int persist_per_sm[4] = {1, 1, 1, 1};     // resident CTAs per SM of the persistent Env_2 kernels on this handle's device
   int64_t launches;
 };
 
@@ -102,6 +108,15 @@ static void set_round_keys(DevConfig& d, uint64_t seed) {
   }
 }
 
+// Python-float round(x, 2) (float.__round__: correctly rounded on the exact decimal value of the double) — what
+// glibc's "%.2f" prints.  The reference applies it to an EMPTY container: purity = round(threshold, 2)
+// (env_super.py:788-789) and purity difference round(purity - threshold, 2) (:222-225), both on plain Python floats.
+static double py_round2(double x) {
+  char buf[64];
+  snprintf(buf, sizeof buf, "%.2f", x);
+  return strtod(buf, nullptr);
+}
+
 // float64 restatement of the reference's obs purity difference, used to validate the fast path
 static float pdiff_reference(int k, double qthr) {
   double d = (double)k / 100.0 - qthr;
@@ -168,7 +183,13 @@ static int digest_config(const msort_config_t& c, DevConfig& d) {
   d.rem_new_bale = c.bale_size + 1;  // `rem > S*threshold` (env_super.py:675); rem < S always
   for (int r = 0; r <= c.bale_size; ++r)
     if ((double)r > (double)c.bale_size * c.bale_remainder_threshold) { d.rem_new_bale = r; break; }
-  for (int m = 0; m < 4; ++m) { d.base_acc[m] = c.baseline_accuracy[m]; d.qthr[m] = c.quality_threshold[m]; }
+  for (int m = 0; m < 4; ++m) {
+    d.base_acc[m] = c.baseline_accuracy[m]; d.qthr[m] = c.quality_threshold[m];
+    d.qthr_empty[m] = py_round2(c.quality_threshold[m]);
+    d.pdiff_empty[m] = (float)py_round2(d.qthr_empty[m] - c.quality_threshold[m]);
+    if (d.pdiff_empty[m] < -1.f) d.pdiff_empty[m] = -1.f;
+    if (d.pdiff_empty[m] > 1.f) d.pdiff_empty[m] = 1.f;
+  }
   d.boost = c.boost;
   d.noise_low = -c.noise;                 // numpy uniform(low, high): low + (high-low)*u
   d.noise_range = c.noise - d.noise_low;
@@ -281,6 +302,9 @@ extern "C" int msort_create(const msort_config_t* cfg, int device, msort_t** out
   h->lut_dev = nullptr;
   h->policy_set = false;
   h->launches = 0;
+  if (d.kind == MSORT_ENV_PRESS) query_persist_occupancy(h->persist_per_sm);
+  e = prepare_policy_kernels();
+  if (e != cudaSuccess) { cudaSetDevice(prev_device); delete h; return cuda_fail(e, "cudaFuncSetAttribute(policy kernels)"); }   // per handle, on its own device, outside any capture
   cudaSetDevice(prev_device);  // launches run on the caller's current device, which must be `device`
   // sorting-reward table (see sort_reward_f64 in msort_device.cuh): same formula, host float64
   {
@@ -303,6 +327,7 @@ extern "C" int msort_create(const msort_config_t* cfg, int device, msort_t** out
 extern "C" int msort_destroy(msort_t* h) {
   if (!h) return MSORT_OK;
   if (h->lut_dev) cudaFree(h->lut_dev);
+  if (h->policy_tc_dev) cudaFree(h->policy_tc_dev);
   delete h;
   return MSORT_OK;
 }
@@ -324,6 +349,14 @@ extern "C" int msort_set_seed(msort_t* h, uint64_t seed) {
   h->cfg.seed = seed;
   set_round_keys(h->dev, seed);
   return MSORT_OK;
+}
+
+extern "C" int msort_set_option(msort_t* h, int option, int64_t value) {
+  if (!h) return fail(MSORT_E_INVALID, "msort_set_option: NULL handle");
+  switch (option) {
+    case MSORT_OPT_TENSOR_POLICY: h->policy_tc_enabled = value != 0; return MSORT_OK;
+    default: return fail(MSORT_E_INVALID, "msort_set_option: unknown option %d", option);
+  }
 }
 
 extern "C" int msort_set_flags(msort_t* h, uint32_t flags) {
@@ -401,7 +434,9 @@ static int step_impl(msort_t* h, long long first, long long count, void* state, 
       info = &sub;
     }
   }
-  StepLaunch l{state, actions, obs, reward, terminated, mask, info, replay, &h->step_variant, h->imported ? 0 : 1, h->policy_set ? h->policy_host : nullptr};
+  StepLaunch l{state, actions, obs, reward, terminated, mask, info, replay, &h->step_variant, h->imported ? 0 : 1,
+               h->policy_set ? h->policy_host : nullptr,
+               (h->policy_set && h->policy_tc_ok && h->policy_tc_enabled) ? h->policy_tc_dev : nullptr, h->persist_per_sm};
   MSORT_TRY_CUDA(launch_step(d, l, h->cfg.rng_mode, (cudaStream_t)stream), "step kernel");
   h->launches += 1;
   return MSORT_OK;
@@ -435,7 +470,23 @@ extern "C" int msort_set_policy(msort_t* h, const float* weights, int weights_on
     memcpy(sb3, weights, sizeof(sb3));
   }
   pack_policy_pairs(sb3, h->policy_host);
+  // tensor-core form (Env_2's persistent HOT kernel): fp16-split weight tiles in a small device buffer the handle owns
+  h->policy_tc_ok = pack_policy_tc(sb3, h->policy_tc_host);
+  if (h->policy_tc_ok) {
+    if (!h->policy_tc_dev) MSORT_TRY_CUDA(cudaMalloc(&h->policy_tc_dev, sizeof(h->policy_tc_host)), "cudaMalloc(tensor-core policy)");
+    MSORT_TRY_CUDA(cudaMemcpyAsync(h->policy_tc_dev, h->policy_tc_host, sizeof(h->policy_tc_host), cudaMemcpyHostToDevice,
+                                   (cudaStream_t)stream), "cudaMemcpyAsync(tensor-core policy)");
+  }
   h->policy_set = true;
+  return MSORT_OK;
+}
+
+extern "C" int msort_debug_policy_logits(msort_t* h, const float* sort_obs, int64_t count, float* logits, void* stream) {
+  if (!h || !sort_obs || !logits || count < 0) return fail(MSORT_E_INVALID, "msort_debug_policy_logits: bad argument");
+  if (!h->policy_set || !h->policy_tc_ok || !h->policy_tc_dev)
+    return fail(MSORT_E_UNSUPPORTED, "msort_debug_policy_logits: no tensor-core policy (msort_set_policy not called, or the weights do not fit the fp16 split)");
+  MSORT_TRY_CUDA(launch_tc_logits(sort_obs, h->policy_tc_dev, count, logits, h->sm_count, (cudaStream_t)stream), "tc_logits kernel");
+  h->launches += 1;
   return MSORT_OK;
 }
 

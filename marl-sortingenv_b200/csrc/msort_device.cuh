@@ -47,16 +47,34 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
 }
 
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar_saddr, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(bar_saddr), "r"(parity) : "memory");
+  return done;
+}
+
+// Wait for a phase of an mbarrier.  Fast polls first; a wait that outlasts them (time-slicing, a debugger, a
+// profiler replay) backs off with nanosleep and is bounded by WALL CLOCK — 20 s of %globaltimer — so that a
+// mis-programmed copy / MMA still fails loudly instead of hanging the GPU, while a legitimately slow wait survives.
+static __device__ __noinline__ void mbar_wait_slow(uint32_t a, uint32_t parity) {
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    if (mbar_try_wait(a, parity)) return;
+    __nanosleep(256);
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > 20000000000ull) __trap();
+  }
+}
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
-  for (uint32_t spin = 0;; ++spin) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(a), "r"(parity) : "memory");
-    if (done) return;
-    if (spin > (1u << 24)) __trap();   // a mis-programmed MMA must fail loudly, never hang the GPU
-  }
+#pragma unroll 1
+  for (uint32_t spin = 0; spin < 2048u; ++spin)
+    if (mbar_try_wait(a, parity)) return;
+  mbar_wait_slow(a, parity);
 }
 
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
@@ -103,11 +121,26 @@ struct DevConfig {
   float inv_cap, inv_stage, inv_pt[2];
   double base_acc[4], boost, noise_low, noise_range;
   double qthr[4];
+  double qthr_empty[4];            // purity an EMPTY container reports: Python round(threshold, 2) (env_super.py:788-789)
+  float pdiff_empty[4];            // ... and its purity-difference observation round(qthr_empty - threshold, 2) (:222-225); 0 for whole percents
   double theta4, c_sort;           // sum of 4 thetas; (scaling/4)/temperature
   double c_state, c_eff;           // max_state/(5*cap); 4/S
   double pen_cat, pen_sev, pen_mild, bef, ovf_pen;
   const double* sort_lut;          // kSortLut float64 sorting rewards indexed by the purity sum (see sort_reward)
 };
+
+// Env_2's embedded 13->32->32->2 policy on the tensor cores (step kernel, TCMLP instantiation):
+// packed operand buffer built by pack_policy_tc() (msort_kernels.cu).  fp16 weight tiles in the K-major core-matrix
+// order [k/8][n][k%8], each weight as a THREE-term fp16 split (two for the scaled last layer), then the fp32 biases
+// the epilogues add.  Offsets in fp16 elements / 32-bit words.
+constexpr int kTcB1 = 0;                          // layer 1: 3 term tiles [K=16 x N=32] (rows 13..15 of term 0 = bias split)
+constexpr int kTcB2 = kTcB1 + 3 * 16 * 32;        // layer 2: 3 term tiles [K=32 x N=32]
+constexpr int kTcB3 = kTcB2 + 3 * 32 * 32;        // layer 3: 2 term tiles [K=32 x N=16] (rows 0, 1 = the two logits)
+constexpr int kTcHalves = kTcB3 + 2 * 32 * 16;
+constexpr int kTcBias2 = kTcHalves / 2;           // 32 floats
+constexpr int kTcBias3 = kTcBias2 + 32;           // 2 floats (+2 padding)
+constexpr int kTcWords = kTcBias3 + 4;            // 2852 words = 11 408 B (a multiple of 16)
+static_assert(kTcWords % 4 == 0, "whole 16-byte vectors");
 
 constexpr int kSortLut = 401;      // purity sum in hundredths: 4 containers x (0..100)
 
@@ -395,10 +428,10 @@ __device__ __forceinline__ int purity_k(const DevConfig& c, int tr, int tot) {  
 static __device__ __noinline__ double sort_reward_f64(const DevConfig& c, int k0, int k1, int k2, int k3) {
   int ksum = 0;
   double extra = 0.0;
-  if (k0 >= 0) ksum += k0; else extra += c.qthr[0];
-  if (k1 >= 0) ksum += k1; else extra += c.qthr[1];
-  if (k2 >= 0) ksum += k2; else extra += c.qthr[2];
-  if (k3 >= 0) ksum += k3; else extra += c.qthr[3];
+  if (k0 >= 0) ksum += k0; else extra += c.qthr_empty[0];
+  if (k1 >= 0) ksum += k1; else extra += c.qthr_empty[1];
+  if (k2 >= 0) ksum += k2; else extra += c.qthr_empty[2];
+  if (k3 >= 0) ksum += k3; else extra += c.qthr_empty[3];
   return tanh(((double)ksum * 0.01 + (extra - c.theta4)) * c.c_sort);
 }
 
@@ -425,11 +458,11 @@ __device__ __forceinline__ void obs_acc(const double acc[4], float* o) {  // o[5
   for (int m = 0; m < 4; ++m) o[5 + m] = (float)acc[m];
 }
 
-// kq[m] = purity k (0..100) of container m, or -1 when the container is empty (purity == threshold)
+// kq[m] = purity k (0..100) of container m, or -1 when the container is empty (purity == round(threshold, 2))
 __device__ __forceinline__ void obs_pdiff(const DevConfig& c, const int kq[4], float* o) {  // o[9..12]
 #pragma unroll
   for (int m = 0; m < 4; ++m) {
-    float d = 0.f;
+    float d = c.pdiff_empty[m];
     if (kq[m] >= 0) d = c.fast_pdiff ? (float)(kq[m] - c.qthr100[m]) * 0.01f : pdiff_f64(kq[m], c.qthr[m]);
     o[9 + m] = clipf(d, -1.f, 1.f);
   }

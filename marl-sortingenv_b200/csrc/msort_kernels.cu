@@ -5,11 +5,13 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <type_traits>
 
 #include "msort_device.cuh"
 #include "msort_launch.h"
+#include "msort_umma.cuh"
 
 #ifndef MSORT_PREFETCH_TILES
 #define MSORT_PREFETCH_TILES 296  // L2 prefetch distance of the step kernel in tiles (2 per SM; 0 = off): 148..518 measured alike, +3.4 %
@@ -19,6 +21,9 @@
 #endif
 #ifndef MSORT_PRESS_MIN_BLOCKS
 #define MSORT_PRESS_MIN_BLOCKS 5  // Env_2 (embedded MLP: 32 activations + FFMA2 accumulator pairs in registers)
+#endif
+#ifndef MSORT_PRESS_TC_MIN_BLOCKS
+#define MSORT_PRESS_TC_MIN_BLOCKS 5  // Env_2 with the embedded policy on the tensor cores (TCMLP): 39.7 KB of shared memory per CTA
 #endif
 #ifndef MSORT_HOT_MONO_MIN_BLOCKS
 #define MSORT_HOT_MONO_MIN_BLOCKS 8  // Env_3's HOT kernel fits 64 registers without a spill: 8 CTAs (32 warps) per SM, +3..5 %
@@ -122,6 +127,7 @@ struct StepArgs {
   float* info_r_press;
   int any_step_info;  // any of the six per-step info arrays above is present
   int act_tma;        // actions are 16-byte aligned: the persistent kernel may fetch a tile's actions by TMA
+  const uint4* policy_tc;   // Env_2 TCMLP: packed tensor-core policy (kTcWords words, device memory) or nullptr
   float* terminal_obs;
   double* episode_return;
   int* episode_length;
@@ -152,6 +158,162 @@ struct alignas(16) PolicyW { float w[(MSORT_POLICY_WEIGHTS + 3) / 4 * 4]; };   /
 struct NoPolicy {};
 template <int KIND> using PolicyParam = typename std::conditional<KIND == MSORT_ENV_PRESS, PolicyW, NoPolicy>::type;
 
+// ---------------------------------------------------------------- Env_2's embedded policy on the tensor cores (TCMLP)
+// ref: sort_agent.predict(sort_obs, deterministic=True) env_2_press.py:106-109 — SB3 MlpPolicy 13 -> 32 -> 32 -> 2, tanh
+// (training.py:115), argmax.  The CTA's tile of 128 envs is one UMMA M = 128 tile (TMEM lane = thread = env), so the
+// three layers run as tcgen05.mma kind::f16 with fp32 accumulation in 32 TMEM columns.  To keep the fp32 reference's
+// argmax (parity contract: identical except where |logit0 - logit1| < 1e-5) every operand is an fp16 SPLIT:
+//   activation x = x_hi + x_lo (umma::split2, 22 significand bits), weight w = w_1 + w_2 + w_3 (host, 33 bits)
+//   x*w ~ x_hi*w_1 + x_hi*w_2 + x_lo*w_1 + x_hi*w_3 + x_lo*w_2         (five MMAs per K step; each product exact,
+//   fp32 accumulation, smallest terms first), error <= ~2^-23 relative + 2^-25 absolute per product.
+// tanh is evaluated as 1 - 2r with r = 1 / (1 + 2^(c z)), c = 2 log2(e): the host folds c into this layer's weights
+// and the affine map h = 1 - 2r into the NEXT layer's weights and bias (pack_policy_tc), so an activation costs
+// MUFU.EX2 + FADD + MUFU.RCP and r (in (0, 1]) is what is split and stored as the next A operand.  Layer 1's bias rides
+// in the three padding columns of the 13-wide observation (A = 1.0, B = the bias's three split terms); layers 2 / 3
+// add theirs in the epilogue.  Measured logit error against the fp32 sum: see tests/test_tc_mlp_gpu.py.
+struct TcMlp {
+  uint4* a;            // A operand: hi chunks [4][128] then lo chunks [4][128] (16 KB; the first 8 KB alias the obs tile)
+  const uint32_t* w;   // packed weights in shared memory (kTcWords)
+  uint64_t* bar;       // MMA completion
+  uint32_t tmem;       // base address of the 32 accumulator columns
+};
+
+__device__ __forceinline__ float tc_sigmoid2(float zp) {   // 1 / (1 + 2^zp); +inf -> 0, -inf -> 1
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(zp));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+  return r;
+}
+
+// one thread: all split products of one layer, smallest terms first, then commit
+template <int KSTEPS, int N, int NTERMS>
+__device__ __forceinline__ void tc_issue_layer(const TcMlp& m, int b_off_halves) {
+  const uint32_t a0 = smem_u32(m.a), b0 = smem_u32(m.w) + 2u * (uint32_t)b_off_halves;
+  constexpr uint32_t kTermBytes = (uint32_t)(KSTEPS * 16 * N * 2), kLoBytes = 4u * kTile * 16u;
+  uint32_t acc = 0u;
+  auto mm = [&](int aterm, int bterm, int s) {
+    const uint64_t ad = umma::smem_desc(a0 + (aterm ? kLoBytes : 0u) + (uint32_t)(2 * s) * kTile * 16u, kTile * 16u, 128u);
+    const uint64_t bd = umma::smem_desc(b0 + (uint32_t)bterm * kTermBytes + (uint32_t)(2 * s) * N * 16u, N * 16u, 128u);
+    umma::mma_f16(m.tmem, ad, bd, umma::idesc_f16(N), acc);
+    acc = 1u;
+  };
+#ifndef MSORT_TC_TERMS
+#define MSORT_TC_TERMS 5   // 5 = all split products (product build); 3 / 1 = timing experiments only (lose accuracy)
+#endif
+  if (NTERMS == 3 && MSORT_TC_TERMS >= 5) {
+#pragma unroll
+    for (int s = 0; s < KSTEPS; ++s) { mm(1, 1, s); mm(0, 2, s); }
+  }
+  if (MSORT_TC_TERMS >= 3) {
+#pragma unroll
+    for (int s = 0; s < KSTEPS; ++s) { mm(1, 0, s); mm(0, 1, s); }
+  }
+#pragma unroll
+  for (int s = 0; s < KSTEPS; ++s) mm(0, 0, s);
+  umma::commit(m.bar);
+}
+
+// hidden-layer epilogue of this thread's env: 32 accumulators -> (+bias) -> r -> fp16 split -> the next A operand
+template <bool BIAS>
+__device__ __forceinline__ void tc_hidden_epilogue(const TcMlp& m, uint32_t tlane, const float* __restrict__ bias, int tid) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    float v[16];
+    umma::tmem_ld16(tlane + 16u * half, v);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        float z0 = v[8 * q + 2 * p], z1 = v[8 * q + 2 * p + 1];
+        if (BIAS) { z0 += bias[16 * half + 8 * q + 2 * p]; z1 += bias[16 * half + 8 * q + 2 * p + 1]; }
+        umma::split2(tc_sigmoid2(z0), tc_sigmoid2(z1), h[p], l[p]);
+      }
+      m.a[(2 * half + q) * kTile + tid] = make_uint4(h[0], h[1], h[2], h[3]);
+      m.a[(4 + 2 * half + q) * kTile + tid] = make_uint4(l[0], l[1], l[2], l[3]);
+    }
+  }
+}
+
+// All 128 threads of a tile call this together (it contains CTA barriers); `so` = this env's 13-wide sort
+// observation.  l0 / l1 = the two logits times the host's power-of-two scale (fw[kTcBias3 + 2] holds its inverse).
+__device__ __forceinline__ void tc_mlp_logits(const TcMlp& m, const float (&so)[13], int tid, uint32_t& phase, float& l0, float& l1) {
+  const uint32_t tlane = m.tmem + ((uint32_t)(tid & ~31) << 16);
+  {   // layer-1 operand: obs columns 0..12, then 1, 1, 1 (bias terms); the lo part of an exact 1.0 is 0
+    uint32_t h[8], l[8];
+#pragma unroll
+    for (int p = 0; p < 6; ++p) umma::split2(so[2 * p], so[2 * p + 1], h[p], l[p]);
+    umma::split2(so[12], 1.0f, h[6], l[6]);
+    umma::split2(1.0f, 1.0f, h[7], l[7]);
+    m.a[tid] = make_uint4(h[0], h[1], h[2], h[3]);
+    m.a[kTile + tid] = make_uint4(h[4], h[5], h[6], h[7]);
+    m.a[4 * kTile + tid] = make_uint4(l[0], l[1], l[2], l[3]);
+    m.a[5 * kTile + tid] = make_uint4(l[4], l[5], l[6], l[7]);
+  }
+  const float* const fw = reinterpret_cast<const float*>(m.w);
+#pragma unroll
+  for (int layer = 0; layer < 3; ++layer) {
+    umma::fence_async_proxy();       // this thread's operand writes -> visible to the MMA's async-proxy reads
+    umma::fence_before_sync();       // ... and its TMEM reads are done before the next MMA overwrites the columns
+    __syncthreads();
+    if (tid == 0) {
+      umma::fence_after_sync();
+      if (layer == 0) tc_issue_layer<1, 32, 3>(m, kTcB1);
+      else if (layer == 1) tc_issue_layer<2, 32, 3>(m, kTcB2);
+      else tc_issue_layer<2, 16, 2>(m, kTcB3);
+    }
+    mbar_wait(m.bar, phase); phase ^= 1u;
+    umma::fence_after_sync();
+    if (layer == 0) tc_hidden_epilogue<false>(m, tlane, nullptr, tid);
+    else if (layer == 1) tc_hidden_epilogue<true>(m, tlane, fw + kTcBias2, tid);
+  }
+  umma::tmem_ld2(tlane, l0, l1);
+  umma::fence_before_sync();         // ordered before the next tile's first MMA by the barriers in between
+  l0 += fw[kTcBias3]; l1 += fw[kTcBias3 + 1];
+}
+
+// the sort mode: argmax of the two logits, ties -> 0 like np.argmax (sort_agent.predict(..., deterministic=True))
+__device__ __forceinline__ int tc_mlp_mode(const TcMlp& m, const float (&so)[13], int tid, uint32_t& phase) {
+  float l0, l1;
+  tc_mlp_logits(m, so, tid, phase, l0, l1);
+  return l1 > l0 ? 1 : 0;
+}
+
+// Diagnostics (msort_debug_policy_logits): the tensor-core policy alone on caller-given sort observations, logits out
+// (unscaled), so tests can measure its error against an fp32 / fp64 evaluation of the same network.
+__global__ void __launch_bounds__(kTile)
+tc_logits_kernel(const float* __restrict__ obs13, const uint4* __restrict__ tcw, long long n, float* __restrict__ logits) {
+  __shared__ __align__(128) uint4 s_a[8 * kTile];
+  __shared__ __align__(128) uint32_t s_w[kTcWords];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ uint32_t s_tm;
+  const int tid = threadIdx.x;
+  if (tid == 0) { mbar_init(&s_bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (tid < 32) umma::tmem_alloc(&s_tm, 32u);
+  for (int e = tid; e < kTcWords / 4; e += kTile) reinterpret_cast<uint4*>(s_w)[e] = tcw[e];
+  umma::fence_async_proxy();
+  umma::fence_before_sync();
+  __syncthreads();
+  umma::fence_after_sync();
+  const TcMlp m{s_a, s_w, &s_bar, s_tm};
+  uint32_t phase = 0;
+  const long long ntiles = (n + kTile - 1) / kTile;
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long i = tile * kTile + tid;
+    float so[13];
+#pragma unroll
+    for (int k = 0; k < 13; ++k) so[k] = i < n ? obs13[i * 13 + k] : 0.f;
+    float l0, l1;
+    tc_mlp_logits(m, so, tid, phase, l0, l1);
+    const float inv = reinterpret_cast<const float*>(s_w)[kTcBias3 + 2];
+    if (i < n) { logits[2 * i] = l0 * inv; logits[2 * i + 1] = l1 * inv; }
+    __syncthreads();   // every thread is done with the operand buffer before the next tile overwrites it
+  }
+  umma::fence_before_sync();
+  __syncthreads();
+  if (tid < 32) umma::tmem_dealloc(m.tmem, 32u);
+}
+
 // FAST (PHILOX only, chosen by the host when DevConfig::fast holds): boosted accuracies are exactly 1.0,
 // unboosted ones need no clip, and the redistribution classes fit one register of packed bytes.
 // Results are identical to the generic instantiation; only the instruction count differs.
@@ -161,14 +323,24 @@ template <int KIND> using PolicyParam = typename std::conditional<KIND == MSORT_
 // max_steps 50), otherwise < 2^16 (compact layout, e.g. the reference's 200-step episodes) — and are
 // compiled in, which removes ~20 uniform branches (and the basic-block boundaries they put in the
 // scheduler's way).  Chosen per launch by launch_step_kind.
-template <int KIND, int RNG, int LAYOUT, bool FAST, bool HOT = false, bool SMALL = HOT>
-__global__ void __launch_bounds__(kTile, (KIND == MSORT_ENV_PRESS ? MSORT_PRESS_MIN_BLOCKS   // Env_2 keeps 32 MLP activations in registers
+// TCMLP (Env_2's persistent HOT kernel only; full tiles only — the launcher gives a ragged tail to the plain HOT kernel):
+// the embedded policy is evaluated on the tensor cores (tc_mlp_mode above) instead of per-thread FFMA2.
+template <int KIND, int RNG, int LAYOUT, bool FAST, bool HOT = false, bool SMALL = HOT, bool TCMLP = false>
+__global__ void __launch_bounds__(kTile, (KIND == MSORT_ENV_PRESS ? (TCMLP ? MSORT_PRESS_TC_MIN_BLOCKS : MSORT_PRESS_MIN_BLOCKS)   // Env_2 (FFMA2 form) keeps 32 MLP activations in registers
                                            : (KIND == MSORT_ENV_MONO && HOT) ? MSORT_HOT_MONO_MIN_BLOCKS : MSORT_STEP_MIN_BLOCKS) * (128 / kTile))
 step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArgs a,
             const __grid_constant__ PolicyParam<KIND> pw) {
   constexpr int D = Dims<KIND>::D, A = Dims<KIND>::A;
-  __shared__ __align__(16) float s_obs[kTile * D];
+  static_assert(!TCMLP || (KIND == MSORT_ENV_PRESS && HOT && MSORT_HOT_PERSIST && kTile == 128), "TCMLP specialises Env_2's persistent HOT kernel");
+  // obs tile; with TCMLP the 16 KB MMA A-operand buffer, whose first half the obs tile aliases (the operand is dead
+  // once the last layer's MMAs are complete, long before the first obs entry of the tile is written)
+  constexpr int kObsBytes = kTile * D * (int)sizeof(float);
+  __shared__ __align__(128) unsigned char s_tile_raw[TCMLP ? (8 * kTile * 16 > kObsBytes ? 8 * kTile * 16 : kObsBytes) : kObsBytes];
+  float* const s_obs = reinterpret_cast<float*>(s_tile_raw);
   __shared__ __align__(16) uint8_t s_mask[kTile * A];
+  __shared__ __align__(128) uint32_t s_tcw[TCMLP ? kTcWords : 4];   // TCMLP: packed fp16 weight tiles + biases
+  __shared__ __align__(8) uint64_t s_mma;                           // TCMLP: MMA completion
+  __shared__ uint32_t s_tmem;                                       // TCMLP: TMEM base address
   __shared__ double s_accs[RNG == MSORT_RNG_REPLAY ? 4 : 1][RNG == MSORT_RNG_REPLAY ? kTile : 1];  // accuracy_sorter (REPLAY)
   __shared__ double s_stat[kTile / 32][ST_COUNT];   // per-warp partial sums (plain stores: no init, no atomics)
 
@@ -176,8 +348,8 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   const bool masking = HOT || (c.flags & MSORT_F_ACTION_MASKING);
   const bool auto_reset = HOT || (c.flags & MSORT_F_AUTO_RESET);
   const bool want_mask = HOT || a.mask != nullptr;
-  const bool use_mlp = KIND == MSORT_ENV_PRESS && (c.flags & MSORT_F_SORT_POLICY_MLP) &&
-                       !(RNG == MSORT_RNG_REPLAY && a.sort_mode_in);
+  const bool use_mlp = TCMLP || (KIND == MSORT_ENV_PRESS && (c.flags & MSORT_F_SORT_POLICY_MLP) &&
+                                 !(RNG == MSORT_RNG_REPLAY && a.sort_mode_in));
   const int tid = threadIdx.x;
 
   // PERSIST (Env_2's HOT instantiation): the grid is one wave of resident CTAs, each looping over tiles
@@ -202,14 +374,23 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   // two barriers: lane 0 of warp 1 stages the next tile, warp 2 adds the statistics, lane 0 of warp 3 issues
   // (and later waits for) the bulk stores.  Without PERSIST everything stays with warp 0: the other warps exit.
   constexpr int kStageTid = 32 % kTile, kStatTid = PERSIST ? 64 % kTile : 0, kStoreTid = PERSIST ? 96 % kTile : 0;
-  uint32_t phase = 0;
+  uint32_t phase = 0, mma_phase = 0;
+  TcMlp tcm{reinterpret_cast<uint4*>(s_tile_raw), s_tcw, &s_mma, 0u};
   if (PERSIST) {
     if (tid == kStageTid) {
       mbar_init(&s_full, 1);
+      if (TCMLP) mbar_init(&s_mma, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       stage_tile(blockIdx.x);
     }
+    if (TCMLP) {   // once per resident CTA: 32 TMEM columns (warp 0) and the packed weights
+      if (tid < 32) umma::tmem_alloc(&s_tmem, 32u);
+      for (int e = tid; e < kTcWords / 4; e += kTile) reinterpret_cast<uint4*>(s_tcw)[e] = a.policy_tc[e];
+      umma::fence_async_proxy();
+      umma::fence_before_sync();
+    }
     __syncthreads();
+    if (TCMLP) { umma::fence_after_sync(); tcm.tmem = s_tmem; }
   }
   long long tile = blockIdx.x;
   do {   // one pass unless PERSIST
@@ -331,7 +512,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
           obs_belt(s, orow);
         }
       }
-      if (KIND != MSORT_ENV_SORT) {
+      if (KIND != MSORT_ENV_SORT && !TCMLP) {   // TCMLP: the obs tile is still the MMA operand buffer; written after the policy
         const bool s0 = s.sort4 == c.pat[0], s1 = s.sort4 == c.pat[1];
         if (s0 || s1 || s.sort4 == 0u) {
           const float* ts = c.obs_sort_tab[s0 ? 0 : (s1 ? 1 : 2)];
@@ -364,7 +545,10 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
         int kq[4];
         purity_ks(c, s, kq);
         sort_obs(c, s, kq, so);
-        if constexpr (KIND == MSORT_ENV_PRESS) mode = mlp_sort_mode<HOT>(pw.w, so);
+        if constexpr (TCMLP) {
+          mode = tc_mlp_mode(tcm, so, tid, mma_phase);   // every thread of the (full) tile is here: CTA barriers inside
+          obs_sorting(c, s, prow);                       // the operand buffer is free again: the deferred obs entries
+        } else if constexpr (KIND == MSORT_ENV_PRESS) mode = mlp_sort_mode<HOT>(pw.w, so);
       } else {  // sorting_rules env_super.py:469-482: pA+pC > pB+pD on float64 proportions
         int ac = b4(s.belt4, 0) + b4(s.belt4, 2), bd = b4(s.belt4, 1) + b4(s.belt4, 3);
         if (ac != bd) mode = ac > bd ? 0 : 1;  // strict integer inequality survives the float64 rounding
@@ -863,6 +1047,11 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   tile += gridDim.x;
   } while (PERSIST && tile < ntiles);
   if (PERSIST && tid == kStoreTid) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // shared memory outlives the last copies
+  if (TCMLP) {
+    umma::fence_before_sync();
+    __syncthreads();
+    if (tid < 32) umma::tmem_dealloc(tcm.tmem, 32u);
+  }
 }
 
 // ---------------------------------------------------------------- K2: reset
@@ -1085,7 +1274,7 @@ stats_kernel(const __grid_constant__ DevConfig c, const uint4* __restrict__ stat
     int kq[4];
     purity_ks(c, s, kq);
 #pragma unroll
-    for (int m = 0; m < 4; ++m) { lvl += (double)(s.tr[m] + s.fl[m]); pm += kq[m] >= 0 ? 0.01 * (double)kq[m] : c.qthr[m]; }
+    for (int m = 0; m < 4; ++m) { lvl += (double)(s.tr[m] + s.fl[m]); pm += kq[m] >= 0 ? 0.01 * (double)kq[m] : c.qthr_empty[m]; }
     v[1] += lvl;
 #pragma unroll
     for (int m = 0; m < 5; ++m) {
@@ -1135,10 +1324,113 @@ void pack_policy_pairs(const float* sb3, float* paired) {
 }
 
 static inline unsigned tiles(long long n) { return (unsigned)((n + kTile - 1) / kTile); }
+int policy_tc_words() { return kTcWords; }
+
+// Env_2's embedded policy for the tensor-core path (tc_mlp_mode): SB3 order -> kTcWords packed words.
+//   layer 1: B[n][k] = c*W1[n][k] (k < 13), rows 13..15 of term 0 = the three split terms of c*b1[n]      (c = 2 log2 e)
+//   layer 2: B[n][k] = -2c*W2[n][k],  bias2'[n] = c*(b2[n] + sum_k W2[n][k])      (input r1 with h1 = 1 - 2 r1)
+//   layer 3: B[n][k] = -2s*W3[n][k],  bias3'[n] = s*(b3[n] + sum_k W3[n][k])      (s = a power of two that lifts the
+//            largest |weight| to [8192, 16384): the argmax does not see it and the two-term split stays out of fp16's
+//            subnormals)
+// every weight v (float64) as fp16 terms t1 = fp16(v), t2 = fp16(v - t1), t3 = fp16(v - t1 - t2).  Returns false when a
+// value does not fit fp16's range (the caller keeps the FFMA2 kernel for such a policy).
+bool pack_policy_tc(const float* sb3, uint32_t* words) {
+  constexpr int W1 = 0, b1 = 416, W2 = 448, b2 = 1472, W3 = 1504, b3 = 1568;
+  const double cc = 2.0 * 1.4426950408889634;
+  __half* hw = reinterpret_cast<__half*>(words);
+  float* fw = reinterpret_cast<float*>(words);
+  memset(words, 0, sizeof(uint32_t) * kTcWords);
+  bool ok = true;
+  auto put = [&](int base, int K, int N, int nterms, int n, int k, double v) {   // tile element [k][n] of every term
+    if (!(std::fabs(v) < 32768.0)) { ok = false; return; }
+    double r = v;
+    for (int t = 0; t < nterms; ++t) {
+      const __half q = __float2half_rn((float)r);
+      hw[base + t * K * N + ((k >> 3) * N + n) * 8 + (k & 7)] = q;
+      r -= (double)__half2float(q);
+    }
+  };
+  for (int n = 0; n < 32; ++n) {
+    for (int k = 0; k < 13; ++k) put(kTcB1, 16, 32, 3, n, k, cc * (double)sb3[W1 + n * 13 + k]);
+    double r = cc * (double)sb3[b1 + n];           // the bias: its three terms sit in rows 13..15 of term 0 (A holds 1.0 there)
+    if (!(std::fabs(r) < 32768.0)) ok = false;
+    for (int t = 0; t < 3 && ok; ++t) {
+      const __half q = __float2half_rn((float)r);
+      hw[kTcB1 + ((13 + t) / 8 * 32 + n) * 8 + ((13 + t) & 7)] = q;
+      r -= (double)__half2float(q);
+    }
+  }
+  for (int n = 0; n < 32; ++n) {
+    double sum = (double)sb3[b2 + n];
+    for (int k = 0; k < 32; ++k) {
+      const double w = (double)sb3[W2 + n * 32 + k];
+      put(kTcB2, 32, 32, 3, n, k, -2.0 * cc * w);
+      sum += w;
+    }
+    fw[kTcBias2 + n] = (float)(cc * sum);
+  }
+  double mx = 0.0;
+  for (int j = 0; j < 64; ++j) mx = std::max(mx, std::fabs(2.0 * (double)sb3[W3 + j]));
+  double sc = 1.0;
+  if (mx > 0.0 && std::isfinite(mx)) {
+    while (mx * sc < 8192.0) sc *= 2.0;
+    while (mx * sc >= 16384.0) sc *= 0.5;
+  }
+  for (int n = 0; n < 2; ++n) {
+    double sum = (double)sb3[b3 + n];
+    for (int k = 0; k < 32; ++k) {
+      const double w = (double)sb3[W3 + n * 32 + k];
+      put(kTcB3, 32, 16, 2, n, k, -2.0 * sc * w);
+      sum += w;
+    }
+    const double bb = sc * sum;
+    if (!std::isfinite(bb) || std::fabs(bb) > 3.0e38) ok = false;
+    fw[kTcBias3 + n] = (float)bb;
+  }
+  fw[kTcBias3 + 2] = (float)(1.0 / sc);   // diagnostics only (tc_logits_kernel): undoes the scale
+  for (int j = 0; j < MSORT_POLICY_WEIGHTS; ++j) if (!std::isfinite(sb3[j])) ok = false;
+  return ok;
+}
+
+// StepArgs of the env range starting `first` envs into the launch (whole-tile starts; D / A of the env kind)
+static StepArgs shift_args(StepArgs a, long long first, int D, int A) {
+  a.state += first; a.actions += first; a.obs += first * D; a.reward += first; a.terminated += first;
+  if (a.mask) a.mask += first * A;
+  if (a.info_action) a.info_action += first;
+  if (a.info_overflow) a.info_overflow += first;
+  if (a.info_overflow_mat) a.info_overflow_mat += first;
+  if (a.info_sort_mode) a.info_sort_mode += first;
+  if (a.info_press_action) a.info_press_action += first;
+  if (a.info_invalid) a.info_invalid += first;
+  if (a.info_sorted_true) a.info_sorted_true += first;
+  if (a.info_r_sort) a.info_r_sort += first;
+  if (a.info_r_press) a.info_r_press += first;
+  if (a.terminal_obs) a.terminal_obs += first * D;
+  if (a.episode_return) a.episode_return += first;
+  if (a.episode_length) a.episode_length += first;
+  a.act_tma = ((uintptr_t)a.actions & 15u) == 0;
+  return a;
+}
+
+// Resident CTAs per SM of the four persistent Env_2 kernels (index = SMALL + 2 * TCMLP), asked from the occupancy
+// calculator on the CURRENT device (msort_create); also sets the shared-memory carve-out those kernels want.
+void query_persist_occupancy(int per_sm[4]) {
+  auto ask = [](auto kern) {
+    int v = 0;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, kTile, 0) != cudaSuccess || v < 1) v = 1;
+    return v;
+  };
+  per_sm[0] = ask(step_kernel<MSORT_ENV_PRESS, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true, false, false>);
+  per_sm[1] = ask(step_kernel<MSORT_ENV_PRESS, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true, true, false>);
+  per_sm[2] = ask(step_kernel<MSORT_ENV_PRESS, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true, false, true>);
+  per_sm[3] = ask(step_kernel<MSORT_ENV_PRESS, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true, true, true>);
+  cudaGetLastError();
+}
 
 template <int KIND>
 static cudaError_t launch_step_kind(const DevConfig& c, const StepArgs& a, const float* policy_host, int rng, cudaStream_t st, int* variant,
-                                    int allow_hot) {
+                                    int allow_hot, const int* persist_per_sm) {
   const unsigned g = tiles(c.n);
   int dummy;
   int& var = variant ? *variant : dummy;
@@ -1155,19 +1447,32 @@ static cudaError_t launch_step_kind(const DevConfig& c, const StepArgs& a, const
     if (hot) {
       auto kern = c.small_lv ? step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true, true>
                              : step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true, false>;
-      unsigned gp = g;
       var = MSORT_STEP_HOT;
-      if (MSORT_HOT_PERSIST && KIND == MSORT_ENV_PRESS) {
-        var = MSORT_STEP_HOT_PERSISTENT;   // persistent: exactly one wave of resident CTAs (asked from the occupancy calculator once)
-        static int per_sm_of[2] = {0, 0};
-        int& per_sm = per_sm_of[c.small_lv ? 1 : 0];
-        if (per_sm == 0) {
-          cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTile, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+      if constexpr (MSORT_HOT_PERSIST && KIND == MSORT_ENV_PRESS) {
+        // persistent: exactly one wave of resident CTAs (per-SM count from the occupancy calculator, cached in the handle)
+        var = MSORT_STEP_HOT_PERSISTENT;
+        const int sm = c.small_lv ? 1 : 0;
+        auto wave = [&](long long n, int tc) { return std::min(tiles(n), (unsigned)(c.sm_count * std::max(1, persist_per_sm[sm + 2 * tc]))); };
+        const long long n_full = c.n / kTile * kTile;
+        if (a.policy_tc && (c.flags & MSORT_F_SORT_POLICY_MLP)) {
+          // embedded policy on the tensor cores: whole tiles only; a ragged tail goes to the FFMA2 kernel below
+          var = MSORT_STEP_HOT_TENSOR;
+          if (n_full > 0) {
+            DevConfig cf = c; cf.n = n_full;
+            auto tk = c.small_lv ? step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true, true, true>
+                                 : step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true, false, true>;
+            tk<<<wave(n_full, 1), kTile, 0, st>>>(cf, a, pw);
+          }
+          if (c.n > n_full) {
+            DevConfig ct = c; ct.n = c.n - n_full; ct.gid0 += n_full;
+            kern<<<1, kTile, 0, st>>>(ct, shift_args(a, n_full, Dims<KIND>::D, Dims<KIND>::A), pw);
+          }
+        } else {
+          kern<<<wave(c.n, 0), kTile, 0, st>>>(c, a, pw);
         }
-        gp = std::min(g, (unsigned)(c.sm_count * per_sm));
+      } else {
+        kern<<<g, kTile, 0, st>>>(c, a, pw);
       }
-      kern<<<gp, kTile, 0, st>>>(c, a, pw);
     }
     else if (c.fast) step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true><<<g, kTile, 0, st>>>(c, a, pw);
     else step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, false><<<g, kTile, 0, st>>>(c, a, pw);
@@ -1195,6 +1500,7 @@ cudaError_t launch_step(const DevConfig& c, const StepLaunch& l, int rng, cudaSt
   a.any_step_info = a.info_action || a.info_overflow || a.info_overflow_mat || a.info_sort_mode ||
                     a.info_press_action || a.info_invalid || a.info_r_sort || a.info_r_press || a.info_sorted_true;
   a.act_tma = ((uintptr_t)l.actions & 15u) == 0;
+  a.policy_tc = reinterpret_cast<const uint4*>(l.policy_tc);
   a.terminal_obs = f ? f->terminal_obs : nullptr;
   a.episode_return = f ? f->episode_return : nullptr;
   a.episode_length = f ? f->episode_length : nullptr;
@@ -1204,10 +1510,17 @@ cudaError_t launch_step(const DevConfig& c, const StepLaunch& l, int rng, cudaSt
   a.redis_len = r ? r->redis_len : 0; a.input_counts = r ? r->input_counts : nullptr;
   a.press_choice = r ? r->press_choice : nullptr; a.sort_mode_in = r ? r->sort_mode : nullptr;
   switch (c.kind) {
-    case MSORT_ENV_SORT: return launch_step_kind<MSORT_ENV_SORT>(c, a, l.policy_host, rng, st, l.variant, l.allow_hot);
-    case MSORT_ENV_PRESS: return launch_step_kind<MSORT_ENV_PRESS>(c, a, l.policy_host, rng, st, l.variant, l.allow_hot);
-    default: return launch_step_kind<MSORT_ENV_MONO>(c, a, l.policy_host, rng, st, l.variant, l.allow_hot);
+    case MSORT_ENV_SORT: return launch_step_kind<MSORT_ENV_SORT>(c, a, l.policy_host, rng, st, l.variant, l.allow_hot, l.persist_per_sm);
+    case MSORT_ENV_PRESS: return launch_step_kind<MSORT_ENV_PRESS>(c, a, l.policy_host, rng, st, l.variant, l.allow_hot, l.persist_per_sm);
+    default: return launch_step_kind<MSORT_ENV_MONO>(c, a, l.policy_host, rng, st, l.variant, l.allow_hot, l.persist_per_sm);
   }
+}
+
+cudaError_t launch_tc_logits(const float* obs13, const uint32_t* tcw, long long n, float* logits, int sm_count, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const unsigned grid = (unsigned)std::min<long long>((n + kTile - 1) / kTile, 4ll * sm_count);
+  tc_logits_kernel<<<grid, kTile, 0, st>>>(obs13, reinterpret_cast<const uint4*>(tcw), n, logits);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_reset(const DevConfig& c, void* state, const uint8_t* which, const uint8_t* first_pattern,

@@ -22,10 +22,16 @@ struct StepLaunch {
   int* variant;              // out (nullable): MSORT_STEP_* of the instantiation launched
   int allow_hot;             // 0: the state may hold stage contents no reset/step produces (imported): no HOT kernel
   const float* policy_host;  // Env_2 embedded policy (host copy in the paired layout, MSORT_POLICY_WEIGHTS floats) or nullptr
+  const uint32_t* policy_tc; // the same policy packed for the tensor-core path (pack_policy_tc; DEVICE memory) or nullptr
+  const int* persist_per_sm; // resident CTAs per SM of the persistent Env_2 kernels (query_persist_occupancy)
 };
 
 void pack_policy_pairs(const float* sb3, float* paired);   // SB3 weight order -> the step kernel's FFMA2 operand order
+bool pack_policy_tc(const float* sb3, uint32_t* words);    // ... -> the tensor-core path's packed tiles (false: out of fp16 range)
+int policy_tc_words();                                     // size of that buffer in 32-bit words
+void query_persist_occupancy(int per_sm[4]);               // current device; index = SMALL + 2 * TCMLP
 cudaError_t launch_step(const DevConfig& c, const StepLaunch& l, int rng, cudaStream_t st);
+cudaError_t launch_tc_logits(const float* obs13, const uint32_t* tcw, long long n, float* logits, int sm_count, cudaStream_t st);
 cudaError_t launch_reset(const DevConfig& c, void* state, const uint8_t* which, const uint8_t* first_pattern,
                          float* obs, uint8_t* mask, uint32_t reset_flags, cudaStream_t st);
 cudaError_t launch_observe(const DevConfig& c, const void* state, float* obs, uint8_t* mask, int after_shift, cudaStream_t st);
@@ -35,6 +41,7 @@ cudaError_t launch_rule_actions(const DevConfig& c, const void* state, int after
 cudaError_t launch_policy_act(const DevConfig& c, const float* obs, const uint8_t* mask, const float* packed,
                               int D, int A, uint64_t seed, uint32_t t, int deterministic, int64_t* actions,
                               float* logp, float* value, int sm_count, cudaStream_t st);
+cudaError_t prepare_policy_kernels();                      // current device: opt-in shared-memory sizes of the policy kernels
 cudaError_t launch_export(const DevConfig& c, const void* state, msort_env_state_t* out, cudaStream_t st);
 cudaError_t launch_gather(const DevConfig& c, const void* state, const int64_t* env_ids, long long count,
                           msort_env_state_t* out, cudaStream_t st);

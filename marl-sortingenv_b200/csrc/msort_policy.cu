@@ -31,6 +31,7 @@
 
 #include "msort_device.cuh"
 #include "msort_launch.h"
+#include "msort_umma.cuh"
 
 namespace msort {
 
@@ -49,47 +50,11 @@ static_assert(kPacked == MSORT_POLICY_ACT_WEIGHTS, "packed actor-critic size");
 constexpr int kTmemCols = 64;
 
 
-// shared-memory matrix descriptor, no swizzle, K-major: 8x16B core matrices; SBO = distance between
-// 8-row groups, LBO = distance between the two 16-byte K chunks one instruction consumes
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
-}
-
-// instruction descriptor: D fp32, A/B fp16, both K-major, M = 128
-__device__ __forceinline__ constexpr uint32_t umma_idesc(int n) {
-  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-}
-
-__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+using umma::fence_after_sync;
+using umma::fence_async_proxy;
+using umma::fence_before_sync;
+using umma::pack8;
+using umma::tmem_ld32;
 
 template <int D, int A>
 struct __align__(16) PolicySmem {
@@ -110,22 +75,14 @@ __device__ __forceinline__ void issue_layer(const Smem& sm, int b_off, uint32_t 
   const uint32_t a0 = smem_u32(sm.a), b0 = smem_u32(sm.b + b_off);
 #pragma unroll
   for (int s = 0; s < K / 16; ++s) {   // one instruction = K 16 (fp16) = two 16-byte chunks
-    const uint64_t ad = umma_desc(a0 + (uint32_t)(2 * s) * kRows * 16u, kRows * 16u, 128u);
-    const uint64_t bd = umma_desc(b0 + (uint32_t)(2 * s) * N * 16u, N * 16u, 128u);
-    umma_f16(tmem_d, ad, bd, umma_idesc(N), s > 0 ? 1u : 0u);
+    const uint64_t ad = umma::smem_desc(a0 + (uint32_t)(2 * s) * kRows * 16u, kRows * 16u, 128u);
+    const uint64_t bd = umma::smem_desc(b0 + (uint32_t)(2 * s) * N * 16u, N * 16u, 128u);
+    umma::mma_f16(tmem_d, ad, bd, umma::idesc_f16(N), s > 0 ? 1u : 0u);
   }
-  umma_commit(bar);
+  umma::commit(bar);
 }
 
 }  // namespace
-
-// eight fp32 values -> one 16-byte chunk of fp16 (the K-major core-matrix row)
-__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
-  const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
-  const __half2 c = __floats2half2_rn(v[4], v[5]), d = __floats2half2_rn(v[6], v[7]);
-  return make_uint4(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b),
-                    *reinterpret_cast<const uint32_t*>(&c), *reinterpret_cast<const uint32_t*>(&d));
-}
 
 // tanh for the hidden layers.  Default: the hardware tanh (MUFU.TANH, |error| <~ 5e-4 — the same size as the
 // tf32 rounding of the operands); -DMSORT_POLICY_TANH_APPROX=0 selects 1 - 2/(exp2(c*x)+1) (error ~1e-7).
@@ -348,9 +305,7 @@ static cudaError_t launch_policy_act_da(const DevConfig& c, const float* obs, co
                                         uint64_t seed, uint32_t t, int deterministic, int64_t* actions, float* logp,
                                         float* value, int sm_count, cudaStream_t st) {
   static_assert(sizeof(PolicySmem<D, A>) <= 55 * 1024, "four CTAs per SM");
-  const size_t smem = sizeof(PolicySmem<D, A>);
-  cudaError_t e = cudaFuncSetAttribute(policy_act_kernel<D, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
+  const size_t smem = sizeof(PolicySmem<D, A>);   // opt-in size set once per device by prepare_policy_kernels (msort_create)
   const long long ntiles = (c.n + kRows - 1) / kRows;
   const unsigned grid = (unsigned)std::min<long long>(ntiles, 4ll * sm_count);
   // TMA bulk copies need 16-byte aligned tile addresses (tile sizes are multiples of 16 bytes)
@@ -359,6 +314,14 @@ static cudaError_t launch_policy_act_da(const DevConfig& c, const float* obs, co
                                                         (unsigned)(seed >> 32), t, deterministic, use_tma, (long long*)actions,
                                                         logp, value);
   return cudaGetLastError();
+}
+
+// once per handle, on the handle's device (msort_create): the kernels' dynamic shared memory exceeds the 48 KB default
+cudaError_t prepare_policy_kernels() {
+  cudaError_t e = cudaFuncSetAttribute(policy_act_kernel<29, 22>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PolicySmem<29, 22>));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(policy_act_kernel<16, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PolicySmem<16, 11>));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(policy_act_kernel<13, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PolicySmem<13, 2>));
+  return e;
 }
 
 cudaError_t launch_policy_act(const DevConfig& c, const float* obs, const uint8_t* mask, const float* packed,

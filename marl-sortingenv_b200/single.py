@@ -46,6 +46,8 @@ class _SingleEnv:
         self.container_global_max = int(self._b.cfg.container_capacity)
         self._act = torch.zeros(1, dtype=torch.int64, device=self._b.device)
         self._masking, self._overflow = True, False
+        self._state_cache = None          # exported plain state of the current step (one export kernel + copy per step at most)
+        self._set_host_streams(seed)
         from .telemetry import TraceRecorder
         self._b._trace = TraceRecorder(self._b, [0], capacity=max(int(max_steps), 1), growable=True)
 
@@ -54,8 +56,19 @@ class _SingleEnv:
     def unwrapped(self):
         return self
 
+    def _set_host_streams(self, seed):
+        """The host-side random streams of the reference's action fallbacks, seeded like Env_Super.set_seed
+        (env_super.py:165-175): rng_sorting = default_rng(seed + 2), rng_pressing = default_rng(seed + 3).  (The plant's
+        own draws — noise, redistribution, pattern order — are Philox streams on the device.)"""
+        s = int(seed or 0)
+        self.rng_sorting = np.random.default_rng(s + 2)
+        self.rng_pressing = np.random.default_rng(s + 3)
+
     def reset(self, seed=None, options=None):
         """ref: Env_X.reset(seed) → (obs, {}) (env_super.py:365-420)."""
+        if seed is not None:
+            self._set_host_streams(seed)      # reset(seed=s) re-seeds every stream (env_super.py:377-378)
+        self._state_cache = None
         obs, _ = self._b.reset(seed=seed)
         return obs[0].cpu().numpy().copy(), {}
 
@@ -76,6 +89,7 @@ class _SingleEnv:
     def _do_step(self, action: int, use_action_masking=True, check_overflow=False):
         self._set_step_flags(bool(use_action_masking), bool(check_overflow))
         self._act[0] = int(action)
+        self._state_cache = None
         obs, rew, term, trunc, info = self._b.step(self._act)
         out_obs = obs[0].cpu().numpy().copy()
         reward = float(rew[0].item())
@@ -88,7 +102,9 @@ class _SingleEnv:
 
     # ------------------------------------------------------------------ state views (read-only)
     def _state(self):
-        return self._b.export_state()[0]
+        if self._state_cache is None:
+            self._state_cache = self._b.export_state()[0]
+        return self._state_cache
 
     @property
     def current_step(self):
@@ -270,7 +286,7 @@ class Env_3_Monolith(_SingleEnv):
         if mode == "random":                                              # :152-164
             if use_action_masking:
                 return int(self._b.sample_actions(seed=(self.seed or 0) + 0x5EED, t=self.current_step)[0].item())
-            return int(np.random.randint(0, self.action_space.n))
+            return int(np.random.randint(0, self.action_space.n))   # the reference draws this one from the GLOBAL numpy stream (:163)
         if mode == "rule_based":                                          # :166-184 (device kernel)
             # the reference evaluates sorting_rules() AFTER update_environment has moved input -> belt
             return int(self._b.rule_based_actions(after_shift=True)[0].item())
@@ -280,7 +296,7 @@ class Env_3_Monolith(_SingleEnv):
                 sm, _ = self.sort_agent.predict(obs[:13], deterministic=True)
                 sort_mode = int(sm)
             else:
-                sort_mode = int(np.random.randint(0, 2))
+                sort_mode = int(self.rng_sorting.choice([0, 1]))                  # the env's own stream (:193)
             mask = self.action_masks()[:11]
             if self.press_agent is not None:
                 # masks go to the agent only with masking on and a MaskablePPO-like agent (env_monolith.py:199-210)
@@ -292,7 +308,7 @@ class Env_3_Monolith(_SingleEnv):
                 press = int(pa)
             else:
                 valid = np.flatnonzero(mask) if use_action_masking else np.arange(11)
-                press = int(np.random.choice(valid)) if valid.size else 0
+                press = int(self.rng_pressing.choice(valid)) if valid.size else 0  # the env's own stream (:216-219)
             return sort_mode * 11 + press
         raise ValueError("Invalid action source: Provide 'action', set 'mode' to 'random', 'rule_based', "
                          "or 'model', or assign a mono_agent.")   # ref: env_monolith.py:224-225

@@ -24,6 +24,7 @@
  */
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <pthread.h>
@@ -71,6 +72,15 @@ static void env_draw(const msort_config_t* cfg, int64_t gid, uint32_t block, uin
 
 /* ---------------------------------------------------------------- helpers */
 static double round2(double x) { return rint(x * 100.0) / 100.0; } /* numpy-scalar round(x, 2) */
+/* Python-float round(x, 2): correctly rounded on the exact decimal value of the double (float.__round__ goes
+ * through dtoa), which is what glibc's "%.2f" prints.  The reference applies it where both operands are plain
+ * Python floats: an EMPTY container's purity round(threshold, 2) (env_super.py:788-789) and that container's
+ * purity difference round(purity - threshold, 2) (env_super.py:222-225). */
+static double py_round2(double x) {
+  char buf[64];
+  snprintf(buf, sizeof buf, "%.2f", x);
+  return strtod(buf, NULL);
+}
 static double clipd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 static float clipf(float x, float lo, float hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
@@ -90,7 +100,7 @@ static void container_purity(const msort_config_t* cfg, const msort_env_state_t*
   for (int m = 0; m < 4; ++m) {
     int tot = s->cont_true[m] + s->cont_false[m];
     if (tot > 0) pur[m] = round2((double)s->cont_true[m] / (double)tot);
-    else pur[m] = cfg->quality_threshold[m]; /* Python round(0.9, 2) == 0.9 */
+    else pur[m] = py_round2(cfg->quality_threshold[m]); /* Python float: round(0.9, 2) == 0.9, round(0.905, 2) == 0.91 */
   }
 }
 
@@ -113,7 +123,7 @@ static void sort_obs(const msort_config_t* cfg, const msort_env_state_t* s, floa
     v[5 + m] = s->acc_belt[m];
     int tot = s->cont_true[m] + s->cont_false[m];
     double diff = pur[m] - cfg->quality_threshold[m];
-    v[9 + m] = tot > 0 ? round2(diff) : diff; /* empty: Python round(0.0, 2) */
+    v[9 + m] = tot > 0 ? round2(diff) : py_round2(diff); /* empty: both Python floats (0.0 for whole-percent thresholds) */
   }
   for (int i = 0; i < 13; ++i) o[i] = clipf((float)v[i], -1.0f, 1.0f);
 }

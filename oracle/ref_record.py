@@ -172,12 +172,17 @@ class MaskablePressStubAgent:
 def record(kind: str, *, seed: int, steps: int, max_steps: int = 50, noise: float = 0.05,
            balesize: int = 200, policy="masked_random", action_seed: int = 0,
            use_action_masking: bool = True, check_overflow: bool = False,
-           auto_reset: bool = True, mlp_weights=None, actions=None, keep_env: bool = False) -> dict:
+           auto_reset: bool = True, mlp_weights=None, actions=None, keep_env: bool = False,
+           thresholds=None) -> dict:
     """Run the reference for `steps` env-steps (auto-resetting unseeded like SB3's VecEnv when
     an episode ends, if `auto_reset`) and return everything needed to replay and compare."""
     D, A = KIND_DIMS[kind]
     env = make_reference_env(kind, max_steps=max_steps, seed=seed, noise_sorting=noise,
                              balesize=balesize)
+    if thresholds is not None:
+        # a user config.yml's pressing_station.bale_quality_thresholds (env_super.py:98): plain Python floats, set on
+        # the instance exactly as Env_Super.__init__ leaves them — the reference source and its config.yml stay untouched
+        env.quality_thresholds = {m: float(v) for m, v in zip(MATS, thresholds)}
     agent = None
     if kind == "press" and mlp_weights is not None:
         agent = NumpyMlpSortAgent(mlp_weights)

@@ -11,7 +11,9 @@ cls = {"mono": ms.BatchedMonolithEnv, "sort": ms.BatchedSortingEnv, "press": ms.
 env = cls(n, max_steps=50, seed=42, info_level=os.environ.get("INFO", "episode"))
 if kind == 'press':
     from marl_sortingenv_b200.policy import sb3_style_init
-    env.set_sort_policy(sb3_style_init(0))
+    env.set_sort_policy(sb3_style_init(0, action_gain=float(os.environ.get("GAIN", 0.01))))
+    if os.environ.get("TENSOR") is not None:                      # A/B: embedded policy on the tensor cores (1) or FFMA2 (0)
+        env.set_option(ms._abi.OPT_TENSOR_POLICY, int(os.environ["TENSOR"]))
 env.reset()
 if os.environ.get("L2PERSIST"):
     # experiment: pin the hot state planes in L2 with an access-policy window on the stream (captured into the graph's kernel nodes)
@@ -44,4 +46,4 @@ for rep in range(3):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
     best = min(best, e0.elapsed_time(e1) / 512 * 1e3)
-print(f"{os.path.basename(lib):28s} {kind:5s} state {h} obs {ho} rsum {rsum.item():.6f}  us/step {best:.2f}  G/s {n/best/1e3:.2f}", flush=True)
+print(f"{os.path.basename(lib):28s} {kind:5s} n {n} [{env.step_variant}] state {h} obs {ho} rsum {rsum.item():.6f}  us/step {best:.2f}  G/s {n/best/1e3:.2f}", flush=True)

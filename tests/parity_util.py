@@ -52,7 +52,19 @@ def pack_counts(counts) -> np.ndarray:
     return (c[..., 0] | (c[..., 1] << 8) | (c[..., 2] << 16) | (c[..., 3] << 24)).astype(np.uint32)
 
 
+def config_dict_for(meta: dict):
+    """The config.yml dict a fixture group was recorded under (None = the reference's shipped config.yml)."""
+    if not meta.get("thresholds"):
+        return None
+    from marl_sortingenv_b200.config import load_config
+    cfg = load_config(None)
+    cfg["pressing_station"]["bale_quality_thresholds"] = dict(zip("ABCD", [float(x) for x in meta["thresholds"]]))
+    return cfg
+
+
 def config_for(meta: dict, num_envs: int, rng_mode="replay", **over) -> _abi.MsortConfig:
+    if "config" not in over and config_dict_for(meta) is not None:
+        over["config"] = config_dict_for(meta)
     kw = dict(max_steps=meta["max_steps"], seed=0, noise_sorting=meta["noise"],
               balesize=meta["balesize"], use_action_masking=meta["use_action_masking"],
               check_overflow=meta["check_overflow"], auto_reset=meta["auto_reset"],
@@ -151,15 +163,36 @@ def _col(name):
 import json as _json
 import os as _os
 
-GOLDEN_PATH = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden",
-                            "reference_trajectories.npz")
+_GOLDEN_DIR = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden")
+GOLDEN_PATH = _os.path.join(_GOLDEN_DIR, "reference_trajectories.npz")
+# round-2 additions (tests/golden/make_golden.py --set r02): non-whole-percent quality thresholds, a 16-seed grid,
+# 200-step episodes without masking
+GOLDEN_PATHS = [GOLDEN_PATH, _os.path.join(_GOLDEN_DIR, "reference_trajectories_r02.npz")]
+
+
+class _Golden(dict):
+    @property
+    def files(self):
+        return list(self.keys())
+
+
 _golden_cache = None
 
 
 def golden():
     global _golden_cache
     if _golden_cache is None:
-        _golden_cache = np.load(GOLDEN_PATH, allow_pickle=False)
+        g, names = _Golden(), []
+        for p in GOLDEN_PATHS:
+            if not _os.path.isfile(p):
+                continue
+            d = np.load(p, allow_pickle=False)
+            names += _json.loads(str(d["groups"]))
+            for k in d.files:
+                if k not in ("groups", "numpy_version"):
+                    g[k] = d[k]
+        g["groups"] = np.asarray(_json.dumps(names))
+        _golden_cache = g
     return _golden_cache
 
 

@@ -196,20 +196,25 @@ def test_persistent_env2_kernel_with_unaligned_actions_and_kernel_variants():
     from marl_sortingenv_b200 import BatchedPressingEnv
     from marl_sortingenv_b200.policy import sb3_style_init
     n = 128 * 148 * 6 + 77
-    envs = [BatchedPressingEnv(n, max_steps=20, seed=21, info_level=lvl) for lvl in ("episode", "episode", "full")]
+    from marl_sortingenv_b200 import _abi
+    envs = [BatchedPressingEnv(n, max_steps=20, seed=21, info_level=lvl) for lvl in ("episode", "episode", "full", "episode")]
     for e in envs:
         e.set_sort_policy(sb3_style_init(4, action_gain=1.0))
         e.reset()
+    envs[3].set_option(_abi.OPT_TENSOR_POLICY, 0)      # the per-thread FFMA2 policy instead of the tensor-core one
     buf = torch.zeros(n + 1, dtype=torch.int64, device="cuda")
     for t in range(45):
         a = envs[0].sample_actions(seed=2, t=t)
         buf[1:].copy_(a)
         assert buf[1:].data_ptr() % 16 == 8
-        envs[0].step(a); envs[1].step(buf[1:]); envs[2].step(a)
-    assert envs[0].step_variant == "hot_persistent" and envs[1].step_variant == "hot_persistent" and envs[2].step_variant == "fast"
-    assert torch.equal(envs[0].state, envs[1].state) and torch.equal(envs[0].state, envs[2].state)
-    assert torch.equal(envs[0].obs, envs[1].obs) and torch.equal(envs[0].obs, envs[2].obs)
-    assert torch.equal(envs[0].mask, envs[2].mask) and torch.equal(envs[0].reward, envs[1].reward)
+        envs[0].step(a); envs[1].step(buf[1:]); envs[2].step(a); envs[3].step(a)
+    assert [e.step_variant for e in envs] == ["hot_tensor", "hot_tensor", "fast", "hot_persistent"]
+    assert torch.equal(envs[0].state, envs[1].state) and torch.equal(envs[3].state, envs[2].state)
+    assert torch.equal(envs[0].obs, envs[1].obs) and torch.equal(envs[3].obs, envs[2].obs)
+    assert torch.equal(envs[3].mask, envs[2].mask) and torch.equal(envs[0].reward, envs[1].reward)
+    # tensor-core vs fp32 policy: the argmax may differ only on a numerical tie of the two logits (tests/test_tc_mlp_gpu.py)
+    diverged = (envs[0].state.view(torch.int32).reshape(13, -1, 4) != envs[3].state.view(torch.int32).reshape(13, -1, 4)).any(2).any(0)
+    assert int(diverged.sum()) <= 3, f"{int(diverged.sum())} envs diverged between the tensor-core and the FFMA2 policy"
 
 
 def test_imported_state_with_unusual_stages_is_stepped_exactly():

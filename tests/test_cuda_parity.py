@@ -27,7 +27,7 @@ def test_cuda_replays_reference(cuda_backend, name):
     """REPLAY mode on the recorded numpy streams of the unmodified reference."""
     meta, batch = golden_group(name)
     n = batch["action"].shape[1]
-    env = cuda_backend(config_for(meta, n))
+    env = cuda_backend(config_for(meta, n), config=config_dict_for(meta))
     if meta.get("mlp"):
         env.set_policy(batch["mlp_weights"])
     use_counts = not name.startswith("gen_")
@@ -132,11 +132,16 @@ def test_cuda_matches_oracle_philox_wide_layout(cuda_backend, config_kind):
     _philox_cross_check(cuda_backend, "sort", 700, 60, max_steps=400, auto_reset=False, config=cfg, masking=False)
 
 
-def _hot_cross_check(cuda_backend, kind, n, T, *, mlp=None, seed=11, max_steps=25):
+TIE_BAND = 1e-5      # parity contract for the embedded policy: identical argmax except where |logit0 - logit1| < 1e-5
+
+
+def _hot_cross_check(cuda_backend, kind, n, T, *, mlp=None, seed=11, max_steps=25, variant=None):
     """The HOT instantiation of the step kernel — the one bench.py times: FAST config, compact layout, action
     masking + auto-reset, mask output, NO per-step info arrays (`info_level='episode'`), and for Env_2 the
     persistent TMA-staged form — against the oracle: exported state bit-exact, masks / terminated equal,
-    obs / reward / terminal observation / episode return within the float tolerance, statistics equal."""
+    obs / reward / terminal observation / episode return within the float tolerance, statistics equal.
+    With an embedded policy (Env_2) the tensor-core kernel may pick the other sort mode only inside the
+    contract's tie band (the oracle reports its fp32 margin); such an env is re-synchronised and counted."""
     from oracle.cpu_oracle import OracleEnv
     meta = dict(kind=kind, max_steps=max_steps, noise=0.05, balesize=200, use_action_masking=True,
                 check_overflow=False, auto_reset=True, mlp=mlp is not None)
@@ -144,30 +149,44 @@ def _hot_cross_check(cuda_backend, kind, n, T, *, mlp=None, seed=11, max_steps=2
     gpu = cuda_backend(config_for(meta, n, rng_mode="philox", seed=seed), info_level="episode")
     if mlp is not None:
         ora.set_policy(mlp); gpu.set_policy(mlp)
+    if variant is None:
+        variant = ("hot_tensor" if mlp is not None else "hot_persistent") if kind == "press" else "hot"
     o0, m0 = ora.reset()
     g0, gm0 = gpu.reset()
     assert np.array_equal(o0, g0) and np.array_equal(m0, gm0)
-    n_done = 0
+    n_done = n_flips = 0
     for t in range(T):
         a = ora.sample_masked_actions(5, t)
         oo, orw, ot, om, oi = ora.step(a)
         go, grw, gt, gm, gi = gpu.step(a)
         assert set(gi) == {"terminal_obs", "episode_return", "episode_length"}      # no per-step info arrays ...
-        assert gpu.env.step_variant == ("hot_persistent" if kind == "press" else "hot")   # ... so the HOT kernel ran
-        so, sg = state_rows(ora.state), state_rows(gpu.export_state())
+        assert gpu.env.step_variant == variant, gpu.env.step_variant                # ... so the HOT kernel ran
+        gstate = gpu.export_state()
+        ok = np.ones(n, dtype=bool)
+        if mlp is not None:
+            flipped = ora.state["sensor_mode"] != gstate["sensor_mode"]
+            if flipped.any():
+                worst = float(np.max(oi["mlp_margin"][flipped]))
+                assert worst < TIE_BAND, f"step {t}: sort-policy argmax differs at an fp32 margin of {worst:g} (band {TIE_BAND:g})"
+                ora.state[flipped] = gstate[flipped]          # both sides continue from the same plant
+                n_flips += int(flipped.sum()); ok = ~flipped
+        so, sg = state_rows(ora.state), state_rows(gstate)
         if not np.array_equal(so, sg):
             bad = np.argwhere(so != sg)[0]
             raise AssertionError(f"{kind} step {t}: state mismatch env {bad[0]} col {bad[1]}: oracle {so[bad[0]]} cuda {sg[bad[0]]}")
         assert np.array_equal(ot, gt), f"step {t}: terminated"
         assert np.array_equal(om, gm), f"step {t}: mask"
-        assert_float_close(grw, orw, f"step {t}: reward")
-        assert_float_close(go, oo, f"step {t}: obs")
+        assert_float_close(grw[ok], orw[ok], f"step {t}: reward")
+        assert_float_close(go[ok], oo[ok], f"step {t}: obs")
         if ot.any():
             assert_float_close(gi["terminal_obs"][ot], oi["terminal_obs"][ot], "terminal obs")
             assert_float_close(gi["episode_return"][ot], oi["episode_return"][ot], "episode return")
             assert np.array_equal(gi["episode_length"][ot], oi["episode_length"][ot])
             n_done += int(ot.sum())
     assert_float_close(gpu.env.stats.cpu().numpy()[:10], ora.stats[:10], "stats accumulators", rtol=1e-9)
+    if mlp is not None:
+        print(f"embedded policy [{variant}]: {n_flips} tie-band flips in {n * T} env-steps")
+        assert n_flips <= max(3, n * T // 20000), f"{n_flips} tie-band flips in {n * T} env-steps"
     return n_done
 
 
@@ -187,7 +206,7 @@ def test_cuda_hot_kernel_matches_oracle_long_episodes(cuda_backend, kind):
 def test_cuda_hot_kernel_matches_oracle_more_than_one_wave(cuda_backend):
     """More tiles than resident CTAs, so Env_2's persistent kernel really loops (its second and later tiles come
     from the TMA-staged buffer) and Env_3's L2 prefetch reaches real tiles; ragged last tile; Env_2 with the
-    embedded policy evaluated by the FFMA2 MLP."""
+    embedded policy evaluated on the tensor cores (whole tiles) and by the FFMA2 kernel (the ragged tail)."""
     from marl_sortingenv_b200.policy import sb3_style_init
     n = 128 * 148 * 8 + 128 + 5
     _hot_cross_check(cuda_backend, "press", n, 30, mlp=sb3_style_init(3, action_gain=1.0).numpy())
