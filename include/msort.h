@@ -33,7 +33,7 @@ extern "C" {
 
 /* ABI history: 2 telemetry (msort_gather_state, reward terms) and msort_policy_act; 3 msort_observe_after_shift,
  * msort_step_variant, obs / mask must be 16-byte aligned; 4 msort_step_range, msort_policy_act_range;
- * 5 msort_set_option, MSORT_STEP_HOT_TENSOR. */
+ * 5 msort_set_option, MSORT_STEP_HOT_TENSOR, msort_step_host. */
 #define MSORT_ABI_VERSION 5
 
 /* ------------------------------------------------------------------ enums */
@@ -326,6 +326,42 @@ int msort_policy_act_range(msort_t* h, int64_t first_env, int64_t num_envs, cons
                            const float* packed_weights, uint64_t seed, uint32_t t, int deterministic,
                            int64_t* actions, float* logp, float* value, void* stream);
 
+/* ------------------------------------------------------------------ host-buffer step
+ * step() for a caller whose actions and results live in HOST memory (an SB3-style loop; ref: the VecEnv contract
+ * of training.py:64-69: actions in, obs / reward / done / action mask out, every step).  The batch is cut into
+ * `chunks` env ranges; per range the library queues, on its own streams,
+ *     H2D of the range's actions -> step kernel of the range -> D2H of the range's obs, reward and flag words,
+ * so the host->device copy of range k+1, the kernel of range k and the device->host copy of range k-1 overlap
+ * (PCIe is full duplex).  What travels: 1 byte per env in (Discrete(22) fits a byte; or 8 with actions_i64), and
+ * 4*D + 4 + 2 bytes per env out — the action mask as its 11 information bits and `terminated` share one 16-bit
+ * word (bit k = press action k valid, bit 15 = terminated; Env_3's 22-wide mask is that 11-bit mask twice,
+ * env_super.py:887-898; Env_1's two actions are always valid).
+ * All work is ordered after everything already queued on `stream`, and `stream` waits for it: the call returns at
+ * once, the host buffers are complete when `stream` has drained (msort_sync_check).
+ *  io->actions_u8 / actions_i64 : exactly one non-NULL, [N], host (pinned memory for real overlap)
+ *  io->obs [N,D] f32, io->reward [N] f32, io->flags [N] u16 : host outputs
+ *  io->dev_obs / dev_reward / dev_terminated / dev_mask : the DEVICE outputs of msort_step (same shapes and alignment
+ *            rules); the step kernel writes them as usual and the host copies are taken from them, so the device-side
+ *            view of the batch (action_masks(), obs) stays current
+ *  scratch : DEVICE memory of msort_host_scratch_bytes(h) bytes, 256-byte aligned (action staging + flag words; caller-owned)
+ *  info    : as for msort_step (per-step info arrays stay on the device) */
+typedef struct msort_host_io {
+  uint32_t struct_size;
+  uint32_t chunks;              /* env ranges per step; 0 = library default (8) */
+  const uint8_t* actions_u8;
+  const int64_t* actions_i64;
+  float* obs;
+  float* reward;
+  uint16_t* flags;
+  float* dev_obs;
+  float* dev_reward;
+  uint8_t* dev_terminated;
+  uint8_t* dev_mask;
+} msort_host_io_t;
+size_t msort_host_scratch_bytes(const msort_t* h);
+int msort_step_host(msort_t* h, void* state, void* scratch, const msort_host_io_t* io,
+                    const msort_info_out_t* info, void* stream);
+
 /* Which instantiation of the step kernel the handle's last msort_step launched (diagnostics / tests):
  * 0 none yet, 1 REPLAY, 2 generic, 3 FAST (host-proved config facts compiled in),
  * 4 HOT (FAST + the training-loop switches compiled in), 5 HOT persistent (Env_2: TMA-staged tiles). */
@@ -343,7 +379,12 @@ int msort_step_variant(const msort_t* h);
  *    is evaluated on the tensor cores when the HOT persistent kernel runs and the weights fit the fp16 split;
  *    0 = always the per-thread fp32 FFMA2 form. */
 #define MSORT_OPT_TENSOR_POLICY 1
+/*  MSORT_OPT_PERSIST_CTAS: resident CTAs per SM the persistent Env_2 kernels are launched with (default: what the
+ *    kernel's registers and shared memory allow, asked at msort_create); get = the count of the kernel the next
+ *    step would launch. */
+#define MSORT_OPT_PERSIST_CTAS 2
 int msort_set_option(msort_t* h, int option, int64_t value);
+int msort_get_option(const msort_t* h, int option, int64_t* value);
 
 /* Diagnostics: the tensor-core form of Env_2's embedded policy alone.  sort_obs [count,13] f32 (device) -> logits
  * [count,2] f32 (device), evaluated exactly as the HOT_TENSOR step kernel evaluates it (fp16-split operands, fp32

@@ -124,6 +124,13 @@ class MsortInfoOut(C.Structure):
     ]
 
 
+class MsortHostIO(C.Structure):
+    """msort_host_io_t (include/msort.h)."""
+    _fields_ = [("struct_size", C.c_uint32), ("chunks", C.c_uint32), ("actions_u8", C.c_void_p),
+                ("actions_i64", C.c_void_p), ("obs", C.c_void_p), ("reward", C.c_void_p), ("flags", C.c_void_p),
+                ("dev_obs", C.c_void_p), ("dev_reward", C.c_void_p), ("dev_terminated", C.c_void_p), ("dev_mask", C.c_void_p)]
+
+
 # name -> (restype, argtypes): every symbol include/msort.h declares
 _P = C.c_void_p
 SYMBOLS = {
@@ -155,10 +162,14 @@ SYMBOLS = {
     "msort_sync_check": (C.c_int, [_P, _P]),
     "msort_launch_count": (C.c_int64, [_P]),
     "msort_step_variant": (C.c_int, [_P]),
+    "msort_host_scratch_bytes": (C.c_size_t, [_P]),
+    "msort_step_host": (C.c_int, [_P, _P, _P, C.POINTER(MsortHostIO), C.POINTER(MsortInfoOut), _P]),
     "msort_set_option": (C.c_int, [_P, C.c_int, C.c_int64]),
+    "msort_get_option": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int64)]),
     "msort_debug_policy_logits": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
 }
 OPT_TENSOR_POLICY = 1
+OPT_PERSIST_CTAS = 2
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "csrc", "libmsort.so")

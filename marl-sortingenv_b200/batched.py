@@ -21,6 +21,47 @@ from .spaces import make_spaces
 _KIND_NAME = {_abi.ENV_SORT: "sort", _abi.ENV_PRESS: "press", _abi.ENV_MONO: "mono"}
 
 
+def expand_mask_bits(flags: np.ndarray, num_actions: int) -> np.ndarray:
+    """uint16 flag words of `msort_step_host` -> bool [N, A] action masks: bit k = press action k valid
+    (press_action_masks, env_super.py:869-885); Env_3's 22-wide mask is that mask twice (monolith_action_masks,
+    :887-898); Env_1's two actions are always valid (env_1_sort.py:74-76)."""
+    f = np.asarray(flags, dtype=np.uint16)
+    m = ((f[:, None] >> np.arange(min(num_actions, 11), dtype=np.uint16)) & 1).astype(bool)
+    return np.concatenate([m, m], axis=1) if num_actions == 22 else m
+
+
+class LazyHostArray:
+    """A host result that is produced from the packed flag words only when somebody looks at it."""
+
+    def __init__(self, make, shape):
+        self._make, self._value, self.shape = make, None, shape
+
+    @property
+    def value(self) -> np.ndarray:
+        if self._value is None:
+            self._value = self._make()
+        return self._value
+
+    def __array__(self, dtype=None, copy=None):
+        v = self.value
+        return v if dtype is None else v.astype(dtype)
+
+    def __getitem__(self, i):
+        return self.value[i]
+
+    def __len__(self):
+        return self.shape[0]
+
+    def any(self, *a, **k):
+        return self.value.any(*a, **k)
+
+    def all(self, *a, **k):
+        return self.value.all(*a, **k)
+
+    def sum(self, *a, **k):
+        return self.value.sum(*a, **k)
+
+
 def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -145,6 +186,11 @@ class BatchedEnv:
     def set_option(self, option: int, value: int):
         """Handle options of include/msort.h (MSORT_OPT_*), e.g. `_abi.OPT_TENSOR_POLICY`."""
         _abi.check(self.lib, self.lib.msort_set_option(self._h, int(option), int(value)), "msort_set_option")
+
+    def get_option(self, option: int) -> int:
+        v = C.c_int64(0)
+        _abi.check(self.lib, self.lib.msort_get_option(self._h, int(option), C.byref(v)), "msort_get_option")
+        return int(v.value)
 
     def set_flags(self, *, use_action_masking=None, check_overflow=None, auto_reset=None):
         f = int(self.cfg.flags)
@@ -305,40 +351,61 @@ class BatchedEnv:
     # ------------------------------------------------------------------ host-buffer surface
     def _host_buffers(self):
         if getattr(self, "_hb", None) is None:
-            n, D, A = self.num_envs, self.D, self.A
+            n, D = self.num_envs, self.D
             pin = dict(pin_memory=True)
-            self._hb = dict(actions=torch.zeros(n, dtype=torch.int64, **pin),
+            self._hb = dict(actions=torch.zeros(n, dtype=torch.uint8, **pin),
                             obs=torch.zeros((n, D), dtype=torch.float32, **pin),
                             reward=torch.zeros(n, dtype=torch.float32, **pin),
-                            terminated=torch.zeros(n, dtype=torch.bool, **pin),
-                            mask=torch.zeros((n, A), dtype=torch.bool, **pin))
-            self._dev_actions = torch.zeros(n, dtype=torch.int64, device=self.device)
+                            flags=torch.zeros(n, dtype=torch.int16, **pin))
+            self._host_scratch = torch.zeros(int(self.lib.msort_host_scratch_bytes(self._h)), dtype=torch.uint8, device=self.device)
+            assert self._host_scratch.data_ptr() % 256 == 0
+            self._hio = _abi.MsortHostIO()
+            self._hio.struct_size = C.sizeof(self._hio)
+            self._hio.obs, self._hio.reward, self._hio.flags = (C.c_void_p(self._hb[k].data_ptr()) for k in ("obs", "reward", "flags"))
+            self._hb_np = {k: v.numpy() for k, v in self._hb.items()}
+            self._hb_np["flags"] = self._hb_np["flags"].view(np.uint16)
         return self._hb
 
-    def step_host(self, actions):
-        """step() for callers that live on the host (SB3-style loops): `actions` is a numpy array /
-        CPU tensor [N]; obs, reward, terminated and the next action mask come back as numpy views
-        of pinned host buffers.  Host->device and device->host copies are part of the call.
-        Returns (obs, reward, terminated, truncated, mask); also counts the bytes moved in
-        `self.h2d_bytes` / `self.d2h_bytes`."""
+    def step_host(self, actions, chunks: int = 0):
+        """step() for callers that live on the host (SB3-style loops; the VecEnv contract of training.py:64-69).
+        `actions`: numpy array / CPU tensor [N] of any integer dtype — a pinned uint8 or int64 tensor is used in place,
+        anything else is converted into the env's pinned uint8 buffer.  One native call (`msort_step_host`) cuts the batch
+        into `chunks` env ranges (0 = the library's default) and pipelines, on the library's own streams, the H2D copy of
+        a range's actions, its step kernel and the D2H copies of its results, so both PCIe directions and the kernel
+        overlap.  Back come numpy views of pinned host buffers: obs [N,D] f32, reward [N] f32, and two LAZY arrays —
+        `terminated` [N] bool and the action mask [N,A] bool — that expand the 16-bit flag word per env the device sent
+        (11 mask bits + the done bit) only when they are read (`np.asarray(x)`, indexing); `self.host_flags` is the raw
+        uint16 array.  Returns (obs, reward, terminated, truncated, mask); `self.h2d_bytes` / `self.d2h_bytes` count the
+        bytes that crossed PCIe."""
+        if not self._was_reset:
+            raise AttributeError("step() called before reset()")
         hb = self._host_buffers()
         a = actions if isinstance(actions, torch.Tensor) else torch.as_tensor(np.asarray(actions))
-        if a.is_pinned() and a.dtype == torch.int64 and a.is_contiguous():
+        a = a.reshape(-1)
+        if a.numel() != self.num_envs:
+            raise ValueError(f"expected {self.num_envs} actions, got {a.numel()}")
+        io = self._hio
+        io.chunks = int(chunks)
+        io.dev_obs, io.dev_reward, io.dev_terminated, io.dev_mask = (C.c_void_p(t.data_ptr()) for t in (self.obs, self.reward, self.terminated, self.mask))
+        if a.is_pinned() and a.is_contiguous() and a.dtype in (torch.uint8, torch.int64):
             src = a                                    # the caller already holds a pinned buffer
         else:
-            hb["actions"].copy_(a.reshape(-1))
+            hb["actions"].copy_(a)
             src = hb["actions"]
-        self._dev_actions.copy_(src, non_blocking=True)
-        obs, rew, term, _, _ = self.step(self._dev_actions)
-        hb["obs"].copy_(obs, non_blocking=True)
-        hb["reward"].copy_(rew, non_blocking=True)
-        hb["terminated"].copy_(term, non_blocking=True)
-        hb["mask"].copy_(self.mask, non_blocking=True)
+        if src.dtype == torch.uint8:
+            io.actions_u8, io.actions_i64 = C.c_void_p(src.data_ptr()), None
+        else:
+            io.actions_u8, io.actions_i64 = None, C.c_void_p(src.data_ptr())
+        with torch.cuda.device(self.device):
+            rc = self.lib.msort_step_host(self._h, _ptr(self.state), _ptr(self._host_scratch), C.byref(io),
+                                          C.byref(self._info) if self._has_info else None, self._stream())
+        _abi.check(self.lib, rc, "msort_step_host")
         torch.cuda.current_stream(self.device).synchronize()
-        self.h2d_bytes = src.numel() * 8
-        self.d2h_bytes = sum(hb[k].numel() * hb[k].element_size() for k in ("obs", "reward", "terminated", "mask"))
-        return (hb["obs"].numpy(), hb["reward"].numpy(), hb["terminated"].numpy(),
-                np.zeros(self.num_envs, dtype=bool), hb["mask"].numpy())
+        self.h2d_bytes = src.numel() * src.element_size()
+        self.d2h_bytes = sum(hb[k].numel() * hb[k].element_size() for k in ("obs", "reward", "flags"))
+        flags = self.host_flags = self._hb_np["flags"]
+        return (self._hb_np["obs"], self._hb_np["reward"], LazyHostArray(lambda: (flags >> 15).astype(bool), (self.num_envs,)),
+                np.zeros(self.num_envs, dtype=bool), LazyHostArray(lambda: expand_mask_bits(flags, self.A), (self.num_envs, self.A)))
 
     def get_obs(self):
         with torch.cuda.device(self.device):

@@ -32,6 +32,11 @@ struct msort_handle {
   bool policy_tc_ok = false;                // the policy fits the fp16 split (else the FFMA2 kernel evaluates it)
   bool policy_tc_enabled = true;            // msort_set_option(MSORT_OPT_TENSOR_POLICY)
   int persist_per_sm[4] = {1, 1, 1, 1};     // resident CTAs per SM of the persistent Env_2 kernels on this handle's device
+  // msort_step_host: the library's own streams / events (created by the first call, on the handle's device)
+  static constexpr int kHostStreams = 4;
+  cudaStream_t host_stream[kHostStreams] = {};
+  cudaEvent_t host_start = nullptr, host_done[kHostStreams] = {};
+  bool host_ready = false;
   int64_t launches;
 };
 
@@ -328,6 +333,10 @@ extern "C" int msort_destroy(msort_t* h) {
   if (!h) return MSORT_OK;
   if (h->lut_dev) cudaFree(h->lut_dev);
   if (h->policy_tc_dev) cudaFree(h->policy_tc_dev);
+  if (h->host_ready) {
+    for (int k = 0; k < msort_handle::kHostStreams; ++k) { cudaStreamDestroy(h->host_stream[k]); cudaEventDestroy(h->host_done[k]); }
+    cudaEventDestroy(h->host_start);
+  }
   delete h;
   return MSORT_OK;
 }
@@ -355,7 +364,22 @@ extern "C" int msort_set_option(msort_t* h, int option, int64_t value) {
   if (!h) return fail(MSORT_E_INVALID, "msort_set_option: NULL handle");
   switch (option) {
     case MSORT_OPT_TENSOR_POLICY: h->policy_tc_enabled = value != 0; return MSORT_OK;
+    case MSORT_OPT_PERSIST_CTAS:
+      if (value < 1 || value > 32) return fail(MSORT_E_INVALID, "msort_set_option: MSORT_OPT_PERSIST_CTAS must be in [1, 32]");
+      for (int k = 0; k < 4; ++k) h->persist_per_sm[k] = (int)value;
+      return MSORT_OK;
     default: return fail(MSORT_E_INVALID, "msort_set_option: unknown option %d", option);
+  }
+}
+
+extern "C" int msort_get_option(const msort_t* h, int option, int64_t* value) {
+  if (!h || !value) return fail(MSORT_E_INVALID, "msort_get_option: NULL argument");
+  switch (option) {
+    case MSORT_OPT_TENSOR_POLICY: *value = (h->policy_tc_enabled && h->policy_set && h->policy_tc_ok) ? 1 : 0; return MSORT_OK;
+    case MSORT_OPT_PERSIST_CTAS:
+      *value = h->persist_per_sm[(h->dev.small_lv ? 1 : 0) + ((h->policy_tc_enabled && h->policy_set && h->policy_tc_ok) ? 2 : 0)];
+      return MSORT_OK;
+    default: return fail(MSORT_E_INVALID, "msort_get_option: unknown option %d", option);
   }
 }
 
@@ -455,6 +479,88 @@ extern "C" int msort_step_range(msort_t* h, int64_t first_env, int64_t num_envs,
   if (first_env < 0 || num_envs <= 0 || first_env + num_envs > h->dev.n || first_env % kTile != 0)
     return fail(MSORT_E_INVALID, "msort_step_range: range must lie inside the batch and start on a multiple of %d envs", kTile);
   return step_impl(h, first_env, num_envs, state, actions, obs, reward, terminated, mask, info, nullptr, stream);
+}
+
+// ---------------------------------------------------------------- host-buffer step
+// device scratch layout (every section 256-byte aligned): actions i64 | actions u8 | flag words
+namespace {
+struct HostScratch { size_t act64, act8, flags, total; };
+HostScratch host_scratch_layout(const msort_t* h) {
+  const size_t n = (size_t)h->dev.n_pad;
+  auto up = [](size_t x) { return (x + 255) / 256 * 256; };
+  HostScratch s;
+  size_t o = 0;
+  s.act64 = o; o += up(n * 8);
+  s.act8 = o; o += up(n);
+  s.flags = o; o += up(n * 2);
+  s.total = o;
+  return s;
+}
+}  // namespace
+
+extern "C" size_t msort_host_scratch_bytes(const msort_t* h) { return h ? host_scratch_layout(h).total : 0; }
+
+extern "C" int msort_step_host(msort_t* h, void* state, void* scratch, const msort_host_io_t* io, const msort_info_out_t* info,
+                               void* stream) {
+  if (!h || !state || !scratch || !io) return fail(MSORT_E_INVALID, "msort_step_host: NULL argument");
+  if (io->struct_size != sizeof(msort_host_io_t)) return fail(MSORT_E_INVALID, "msort_step_host: bad io struct_size");
+  if ((io->actions_u8 != nullptr) == (io->actions_i64 != nullptr))
+    return fail(MSORT_E_INVALID, "msort_step_host: exactly one of actions_u8 / actions_i64 must be given");
+  if (!io->obs || !io->reward || !io->flags) return fail(MSORT_E_INVALID, "msort_step_host: NULL output buffer");
+  if (!io->dev_obs || !io->dev_reward || !io->dev_terminated || !io->dev_mask)
+    return fail(MSORT_E_INVALID, "msort_step_host: NULL device output buffer");
+  if (!aligned(scratch, 256)) return fail(MSORT_E_INVALID, "msort_step_host: scratch must be 256-byte aligned");
+  if (h->cfg.rng_mode != MSORT_RNG_PHILOX) return fail(MSORT_E_INVALID, "msort_step_host: PHILOX mode only");
+  cudaStream_t user = (cudaStream_t)stream;
+  if (!h->host_ready) {
+    MSORT_TRY_CUDA(cudaEventCreateWithFlags(&h->host_start, cudaEventDisableTiming), "cudaEventCreate");
+    for (int k = 0; k < msort_handle::kHostStreams; ++k) {
+      MSORT_TRY_CUDA(cudaStreamCreateWithFlags(&h->host_stream[k], cudaStreamNonBlocking), "cudaStreamCreate");
+      MSORT_TRY_CUDA(cudaEventCreateWithFlags(&h->host_done[k], cudaEventDisableTiming), "cudaEventCreate");
+    }
+    h->host_ready = true;
+  }
+  const HostScratch L = host_scratch_layout(h);
+  char* base = (char*)scratch;
+  int64_t* d_act = (int64_t*)(base + L.act64);
+  uint8_t* d_act8 = (uint8_t*)(base + L.act8);
+  float* d_obs = io->dev_obs;
+  float* d_rew = io->dev_reward;
+  uint8_t* d_term = io->dev_terminated;
+  uint8_t* d_mask = io->dev_mask;
+  uint16_t* d_flags = (uint16_t*)(base + L.flags);
+  const long long n = h->dev.n;
+  const int D = msort_obs_dim(h), A = msort_num_actions(h);
+  int chunks = io->chunks ? (int)io->chunks : 8;
+  long long per = (n + chunks - 1) / chunks;
+  per = (per + kTile - 1) / kTile * kTile;                       // ranges start on whole tiles
+  MSORT_TRY_CUDA(cudaEventRecord(h->host_start, user), "cudaEventRecord");
+  int used = 0, c = 0;
+  for (long long lo = 0; lo < n; lo += per, ++c) {
+    const long long cnt = std::min(per, n - lo);
+    const int k = c % msort_handle::kHostStreams;
+    cudaStream_t s = h->host_stream[k];
+    if (c < msort_handle::kHostStreams) { MSORT_TRY_CUDA(cudaStreamWaitEvent(s, h->host_start, 0), "cudaStreamWaitEvent"); used = c + 1; }
+    if (io->actions_u8) {
+      MSORT_TRY_CUDA(cudaMemcpyAsync(d_act8 + lo, io->actions_u8 + lo, (size_t)cnt, cudaMemcpyHostToDevice, s), "H2D actions");
+      MSORT_TRY_CUDA(launch_widen_actions(d_act8 + lo, d_act + lo, cnt, s), "widen kernel");
+      h->launches += 1;
+    } else {
+      MSORT_TRY_CUDA(cudaMemcpyAsync(d_act + lo, io->actions_i64 + lo, (size_t)cnt * 8, cudaMemcpyHostToDevice, s), "H2D actions");
+    }
+    int rc = step_impl(h, lo, cnt, state, d_act, d_obs, d_rew, d_term, d_mask, info, nullptr, s);
+    if (rc != MSORT_OK) return rc;
+    MSORT_TRY_CUDA(launch_pack_flags(h->dev.kind, d_mask + lo * A, d_term + lo, d_flags + lo, cnt, s), "pack kernel");
+    h->launches += 1;
+    MSORT_TRY_CUDA(cudaMemcpyAsync(io->obs + lo * D, d_obs + lo * D, (size_t)cnt * D * 4, cudaMemcpyDeviceToHost, s), "D2H obs");
+    MSORT_TRY_CUDA(cudaMemcpyAsync(io->reward + lo, d_rew + lo, (size_t)cnt * 4, cudaMemcpyDeviceToHost, s), "D2H reward");
+    MSORT_TRY_CUDA(cudaMemcpyAsync(io->flags + lo, d_flags + lo, (size_t)cnt * 2, cudaMemcpyDeviceToHost, s), "D2H flags");
+  }
+  for (int k = 0; k < used; ++k) {
+    MSORT_TRY_CUDA(cudaEventRecord(h->host_done[k], h->host_stream[k]), "cudaEventRecord");
+    MSORT_TRY_CUDA(cudaStreamWaitEvent(user, h->host_done[k], 0), "cudaStreamWaitEvent");
+  }
+  return MSORT_OK;
 }
 
 extern "C" int msort_set_policy(msort_t* h, const float* weights, int weights_on_device, void* stream) {

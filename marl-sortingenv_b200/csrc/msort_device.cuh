@@ -47,11 +47,13 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
 }
 
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar_saddr, uint32_t parity) {
+// one poll; the thread may stay suspended inside the instruction for up to ~`hint_ns` (suspend-time hint), so a
+// waiting warp costs a handful of issue slots instead of a spin loop's worth
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar_saddr, uint32_t parity, uint32_t hint_ns = 4000u) {
   uint32_t done;
   asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(done) : "r"(bar_saddr), "r"(parity) : "memory");
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(bar_saddr), "r"(parity), "r"(hint_ns) : "memory");
   return done;
 }
 
@@ -135,11 +137,11 @@ struct DevConfig {
 // the epilogues add.  Offsets in fp16 elements / 32-bit words.
 constexpr int kTcB1 = 0;                          // layer 1: 3 term tiles [K=16 x N=32] (rows 13..15 of term 0 = bias split)
 constexpr int kTcB2 = kTcB1 + 3 * 16 * 32;        // layer 2: 3 term tiles [K=32 x N=32]
-constexpr int kTcB3 = kTcB2 + 3 * 32 * 32;        // layer 3: 2 term tiles [K=32 x N=16] (rows 0, 1 = the two logits)
-constexpr int kTcHalves = kTcB3 + 2 * 32 * 16;
-constexpr int kTcBias2 = kTcHalves / 2;           // 32 floats
-constexpr int kTcBias3 = kTcBias2 + 32;           // 2 floats (+2 padding)
-constexpr int kTcWords = kTcBias3 + 4;            // 2852 words = 11 408 B (a multiple of 16)
+constexpr int kTcHalves = kTcB2 + 3 * 32 * 32;
+constexpr int kTcBias2 = kTcHalves / 2;           // 32 floats: layer-2 bias (with the folded constants)
+constexpr int kTcW3 = kTcBias2 + 32;              // 32 float pairs (-2 W3[0][j], -2 W3[1][j]): the output layer runs as fp32 FFMA2
+constexpr int kTcBias3 = kTcW3 + 64;              // 2 floats (+2 padding)
+constexpr int kTcWords = kTcBias3 + 4;            // 2404 words = 9 616 B (a multiple of 16)
 static_assert(kTcWords % 4 == 0, "whole 16-byte vectors");
 
 constexpr int kSortLut = 401;      // purity sum in hundredths: 4 containers x (0..100)

@@ -23,7 +23,7 @@
 #define MSORT_PRESS_MIN_BLOCKS 5  // Env_2 (embedded MLP: 32 activations + FFMA2 accumulator pairs in registers)
 #endif
 #ifndef MSORT_PRESS_TC_MIN_BLOCKS
-#define MSORT_PRESS_TC_MIN_BLOCKS 5  // Env_2 with the embedded policy on the tensor cores (TCMLP): 39.7 KB of shared memory per CTA
+#define MSORT_PRESS_TC_MIN_BLOCKS 6  // Env_2 with the embedded policy on the tensor cores (TCMLP): 37.0 KB of shared memory per CTA, 80 registers
 #endif
 #ifndef MSORT_HOT_MONO_MIN_BLOCKS
 #define MSORT_HOT_MONO_MIN_BLOCKS 8  // Env_3's HOT kernel fits 64 registers without a spill: 8 CTAs (32 warps) per SM, +3..5 %
@@ -169,8 +169,10 @@ template <int KIND> using PolicyParam = typename std::conditional<KIND == MSORT_
 // tanh is evaluated as 1 - 2r with r = 1 / (1 + 2^(c z)), c = 2 log2(e): the host folds c into this layer's weights
 // and the affine map h = 1 - 2r into the NEXT layer's weights and bias (pack_policy_tc), so an activation costs
 // MUFU.EX2 + FADD + MUFU.RCP and r (in (0, 1]) is what is split and stored as the next A operand.  Layer 1's bias rides
-// in the three padding columns of the 13-wide observation (A = 1.0, B = the bias's three split terms); layers 2 / 3
-// add theirs in the epilogue.  Measured logit error against the fp32 sum: see tests/test_tc_mlp_gpu.py.
+// in the three padding columns of the 13-wide observation (A = 1.0, B = the bias's three split terms); layer 2 adds
+// its bias in the epilogue.  Layers 1 and 2 (13 -> 32 -> 32: 1 440 of the 1 504 MACs) are the MMAs; the 32 -> 2 output
+// layer is evaluated in fp32 (FFMA2) on the layer-2 activations while they are still in registers, which saves the
+// third operand store and the third MMA round trip.  Measured logit error: tests/test_tc_mlp_gpu.py.
 struct TcMlp {
   uint4* a;            // A operand: hi chunks [4][128] then lo chunks [4][128] (16 KB; the first 8 KB alias the obs tile)
   const uint32_t* w;   // packed weights in shared memory (kTcWords)
@@ -183,6 +185,16 @@ __device__ __forceinline__ float tc_sigmoid2(float zp) {   // 1 / (1 + 2^zp); +i
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(zp));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
   return r;
+}
+
+// two activations at once: the two "+ 1" share one packed add (FADD2)
+__device__ __forceinline__ void tc_sigmoid2x2(float z0, float z1, float& r0, float& r1) {
+  float e0, e1, d0, d1;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(z0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(z1));
+  umma::fadd2(e0, e1, 1.0f, 1.0f, d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d1));
 }
 
 // one thread: all split products of one layer, smallest terms first, then commit
@@ -214,8 +226,7 @@ __device__ __forceinline__ void tc_issue_layer(const TcMlp& m, int b_off_halves)
 }
 
 // hidden-layer epilogue of this thread's env: 32 accumulators -> (+bias) -> r -> fp16 split -> the next A operand
-template <bool BIAS>
-__device__ __forceinline__ void tc_hidden_epilogue(const TcMlp& m, uint32_t tlane, const float* __restrict__ bias, int tid) {
+__device__ __forceinline__ void tc_hidden_epilogue(const TcMlp& m, uint32_t tlane, int tid) {
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     float v[16];
@@ -225,9 +236,9 @@ __device__ __forceinline__ void tc_hidden_epilogue(const TcMlp& m, uint32_t tlan
       uint32_t h[4], l[4];
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
-        float z0 = v[8 * q + 2 * p], z1 = v[8 * q + 2 * p + 1];
-        if (BIAS) { z0 += bias[16 * half + 8 * q + 2 * p]; z1 += bias[16 * half + 8 * q + 2 * p + 1]; }
-        umma::split2(tc_sigmoid2(z0), tc_sigmoid2(z1), h[p], l[p]);
+        float r0, r1;
+        tc_sigmoid2x2(v[8 * q + 2 * p], v[8 * q + 2 * p + 1], r0, r1);
+        umma::split2(r0, r1, h[p], l[p]);
       }
       m.a[(2 * half + q) * kTile + tid] = make_uint4(h[0], h[1], h[2], h[3]);
       m.a[(4 + 2 * half + q) * kTile + tid] = make_uint4(l[0], l[1], l[2], l[3]);
@@ -236,7 +247,8 @@ __device__ __forceinline__ void tc_hidden_epilogue(const TcMlp& m, uint32_t tlan
 }
 
 // All 128 threads of a tile call this together (it contains CTA barriers); `so` = this env's 13-wide sort
-// observation.  l0 / l1 = the two logits times the host's power-of-two scale (fw[kTcBias3 + 2] holds its inverse).
+// observation; l0 / l1 = the two logits.  Two MMA round trips (layers 1 and 2); the 32 -> 2 output layer is 32 packed
+// fp32 FMAs on the activations that are still in registers (no split, no operand store, no third round trip).
 __device__ __forceinline__ void tc_mlp_logits(const TcMlp& m, const float (&so)[13], int tid, uint32_t& phase, float& l0, float& l1) {
   const uint32_t tlane = m.tmem + ((uint32_t)(tid & ~31) << 16);
   {   // layer-1 operand: obs columns 0..12, then 1, 1, 1 (bias terms); the lo part of an exact 1.0 is 0
@@ -250,26 +262,47 @@ __device__ __forceinline__ void tc_mlp_logits(const TcMlp& m, const float (&so)[
     m.a[4 * kTile + tid] = make_uint4(l[0], l[1], l[2], l[3]);
     m.a[5 * kTile + tid] = make_uint4(l[4], l[5], l[6], l[7]);
   }
-  const float* const fw = reinterpret_cast<const float*>(m.w);
 #pragma unroll
-  for (int layer = 0; layer < 3; ++layer) {
+  for (int layer = 0; layer < 2; ++layer) {
     umma::fence_async_proxy();       // this thread's operand writes -> visible to the MMA's async-proxy reads
     umma::fence_before_sync();       // ... and its TMEM reads are done before the next MMA overwrites the columns
     __syncthreads();
     if (tid == 0) {
       umma::fence_after_sync();
       if (layer == 0) tc_issue_layer<1, 32, 3>(m, kTcB1);
-      else if (layer == 1) tc_issue_layer<2, 32, 3>(m, kTcB2);
-      else tc_issue_layer<2, 16, 2>(m, kTcB3);
+      else tc_issue_layer<2, 32, 3>(m, kTcB2);
     }
     mbar_wait(m.bar, phase); phase ^= 1u;
     umma::fence_after_sync();
-    if (layer == 0) tc_hidden_epilogue<false>(m, tlane, nullptr, tid);
-    else if (layer == 1) tc_hidden_epilogue<true>(m, tlane, fw + kTcBias2, tid);
+    if (layer == 0) tc_hidden_epilogue(m, tlane, tid);
   }
-  umma::tmem_ld2(tlane, l0, l1);
-  umma::fence_before_sync();         // ordered before the next tile's first MMA by the barriers in between
-  l0 += fw[kTcBias3]; l1 += fw[kTcBias3 + 1];
+  // layer-2 epilogue fused with the output layer: z -> +bias -> r2 (registers) -> logits += r2 * (-2 W3) (FFMA2)
+  const float* const fw = reinterpret_cast<const float*>(m.w);
+  const float4* const b2 = reinterpret_cast<const float4*>(fw + kTcBias2);
+  const ulonglong2* const w3 = reinterpret_cast<const ulonglong2*>(fw + kTcW3);   // two (logit0, logit1) weight pairs per 16 bytes
+  unsigned long long acc = *reinterpret_cast<const unsigned long long*>(fw + kTcBias3);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    float v[16];
+    umma::tmem_ld16(tlane + 16u * half, v);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 bb = b2[4 * half + q];
+      float z0, z1, z2, z3;
+      umma::fadd2(v[4 * q], v[4 * q + 1], bb.x, bb.y, z0, z1);
+      umma::fadd2(v[4 * q + 2], v[4 * q + 3], bb.z, bb.w, z2, z3);
+      const ulonglong2 wa = w3[8 * half + 2 * q], wb = w3[8 * half + 2 * q + 1];
+      float r0, r1, r2, r3;
+      tc_sigmoid2x2(z0, z1, r0, r1);
+      tc_sigmoid2x2(z2, z3, r2, r3);
+      acc = ffma2_bcast(wa.x, r0, acc);
+      acc = ffma2_bcast(wa.y, r1, acc);
+      acc = ffma2_bcast(wb.x, r2, acc);
+      acc = ffma2_bcast(wb.y, r3, acc);
+    }
+  }
+  umma::fence_before_sync();         // TMEM reads done: ordered before the next tile's first MMA by the barriers in between
+  f2unpack(acc, l0, l1);
 }
 
 // the sort mode: argmax of the two logits, ties -> 0 like np.argmax (sort_agent.predict(..., deterministic=True))
@@ -305,8 +338,7 @@ tc_logits_kernel(const float* __restrict__ obs13, const uint4* __restrict__ tcw,
     for (int k = 0; k < 13; ++k) so[k] = i < n ? obs13[i * 13 + k] : 0.f;
     float l0, l1;
     tc_mlp_logits(m, so, tid, phase, l0, l1);
-    const float inv = reinterpret_cast<const float*>(s_w)[kTcBias3 + 2];
-    if (i < n) { logits[2 * i] = l0 * inv; logits[2 * i + 1] = l1 * inv; }
+    if (i < n) { logits[2 * i] = l0; logits[2 * i + 1] = l1; }
     __syncthreads();   // every thread is done with the operand buffer before the next tile overwrites it
   }
   umma::fence_before_sync();
@@ -1155,6 +1187,35 @@ sample_kernel(const __grid_constant__ DevConfig c, const uint8_t* __restrict__ m
   actions[row0 + threadIdx.x] = a;
 }
 
+// ---------------------------------------------------------------- host-buffer step (msort_step_host): tiny helpers
+// actions arrive from the host as one byte per env (Discrete(22) fits): widen to the int64 the step kernel reads
+__global__ void __launch_bounds__(256)
+widen_actions_kernel(const uint8_t* __restrict__ in, long long* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i < n) out[i] = in[i];
+}
+
+// one 16-bit word per env for the trip back: bits 0..10 = the 11 press-mask bits (Env_1: its two always-valid
+// actions), bit 15 = terminated.  Mask rows are staged through shared memory like sample_kernel does.
+template <int A>
+__global__ void __launch_bounds__(kTile)
+pack_flags_kernel(const uint8_t* __restrict__ mask, const uint8_t* __restrict__ terminated, uint16_t* __restrict__ flags, long long n) {
+  __shared__ uint32_t s_rows[kTile * A / 4];
+  const long long row0 = (long long)blockIdx.x * kTile;
+  const int rows = (int)min((long long)kTile, n - row0);
+  const uint8_t* src = mask + row0 * A;
+  const int total = rows * A, words = total >> 2;
+  for (int w = threadIdx.x; w < words; w += kTile) s_rows[w] = reinterpret_cast<const uint32_t*>(src)[w];
+  for (int e = 4 * words + threadIdx.x; e < total; e += kTile) reinterpret_cast<uint8_t*>(s_rows)[e] = src[e];
+  __syncthreads();
+  if ((int)threadIdx.x >= rows) return;
+  const uint8_t* row = reinterpret_cast<const uint8_t*>(s_rows) + threadIdx.x * A;
+  uint32_t bits = 0;
+#pragma unroll
+  for (int k = 0; k < (A < 11 ? A : 11); ++k) bits |= (uint32_t)(row[k] != 0) << k;
+  flags[row0 + threadIdx.x] = (uint16_t)(bits | (terminated[row0 + threadIdx.x] ? 0x8000u : 0u));
+}
+
 // ---------------------------------------------------------------- rule-based action source
 // ref: Env_3.step(mode='rule_based') env_monolith.py:166-184
 __global__ void __launch_bounds__(kTile)
@@ -1329,10 +1390,8 @@ int policy_tc_words() { return kTcWords; }
 // Env_2's embedded policy for the tensor-core path (tc_mlp_mode): SB3 order -> kTcWords packed words.
 //   layer 1: B[n][k] = c*W1[n][k] (k < 13), rows 13..15 of term 0 = the three split terms of c*b1[n]      (c = 2 log2 e)
 //   layer 2: B[n][k] = -2c*W2[n][k],  bias2'[n] = c*(b2[n] + sum_k W2[n][k])      (input r1 with h1 = 1 - 2 r1)
-//   layer 3: B[n][k] = -2s*W3[n][k],  bias3'[n] = s*(b3[n] + sum_k W3[n][k])      (s = a power of two that lifts the
-//            largest |weight| to [8192, 16384): the argmax does not see it and the two-term split stays out of fp16's
-//            subnormals)
-// every weight v (float64) as fp16 terms t1 = fp16(v), t2 = fp16(v - t1), t3 = fp16(v - t1 - t2).  Returns false when a
+//   layer 3: fp32 pairs (-2 W3[0][k], -2 W3[1][k]),  bias3'[n] = b3[n] + sum_k W3[n][k]      (FFMA2 in the kernel)
+// every MMA weight v (float64) as fp16 terms t1 = fp16(v), t2 = fp16(v - t1), t3 = fp16(v - t1 - t2).  Returns false when a
 // value does not fit fp16's range (the caller keeps the FFMA2 kernel for such a policy).
 bool pack_policy_tc(const float* sb3, uint32_t* words) {
   constexpr int W1 = 0, b1 = 416, W2 = 448, b2 = 1472, W3 = 1504, b3 = 1568;
@@ -1369,25 +1428,15 @@ bool pack_policy_tc(const float* sb3, uint32_t* words) {
     }
     fw[kTcBias2 + n] = (float)(cc * sum);
   }
-  double mx = 0.0;
-  for (int j = 0; j < 64; ++j) mx = std::max(mx, std::fabs(2.0 * (double)sb3[W3 + j]));
-  double sc = 1.0;
-  if (mx > 0.0 && std::isfinite(mx)) {
-    while (mx * sc < 8192.0) sc *= 2.0;
-    while (mx * sc >= 16384.0) sc *= 0.5;
+  for (int j = 0; j < 32; ++j) {                   // output layer, fp32: pair j = (-2 W3[0][j], -2 W3[1][j]) (exact scaling)
+    fw[kTcW3 + 2 * j] = -2.0f * sb3[W3 + j];
+    fw[kTcW3 + 2 * j + 1] = -2.0f * sb3[W3 + 32 + j];
   }
   for (int n = 0; n < 2; ++n) {
     double sum = (double)sb3[b3 + n];
-    for (int k = 0; k < 32; ++k) {
-      const double w = (double)sb3[W3 + n * 32 + k];
-      put(kTcB3, 32, 16, 2, n, k, -2.0 * sc * w);
-      sum += w;
-    }
-    const double bb = sc * sum;
-    if (!std::isfinite(bb) || std::fabs(bb) > 3.0e38) ok = false;
-    fw[kTcBias3 + n] = (float)bb;
+    for (int k = 0; k < 32; ++k) sum += (double)sb3[W3 + n * 32 + k];
+    fw[kTcBias3 + n] = (float)sum;
   }
-  fw[kTcBias3 + 2] = (float)(1.0 / sc);   // diagnostics only (tc_logits_kernel): undoes the scale
   for (int j = 0; j < MSORT_POLICY_WEIGHTS; ++j) if (!std::isfinite(sb3[j])) ok = false;
   return ok;
 }
@@ -1415,11 +1464,24 @@ static StepArgs shift_args(StepArgs a, long long first, int D, int A) {
 // Resident CTAs per SM of the four persistent Env_2 kernels (index = SMALL + 2 * TCMLP), asked from the occupancy
 // calculator on the CURRENT device (msort_create); also sets the shared-memory carve-out those kernels want.
 void query_persist_occupancy(int per_sm[4]) {
-  auto ask = [](auto kern) {
+  int dev = 0;
+  cudaDeviceProp prop;
+  cudaGetDevice(&dev);
+  const bool have_prop = cudaGetDeviceProperties(&prop, dev) == cudaSuccess;
+  auto ask = [&](auto kern) {
     int v = 0;
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, kTile, 0) != cudaSuccess || v < 1) v = 1;
-    return v;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, kern, kTile, 0) != cudaSuccess) v = 0;
+    // the same bound from the kernel's own resource use (registers, static shared memory + 1 KB the driver reserves
+    // per CTA): the calculator has been seen to answer for the default carve-out rather than the preferred one
+    cudaFuncAttributes fa;
+    if (have_prop && cudaFuncGetAttributes(&fa, kern) == cudaSuccess) {
+      const int by_regs = prop.regsPerMultiprocessor / std::max(1, ((fa.numRegs + 7) / 8 * 8) * kTile);
+      const int by_smem = (int)(prop.sharedMemPerMultiprocessor / (fa.sharedSizeBytes + 1024));
+      const int mine = std::min(std::min(by_regs, by_smem), prop.maxBlocksPerMultiProcessor);
+      v = std::max(v, mine);
+    }
+    return std::max(v, 1);
   };
   per_sm[0] = ask(step_kernel<MSORT_ENV_PRESS, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true, false, false>);
   per_sm[1] = ask(step_kernel<MSORT_ENV_PRESS, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true, true, false>);
@@ -1549,6 +1611,22 @@ cudaError_t launch_sample(const DevConfig& c, const uint8_t* mask, int64_t* acti
     case MSORT_ENV_SORT: sample_kernel<2><<<tiles(c.n), kTile, 0, st>>>(c, mask, (long long*)actions, k0, k1, t); break;
     case MSORT_ENV_PRESS: sample_kernel<11><<<tiles(c.n), kTile, 0, st>>>(c, mask, (long long*)actions, k0, k1, t); break;
     default: sample_kernel<22><<<tiles(c.n), kTile, 0, st>>>(c, mask, (long long*)actions, k0, k1, t); break;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_widen_actions(const uint8_t* in, int64_t* out, long long n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  widen_actions_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, (long long*)out, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack_flags(int kind, const uint8_t* mask, const uint8_t* terminated, uint16_t* flags, long long n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  switch (kind) {
+    case MSORT_ENV_SORT: pack_flags_kernel<2><<<tiles(n), kTile, 0, st>>>(mask, terminated, flags, n); break;
+    case MSORT_ENV_PRESS: pack_flags_kernel<11><<<tiles(n), kTile, 0, st>>>(mask, terminated, flags, n); break;
+    default: pack_flags_kernel<22><<<tiles(n), kTile, 0, st>>>(mask, terminated, flags, n); break;
   }
   return cudaGetLastError();
 }

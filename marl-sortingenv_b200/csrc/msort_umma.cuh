@@ -101,13 +101,24 @@ __device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
                     *reinterpret_cast<const uint32_t*>(&c), *reinterpret_cast<const uint32_t*>(&d));
 }
 
+// packed fp32 add (Blackwell FADD2: two independent IEEE adds per lane and issue slot)
+__device__ __forceinline__ void fadd2(float a0, float a1, float b0, float b1, float& c0, float& c1) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "=f"(c0), "=f"(c1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fsub2(float a0, float a1, float b0, float b1, float& c0, float& c1) {
+  fadd2(a0, a1, -b0, -b1, c0, c1);     // the negations fold into the instruction's operand modifiers
+}
+
 // Two-term fp16 split of a pair of fp32 values: hi = fp16(x), lo = fp16(x - hi) — hi + lo carries 22 significand bits of
 // x (absolute error <= 2^-25 for |x| <= 1 down to fp16's subnormal spacing 2^-24), so an fp16 tensor-core product
 // against a three-term weight split reproduces the fp32 product to fp32 accuracy.  F2FP + 2 HADD2.F32 + 2 FADD + F2FP.
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(a, b);
-  const float2 f = __half22float2(h);
-  const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+  const float2 nf = __half22float2(__hneg2(h));   // -hi (the sign flip folds into the conversion's operand modifier)
+  float ra, rb;
+  fadd2(a, b, nf.x, nf.y, ra, rb);
+  const __half2 l = __floats2half2_rn(ra, rb);
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }

@@ -48,6 +48,7 @@ class MsortVecEnv:
 
     def step_wait(self):
         obs, rew, term, trunc, mask = self.env.step_host(self._actions)
+        term = np.asarray(term)                      # step_host hands `terminated` over lazily (packed flag words)
         infos = [{"TimeLimit.truncated": False} for _ in range(self.num_envs)]
         done_idx = np.flatnonzero(term)
         if done_idx.size:

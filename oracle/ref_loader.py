@@ -25,7 +25,20 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("MSORT_REFERENCE_ROOT", "/root/reference")
+def _find_reference_root() -> str:
+    """$MSORT_REFERENCE_ROOT, else the read-only checkout of the build container, else the copy oracle/make_ref.sh
+    staged into oracle/_ref (git-ignored; it is what travels to the GPU box)."""
+    env = os.environ.get("MSORT_REFERENCE_ROOT")
+    if env:
+        return env
+    staged = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+    for root in ("/root/reference", staged):
+        if os.path.isfile(os.path.join(root, "src", "envs_train", "env_super.py")):
+            return root
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference_root()
 
 
 def reference_available() -> bool:

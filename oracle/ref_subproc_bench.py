@@ -5,8 +5,9 @@ over pipes with the command protocol of SB3's SubprocVecEnv (`step(actions)` →
 dones / infos with `terminal_observation` and an unseeded `reset()` on done; `env_method("action_masks")`).
 stable-baselines3 itself is not installed (and not installable offline), hence the restatement.
 
-Runs only where /root/reference exists (the build container); the GPU box cannot see the reference,
-so the result is committed as profiles/cpu_reference_subproc_r01.json and quoted in DESIGN.md.
+Needs a copy of the reference: /root/reference in the build container, or oracle/_ref, which oracle/make_ref.sh
+stages from it and which travels to the GPU box with the snapshot (git-ignored).  bench.py's reference arm calls
+run_steps(); the round-1 build-container result is profiles/cpu_reference_subproc_r01.json.
 
     python oracle/ref_subproc_bench.py [--seconds 6] [--envs-per-worker 8] [--out profiles/...json]
 """
@@ -50,7 +51,12 @@ def _worker(conn, kind, n_envs, seed0, max_steps, noise):
             return
 
 
-def run(kind: str, seconds: float, envs_per_worker: int, workers: int, max_steps=50, noise=0.05):
+def run_steps(kind: str, steps: int, warmup: int, envs_per_worker: int, workers: int, max_steps=50, noise=0.05):
+    """`warmup` untimed and `steps` timed batched steps (bench.py --impl reference); (env-steps/s, env-steps, seconds)."""
+    return run(kind, None, envs_per_worker, workers, max_steps=max_steps, noise=noise, steps=steps, warmup=warmup)
+
+
+def run(kind: str, seconds, envs_per_worker: int, workers: int, max_steps=50, noise=0.05, steps=None, warmup=5):
     ctx = mp.get_context("fork")
     pipes, procs = [], []
     for w in range(workers):
@@ -73,10 +79,10 @@ def run(kind: str, seconds: float, envs_per_worker: int, workers: int, max_steps
             c.send(("step", acts))
         for c in pipes:
             c.recv()
-    for _ in range(5):
+    for _ in range(warmup):
         one_step()
     n_steps, t0 = 0, time.perf_counter()
-    while time.perf_counter() - t0 < seconds:
+    while (n_steps < steps) if steps is not None else (time.perf_counter() - t0 < seconds):
         one_step()
         n_steps += 1
     dt = time.perf_counter() - t0

@@ -14,6 +14,9 @@ if kind == 'press':
     env.set_sort_policy(sb3_style_init(0, action_gain=float(os.environ.get("GAIN", 0.01))))
     if os.environ.get("TENSOR") is not None:                      # A/B: embedded policy on the tensor cores (1) or FFMA2 (0)
         env.set_option(ms._abi.OPT_TENSOR_POLICY, int(os.environ["TENSOR"]))
+    if os.environ.get("CTAS"):
+        env.set_option(ms._abi.OPT_PERSIST_CTAS, int(os.environ["CTAS"]))
+    print("persistent CTAs per SM:", env.get_option(ms._abi.OPT_PERSIST_CTAS), flush=True)
 env.reset()
 if os.environ.get("L2PERSIST"):
     # experiment: pin the hot state planes in L2 with an access-policy window on the stream (captured into the graph's kernel nodes)

@@ -233,3 +233,38 @@ def test_published_rule_based_return_batched_on_device():
         total += r.double()
     assert bool(term.all())
     assert abs(total.mean().item() - 44.03) < 3 * 1.10 / np.sqrt(10) + 0.3, (total.mean().item(), total.std().item())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["sort", "press", "mono"])
+def test_step_host_pipeline_matches_step(kind):
+    """`step_host` (msort_step_host: chunked H2D -> step kernel -> D2H on the library's own streams, packed flag
+    words back) returns exactly what `step` leaves on the device, for every chunk count, ragged batch sizes,
+    uint8 / int64 / unpinned actions — and leaves the same state behind."""
+    import torch
+    from marl_sortingenv_b200.batched import ENV_CLASSES
+    n = 128 * 37 + 19
+    a_env = ENV_CLASSES[kind](n, max_steps=12, seed=4, info_level="episode")
+    b_env = ENV_CLASSES[kind](n, max_steps=12, seed=4, info_level="episode")
+    a_env.reset(); b_env.reset()
+    pinned_u8 = torch.zeros(n, dtype=torch.uint8).pin_memory()
+    pinned_i64 = torch.zeros(n, dtype=torch.int64).pin_memory()
+    for t in range(30):
+        act = a_env.sample_actions(6, t)
+        obs, rew, term, _, _ = a_env.step(act)
+        host = act.cpu()
+        if t % 3 == 0:
+            pinned_u8.copy_(host); arg = pinned_u8
+        elif t % 3 == 1:
+            pinned_i64.copy_(host); arg = pinned_i64
+        else:
+            arg = host.numpy().astype(np.int32)              # converted into the env's own pinned buffer
+        ho, hr, ht, htr, hm = b_env.step_host(arg, chunks=(0, 1, 3, 5, 64)[t % 5])
+        assert np.array_equal(ho, obs.cpu().numpy()) and np.array_equal(hr, rew.cpu().numpy())
+        assert np.array_equal(np.asarray(ht), term.cpu().numpy()) and not htr.any()
+        assert np.array_equal(np.asarray(hm), a_env.action_masks().cpu().numpy())
+        assert torch.equal(b_env.action_masks(), a_env.action_masks()) and torch.equal(b_env.obs, a_env.obs)
+        assert b_env.h2d_bytes == n * (8 if t % 3 == 1 else 1) and b_env.d2h_bytes == n * (4 * a_env.D + 4 + 2)
+    assert torch.equal(a_env.state, b_env.state)
+    assert torch.allclose(a_env.stats, b_env.stats, rtol=1e-9, atol=0)     # same sums, different atomic order
+    a_env.close(); b_env.close()

@@ -6,7 +6,7 @@ within 1e-5 relative (absolute floor 1e-7 where the reference value is 0)."""
 import numpy as np
 import pytest
 
-from parity_util import (FLOAT_ATOL, FLOAT_RTOL, assert_float_close, config_for, golden_group,
+from parity_util import (FLOAT_ATOL, FLOAT_RTOL, assert_float_close, config_dict_for, config_for, golden_group,
                          golden_group_names, replay_and_compare, state_rows)
 
 pytestmark = pytest.mark.gpu
