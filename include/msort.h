@@ -33,7 +33,7 @@ extern "C" {
 
 /* ABI history: 2 telemetry (msort_gather_state, reward terms) and msort_policy_act; 3 msort_observe_after_shift,
  * msort_step_variant, obs / mask must be 16-byte aligned; 4 msort_step_range, msort_policy_act_range;
- * 5 msort_set_option, MSORT_STEP_HOT_TENSOR, msort_step_host. */
+ * 5 msort_set_option, MSORT_STEP_HOT_TENSOR, msort_step_host, msort_generate_streams. */
 #define MSORT_ABI_VERSION 5
 
 /* ------------------------------------------------------------------ enums */
@@ -265,6 +265,20 @@ int msort_observe_after_shift(msort_t* h, const void* state, float* obs, uint8_t
 int msort_sample_actions(msort_t* h, const uint8_t* mask, int64_t* actions, uint64_t seed, uint32_t t,
                          void* stream);
 
+/* Generator stream export (K3).  The random inputs the PHILOX generator feeds the plant that do NOT depend on the plant's
+ * state, for steps first_step .. first_step + num_steps - 1 of episode `episode` of every env, in the REPLAY
+ * descriptor's form (all device pointers, all nullable):
+ *   input_counts [T,N] u32  the batch the seasonal generator emits at that step, packed A | B<<8 | C<<16 | D<<24
+ *                           (ref: SeasonalInputGenerator.generate_input, input_generator.py:37-64)
+ *   noise_u [T,N,4] f64     the four uniforms of update_accuracy (ref: rng_noise.uniform, env_super.py:508)
+ *   draw_words [T,N,12] u32 the first Philox block of redistribution words of stations 0, 1, 2 (ref: the stream behind
+ *                           rng.choice in sort_material, env_super.py:563; how a word becomes a draw depends on the plant)
+ *   first_pattern [N] u8    pattern_sequence[0] (1 | 2) of that episode (ref: input_generator.py:30)
+ * With these (and the redistribution uniforms, which depend on the state and are recorded by the oracle) a PHILOX
+ * trajectory can be replayed through the REPLAY instantiation and through the reference itself. */
+int msort_generate_streams(msort_t* h, uint32_t episode, uint32_t first_step, uint32_t num_steps, uint32_t* input_counts,
+                           double* noise_u, uint32_t* draw_words, uint8_t* first_pattern, void* stream);
+
 /* Rule-based action source: sort mode from sorting_rules() (env_super.py:469-482), press job from
  * check_container_level() (env_super.py:689-720: first free press, fullest container with level > 0),
  * combined as Env_3.step(mode='rule_based') does (env_monolith.py:166-184).  Env_1 gets the sort mode,
@@ -347,7 +361,7 @@ int msort_policy_act_range(msort_t* h, int64_t first_env, int64_t num_envs, cons
  *  info    : as for msort_step (per-step info arrays stay on the device) */
 typedef struct msort_host_io {
   uint32_t struct_size;
-  uint32_t chunks;              /* env ranges per step; 0 = library default (8) */
+  uint32_t chunks;              /* env ranges per step; 0 = library default (2) */
   const uint8_t* actions_u8;
   const int64_t* actions_i64;
   float* obs;

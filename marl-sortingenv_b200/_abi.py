@@ -162,6 +162,7 @@ SYMBOLS = {
     "msort_sync_check": (C.c_int, [_P, _P]),
     "msort_launch_count": (C.c_int64, [_P]),
     "msort_step_variant": (C.c_int, [_P]),
+    "msort_generate_streams": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P]),
     "msort_host_scratch_bytes": (C.c_size_t, [_P]),
     "msort_step_host": (C.c_int, [_P, _P, _P, C.POINTER(MsortHostIO), C.POINTER(MsortInfoOut), _P]),
     "msort_set_option": (C.c_int, [_P, C.c_int, C.c_int64]),

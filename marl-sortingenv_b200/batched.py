@@ -303,6 +303,24 @@ class BatchedEnv:
         _abi.check(self.lib, rc, "msort_sample_actions")
         return out
 
+    def generate_streams(self, episode: int, first_step: int, num_steps: int, draw_words: bool = False):
+        """The state-independent random inputs of `num_steps` steps of one episode (`msort_generate_streams`): dict of CUDA
+        tensors input_counts [T,N] int32 (packed bytes), noise_u [T,N,4] f64, first_pattern [N] uint8 and, on request,
+        draw_words [T,N,12] int32 — in the form `step(..., replay=...)` of a REPLAY-mode env consumes.
+        ref: SeasonalInputGenerator.generate_input (input_generator.py:37-64), rng_noise.uniform (env_super.py:508)."""
+        T, n, dev = int(num_steps), self.num_envs, self.device
+        out = dict(input_counts=torch.empty((T, n), dtype=torch.int32, device=dev),
+                   noise_u=torch.empty((T, n, 4), dtype=torch.float64, device=dev),
+                   first_pattern=torch.empty(n, dtype=torch.uint8, device=dev))
+        if draw_words:
+            out["draw_words"] = torch.empty((T, n, 12), dtype=torch.int32, device=dev)
+        with torch.cuda.device(self.device):
+            rc = self.lib.msort_generate_streams(self._h, int(episode), int(first_step), T, _ptr(out["input_counts"]),
+                                                 _ptr(out["noise_u"]), _ptr(out.get("draw_words")), _ptr(out["first_pattern"]),
+                                                 self._stream())
+        _abi.check(self.lib, rc, "msort_generate_streams")
+        return out
+
     def rule_based_actions(self, after_shift: bool = True, out: torch.Tensor | None = None) -> torch.Tensor:
         """The reference's heuristic policy for every env (one kernel launch): sorting_rules() +
         check_container_level() combined as Env_3.step(mode='rule_based') does

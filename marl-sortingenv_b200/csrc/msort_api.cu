@@ -531,7 +531,10 @@ extern "C" int msort_step_host(msort_t* h, void* state, void* scratch, const mso
   uint16_t* d_flags = (uint16_t*)(base + L.flags);
   const long long n = h->dev.n;
   const int D = msort_obs_dim(h), A = msort_num_actions(h);
-  int chunks = io->chunks ? (int)io->chunks : 8;
+  // default 2: measured at 1 048 576 Env_3 envs (profiles/e2e_chunks_r02.txt) 1 / 2 / 4 / 8 / 16 / 32 ranges cost 2.44 / 2.43 /
+  // 2.44 / 2.47 / 2.60 / 2.70 ms per step — the D2H engine is the bottleneck (128 MB at 56 GB/s = 2.26 ms), so all a second
+  // range buys is the first range's copy running beside the second range's kernel; more ranges only add copy launches
+  int chunks = io->chunks ? (int)io->chunks : 2;
   long long per = (n + chunks - 1) / chunks;
   per = (per + kTile - 1) / kTile * kTile;                       // ranges start on whole tiles
   MSORT_TRY_CUDA(cudaEventRecord(h->host_start, user), "cudaEventRecord");
@@ -618,6 +621,17 @@ extern "C" int msort_sample_actions(msort_t* h, const uint8_t* mask, int64_t* ac
   if (!h || !mask || !actions) return fail(MSORT_E_INVALID, "msort_sample_actions: NULL argument");
   if (!aligned(mask, 4) || !aligned(actions, 8)) return fail(MSORT_E_INVALID, "msort_sample_actions: misaligned buffer");
   MSORT_TRY_CUDA(launch_sample(h->dev, mask, actions, seed, t, (cudaStream_t)stream), "sample kernel");
+  h->launches += 1;
+  return MSORT_OK;
+}
+
+extern "C" int msort_generate_streams(msort_t* h, uint32_t episode, uint32_t first_step, uint32_t num_steps, uint32_t* input_counts,
+                                      double* noise_u, uint32_t* draw_words, uint8_t* first_pattern, void* stream) {
+  if (!h) return fail(MSORT_E_INVALID, "msort_generate_streams: NULL handle");
+  if ((input_counts && !aligned(input_counts, 4)) || (noise_u && !aligned(noise_u, 16)) || (draw_words && !aligned(draw_words, 16)))
+    return fail(MSORT_E_INVALID, "msort_generate_streams: misaligned buffer");
+  MSORT_TRY_CUDA(launch_generate_streams(h->dev, episode, first_step, num_steps, input_counts, noise_u, draw_words, first_pattern,
+                                         (cudaStream_t)stream), "generate_streams kernel");
   h->launches += 1;
   return MSORT_OK;
 }

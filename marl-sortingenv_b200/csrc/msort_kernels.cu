@@ -1187,6 +1187,51 @@ sample_kernel(const __grid_constant__ DevConfig c, const uint8_t* __restrict__ m
   actions[row0 + threadIdx.x] = a;
 }
 
+// ---------------------------------------------------------------- K3: generator stream export
+// The state-independent random inputs of `num_steps` steps of one episode, written in the REPLAY descriptor's form
+// (ref: SeasonalInputGenerator.generate_input input_generator.py:37-64 for the batches, rng_noise.uniform
+// env_super.py:508 for the noise): what the PHILOX step kernel will consume for (env, episode, step).  Together with the
+// oracle's recording of the redistribution draws (which depend on the plant state) a PHILOX trajectory can be replayed
+// through the REPLAY instantiation and through the reference.  One thread per env, coalesced [t][env] stores.
+__global__ void __launch_bounds__(256)
+generate_streams_kernel(const __grid_constant__ DevConfig c, uint32_t episode, uint32_t first_step, uint32_t num_steps,
+                        uint32_t* __restrict__ input_counts, double* __restrict__ noise_u, uint32_t* __restrict__ draw_words,
+                        uint8_t* __restrict__ first_pattern) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= c.n) return;
+  const unsigned long long g = (unsigned long long)(c.gid0 + i);
+  const uint32_t gid_lo = (uint32_t)g, gid_hi = (uint32_t)(g >> 32) & 0xffffu;
+  const uint32_t gfirst = env_draw(c, gid_lo, gid_hi, kBlkReset, episode, 0u).x & 1u;   // pattern_sequence[0] - 1 of this episode
+  if (first_pattern) first_pattern[i] = (uint8_t)(1u + gfirst);
+  for (uint32_t k = 0; k < num_steps; ++k) {
+    const uint32_t t = first_step + k;
+    const long long o = (long long)k * c.n + i;
+    if (input_counts) {   // step t emits batch number t of the episode: the pattern flips every steps_per_pattern batches
+      uint32_t in4 = c.pat[((t / (uint32_t)c.spp) & 1u) ^ gfirst];
+      for (int r = 0; r < c.pat_remainder; ++r) {
+        const U4 r4 = env_draw(c, gid_lo, gid_hi, kBlkInput + 0x100u * (uint32_t)(r >> 2), episode, t);
+        const uint32_t x = (r & 3) == 0 ? r4.x : ((r & 3) == 1 ? r4.y : ((r & 3) == 2 ? r4.z : r4.w));
+        in4 += 1u << (8 * (x & 3u));
+      }
+      input_counts[o] = in4;
+    }
+    if (noise_u) {
+      const U4 r4 = env_draw(c, gid_lo, gid_hi, kBlkNoise, episode, t);
+      double2* d = reinterpret_cast<double2*>(noise_u) + 2 * o;
+      d[0] = make_double2((double)r4.x * 2.3283064365386963e-10, (double)r4.y * 2.3283064365386963e-10);
+      d[1] = make_double2((double)r4.z * 2.3283064365386963e-10, (double)r4.w * 2.3283064365386963e-10);
+    }
+    if (draw_words) {     // first block of redistribution words of stations 0, 1, 2 (station 3's draws are never simulated)
+      uint4* w = reinterpret_cast<uint4*>(draw_words) + 3 * o;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const U4 r4 = env_draw(c, gid_lo, gid_hi, kBlkRedis + 64u * (uint32_t)s, episode, t);
+        w[s] = make_uint4(r4.x, r4.y, r4.z, r4.w);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- host-buffer step (msort_step_host): tiny helpers
 // actions arrive from the host as one byte per env (Discrete(22) fits): widen to the int64 the step kernel reads
 __global__ void __launch_bounds__(256)
@@ -1612,6 +1657,13 @@ cudaError_t launch_sample(const DevConfig& c, const uint8_t* mask, int64_t* acti
     case MSORT_ENV_PRESS: sample_kernel<11><<<tiles(c.n), kTile, 0, st>>>(c, mask, (long long*)actions, k0, k1, t); break;
     default: sample_kernel<22><<<tiles(c.n), kTile, 0, st>>>(c, mask, (long long*)actions, k0, k1, t); break;
   }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_generate_streams(const DevConfig& c, uint32_t episode, uint32_t first_step, uint32_t num_steps, uint32_t* input_counts,
+                                    double* noise_u, uint32_t* draw_words, uint8_t* first_pattern, cudaStream_t st) {
+  generate_streams_kernel<<<(unsigned)((c.n + 255) / 256), 256, 0, st>>>(c, episode, first_step, num_steps, input_counts, noise_u,
+                                                                         draw_words, first_pattern);
   return cudaGetLastError();
 }
 

@@ -37,6 +37,8 @@ cudaError_t launch_reset(const DevConfig& c, void* state, const uint8_t* which, 
 cudaError_t launch_observe(const DevConfig& c, const void* state, float* obs, uint8_t* mask, int after_shift, cudaStream_t st);
 cudaError_t launch_sample(const DevConfig& c, const uint8_t* mask, int64_t* actions, uint64_t seed, uint32_t t,
                           cudaStream_t st);
+cudaError_t launch_generate_streams(const DevConfig& c, uint32_t episode, uint32_t first_step, uint32_t num_steps, uint32_t* input_counts,
+                                    double* noise_u, uint32_t* draw_words, uint8_t* first_pattern, cudaStream_t st);
 cudaError_t launch_widen_actions(const uint8_t* in, int64_t* out, long long n, cudaStream_t st);
 cudaError_t launch_pack_flags(int kind, const uint8_t* mask, const uint8_t* terminated, uint16_t* flags, long long n, cudaStream_t st);
 cudaError_t launch_rule_actions(const DevConfig& c, const void* state, int after_shift, int64_t* actions, cudaStream_t st);

@@ -20,7 +20,13 @@ _lib = None
 
 
 class _StepOut(C.Structure):
-    _fields_ = [("reward32", C.c_void_p), ("reward64", C.c_void_p), ("mlp_margin", C.c_void_p)]
+    """mso_step_out_t (oracle/msort_oracle.c)."""
+    _fields_ = [("reward32", C.c_void_p), ("reward64", C.c_void_p), ("mlp_margin", C.c_void_p),
+                ("rec_noise_u", C.c_void_p), ("rec_redis_u", C.c_void_p), ("rec_n_draws", C.c_void_p),
+                ("rec_press_choice", C.c_void_p), ("rec_input_counts", C.c_void_p), ("rec_cap", C.c_int32)]
+
+
+REC_CAP = 128      # uniforms recorded per env-step: one per mis-sorted unit, at most the input batch (100 by default)
 
 
 def build(force: bool = False) -> str:
@@ -106,7 +112,10 @@ class OracleEnv:
         return obs, mask.astype(bool)
 
     def step(self, actions, *, noise_u=None, redis_u=None, input_counts=None, press_choice=None,
-             sort_mode=None, want_info=True):
+             sort_mode=None, want_info=True, record=False):
+        """`record=True` (PHILOX mode): the info dict also carries the step's random inputs in REPLAY form — `rec_noise_u`
+        [n,4], `rec_redis_u` [n,REC_CAP] with `rec_n_draws` [n] valid entries each, `rec_press_choice` [n] (Env_1),
+        `rec_input_counts` [n] packed — see mso_step_out_t in msort_oracle.c."""
         n, D, A = self.n, self.D, self.A
         actions = np.ascontiguousarray(actions, dtype=np.int64)
         obs = np.zeros((n, D), dtype=np.float32)
@@ -115,6 +124,13 @@ class OracleEnv:
         r64 = np.zeros(n, dtype=np.float64)
         margin = np.full(n, np.inf, dtype=np.float32)
         so = _StepOut(None, _ptr(r64), _ptr(margin))
+        rec = {}
+        if record:
+            rec = dict(rec_noise_u=np.zeros((n, 4)), rec_redis_u=np.zeros((n, REC_CAP)), rec_n_draws=np.zeros(n, np.int32),
+                       rec_press_choice=np.zeros(n, np.uint8), rec_input_counts=np.zeros(n, np.uint32))
+            for k, v in rec.items():
+                setattr(so, k, _ptr(v))
+            so.rec_cap = REC_CAP
         info = _abi.MsortInfoOut()
         info.struct_size = C.sizeof(info)
         keep = {}
@@ -155,6 +171,9 @@ class OracleEnv:
         if rc != 0:
             raise RuntimeError(f"mso_step returned {rc}")
         keep["mlp_margin"] = margin
+        if record:
+            assert int(rec["rec_n_draws"].max(initial=0)) <= REC_CAP, "more draws in one step than REC_CAP holds"
+            keep.update(rec)
         return obs, r64, term.astype(bool), mask.astype(bool), keep
 
     def sample_masked_actions(self, seed: int, t: int):

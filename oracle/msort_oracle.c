@@ -255,6 +255,24 @@ typedef struct mso_step_out {
   float* reward32;   /* nullable */
   double* reward64;  /* nullable */
   float* mlp_margin; /* nullable: |logit0-logit1| of the embedded policy */
+  /* Recording of a PHILOX step as REPLAY inputs (all nullable).  What the step drew is written in the form the
+   * reference's numpy generators would have had to produce for the SAME outcome, so the trajectory can be replayed
+   * through the REPLAY instantiations and through the unmodified reference (oracle/ref_drive.py):
+   *  rec_noise_u [n,4]   the four uniforms of update_accuracy (env_super.py:508)
+   *  rec_redis_u [n,cap] one uniform per `rng.choice(4, p=leftover/total)` call of sort_material (:563), in call order:
+   *                      a draw that took unit r of the pool of `tot` leftovers becomes u = (r + 1/2) / tot — the middle
+   *                      of that unit's cell of numpy's cdf, whose cells are laid out station 0..3 exactly like the
+   *                      pool here (processed stations = the lump first, then the unprocessed ones); the last
+   *                      station's draws, which cannot change the outcome, are recorded as 1/2
+   *  rec_n_draws [n]     how many were recorded (== total false units of the step)
+   *  rec_press_choice [n] Env_1's internally sampled press action (:291-300)
+   *  rec_input_counts [n] the generator's batch, packed A | B<<8 | C<<16 | D<<24 */
+  double* rec_noise_u;
+  double* rec_redis_u;
+  int32_t* rec_n_draws;
+  uint8_t* rec_press_choice;
+  uint32_t* rec_input_counts;
+  int32_t rec_cap;
 } mso_step_out_t;
 
 typedef struct step_acc { double v[MSORT_NUM_STATS]; } step_acc_t;
@@ -262,7 +280,9 @@ typedef struct step_acc { double v[MSORT_NUM_STATS]; } step_acc_t;
 static void step_one(const msort_config_t* cfg, msort_env_state_t* s, int64_t i, int64_t a_in,
                      float* obs, double* reward_out, uint8_t* term_out, uint8_t* mask,
                      const msort_info_out_t* info, const msort_replay_t* rp, const float* policy,
-                     float* mlp_margin, step_acc_t* acc) {
+                     const mso_step_out_t* out, step_acc_t* acc) {
+  float* const mlp_margin = out ? out->mlp_margin : NULL;
+  int rec_n = 0;   /* recorded choice() uniforms of this step */
   const int kind = cfg->env_kind;
   const int D = kind_obs_dim(kind), A = kind_num_actions(kind);
   const int64_t gid = cfg->global_env_offset + i;
@@ -297,6 +317,8 @@ static void step_one(const msort_config_t* cfg, msort_env_state_t* s, int64_t i,
     }
     s->gen_counter += 1;                                                                    /* :63 */
   }
+  if (out && out->rec_input_counts)
+    out->rec_input_counts[i] = (uint32_t)s->input[0] | ((uint32_t)s->input[1] << 8) | ((uint32_t)s->input[2] << 16) | ((uint32_t)s->input[3] << 24);
   double acc_sorter[4];
   for (int m = 0; m < 4; ++m) acc_sorter[m] = s->acc_belt[m]; /* env_super.py:457 */
 
@@ -332,6 +354,7 @@ static void step_one(const msort_config_t* cfg, msort_env_state_t* s, int64_t i,
       env_draw(cfg, gid, BLK_NOISE, ep, stp, r4);
       for (int m = 0; m < 4; ++m) u[m] = (double)r4[m] * (1.0 / 4294967296.0);
     }
+    if (out && out->rec_noise_u) for (int m = 0; m < 4; ++m) out->rec_noise_u[i * 4 + m] = u[m];
     double low = -cfg->noise, range = cfg->noise - low;  /* numpy uniform: low + (high-low)*u */
     for (int m = 0; m < 4; ++m) {
       double base = cfg->baseline_accuracy[m];
@@ -396,7 +419,11 @@ static void step_one(const msort_config_t* cfg, msort_env_state_t* s, int64_t i,
       s->cont_true[S] += tr; s->cont_false[S] += f;               /* :600-602 */
       sorted_true4 |= (uint32_t)tr << (8 * S);
       tot -= tr;
-      if (S == 3) break;                                          /* its f draws leave lump unchanged */
+      if (S == 3) {                                               /* its f draws leave lump unchanged */
+        if (out && out->rec_redis_u)
+          for (int k = 0; k < f; ++k, ++rec_n) if (rec_n < out->rec_cap) out->rec_redis_u[i * out->rec_cap + rec_n] = 0.5;
+        break;
+      }
       lump += f;                                                  /* leftover[S] = false_val joins the lump */
       uint64_t lane = 0;
       for (int k = 0; k < f; ++k) {
@@ -405,6 +432,10 @@ static void step_one(const msort_config_t* cfg, msort_env_state_t* s, int64_t i,
         unsigned __int128 prod = (unsigned __int128)lane * (uint64_t)(uint32_t)tot;
         int r = (int)(uint32_t)(prod >> 64);
         lane = (uint64_t)prod;
+        if (out && out->rec_redis_u) {
+          if (rec_n < out->rec_cap) out->rec_redis_u[i * out->rec_cap + rec_n] = ((double)r + 0.5) / (double)tot;
+          ++rec_n;
+        }
         int c = lump;
         if (r < c) lump -= 1;
         else {
@@ -418,6 +449,8 @@ static void step_one(const msort_config_t* cfg, msort_env_state_t* s, int64_t i,
     s->cont_e += lump;                                            /* :579,597: sum of all leftovers */
   }
 
+  if (out && out->rec_n_draws) out->rec_n_draws[i] = rec_n;
+
   /* 6: Env_1 samples its own press action under the mask (env_super.py:291-300) */
   if (kind == MSORT_ENV_SORT) {
     if (replay) pa = rp->press_choice[i];
@@ -428,6 +461,7 @@ static void step_one(const msort_config_t* cfg, msort_env_state_t* s, int64_t i,
       int pick = (int)(((uint64_t)r4[0] * (uint64_t)nv) >> 32);
       pa = 0;
       for (int b = 0; b < 11; ++b) if ((vb >> b) & 1u) { if (pick == 0) { pa = b; break; } --pick; }
+      if (out && out->rec_press_choice) out->rec_press_choice[i] = (uint8_t)pa;
     }
   }
   /* Env_2 without masking sanitises HERE, on post-sort levels (env_2_press.py:127-131) */
@@ -557,7 +591,7 @@ static void step_one(const msort_config_t* cfg, msort_env_state_t* s, int64_t i,
 typedef struct step_job {
   const msort_config_t* cfg; msort_env_state_t* st; int64_t lo, hi; const int64_t* actions;
   float* obs; uint8_t* terminated; uint8_t* mask; double* r64; float* r32; float* mm;
-  const msort_info_out_t* info; const msort_replay_t* rp; const float* policy; step_acc_t acc;
+  const msort_info_out_t* info; const msort_replay_t* rp; const float* policy; const mso_step_out_t* out; step_acc_t acc;
 } step_job_t;
 
 static void* step_worker(void* arg) {
@@ -566,7 +600,7 @@ static void* step_worker(void* arg) {
   for (int64_t i = j->lo; i < j->hi; ++i) {
     double r = 0.0;
     step_one(j->cfg, &j->st[i], i, j->actions[i], j->obs, &r, j->terminated, j->mask, j->info, j->rp,
-             j->policy, j->mm, &j->acc);
+             j->policy, j->out, &j->acc);
     if (j->r64) j->r64[i] = r;
     if (j->r32) j->r32[i] = (float)r;
   }
@@ -592,7 +626,7 @@ int mso_step(const msort_config_t* cfg, msort_env_state_t* st, int64_t n, const 
     j->cfg = cfg; j->st = st; j->lo = n * c / nthreads; j->hi = n * (c + 1) / nthreads;
     j->actions = actions; j->obs = obs; j->terminated = terminated; j->mask = mask;
     j->r64 = out ? out->reward64 : NULL; j->r32 = out ? out->reward32 : NULL;
-    j->mm = out ? out->mlp_margin : NULL; j->info = info; j->rp = rp; j->policy = policy;
+    j->mm = out ? out->mlp_margin : NULL; j->info = info; j->rp = rp; j->policy = policy; j->out = out;
   }
   for (int c = 1; c < nthreads; ++c) pthread_create(&tid[c], NULL, step_worker, &jobs[c]);
   step_worker(&jobs[0]);
@@ -674,7 +708,9 @@ static void* roll_worker(void* arg) {
   memset(&info, 0, sizeof(info));
   info.struct_size = sizeof(info);
   info.stats = j->stats;
-  mso_step_out_t out = {rew, NULL, NULL};
+  mso_step_out_t out;
+  memset(&out, 0, sizeof(out));
+  out.reward32 = rew;
   j->done = 0;
   for (int t = 0; t < j->T; ++t) {
     mso_sample_masked_actions(&cc, j->st + j->lo, n, j->action_seed, (uint32_t)t, act);

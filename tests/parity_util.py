@@ -250,3 +250,44 @@ class TorchPressStub:
         score = torch.where(m[:, 1:], level, torch.full_like(level, -1.0))
         best = score.argmax(dim=1) + 1                                    # first maximum = lowest action on ties
         return torch.where(m[:, 1:].any(dim=1), best, torch.zeros_like(best)), None
+
+
+# ---------------------------------------------------------------- the reference on the production generator's random inputs
+def philox_golden():
+    """tests/golden/reference_philox.npz (tests/golden/make_philox_golden.py): outputs of the UNMODIFIED reference driven by
+    the random inputs the Philox generator produces for (seed, global env id, episode, step) -> {name: (meta, batch)}."""
+    d = np.load(_os.path.join(_GOLDEN_DIR, "reference_philox.npz"), allow_pickle=False)
+    out = {}
+    for name in _json.loads(str(d["groups"])):
+        meta = _json.loads(str(d[f"{name}/meta"]))
+        batch = {k[len(name) + 1:]: np.asarray(d[k]) for k in d.files if k.startswith(name + "/") and not k.endswith("/meta")}
+        out[name] = (meta, batch)
+    return out
+
+
+def compare_with_philox_reference(backend, meta, batch):
+    """Step `backend` (PHILOX mode, same seed / global env ids) with the recorded actions and require the reference's
+    outputs: integer state, masks, flags bit-exact on live envs; obs / reward within the float tolerance; terminal
+    observation and episode length where an episode ends (the backend auto-resets, the reference row is pre-reset)."""
+    T = meta["steps"]
+    obs0, _ = backend.reset()
+    assert_float_close(obs0, batch["obs0"], "reset obs")
+    for t in range(T):
+        obs, rew, term, mask, info = backend.step(batch["action"][t].astype(np.int64))
+        want_term = batch["terminated"][t]
+        assert np.array_equal(term, want_term), f"step {t}: terminated"
+        live = ~want_term
+        st = state_rows(backend.export_state() if hasattr(backend, "export_state") else backend.state)
+        if not np.array_equal(st[live], batch["state"][t][live]):
+            bad = np.argwhere(st[live] != batch["state"][t][live])[0]
+            raise AssertionError(f"step {t}: integer state differs from the reference at live-row {bad[0]} col {bad[1]}: "
+                                 f"got {st[live][bad[0]]} want {batch['state'][t][live][bad[0]]}")
+        assert np.array_equal(mask[live], batch["mask"][t][live]), f"step {t}: mask"
+        assert_float_close(rew, batch["reward"][t], f"step {t}: reward")
+        assert_float_close(obs[live], batch["obs"][t][live], f"step {t}: obs")
+        if want_term.any():
+            assert_float_close(info["terminal_obs"][want_term], batch["obs"][t][want_term], f"step {t}: terminal obs")
+            assert np.array_equal(info["episode_length"][want_term], batch["state"][t][want_term][:, _col("step")]), f"step {t}: episode length"
+        if "overflow" in info:
+            assert np.array_equal(np.asarray(info["overflow"]).astype(bool), batch["overflow"][t]), f"step {t}: overflow"
+    return T * batch["action"].shape[1]

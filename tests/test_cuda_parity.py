@@ -219,6 +219,23 @@ def test_cuda_matches_oracle_philox_mlp(cuda_backend):
     _philox_cross_check(cuda_backend, "press", 2048, 60, mlp=w)
 
 
+@pytest.mark.parametrize("info_level", ["episode", "full"])
+@pytest.mark.parametrize("name", ["philox_sort", "philox_press", "philox_mono", "philox_mono_unmasked"])
+def test_cuda_philox_matches_reference(cuda_backend, name, info_level):
+    """The PRODUCTION instantiations of the step kernel — HOT (`info_level='episode'`: what bench.py times) and FAST
+    (`'full'`) with the Philox generator — against the UNMODIFIED reference stepped on the very random inputs that
+    generator produces (tests/golden/reference_philox.npz, made by tests/golden/make_philox_golden.py through
+    oracle/ref_drive.py): integer state, masks, flags bit-exact; obs / reward within 1e-5."""
+    from parity_util import compare_with_philox_reference, philox_golden
+    meta, batch = philox_golden()[name]
+    cfg = config_for(meta, meta["envs"], rng_mode="philox", seed=meta["seed"], global_env_offset=meta["offset"])
+    gpu = cuda_backend(cfg, info_level=info_level)
+    assert compare_with_philox_reference(gpu, meta, batch) == meta["envs"] * meta["steps"]
+    hot = info_level == "episode" and meta["use_action_masking"] and not meta["check_overflow"]
+    want = ("hot_persistent" if meta["kind"] == "press" else "hot") if hot else "fast"
+    assert gpu.env.step_variant == want, gpu.env.step_variant
+
+
 def test_config2_env1_65536_replay_bit_exact(cuda_backend):
     """BASELINE config 2: Env_1_Sorting, 65 536 envs, env i seeded 1+i, random actions, replayed
     numpy streams (generated here with numpy exactly as the reference's generators produce
