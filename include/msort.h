@@ -33,7 +33,7 @@ extern "C" {
 
 /* ABI history: 2 telemetry (msort_gather_state, reward terms) and msort_policy_act; 3 msort_observe_after_shift,
  * msort_step_variant, obs / mask must be 16-byte aligned; 4 msort_step_range, msort_policy_act_range;
- * 5 msort_set_option, MSORT_STEP_HOT_TENSOR, msort_step_host, msort_generate_streams. */
+ * 5 msort_set_option, MSORT_STEP_HOT_TENSOR, msort_step_host, msort_generate_streams, msort_ppo_*. */
 #define MSORT_ABI_VERSION 5
 
 /* ------------------------------------------------------------------ enums */
@@ -376,6 +376,50 @@ size_t msort_host_scratch_bytes(const msort_t* h);
 int msort_step_host(msort_t* h, void* state, void* scratch, const msort_host_io_t* io,
                     const msort_info_out_t* info, void* stream);
 
+/* ------------------------------------------------------------------ MaskablePPO update (the caller of the hot path)
+ * Hand-written kernels for the UPDATE half of the GPU-resident training loop (ref: the reference trains with
+ * sb3_contrib.MaskablePPO, training.py:115-143: net_arch=dict(pi=[32,32], vf=[32,32]), tanh, ent_coef=0.05, SB3
+ * defaults otherwise).  Stateless: every buffer is device memory owned by the caller.
+ * Parameter vector (flat fp32, msort_ppo_param_count(D, A) values; torch Linear layout [out][in]):
+ *   pi: W1[32][D] b1[32] W2[32][32] b2[32] W3[A][32] b3[A]  |  vf: W1[32][D] b1[32] W2[32][32] b2[32] W3[1][32] b3[1] */
+typedef struct msort_ppo_batch {
+  uint32_t struct_size;
+  int32_t obs_dim, num_actions;  /* (13,2) | (16,11) | (29,22) */
+  int32_t reserved;
+  int64_t num_rows;              /* rows of the rollout buffer (n_steps * num_envs) */
+  const float* obs;              /* [rows, D] */
+  const uint8_t* mask;           /* [rows, A] action masks (logits of invalid actions are masked with -1e8) */
+  const int64_t* actions;        /* [rows] */
+  const float* old_logp;         /* [rows] log-prob of the action under the rollout policy   (update only) */
+  const float* adv;              /* [rows] advantages                                        (update only) */
+  const float* ret;              /* [rows] returns = advantage + value                       (update only) */
+} msort_ppo_batch_t;
+
+typedef struct msort_ppo_hparams {
+  uint32_t struct_size;
+  int32_t normalize_advantage;   /* per minibatch: (a - mean) / (std + 1e-8), unbiased std */
+  float clip_range, vf_coef, ent_coef;
+  float learning_rate, beta1, beta2, adam_eps, max_grad_norm;   /* max_grad_norm <= 0: no clipping */
+} msort_ppo_hparams_t;
+
+int msort_ppo_param_count(int obs_dim, int num_actions);
+/* log-prob of every row's action and the value estimate under `params` (forward only; either output nullable) */
+int msort_ppo_forward(const msort_ppo_batch_t* batch, const float* params, float* logp_out, float* value_out, void* stream);
+/* GAE(lambda): rew / val / done [T, n] (done = terminated, u8), last_val [n] -> adv, ret [T, n] */
+int msort_ppo_gae(int32_t T, int64_t n, const float* rew, const float* val, const uint8_t* done, const float* last_val,
+                  float gamma, float gae_lambda, float* adv, float* ret, void* stream);
+/* Gradient of the PPO loss (clipped surrogate + vf_coef * value MSE - ent_coef * entropy, means over the minibatch) for
+ * rows idx[first .. first + count) (idx NULL: the rows themselves), ADDED into grads; stats (nullable, 5 floats) +=
+ * {sum surrogate loss, sum squared value error, sum entropy, clipped rows, rows}; scratch: 2 floats. */
+int msort_ppo_gradient(const msort_ppo_batch_t* batch, const msort_ppo_hparams_t* hp, const float* params, float* grads,
+                       const int64_t* idx, int64_t first, int64_t count, float* scratch, float* stats, void* stream);
+/* The whole update: n_epochs passes over the buffer in minibatches of batch_size rows taken from perms[e] (n_epochs
+ * permutations of 0..rows-1, device int64), each minibatch = gradient -> global-norm clip -> Adam step (torch.optim.Adam
+ * semantics; `step` is the device-side step counter, grads must be zero on entry and are zero on exit). */
+int msort_ppo_update(const msort_ppo_batch_t* batch, const msort_ppo_hparams_t* hp, float* params, float* grads, float* adam_m,
+                     float* adam_v, int32_t* step, const int64_t* perms, int32_t n_epochs, int64_t batch_size, float* scratch,
+                     float* stats, void* stream);
+
 /* Which instantiation of the step kernel the handle's last msort_step launched (diagnostics / tests):
  * 0 none yet, 1 REPLAY, 2 generic, 3 FAST (host-proved config facts compiled in),
  * 4 HOT (FAST + the training-loop switches compiled in), 5 HOT persistent (Env_2: TMA-staged tiles). */
@@ -397,6 +441,10 @@ int msort_step_variant(const msort_t* h);
  *    kernel's registers and shared memory allow, asked at msort_create); get = the count of the kernel the next
  *    step would launch. */
 #define MSORT_OPT_PERSIST_CTAS 2
+/*  MSORT_OPT_DRAW_COUNTER: value = a DEVICE pointer to a uint32 (0 = none, the default).  msort_policy_act then keys its
+ *    categorical draw with t + *pointer instead of t, so a CUDA graph of a whole rollout can be replayed with fresh
+ *    draws: the caller bumps the counter between replays. */
+#define MSORT_OPT_DRAW_COUNTER 3
 int msort_set_option(msort_t* h, int option, int64_t value);
 int msort_get_option(const msort_t* h, int option, int64_t* value);
 

@@ -131,6 +131,20 @@ class MsortHostIO(C.Structure):
                 ("dev_obs", C.c_void_p), ("dev_reward", C.c_void_p), ("dev_terminated", C.c_void_p), ("dev_mask", C.c_void_p)]
 
 
+class MsortPpoBatch(C.Structure):
+    """msort_ppo_batch_t (include/msort.h)."""
+    _fields_ = [("struct_size", C.c_uint32), ("obs_dim", C.c_int32), ("num_actions", C.c_int32), ("reserved", C.c_int32),
+                ("num_rows", C.c_int64), ("obs", C.c_void_p), ("mask", C.c_void_p), ("actions", C.c_void_p),
+                ("old_logp", C.c_void_p), ("adv", C.c_void_p), ("ret", C.c_void_p)]
+
+
+class MsortPpoHparams(C.Structure):
+    """msort_ppo_hparams_t (include/msort.h)."""
+    _fields_ = [("struct_size", C.c_uint32), ("normalize_advantage", C.c_int32), ("clip_range", C.c_float),
+                ("vf_coef", C.c_float), ("ent_coef", C.c_float), ("learning_rate", C.c_float), ("beta1", C.c_float),
+                ("beta2", C.c_float), ("adam_eps", C.c_float), ("max_grad_norm", C.c_float)]
+
+
 # name -> (restype, argtypes): every symbol include/msort.h declares
 _P = C.c_void_p
 SYMBOLS = {
@@ -162,6 +176,12 @@ SYMBOLS = {
     "msort_sync_check": (C.c_int, [_P, _P]),
     "msort_launch_count": (C.c_int64, [_P]),
     "msort_step_variant": (C.c_int, [_P]),
+    "msort_ppo_param_count": (C.c_int, [C.c_int, C.c_int]),
+    "msort_ppo_forward": (C.c_int, [C.POINTER(MsortPpoBatch), _P, _P, _P, _P]),
+    "msort_ppo_gae": (C.c_int, [C.c_int32, C.c_int64, _P, _P, _P, _P, C.c_float, C.c_float, _P, _P, _P]),
+    "msort_ppo_gradient": (C.c_int, [C.POINTER(MsortPpoBatch), C.POINTER(MsortPpoHparams), _P, _P, _P, C.c_int64, C.c_int64, _P, _P, _P]),
+    "msort_ppo_update": (C.c_int, [C.POINTER(MsortPpoBatch), C.POINTER(MsortPpoHparams), _P, _P, _P, _P, _P, _P, C.c_int32,
+                                   C.c_int64, _P, _P, _P]),
     "msort_generate_streams": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P]),
     "msort_host_scratch_bytes": (C.c_size_t, [_P]),
     "msort_step_host": (C.c_int, [_P, _P, _P, C.POINTER(MsortHostIO), C.POINTER(MsortInfoOut), _P]),
@@ -171,6 +191,7 @@ SYMBOLS = {
 }
 OPT_TENSOR_POLICY = 1
 OPT_PERSIST_CTAS = 2
+OPT_DRAW_COUNTER = 3
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "csrc", "libmsort.so")

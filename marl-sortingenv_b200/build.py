@@ -6,8 +6,8 @@ import shutil
 import subprocess
 
 _CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
-SOURCES = ["msort_kernels.cu", "msort_policy.cu", "msort_api.cu"]
-HEADERS = ["msort_device.cuh", "msort_launch.h", os.path.join("..", "..", "include", "msort.h")]
+SOURCES = ["msort_kernels.cu", "msort_policy.cu", "msort_ppo.cu", "msort_api.cu"]
+HEADERS = ["msort_device.cuh", "msort_umma.cuh", "msort_launch.h", os.path.join("..", "..", "include", "msort.h")]
 LIB = os.path.join(_CSRC, "libmsort.so")
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

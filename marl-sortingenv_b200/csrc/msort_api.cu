@@ -31,6 +31,7 @@ struct msort_handle {
   uint32_t* policy_tc_dev = nullptr;        // owned device copy (11 KB, allocated by the first msort_set_policy)
   bool policy_tc_ok = false;                // the policy fits the fp16 split (else the FFMA2 kernel evaluates it)
   bool policy_tc_enabled = true;            // msort_set_option(MSORT_OPT_TENSOR_POLICY)
+  const uint32_t* draw_counter = nullptr;   // MSORT_OPT_DRAW_COUNTER: device-side offset of msort_policy_act's draw index
   int persist_per_sm[4] = {1, 1, 1, 1};     // resident CTAs per SM of the persistent Env_2 kernels on this handle's device
   // msort_step_host: the library's own streams / events (created by the first call, on the handle's device)
   static constexpr int kHostStreams = 4;
@@ -364,6 +365,10 @@ extern "C" int msort_set_option(msort_t* h, int option, int64_t value) {
   if (!h) return fail(MSORT_E_INVALID, "msort_set_option: NULL handle");
   switch (option) {
     case MSORT_OPT_TENSOR_POLICY: h->policy_tc_enabled = value != 0; return MSORT_OK;
+    case MSORT_OPT_DRAW_COUNTER:
+      if (value & 3) return fail(MSORT_E_INVALID, "msort_set_option: MSORT_OPT_DRAW_COUNTER must be a 4-byte aligned device pointer");
+      h->draw_counter = reinterpret_cast<const uint32_t*>((uintptr_t)value);
+      return MSORT_OK;
     case MSORT_OPT_PERSIST_CTAS:
       if (value < 1 || value > 32) return fail(MSORT_E_INVALID, "msort_set_option: MSORT_OPT_PERSIST_CTAS must be in [1, 32]");
       for (int k = 0; k < 4; ++k) h->persist_per_sm[k] = (int)value;
@@ -654,7 +659,7 @@ static int policy_act_impl(msort_t* h, long long first, long long count, const f
   const int D = msort_obs_dim(h), A = msort_num_actions(h);
   DevConfig d = h->dev;
   d.n = count; d.gid0 += first;                     // the draw is keyed by the global env id: ranges compose to the whole
-  MSORT_TRY_CUDA(launch_policy_act(d, obs + first * D, mask + first * A, packed_weights, D, A, seed, t, deterministic,
+  MSORT_TRY_CUDA(launch_policy_act(d, obs + first * D, mask + first * A, packed_weights, D, A, seed, t, h->draw_counter, deterministic,
                                    actions + first, logp + first, value + first, h->sm_count, (cudaStream_t)stream),
                  "policy_act kernel");
   h->launches += 1;
@@ -716,5 +721,65 @@ extern "C" int msort_sync_check(msort_t* h, void* stream) {
   if (!h) return fail(MSORT_E_INVALID, "msort_sync_check: NULL handle");
   MSORT_TRY_CUDA(cudaStreamSynchronize((cudaStream_t)stream), "cudaStreamSynchronize");
   MSORT_TRY_CUDA(cudaGetLastError(), "sticky error");
+  return MSORT_OK;
+}
+
+// ---------------------------------------------------------------- MaskablePPO update kernels (msort_ppo.cu)
+static int ppo_check_batch(const msort_ppo_batch_t* b, bool update, const char* who) {
+  if (!b) return fail(MSORT_E_INVALID, "%s: NULL batch", who);
+  if (b->struct_size != sizeof(msort_ppo_batch_t)) return fail(MSORT_E_INVALID, "%s: bad batch struct_size", who);
+  if (ppo_param_count(b->obs_dim, b->num_actions) <= 0 ||
+      !((b->obs_dim == 29 && b->num_actions == 22) || (b->obs_dim == 16 && b->num_actions == 11) || (b->obs_dim == 13 && b->num_actions == 2)))
+    return fail(MSORT_E_UNSUPPORTED, "%s: (obs_dim, num_actions) must be (13,2), (16,11) or (29,22)", who);
+  if (b->num_rows <= 0 || !b->obs || !b->mask || !b->actions) return fail(MSORT_E_INVALID, "%s: NULL / empty batch buffers", who);
+  if (update && (!b->old_logp || !b->adv || !b->ret)) return fail(MSORT_E_INVALID, "%s: old_logp / adv / ret are required", who);
+  return MSORT_OK;
+}
+
+extern "C" int msort_ppo_param_count(int obs_dim, int num_actions) { return ppo_param_count(obs_dim, num_actions); }
+
+extern "C" int msort_ppo_forward(const msort_ppo_batch_t* batch, const float* params, float* logp_out, float* value_out, void* stream) {
+  int rc = ppo_check_batch(batch, false, "msort_ppo_forward");
+  if (rc != MSORT_OK) return rc;
+  if (!params) return fail(MSORT_E_INVALID, "msort_ppo_forward: NULL params");
+  MSORT_TRY_CUDA(ppo_forward(*batch, params, logp_out, value_out, (cudaStream_t)stream), "ppo forward kernel");
+  return MSORT_OK;
+}
+
+extern "C" int msort_ppo_gae(int32_t T, int64_t n, const float* rew, const float* val, const uint8_t* done, const float* last_val,
+                             float gamma, float gae_lambda, float* adv, float* ret, void* stream) {
+  if (T <= 0 || n <= 0 || !rew || !val || !done || !last_val || !adv || !ret) return fail(MSORT_E_INVALID, "msort_ppo_gae: bad argument");
+  MSORT_TRY_CUDA(ppo_gae(T, n, rew, val, done, last_val, gamma, gae_lambda, adv, ret, (cudaStream_t)stream), "gae kernel");
+  return MSORT_OK;
+}
+
+extern "C" int msort_ppo_gradient(const msort_ppo_batch_t* batch, const msort_ppo_hparams_t* hp, const float* params, float* grads,
+                                  const int64_t* idx, int64_t first, int64_t count, float* scratch, float* stats, void* stream) {
+  int rc = ppo_check_batch(batch, true, "msort_ppo_gradient");
+  if (rc != MSORT_OK) return rc;
+  if (!hp || hp->struct_size != sizeof(msort_ppo_hparams_t)) return fail(MSORT_E_INVALID, "msort_ppo_gradient: bad hparams");
+  if (!params || !grads || !scratch || count <= 0 || first < 0 || first + count > batch->num_rows)
+    return fail(MSORT_E_INVALID, "msort_ppo_gradient: bad argument");
+  MSORT_TRY_CUDA(ppo_gradient(*batch, *hp, params, grads, idx, first, count, scratch, stats, (cudaStream_t)stream), "ppo gradient kernel");
+  return MSORT_OK;
+}
+
+extern "C" int msort_ppo_update(const msort_ppo_batch_t* batch, const msort_ppo_hparams_t* hp, float* params, float* grads, float* adam_m,
+                                float* adam_v, int32_t* step, const int64_t* perms, int32_t n_epochs, int64_t batch_size, float* scratch,
+                                float* stats, void* stream) {
+  int rc = ppo_check_batch(batch, true, "msort_ppo_update");
+  if (rc != MSORT_OK) return rc;
+  if (!hp || hp->struct_size != sizeof(msort_ppo_hparams_t)) return fail(MSORT_E_INVALID, "msort_ppo_update: bad hparams");
+  if (!params || !grads || !adam_m || !adam_v || !step || !perms || !scratch || n_epochs <= 0 || batch_size <= 0)
+    return fail(MSORT_E_INVALID, "msort_ppo_update: bad argument");
+  const int P = ppo_param_count(batch->obs_dim, batch->num_actions);
+  const long long N = batch->num_rows;
+  for (int e = 0; e < n_epochs; ++e)
+    for (long long s = 0; s < N; s += batch_size) {
+      const long long cnt = std::min<long long>(batch_size, N - s);
+      MSORT_TRY_CUDA(ppo_gradient(*batch, *hp, params, grads, perms + (long long)e * N, s, cnt, scratch, stats, (cudaStream_t)stream),
+                     "ppo gradient kernel");
+      MSORT_TRY_CUDA(ppo_adam(params, grads, adam_m, adam_v, step, P, *hp, (cudaStream_t)stream), "adam kernel");
+    }
   return MSORT_OK;
 }

@@ -43,7 +43,7 @@ cudaError_t launch_widen_actions(const uint8_t* in, int64_t* out, long long n, c
 cudaError_t launch_pack_flags(int kind, const uint8_t* mask, const uint8_t* terminated, uint16_t* flags, long long n, cudaStream_t st);
 cudaError_t launch_rule_actions(const DevConfig& c, const void* state, int after_shift, int64_t* actions, cudaStream_t st);
 cudaError_t launch_policy_act(const DevConfig& c, const float* obs, const uint8_t* mask, const float* packed,
-                              int D, int A, uint64_t seed, uint32_t t, int deterministic, int64_t* actions,
+                              int D, int A, uint64_t seed, uint32_t t, const uint32_t* t_dev, int deterministic, int64_t* actions,
                               float* logp, float* value, int sm_count, cudaStream_t st);
 cudaError_t prepare_policy_kernels();                      // current device: opt-in shared-memory sizes of the policy kernels
 cudaError_t launch_export(const DevConfig& c, const void* state, msort_env_state_t* out, cudaStream_t st);
@@ -51,5 +51,14 @@ cudaError_t launch_gather(const DevConfig& c, const void* state, const int64_t* 
                           msort_env_state_t* out, cudaStream_t st);
 cudaError_t launch_import(const DevConfig& c, void* state, const msort_env_state_t* in, cudaStream_t st);
 cudaError_t launch_stats(const DevConfig& c, const void* state, double* out16, int sm_count, cudaStream_t st);
+
+// ---- msort_ppo.cu: the update half of the GPU-resident MaskablePPO loop
+int ppo_param_count(int D, int A);
+cudaError_t ppo_forward(const msort_ppo_batch_t& b, const float* params, float* logp_out, float* value_out, cudaStream_t st);
+cudaError_t ppo_gradient(const msort_ppo_batch_t& b, const msort_ppo_hparams_t& hp, const float* params, float* grads,
+                         const int64_t* idx, long long first, long long count, float* adv_stats, float* stats, cudaStream_t st);
+cudaError_t ppo_adam(float* params, float* grads, float* m, float* v, int* step, int n, const msort_ppo_hparams_t& hp, cudaStream_t st);
+cudaError_t ppo_gae(int T, long long n, const float* rew, const float* val, const uint8_t* done, const float* last_val, float gamma,
+                    float lam, float* adv, float* ret, cudaStream_t st);
 
 }  // namespace msort

@@ -108,13 +108,15 @@ __device__ __forceinline__ float policy_tanh(float x) {
 template <int D, int A>
 __global__ void __launch_bounds__(kThreads, 4)
 policy_act_kernel(const float* __restrict__ obs, const uint8_t* __restrict__ mask, const float* __restrict__ packed,
-                  long long n, long long gid0, unsigned key0, unsigned key1, unsigned t, int deterministic, int use_tma,
+                  long long n, long long gid0, unsigned key0, unsigned key1, unsigned t_in, const unsigned* __restrict__ t_dev,
+                  int deterministic, int use_tma,
                   long long* __restrict__ actions, float* __restrict__ logp_out, float* __restrict__ value_out) {
   static_assert(D <= 32 && A <= 31, "padded layer sizes");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using Smem = PolicySmem<D, A>;
   Smem& sm = *reinterpret_cast<Smem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, row = tid & (kRows - 1), half = tid >> 7;
+  const unsigned t = t_in + (t_dev ? *t_dev : 0u);   // draw index: a graph-replayed rollout bumps *t_dev between replays
 
   // ---- one-time setup: TMEM columns, mbarriers, weights
   if (warp == 0) {
@@ -302,7 +304,7 @@ policy_act_kernel(const float* __restrict__ obs, const uint8_t* __restrict__ mas
 
 template <int D, int A>
 static cudaError_t launch_policy_act_da(const DevConfig& c, const float* obs, const uint8_t* mask, const float* packed,
-                                        uint64_t seed, uint32_t t, int deterministic, int64_t* actions, float* logp,
+                                        uint64_t seed, uint32_t t, const uint32_t* t_dev, int deterministic, int64_t* actions, float* logp,
                                         float* value, int sm_count, cudaStream_t st) {
   static_assert(sizeof(PolicySmem<D, A>) <= 55 * 1024, "four CTAs per SM");
   const size_t smem = sizeof(PolicySmem<D, A>);   // opt-in size set once per device by prepare_policy_kernels (msort_create)
@@ -311,7 +313,7 @@ static cudaError_t launch_policy_act_da(const DevConfig& c, const float* obs, co
   // TMA bulk copies need 16-byte aligned tile addresses (tile sizes are multiples of 16 bytes)
   const int use_tma = ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(mask)) & 15u) == 0;
   policy_act_kernel<D, A><<<grid, kThreads, smem, st>>>(obs, mask, packed, c.n, c.gid0, (unsigned)(seed & 0xffffffffu),
-                                                        (unsigned)(seed >> 32), t, deterministic, use_tma, (long long*)actions,
+                                                        (unsigned)(seed >> 32), t, t_dev, deterministic, use_tma, (long long*)actions,
                                                         logp, value);
   return cudaGetLastError();
 }
@@ -325,11 +327,11 @@ cudaError_t prepare_policy_kernels() {
 }
 
 cudaError_t launch_policy_act(const DevConfig& c, const float* obs, const uint8_t* mask, const float* packed,
-                              int D, int A, uint64_t seed, uint32_t t, int deterministic, int64_t* actions,
+                              int D, int A, uint64_t seed, uint32_t t, const uint32_t* t_dev, int deterministic, int64_t* actions,
                               float* logp, float* value, int sm_count, cudaStream_t st) {
-  if (D == 29 && A == 22) return launch_policy_act_da<29, 22>(c, obs, mask, packed, seed, t, deterministic, actions, logp, value, sm_count, st);
-  if (D == 16 && A == 11) return launch_policy_act_da<16, 11>(c, obs, mask, packed, seed, t, deterministic, actions, logp, value, sm_count, st);
-  if (D == 13 && A == 2) return launch_policy_act_da<13, 2>(c, obs, mask, packed, seed, t, deterministic, actions, logp, value, sm_count, st);
+  if (D == 29 && A == 22) return launch_policy_act_da<29, 22>(c, obs, mask, packed, seed, t, t_dev, deterministic, actions, logp, value, sm_count, st);
+  if (D == 16 && A == 11) return launch_policy_act_da<16, 11>(c, obs, mask, packed, seed, t, t_dev, deterministic, actions, logp, value, sm_count, st);
+  if (D == 13 && A == 2) return launch_policy_act_da<13, 2>(c, obs, mask, packed, seed, t, t_dev, deterministic, actions, logp, value, sm_count, st);
   return cudaErrorInvalidValue;
 }
 

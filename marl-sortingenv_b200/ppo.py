@@ -4,16 +4,26 @@ The reference trains with sb3_contrib.MaskablePPO on one CPU env (training.py:11
 `net_arch=dict(pi=[32,32], vf=[32,32])`, `ent_coef=0.05`, SB3 defaults n_epochs=10, clip 0.2,
 gamma 0.99, lambda 0.95, lr 3e-4, vf_coef 0.5, max_grad_norm 0.5).  SB3's collector loops over
 envs in Python, so it cannot drive 1e4..1e6 device envs; this module is the same algorithm with
-every tensor (observations, masks, actions, advantages, minibatches) resident on the GPU and the
-env stepped by the fused CUDA kernel.  Plain PyTorch — plumbing around the product, not the product.
+every tensor (observations, masks, actions, advantages, minibatches) resident on the GPU:
+
+* rollout  : per env-step the tensor-core policy kernel (`msort_policy_act`) + the fused step kernel, the whole
+             n_steps loop replayed as ONE CUDA graph (`graph_rollout`);
+* update   : hand-written kernels (`csrc/msort_ppo.cu`, C ABI `msort_ppo_*`): GAE scan, fused actor-critic forward +
+             masked log-softmax / entropy / clipped-surrogate loss + backward per minibatch, fused global-norm clip + Adam.
+             The old log-probs and values are recomputed once with the update's own fp32 forward, so the importance
+             ratio starts at exactly 1 whatever precision the rollout kernel used.
+`native_update=False` keeps the PyTorch autograd + torch.optim.Adam path (the reference the gradient tests compare with).
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 import time
 
 import torch
 import torch.nn as nn
+
+from . import _abi
 
 
 def _mlp(inp: int, out: int, gain: float) -> nn.Sequential:
@@ -78,13 +88,31 @@ def pack_actor_critic(policy: "MaskableActorCritic", out: torch.Tensor | None = 
     return packed.contiguous()
 
 
+def flatten_parameters(policy: "MaskableActorCritic") -> torch.Tensor:
+    """Move the two towers' parameters into ONE flat fp32 buffer in the order `msort_ppo_*` expects (include/msort.h: pi W1 b1
+    W2 b2 W3 b3 | vf W1 b1 W2 b2 W3 b3, torch Linear layout) and make every nn.Parameter a view of it, so PyTorch code and
+    the native kernels see the same weights."""
+    ps = [policy.pi[0].weight, policy.pi[0].bias, policy.pi[2].weight, policy.pi[2].bias, policy.pi[4].weight, policy.pi[4].bias,
+          policy.vf[0].weight, policy.vf[0].bias, policy.vf[2].weight, policy.vf[2].bias, policy.vf[4].weight, policy.vf[4].bias]
+    flat = torch.cat([p.detach().reshape(-1) for p in ps]).contiguous()
+    o = 0
+    for p in ps:
+        p.data = flat[o:o + p.numel()].view_as(p)
+        o += p.numel()
+    return flat
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
 class MaskablePPO:
-    MIN_ENVS_PER_STREAM = 65536      # below this a second stream only adds launches to the eager rollout loop
+    MIN_ENVS_PER_STREAM = 65536      # below this a second stream only adds launches to the rollout loop
 
     def __init__(self, env, n_steps: int = 64, batch_size: int = 8192, n_epochs: int = 10, gamma: float = 0.99,
                  gae_lambda: float = 0.95, clip_range: float = 0.2, ent_coef: float = 0.05, vf_coef: float = 0.5,
                  learning_rate: float = 3e-4, max_grad_norm: float = 0.5, seed: int = 42, fused_act: bool = True,
-                 rollout_streams: int = 2):
+                 rollout_streams: int = 2, native_update: bool = True, graph_rollout: bool = True):
         self.env = env
         # rollout inference: one fused tensor-core kernel (msort_policy_act) instead of ~25 torch kernels/step
         self.fused_act = fused_act and hasattr(env, "policy_act")
@@ -93,7 +121,25 @@ class MaskablePPO:
         self.dev = env.device
         torch.manual_seed(seed)
         self.policy = MaskableActorCritic(self.D, self.A).to(self.dev)
+        self.lib = env.lib if hasattr(env, "lib") else None
+        self.native_update = native_update and self.lib is not None
+        self.graph_rollout = graph_rollout and fused_act and hasattr(env, "policy_act")
+        self.flat = flatten_parameters(self.policy)
         self.opt = torch.optim.Adam(self.policy.parameters(), lr=learning_rate, eps=1e-5)
+        self.lr = learning_rate
+        if self.native_update:
+            P = int(self.lib.msort_ppo_param_count(self.D, self.A))
+            assert P == self.flat.numel(), (P, self.flat.numel())
+            z = lambda *sh, dt=torch.float32: torch.zeros(*sh, dtype=dt, device=self.dev)   # noqa: E731
+            self._grads, self._m, self._v, self._step = z(P), z(P), z(P), z(1, dt=torch.int32)
+            self._scratch, self._stats = z(2), z(5)
+            self._hp = _abi.MsortPpoHparams(C.sizeof(_abi.MsortPpoHparams), 1, clip_range, vf_coef, ent_coef, learning_rate,
+                                            0.9, 0.999, 1e-5, max_grad_norm)
+        self._graph = None
+        self._packed = None
+        self._tail = None
+        self._warm = False
+        self._draw_counter = torch.zeros(1, dtype=torch.int32, device=self.dev)
         self.n_steps, self.batch_size, self.n_epochs = n_steps, batch_size, n_epochs
         self.gamma, self.lam, self.clip = gamma, gae_lambda, clip_range
         self.ent_coef, self.vf_coef, self.max_grad_norm = ent_coef, vf_coef, max_grad_norm
@@ -102,6 +148,8 @@ class MaskablePPO:
                         act=torch.zeros((T, n), dtype=torch.int64, device=dev), logp=torch.zeros((T, n), device=dev),
                         val=torch.zeros((T, n), device=dev), rew=torch.zeros((T, n), device=dev),
                         done=torch.zeros((T, n), dtype=torch.bool, device=dev))
+        self._adv, self._ret = torch.zeros((T, n), device=dev), torch.zeros((T, n), device=dev)
+        self._last_v = torch.zeros(n, device=dev)
         self.num_timesteps = 0
         self._obs = None
         self.log = []
@@ -117,80 +165,139 @@ class MaskablePPO:
         self._streams = [torch.cuda.Stream(device=self.dev) for _ in self._ranges] if len(self._ranges) > 1 else []
 
     # ------------------------------------------------------------------ rollout
+    def _batch(self, rows, obs, mask, act, logp=None, adv=None, ret=None):
+        return _abi.MsortPpoBatch(C.sizeof(_abi.MsortPpoBatch), self.D, self.A, 0, int(rows), _p(obs), _p(mask), _p(act),
+                                  _p(logp), _p(adv), _p(ret))
+
+    def _cstream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+
+    def _rollout_body(self, packed, t0: int):
+        """The n_steps loop on the rollout buffers (fused_act): slot 0 <- the last observation / mask, then per step
+        policy_act -> step, the step writing its observation / mask straight into slot t+1 (the last one into the
+        `_tail` pair), every env range on its own stream.  Only stream-ordered device work: capturable as a CUDA graph."""
+        env, b = self.env, self.buf
+        b["obs"][0].copy_(self._tail[0]); b["mask"][0].copy_(self._tail[1])
+        cur = torch.cuda.current_stream(self.dev)
+        streams = self._streams or [cur]
+        for s in self._streams:
+            s.wait_stream(cur)
+        for t in range(self.n_steps):
+            oo, om = self._tail if t + 1 == self.n_steps else (b["obs"][t + 1], b["mask"][t + 1])
+            for s, (lo, hi) in zip(streams, self._ranges):
+                with torch.cuda.stream(s):
+                    rng = None if len(self._ranges) == 1 else (lo, hi)
+                    env.policy_act(packed, seed=self.seed, t=t0 + t, obs=b["obs"][t], mask=b["mask"][t],
+                                   out=(b["act"][t], b["logp"][t], b["val"][t]), env_range=rng)
+                    env.step(b["act"][t], out_obs=oo, out_mask=om, env_range=rng)   # fused CUDA step (auto-reset inside)
+                    b["rew"][t][lo:hi].copy_(env.reward[lo:hi]); b["done"][t][lo:hi].copy_(env.terminated[lo:hi])
+        for s in self._streams:
+            cur.wait_stream(s)
+
     @torch.no_grad()
     def collect_rollout(self):
         env, b = self.env, self.buf
         if self._obs is None:
             self._obs, _ = env.reset()
-        packed = pack_actor_critic(self.policy) if self.fused_act else None
+        t0 = self.num_timesteps // self.n
         # zero-copy rollout: step t writes its observation / mask straight into slot t+1 of the buffers
         # (the last step into a spare pair), so nothing but the first slot is ever copied
         direct = self.fused_act and (self.n * self.D * 4) % 16 == 0 and (self.n * self.A) % 16 == 0
-        if direct and not hasattr(self, "_tail"):
-            self._tail = (torch.zeros((self.n, self.D), device=self.dev), torch.zeros((self.n, self.A), dtype=torch.bool, device=self.dev))
-        b["obs"][0].copy_(self._obs)
-        b["mask"][0].copy_(env.action_masks())
-        if direct and self._streams:
-            return self._finish_rollout(self._collect_on_streams(packed))
+        if direct:
+            if self._tail is None:
+                self._tail = (torch.zeros((self.n, self.D), device=self.dev), torch.zeros((self.n, self.A), dtype=torch.bool, device=self.dev))
+                self._tail[0].copy_(self._obs); self._tail[1].copy_(env.action_masks())
+                self._packed = torch.zeros(_abi.POLICY_ACT_WEIGHTS, device=self.dev)
+                if self.graph_rollout:
+                    env.set_option(_abi.OPT_DRAW_COUNTER, self._draw_counter.data_ptr())
+            packed = pack_actor_critic(self.policy, out=self._packed)
+            if self.graph_rollout and self._warm:
+                # ONE CUDA graph of the whole n_steps loop, replayed every rollout: the draw index of step t is
+                # t + *draw_counter (MSORT_OPT_DRAW_COUNTER), the weights live in the fixed `_packed` buffer.
+                # (the first rollout ran eagerly: it is the warm-up every lazy initialisation needs before a capture)
+                self._draw_counter.fill_(t0)
+                if self._graph is None:
+                    self._graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self._graph):
+                        self._rollout_body(packed, 0)
+                self._graph.replay()
+            else:
+                self._draw_counter.zero_()
+                self._rollout_body(packed, t0)
+                self._warm = True
+            return self._finish_rollout(*self._tail)
+        packed = pack_actor_critic(self.policy) if self.fused_act else None
+        b["obs"][0].copy_(self._obs); b["mask"][0].copy_(env.action_masks())
         for t in range(self.n_steps):
             if self.fused_act:                                           # writes straight into the rollout buffers
-                a, _, _ = env.policy_act(packed, seed=self.seed, t=self.num_timesteps // self.n + t,
-                                         obs=b["obs"][t], mask=b["mask"][t],
+                a, _, _ = env.policy_act(packed, seed=self.seed, t=t0 + t, obs=b["obs"][t], mask=b["mask"][t],
                                          out=(b["act"][t], b["logp"][t], b["val"][t]))
             else:
                 a, logp, v = self.policy.act(b["obs"][t], b["mask"][t])
                 b["act"][t], b["logp"][t], b["val"][t] = a, logp, v
-            last = t + 1 == self.n_steps
-            if direct:
-                oo, om = (self._tail if last else (b["obs"][t + 1], b["mask"][t + 1]))
-                obs, rew, term, _, _ = env.step(a, out_obs=oo, out_mask=om)   # fused CUDA step (auto-reset inside)
-            else:
-                obs, rew, term, _, _ = env.step(a)
-                if not last:
-                    b["obs"][t + 1].copy_(obs); b["mask"][t + 1].copy_(env.action_masks())
+            obs, rew, term, _, _ = env.step(a)
+            if t + 1 < self.n_steps:
+                b["obs"][t + 1].copy_(obs); b["mask"][t + 1].copy_(env.action_masks())
             b["rew"][t].copy_(rew); b["done"][t].copy_(term)
             self._obs = obs
-        return self._finish_rollout(self._obs)
+        return self._finish_rollout(self._obs, env.action_masks())
 
-    def _collect_on_streams(self, packed):
-        """The zero-copy rollout with every env range on its own stream: per range and step policy_act -> step ->
-        reward / done slices into the buffers, all in stream order; ranges never touch each other's rows."""
-        env, b = self.env, self.buf
-        cur = torch.cuda.current_stream(self.dev)
-        for s in self._streams:
-            s.wait_stream(cur)
-        t0 = self.num_timesteps // self.n
-        for t in range(self.n_steps):
-            oo, om = self._tail if t + 1 == self.n_steps else (b["obs"][t + 1], b["mask"][t + 1])
-            for s, (lo, hi) in zip(self._streams, self._ranges):
-                with torch.cuda.stream(s):
-                    env.policy_act(packed, seed=self.seed, t=t0 + t, obs=b["obs"][t], mask=b["mask"][t],
-                                   out=(b["act"][t], b["logp"][t], b["val"][t]), env_range=(lo, hi))
-                    env.step(b["act"][t], out_obs=oo, out_mask=om, env_range=(lo, hi))
-                    b["rew"][t][lo:hi].copy_(env.reward[lo:hi]); b["done"][t][lo:hi].copy_(env.terminated[lo:hi])
-        for s in self._streams:
-            cur.wait_stream(s)
-        return self._tail[0]
-
-    def _finish_rollout(self, last_obs):
-        b = self.buf
+    def _finish_rollout(self, last_obs, last_mask):
+        """Old log-probs / values recomputed in fp32, the bootstrap value of the last observation, GAE(lambda).
+        Returns (advantages, returns), both [n_steps, n]."""
+        b, T, n = self.buf, self.n_steps, self.n
         self._obs = last_obs
-        last_v = self.policy.vf(self._obs).squeeze(1)
-        adv = torch.zeros_like(b["rew"])
-        gae = torch.zeros(self.n, device=self.dev)
-        for t in reversed(range(self.n_steps)):                          # GAE(lambda); `terminated` ends the episode
-            nonterm = (~b["done"][t]).float()
-            next_v = last_v if t == self.n_steps - 1 else b["val"][t + 1]
-            delta = b["rew"][t] + self.gamma * next_v * nonterm - b["val"][t]
-            gae = delta + self.gamma * self.lam * nonterm * gae
-            adv[t] = gae
-        self.num_timesteps += self.n_steps * self.n
+        self.num_timesteps += T * n
+        if self.native_update:
+            # the update's own fp32 forward over the whole buffer: the importance ratio of epoch 0 is exactly 1 whatever
+            # precision the rollout kernel computed its log-probs in (fp16 operands on the tensor cores)
+            with torch.cuda.device(self.dev):
+                whole = self._batch(T * n, b["obs"], b["mask"], b["act"])
+                _abi.check(self.lib, self.lib.msort_ppo_forward(C.byref(whole), _p(self.flat), _p(b["logp"]), _p(b["val"]), self._cstream()),
+                           "msort_ppo_forward")
+                last = self._batch(n, last_obs, last_mask, b["act"])
+                _abi.check(self.lib, self.lib.msort_ppo_forward(C.byref(last), _p(self.flat), None, _p(self._last_v), self._cstream()),
+                           "msort_ppo_forward")
+                _abi.check(self.lib, self.lib.msort_ppo_gae(T, n, _p(b["rew"]), _p(b["val"]), _p(b["done"]), _p(self._last_v),
+                                                            self.gamma, self.lam, _p(self._adv), _p(self._ret), self._cstream()),
+                           "msort_ppo_gae")
+            return self._adv, self._ret
+        with torch.no_grad():
+            if self.fused_act:
+                for t in range(T):                                       # same purpose, PyTorch fp32
+                    b["logp"][t], _, b["val"][t] = self.policy.evaluate(b["obs"][t], b["mask"][t], b["act"][t])
+            last_v = self.policy.vf(last_obs).squeeze(1)
+            adv = torch.zeros_like(b["rew"])
+            gae = torch.zeros(n, device=self.dev)
+            for t in reversed(range(T)):                                 # GAE(lambda); `terminated` ends the episode
+                nonterm = (~b["done"][t]).float()
+                next_v = last_v if t == T - 1 else b["val"][t + 1]
+                delta = b["rew"][t] + self.gamma * next_v * nonterm - b["val"][t]
+                gae = delta + self.gamma * self.lam * nonterm * gae
+                adv[t] = gae
         return adv, adv + b["val"]
 
     # ------------------------------------------------------------------ update
     def update(self, adv, ret):
+        """n_epochs passes over the rollout buffer in shuffled minibatches (SB3 PPO.train with MaskablePPO's masked
+        distribution, training.py:118-143).  Native: per epoch ONE `msort_ppo_update` call = per minibatch the advantage
+        statistics kernel, the fused forward + loss + backward kernel and the clip + Adam kernel; nothing returns to the
+        host until the loss statistics are read."""
         b = self.buf
         N = self.n_steps * self.n
+        if self.native_update:
+            batch = self._batch(N, b["obs"], b["mask"], b["act"], b["logp"], adv, ret)
+            nb = -(-N // self.batch_size)
+            with torch.cuda.device(self.dev):
+                for _ in range(self.n_epochs):
+                    perm = torch.randperm(N, device=self.dev)
+                    self._stats.zero_()
+                    _abi.check(self.lib, self.lib.msort_ppo_update(C.byref(batch), C.byref(self._hp), _p(self.flat), _p(self._grads),
+                                                                  _p(self._m), _p(self._v), _p(self._step), _p(perm), 1,
+                                                                  self.batch_size, _p(self._scratch), _p(self._stats), self._cstream()),
+                               "msort_ppo_update")
+            self._last_stats = (self._stats, nb)
+            return {}
         flat = {k: v.reshape(N, *v.shape[2:]) for k, v in b.items()}
         adv, ret = adv.reshape(N), ret.reshape(N)
         stats = {}
@@ -212,6 +319,15 @@ class MaskablePPO:
             stats = dict(pg=float(pg.detach()), vf=float(vl.detach()), ent=float(ent.detach().mean()))
         return stats
 
+    def last_update_stats(self) -> dict:
+        """Loss terms of the last epoch of the last native update (means over that epoch's rows; one device read)."""
+        if not self.native_update or getattr(self, "_last_stats", None) is None:
+            return {}
+        s, nb = self._last_stats
+        s = s.tolist()
+        # the surrogate sum adds per-minibatch-normalised terms: its mean over minibatches is sum / rows as well
+        return dict(pg=s[0] / max(s[4], 1.0), vf=s[1] / max(s[4], 1.0), ent=s[2] / max(s[4], 1.0), clip_fraction=s[3] / max(s[4], 1.0))
+
     def learn(self, total_timesteps: int, log_every: int = 10):
         it, t0 = 0, time.time()
         while self.num_timesteps < total_timesteps:
@@ -219,6 +335,7 @@ class MaskablePPO:
             st = self.update(adv, ret)
             it += 1
             if it % log_every == 0:
+                st = st or self.last_update_stats()
                 st.update(timesteps=self.num_timesteps, mean_step_reward=float(self.buf["rew"].mean()),
                           sps=self.num_timesteps / (time.time() - t0))
                 self.log.append(st)

@@ -6,5 +6,5 @@ cd "$(dirname "$0")/../../marl-sortingenv_b200/csrc"
 name=$1; shift
 mkdir -p variants
 nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared -Xptxas -v "$@" \
-  -o variants/libmsort_$name.so msort_kernels.cu msort_policy.cu msort_api.cu > variants/build_$name.log 2>&1 || { tail -20 variants/build_$name.log; exit 1; }
+  -o variants/libmsort_$name.so msort_kernels.cu msort_policy.cu msort_ppo.cu msort_api.cu > variants/build_$name.log 2>&1 || { tail -20 variants/build_$name.log; exit 1; }
 echo "built variants/libmsort_$name.so"

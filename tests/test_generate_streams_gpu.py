@@ -40,7 +40,7 @@ def test_philox_trajectory_replays_through_the_replay_kernel(kind):
             redis[i, cur[i]:cur[i] + k] = oi["rec_redis_u"][i, :k]
             cur[i] += k
         po, prw, pt, pm, _ = phi.step(a)
-        ro, rrw, rt, rm, _ = rep.step(a, noise_u=noise[t], redis_u=redis, input_counts=counts[t],
+        ro, rrw, rt, rm, _ = rep.step(a, noise_u=noise[t], redis_u=redis.copy(), input_counts=counts[t],   # (a fresh array: the backend caches the upload by identity)
                                       press_choice=oi["rec_press_choice"])
         sp, sr, so = state_rows(phi.export_state()), state_rows(rep.export_state()), state_rows(ora.state)
         assert np.array_equal(sp, so), f"step {t}: PHILOX kernel vs oracle"
