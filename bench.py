@@ -459,10 +459,43 @@ def measure_rollout(ctx, args, env, W):
     r0.record(); gr.replay(); r1.record()
     ctx.barrier()
     ms = ctx.max_over_ranks(r0.elapsed_time(r1))
-    return {"value": n * world * Kr / (ms * 1e-3), "unit": "env-steps/s", "steps": Kr, "ms_per_step": ms / Kr,
-            "launches_per_step": 2 * len(ranges), "streams": len(ranges),
-            "what": "per env-step: msort_policy_act (actor-critic 29-32-32-{22|1} on tcgen05, masked categorical draw) + fused "
-                    "step(), env ranges on separate streams; obs/mask never leave HBM"}
+    two = {"value": n * world * Kr / (ms * 1e-3), "unit": "env-steps/s", "steps": Kr, "ms_per_step": ms / Kr,
+           "launches_per_step": 2 * len(ranges), "streams": len(ranges),
+           "what": "per env-step: msort_policy_act (actor-critic 29-32-32-{22|1} on tcgen05, masked categorical draw) + fused "
+                   "step(), env ranges on separate streams; obs/mask never leave HBM"}
+    if env.kind != "mono":
+        return two
+    # the same loop as ONE kernel per env-step: msort_rollout_step = step(a_t) + the policy forward / masked draw for step
+    # t+1 on the observation tile still in shared memory (the first action of the rollout comes from msort_policy_act)
+    from marl_sortingenv_b200.ppo import flatten_parameters
+    torch.manual_seed(0)
+    pol = MaskableActorCritic(env.D, env.A).to(dev)
+    flat = flatten_parameters(pol)
+    packed = pack_actor_critic(pol)
+    pf = env.rollout_pack(flat)
+    outs = [out, (torch.empty(n, dtype=torch.int64, device=dev), torch.empty(n, device=dev), torch.empty(n, device=dev))]
+    env.reset(seed=SEED)
+    env.policy_act(packed, seed=ACTION_SEED, t=0, out=outs[0])
+    for t in range(W):
+        env.rollout_step(outs[t % 2][0], pf, ACTION_SEED, t + 1, outs[(t + 1) % 2])
+    torch.cuda.synchronize(dev)
+    assert env.step_variant == "hot_fused", env.step_variant
+    gf = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gf):
+        env.policy_act(packed, seed=ACTION_SEED, t=W, out=outs[W % 2])
+        for t in range(Kr):
+            env.rollout_step(outs[(W + t) % 2][0], pf, ACTION_SEED, W + t + 1, outs[(W + t + 1) % 2])
+    gf.replay()
+    ctx.barrier()
+    r0.record(); gf.replay(); r1.record()
+    ctx.barrier()
+    msf = ctx.max_over_ranks(r0.elapsed_time(r1))
+    return {"value": n * world * Kr / (msf * 1e-3), "unit": "env-steps/s", "steps": Kr, "ms_per_step": msf / Kr,
+            "launches_per_step": 1, "streams": 1, "variant": env.step_variant,
+            "what": "per env-step ONE kernel (msort_rollout_step): fused step() + the next step's actor-critic forward "
+                    "(29-32-32-{22|1}, tcgen05) and masked categorical draw on the observation tile still in shared memory; "
+                    "one msort_policy_act per rollout for the first action",
+            "two_kernels": two}
 
 
 def measure_shard_invariance(ctx):

@@ -33,7 +33,7 @@ extern "C" {
 
 /* ABI history: 2 telemetry (msort_gather_state, reward terms) and msort_policy_act; 3 msort_observe_after_shift,
  * msort_step_variant, obs / mask must be 16-byte aligned; 4 msort_step_range, msort_policy_act_range;
- * 5 msort_set_option, MSORT_STEP_HOT_TENSOR, msort_step_host, msort_generate_streams, msort_ppo_*. */
+ * 5 msort_set_option, MSORT_STEP_HOT_TENSOR, msort_step_host, msort_generate_streams, msort_ppo_*, msort_rollout_*. */
 #define MSORT_ABI_VERSION 5
 
 /* ------------------------------------------------------------------ enums */
@@ -420,6 +420,25 @@ int msort_ppo_update(const msort_ppo_batch_t* batch, const msort_ppo_hparams_t* 
                      float* adam_v, int32_t* step, const int64_t* perms, int32_t n_epochs, int64_t batch_size, float* scratch,
                      float* stats, void* stream);
 
+/* ------------------------------------------------------------------ fused rollout step (Env_3_Monolith)
+ * One launch per env-step of the MaskablePPO rollout loop (ref: training.py:118-143 -> sb3 collect_rollouts: policy forward
+ * on the last observation, masked categorical draw, env.step): msort_rollout_step = msort_step on `actions` AND, on the
+ * observation / mask tile the step has just built in shared memory, the actor-critic forward + masked draw for the NEXT
+ * step (tcgen05, fp16 operands, fp32 accumulation; the same 128 envs, the same threads).  Outputs of the policy half:
+ * next_actions / next_logp / next_value [N] for the observation written to `obs` — what msort_policy_act(obs, mask, ...)
+ * with draw index t would return, up to the kernels' rounding (both within ~2e-3 of an fp32 evaluation).  The first
+ * action of a rollout comes from msort_policy_act.  Env_3, PHILOX mode, the HOT configuration only (action masking and
+ * auto-reset on, no overflow check, mask wanted, no per-step info arrays, config passes the FAST checks): anything else
+ * is MSORT_E_UNSUPPORTED and the caller runs msort_policy_act + msort_step.
+ *  packed : MSORT_ROLLOUT_WEIGHTS words written by msort_rollout_pack from the flat fp32 parameter vector of
+ *           msort_ppo_* (obs_dim 29, 22 actions), device memory, 16-byte aligned.
+ *  seed, t, deterministic : as msort_policy_act (MSORT_OPT_DRAW_COUNTER is added to t the same way). */
+#define MSORT_ROLLOUT_WEIGHTS 2688
+int msort_rollout_pack(const float* params, uint32_t* packed, void* stream);
+int msort_rollout_step(msort_t* h, void* state, const int64_t* actions, float* obs, float* reward, uint8_t* terminated,
+                       uint8_t* mask, const msort_info_out_t* info, const uint32_t* packed, uint64_t seed, uint32_t t,
+                       int deterministic, int64_t* next_actions, float* next_logp, float* next_value, void* stream);
+
 /* Which instantiation of the step kernel the handle's last msort_step launched (diagnostics / tests):
  * 0 none yet, 1 REPLAY, 2 generic, 3 FAST (host-proved config facts compiled in),
  * 4 HOT (FAST + the training-loop switches compiled in), 5 HOT persistent (Env_2: TMA-staged tiles). */
@@ -430,6 +449,7 @@ int msort_ppo_update(const msort_ppo_batch_t* batch, const msort_ppo_hparams_t* 
 #define MSORT_STEP_HOT 4
 #define MSORT_STEP_HOT_PERSISTENT 5
 #define MSORT_STEP_HOT_TENSOR 6 /* HOT persistent with Env_2's embedded policy on the tensor cores (tcgen05, fp16-split operands) */
+#define MSORT_STEP_HOT_FUSED 7  /* Env_3 HOT + the next step's rollout policy in the same kernel (msort_rollout_step) */
 int msort_step_variant(const msort_t* h);
 
 /* Handle options (diagnostics / experiments; defaults are the production choice).

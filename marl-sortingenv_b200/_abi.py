@@ -182,6 +182,9 @@ SYMBOLS = {
     "msort_ppo_gradient": (C.c_int, [C.POINTER(MsortPpoBatch), C.POINTER(MsortPpoHparams), _P, _P, _P, C.c_int64, C.c_int64, _P, _P, _P]),
     "msort_ppo_update": (C.c_int, [C.POINTER(MsortPpoBatch), C.POINTER(MsortPpoHparams), _P, _P, _P, _P, _P, _P, C.c_int32,
                                    C.c_int64, _P, _P, _P]),
+    "msort_rollout_pack": (C.c_int, [_P, _P, _P]),
+    "msort_rollout_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.POINTER(MsortInfoOut), _P, C.c_uint64, C.c_uint32, C.c_int,
+                                     _P, _P, _P, _P]),
     "msort_generate_streams": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P, _P, _P]),
     "msort_host_scratch_bytes": (C.c_size_t, [_P]),
     "msort_step_host": (C.c_int, [_P, _P, _P, C.POINTER(MsortHostIO), C.POINTER(MsortInfoOut), _P]),
@@ -189,6 +192,7 @@ SYMBOLS = {
     "msort_get_option": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int64)]),
     "msort_debug_policy_logits": (C.c_int, [_P, _P, C.c_int64, _P, _P]),
 }
+ROLLOUT_WEIGHTS = 2688
 OPT_TENSOR_POLICY = 1
 OPT_PERSIST_CTAS = 2
 OPT_DRAW_COUNTER = 3

@@ -181,7 +181,7 @@ class BatchedEnv:
     @property
     def step_variant(self) -> str:
         """Which instantiation of the step kernel the last step() launched (include/msort.h MSORT_STEP_*)."""
-        return ("none", "replay", "generic", "fast", "hot", "hot_persistent", "hot_tensor")[int(self.lib.msort_step_variant(self._h))]
+        return ("none", "replay", "generic", "fast", "hot", "hot_persistent", "hot_tensor", "hot_fused")[int(self.lib.msort_step_variant(self._h))]
 
     def set_option(self, option: int, value: int):
         """Handle options of include/msort.h (MSORT_OPT_*), e.g. `_abi.OPT_TENSOR_POLICY`."""
@@ -365,6 +365,47 @@ class BatchedEnv:
                                                      1 if deterministic else 0, _ptr(a), _ptr(lp), _ptr(v), self._stream())
         _abi.check(self.lib, rc, "msort_policy_act")
         return a, lp, v
+
+    def rollout_pack(self, params: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+        """The flat fp32 actor-critic parameter vector (`ppo.flatten_parameters`, the layout of `msort_ppo_*`) packed for the
+        fused rollout kernel (`msort_rollout_pack`, one small kernel): `_abi.ROLLOUT_WEIGHTS` 32-bit words."""
+        if out is None:
+            out = torch.empty(_abi.ROLLOUT_WEIGHTS, dtype=torch.int32, device=self.device)
+        if not (params.is_cuda and params.dtype == torch.float32 and params.is_contiguous()):
+            raise ValueError("rollout_pack needs a contiguous float32 CUDA parameter vector")
+        with torch.cuda.device(self.device):
+            rc = self.lib.msort_rollout_pack(_ptr(params), _ptr(out), self._stream())
+        _abi.check(self.lib, rc, "msort_rollout_pack")
+        return out
+
+    def rollout_step(self, actions: torch.Tensor, packed: torch.Tensor, seed: int, t: int, next_out,
+                     out_obs: torch.Tensor | None = None, out_mask: torch.Tensor | None = None, deterministic: bool = False):
+        """One env-step of the MaskablePPO rollout loop as ONE kernel (`msort_rollout_step`; Env_3, training configuration):
+        step(actions) AND the actor-critic forward + masked categorical draw for the NEXT step on the observation / mask tile
+        the step has just built on chip.  `next_out` = (actions int64 [N], log-prob f32 [N], value f32 [N]) receives what
+        `policy_act(obs, mask, seed=seed, t=t)` would return for the new observation (up to the kernels' rounding).
+        Returns what step() returns.  ref: training.py:118-143 (sb3 collect_rollouts)."""
+        if not self._was_reset:
+            raise AttributeError("step() called before reset()")
+        if self.kind != "mono":
+            raise ValueError("rollout_step exists for Env_3_Monolith only")
+        for name, t_, shape, dt in (("out_obs", out_obs, (self.num_envs, self.D), torch.float32),
+                                    ("out_mask", out_mask, (self.num_envs, self.A), torch.bool)):
+            if t_ is not None and not (t_.is_cuda and t_.is_contiguous() and tuple(t_.shape) == shape and t_.dtype == dt
+                                       and t_.data_ptr() % 16 == 0):
+                raise ValueError(f"{name} must be a contiguous, 16-byte aligned CUDA tensor of shape {shape}, dtype {dt}")
+        if out_obs is not None:
+            self.obs = out_obs
+        if out_mask is not None:
+            self.mask = out_mask
+        na, nlp, nv = next_out
+        with torch.cuda.device(self.device):
+            rc = self.lib.msort_rollout_step(self._h, _ptr(self.state), _ptr(actions), _ptr(self.obs), _ptr(self.reward),
+                                             _ptr(self.terminated), _ptr(self.mask), C.byref(self._info) if self._has_info else None,
+                                             _ptr(packed), int(seed) & 0xFFFFFFFFFFFFFFFF, int(t) & 0xFFFFFFFF,
+                                             1 if deterministic else 0, _ptr(na), _ptr(nlp), _ptr(nv), self._stream())
+        _abi.check(self.lib, rc, "msort_rollout_step")
+        return self.obs, self.reward, self.terminated, self.truncated, self.info_buffers
 
     # ------------------------------------------------------------------ host-buffer surface
     def _host_buffers(self):

@@ -413,7 +413,8 @@ extern "C" int msort_reset(msort_t* h, void* state, const uint8_t* which, const 
 // `first` / `count`: the env range [first, first + count) the launch covers (whole batch: 0 / N).  Every pointer is the
 // whole-batch base; the range's slice of each buffer is taken here.
 static int step_impl(msort_t* h, long long first, long long count, void* state, const int64_t* actions, float* obs, float* reward,
-                     uint8_t* terminated, uint8_t* mask, const msort_info_out_t* info, const msort_replay_t* replay, void* stream) {
+                     uint8_t* terminated, uint8_t* mask, const msort_info_out_t* info, const msort_replay_t* replay, void* stream,
+                     const FusedLaunch* fused = nullptr) {
   if (!h || !state || !actions || !obs || !reward || !terminated)
     return fail(MSORT_E_INVALID, "msort_step: NULL required argument");
   if (!aligned(state, 16)) return fail(MSORT_E_INVALID, "msort_step: state must be 16-byte aligned");
@@ -466,6 +467,16 @@ static int step_impl(msort_t* h, long long first, long long count, void* state, 
   StepLaunch l{state, actions, obs, reward, terminated, mask, info, replay, &h->step_variant, h->imported ? 0 : 1,
                h->policy_set ? h->policy_host : nullptr,
                (h->policy_set && h->policy_tc_ok && h->policy_tc_enabled) ? h->policy_tc_dev : nullptr, h->persist_per_sm};
+  l.fused = fused;
+  if (fused) {
+    cudaError_t e = launch_step(d, l, h->cfg.rng_mode, (cudaStream_t)stream);
+    if (e == cudaErrorNotSupported)
+      return fail(MSORT_E_UNSUPPORTED, "msort_rollout_step: the fused kernel exists for Env_3 in PHILOX mode with action masking and auto-reset on, "
+                                       "no overflow check, a mask output and no per-step info arrays; use msort_policy_act + msort_step");
+    MSORT_TRY_CUDA(e, "fused rollout kernel");
+    h->launches += 1;
+    return MSORT_OK;
+  }
   MSORT_TRY_CUDA(launch_step(d, l, h->cfg.rng_mode, (cudaStream_t)stream), "step kernel");
   h->launches += 1;
   return MSORT_OK;
@@ -484,6 +495,27 @@ extern "C" int msort_step_range(msort_t* h, int64_t first_env, int64_t num_envs,
   if (first_env < 0 || num_envs <= 0 || first_env + num_envs > h->dev.n || first_env % kTile != 0)
     return fail(MSORT_E_INVALID, "msort_step_range: range must lie inside the batch and start on a multiple of %d envs", kTile);
   return step_impl(h, first_env, num_envs, state, actions, obs, reward, terminated, mask, info, nullptr, stream);
+}
+
+// ---------------------------------------------------------------- fused rollout step (Env_3)
+extern "C" int msort_rollout_pack(const float* params, uint32_t* packed, void* stream) {
+  if (!params || !packed) return fail(MSORT_E_INVALID, "msort_rollout_pack: NULL argument");
+  if (!aligned(packed, 16)) return fail(MSORT_E_INVALID, "msort_rollout_pack: packed must be 16-byte aligned");
+  MSORT_TRY_CUDA(launch_pack_fused(params, packed, (cudaStream_t)stream), "pack kernel");
+  return MSORT_OK;
+}
+
+extern "C" int msort_rollout_step(msort_t* h, void* state, const int64_t* actions, float* obs, float* reward, uint8_t* terminated,
+                                  uint8_t* mask, const msort_info_out_t* info, const uint32_t* packed, uint64_t seed, uint32_t t,
+                                  int deterministic, int64_t* next_actions, float* next_logp, float* next_value, void* stream) {
+  if (!h || !packed || !next_actions || !next_logp || !next_value || !mask)
+    return fail(MSORT_E_INVALID, "msort_rollout_step: NULL argument");
+  if (!aligned(packed, 16) || !aligned(next_actions, 8) || !aligned(next_logp, 4) || !aligned(next_value, 4))
+    return fail(MSORT_E_INVALID, "msort_rollout_step: misaligned buffer");
+  if (h->dev.kind != MSORT_ENV_MONO || h->cfg.rng_mode != MSORT_RNG_PHILOX)
+    return fail(MSORT_E_UNSUPPORTED, "msort_rollout_step: Env_3_Monolith in PHILOX mode only");
+  const FusedLaunch f{packed, next_actions, next_logp, next_value, seed, t, h->draw_counter, deterministic};
+  return step_impl(h, 0, h->dev.n, state, actions, obs, reward, terminated, mask, info, nullptr, stream, &f);
 }
 
 // ---------------------------------------------------------------- host-buffer step

@@ -49,8 +49,17 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 
 // one poll; the thread may stay suspended inside the instruction for up to ~`hint_ns` (suspend-time hint), so a
 // waiting warp costs a handful of issue slots instead of a spin loop's worth
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar_saddr, uint32_t parity, uint32_t hint_ns = 4000u) {
+#ifndef MSORT_MBAR_HINT_NS
+#define MSORT_MBAR_HINT_NS 4000
+#endif
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar_saddr, uint32_t parity, uint32_t hint_ns = MSORT_MBAR_HINT_NS) {
   uint32_t done;
+#if MSORT_MBAR_HINT_NS == 0   // experiment: non-blocking poll
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(bar_saddr), "r"(parity) : "memory");
+  return done;
+#endif
   asm volatile(
       "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(done) : "r"(bar_saddr), "r"(parity), "r"(hint_ns) : "memory");

@@ -22,11 +22,17 @@
 #ifndef MSORT_PRESS_MIN_BLOCKS
 #define MSORT_PRESS_MIN_BLOCKS 5  // Env_2 (embedded MLP: 32 activations + FFMA2 accumulator pairs in registers)
 #endif
+#ifndef MSORT_EXP_SIGMOID
+#define MSORT_EXP_SIGMOID 0
+#endif
 #ifndef MSORT_PRESS_TC_MIN_BLOCKS
-#define MSORT_PRESS_TC_MIN_BLOCKS 6  // Env_2 with the embedded policy on the tensor cores (TCMLP): 37.0 KB of shared memory per CTA, 80 registers
+#define MSORT_PRESS_TC_MIN_BLOCKS 8  // Env_2 with the embedded policy on the tensor cores (TCMLP): 27.1 KB of shared memory per CTA, 64 registers
 #endif
 #ifndef MSORT_HOT_MONO_MIN_BLOCKS
 #define MSORT_HOT_MONO_MIN_BLOCKS 8  // Env_3's HOT kernel fits 64 registers without a spill: 8 CTAs (32 warps) per SM, +3..5 %
+#endif
+#ifndef MSORT_FUSE_MIN_BLOCKS
+#define MSORT_FUSE_MIN_BLOCKS 7  // Env_3's HOT kernel fused with the rollout policy: 30.4 KB of shared memory per CTA, 72 registers
 #endif
 #ifndef MSORT_STEP_MIN_BLOCKS
 #define MSORT_STEP_MIN_BLOCKS 7  // resident CTAs per SM the step kernel is compiled for (register cap)
@@ -128,6 +134,14 @@ struct StepArgs {
   int any_step_info;  // any of the six per-step info arrays above is present
   int act_tma;        // actions are 16-byte aligned: the persistent kernel may fetch a tile's actions by TMA
   const uint4* policy_tc;   // Env_2 TCMLP: packed tensor-core policy (kTcWords words, device memory) or nullptr
+  // FUSE (Env_3 rollout kernel): the actor-critic packed by pack_fused_kernel and where the NEXT step's action goes
+  const uint4* fused_w;     // kFwWords words (device memory, 16-byte aligned) or nullptr
+  long long* next_actions;
+  float* next_logp;
+  float* next_value;
+  unsigned draw_key0, draw_key1, draw_t;
+  const unsigned* draw_t_dev;   // nullable: added to draw_t (a graph-replayed rollout bumps it between replays)
+  int deterministic;
   float* terminal_obs;
   double* episode_return;
   int* episode_length;
@@ -173,6 +187,14 @@ template <int KIND> using PolicyParam = typename std::conditional<KIND == MSORT_
 // its bias in the epilogue.  Layers 1 and 2 (13 -> 32 -> 32: 1 440 of the 1 504 MACs) are the MMAs; the 32 -> 2 output
 // layer is evaluated in fp32 (FFMA2) on the layer-2 activations while they are still in registers, which saves the
 // third operand store and the third MMA round trip.  Measured logit error: tests/test_tc_mlp_gpu.py.
+// Env_2's observation row (16 floats) from the final state, written as four STS.128
+__device__ __forceinline__ void put_press_row(const DevConfig& c, const Env& s, float* __restrict__ row) {
+  float o[16];
+  press_obs(c, s, o);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(row)[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+}
+
 struct TcMlp {
   uint4* a;            // A operand: hi chunks [4][128] then lo chunks [4][128] (16 KB; the first 8 KB alias the obs tile)
   const uint32_t* w;   // packed weights in shared memory (kTcWords)
@@ -190,6 +212,15 @@ __device__ __forceinline__ float tc_sigmoid2(float zp) {   // 1 / (1 + 2^zp); +i
 // two activations at once: the two "+ 1" share one packed add (FADD2)
 __device__ __forceinline__ void tc_sigmoid2x2(float z0, float z1, float& r0, float& r1) {
   float e0, e1, d0, d1;
+#if MSORT_EXP_SIGMOID == 1      // timing experiment: no MUFU at all (wrong values)
+  umma::fadd2(z0, z1, 0.5f, 0.5f, r0, r1);
+  return;
+#elif MSORT_EXP_SIGMOID == 2    // timing experiment: EX2 only, the reciprocal replaced by one packed add (wrong values)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(z0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(z1));
+  umma::fadd2(e0, e1, 1.0f, 1.0f, r0, r1);
+  return;
+#endif
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(z0));
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(z1));
   umma::fadd2(e0, e1, 1.0f, 1.0f, d0, d1);
@@ -202,10 +233,13 @@ template <int KSTEPS, int N, int NTERMS>
 __device__ __forceinline__ void tc_issue_layer(const TcMlp& m, int b_off_halves) {
   const uint32_t a0 = smem_u32(m.a), b0 = smem_u32(m.w) + 2u * (uint32_t)b_off_halves;
   constexpr uint32_t kTermBytes = (uint32_t)(KSTEPS * 16 * N * 2), kLoBytes = 4u * kTile * 16u;
+  // the descriptors of one layer differ only in the 14-bit start-address field (bytes >> 4; shared memory is < 256 KB, so
+  // base + offset never carries out of the field): two base words, then one immediate add per operand and MMA
+  const uint64_t abase = umma::smem_desc(a0, kTile * 16u, 128u), bbase = umma::smem_desc(b0, N * 16u, 128u);
   uint32_t acc = 0u;
   auto mm = [&](int aterm, int bterm, int s) {
-    const uint64_t ad = umma::smem_desc(a0 + (aterm ? kLoBytes : 0u) + (uint32_t)(2 * s) * kTile * 16u, kTile * 16u, 128u);
-    const uint64_t bd = umma::smem_desc(b0 + (uint32_t)bterm * kTermBytes + (uint32_t)(2 * s) * N * 16u, N * 16u, 128u);
+    const uint64_t ad = abase + (uint64_t)(((aterm ? kLoBytes : 0u) + (uint32_t)(2 * s) * kTile * 16u) >> 4);
+    const uint64_t bd = bbase + (uint64_t)(((uint32_t)bterm * kTermBytes + (uint32_t)(2 * s) * N * 16u) >> 4);
     umma::mma_f16(m.tmem, ad, bd, umma::idesc_f16(N), acc);
     acc = 1u;
   };
@@ -249,8 +283,18 @@ __device__ __forceinline__ void tc_hidden_epilogue(const TcMlp& m, uint32_t tlan
 // All 128 threads of a tile call this together (it contains CTA barriers); `so` = this env's 13-wide sort
 // observation; l0 / l1 = the two logits.  Two MMA round trips (layers 1 and 2); the 32 -> 2 output layer is 32 packed
 // fp32 FMAs on the activations that are still in registers (no split, no operand store, no third round trip).
+#ifndef MSORT_EXP_TCPROF
+#define MSORT_EXP_TCPROF 0
+#endif
+#if MSORT_EXP_TCPROF
+__device__ long long g_tcprof[16];
+#define TCPROF(k) do { if (tid == 0 && blockIdx.x == 0) g_tcprof[k] = clock64(); } while (0)
+#else
+#define TCPROF(k) do { } while (0)
+#endif
 __device__ __forceinline__ void tc_mlp_logits(const TcMlp& m, const float (&so)[13], int tid, uint32_t& phase, float& l0, float& l1) {
   const uint32_t tlane = m.tmem + ((uint32_t)(tid & ~31) << 16);
+  TCPROF(0);
   {   // layer-1 operand: obs columns 0..12, then 1, 1, 1 (bias terms); the lo part of an exact 1.0 is 0
     uint32_t h[8], l[8];
 #pragma unroll
@@ -264,17 +308,22 @@ __device__ __forceinline__ void tc_mlp_logits(const TcMlp& m, const float (&so)[
   }
 #pragma unroll
   for (int layer = 0; layer < 2; ++layer) {
+    TCPROF(1 + 5 * layer);
     umma::fence_async_proxy();       // this thread's operand writes -> visible to the MMA's async-proxy reads
     umma::fence_before_sync();       // ... and its TMEM reads are done before the next MMA overwrites the columns
     __syncthreads();
+    TCPROF(2 + 5 * layer);
     if (tid == 0) {
       umma::fence_after_sync();
       if (layer == 0) tc_issue_layer<1, 32, 3>(m, kTcB1);
       else tc_issue_layer<2, 32, 3>(m, kTcB2);
     }
+    TCPROF(3 + 5 * layer);
     mbar_wait(m.bar, phase); phase ^= 1u;
     umma::fence_after_sync();
+    TCPROF(4 + 5 * layer);
     if (layer == 0) tc_hidden_epilogue(m, tlane, tid);
+    TCPROF(5 + 5 * layer);
   }
   // layer-2 epilogue fused with the output layer: z -> +bias -> r2 (registers) -> logits += r2 * (-2 W3) (FFMA2)
   const float* const fw = reinterpret_cast<const float*>(m.w);
@@ -303,6 +352,7 @@ __device__ __forceinline__ void tc_mlp_logits(const TcMlp& m, const float (&so)[
   }
   umma::fence_before_sync();         // TMEM reads done: ordered before the next tile's first MMA by the barriers in between
   f2unpack(acc, l0, l1);
+  TCPROF(11);
 }
 
 // the sort mode: argmax of the two logits, ties -> 0 like np.argmax (sort_agent.predict(..., deterministic=True))
@@ -344,6 +394,87 @@ tc_logits_kernel(const float* __restrict__ obs13, const uint4* __restrict__ tcw,
   umma::fence_before_sync();
   __syncthreads();
   if (tid < 32) umma::tmem_dealloc(m.tmem, 32u);
+#if MSORT_EXP_TCPROF
+  if (blockIdx.x == 0 && tid == 0) for (int k = 0; k < 12; ++k) logits[k] = (float)(g_tcprof[k] - g_tcprof[0]);
+#endif
+}
+
+// ---------------------------------------------------------------- FUSE: Env_3's step + the rollout policy in one kernel
+// ref: the MaskablePPO rollout loop (training.py:118-143 -> sb3 collect_rollouts): per env-step the policy forward on the
+// observation the previous step() returned, a masked categorical draw, then step().  The HOT Env_3 kernel with FUSE runs
+// the policy of the NEXT step on the observation / mask tile it has just built in shared memory — same 128-env tile, same
+// threads (thread = env = TMEM lane) — so the rollout is ONE launch per env-step and the policy never re-reads the 138 B of
+// observation + mask per env from HBM.  The actor-critic (two tanh towers 29 -> 32 -> 32 -> {22 | 1}) runs on tcgen05:
+//   layer 1  [128 x 32] x [32 x 64]   both towers side by side; K 29 = 1.0 carries the bias            -> TMEM columns 0..63
+//   layer 2  [128 x 32] x [32 x 32]   twice (policy tower -> columns 0..31, value tower -> 32..63), bias in the epilogue
+//   layer 3  [128 x 32] x [32 x 32]   the 22 logits; the value head (32 MACs) stays in fp32 registers
+// fp16 operands in the canonical no-swizzle K-major layout, fp32 accumulation.  The 16 KB operand buffer aliases the
+// observation tile (its bulk store has been read out by then), so a CTA needs 30.4 KB: 7 CTAs (28 warps) per SM.
+constexpr int kFwB1 = 0;                        // fp16 elements: layer 1 [K 32][N 64]
+constexpr int kFwB2p = kFwB1 + 32 * 64;         // layer 2, policy tower [32][32]
+constexpr int kFwB2v = kFwB2p + 32 * 32;        // layer 2, value tower [32][32]
+constexpr int kFwB3 = kFwB2v + 32 * 32;         // layer 3 [32][32] (rows 22..31 zero)
+constexpr int kFwHalves = kFwB3 + 32 * 32;      // 5120 fp16 = 10 240 B
+constexpr int kFwBias2 = kFwHalves / 2;         // 32-bit words from here: layer-2 bias, policy | value (64 floats)
+constexpr int kFwW3v = kFwBias2 + 64;           // value head weights (32 floats)
+constexpr int kFwBias3 = kFwW3v + 32;           // 22 logit biases, ..., [31] = value head bias (32 floats)
+constexpr int kFwWords = kFwBias3 + 32;         // 2688 words = 10 752 B
+static_assert(kFwWords == MSORT_ROLLOUT_WEIGHTS && (kFwWords * 4) % 16 == 0, "packed rollout policy size");
+
+// flat fp32 parameters (msort_ppo_* order: pi W1 b1 W2 b2 W3 b3 | vf W1 b1 W2 b2 W3 b3, torch Linear layout) -> kFwWords
+__global__ void __launch_bounds__(256)
+pack_fused_kernel(const float* __restrict__ p, uint32_t* __restrict__ out) {
+  constexpr int D = 29, A = 22, H = 32;
+  constexpr int pi_w1 = 0, pi_b1 = pi_w1 + H * D, pi_w2 = pi_b1 + H, pi_b2 = pi_w2 + H * H, pi_w3 = pi_b2 + H, pi_b3 = pi_w3 + A * H;
+  constexpr int vf_w1 = pi_b3 + A, vf_b1 = vf_w1 + H * D, vf_w2 = vf_b1 + H, vf_b2 = vf_w2 + H * H, vf_w3 = vf_b2 + H, vf_b3 = vf_w3 + H;
+  const int e = blockIdx.x * 256 + threadIdx.x;
+  if (e < kFwHalves / 2) {                       // two fp16 weights per word; canonical order [k/8][n][k%8]
+    float v[2];
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      int x = 2 * e + hh;
+      float w = 0.f;
+      if (x < kFwB2p) {                          // layer 1, N = 64
+        const int j = x & 7, n = (x >> 3) & 63, k = 8 * (x >> 9) + j;
+        const int w1 = n < 32 ? pi_w1 : vf_w1, b1 = n < 32 ? pi_b1 : vf_b1, r = n & 31;
+        w = k < D ? p[w1 + r * D + k] : (k == D ? p[b1 + r] : 0.f);
+      } else {                                   // the three [32][32] tiles
+        const int tile = (x - kFwB2p) >> 10; x = (x - kFwB2p) & 1023;
+        const int j = x & 7, n = (x >> 3) & 31, k = 8 * (x >> 8) + j;
+        w = tile == 0 ? p[pi_w2 + n * H + k] : (tile == 1 ? p[vf_w2 + n * H + k] : (n < A ? p[pi_w3 + n * H + k] : 0.f));
+      }
+      v[hh] = w;
+    }
+    const __half2 h = __floats2half2_rn(v[0], v[1]);
+    out[e] = *reinterpret_cast<const uint32_t*>(&h);
+  } else if (e < kFwWords) {
+    const int f = e - kFwBias2;
+    float w = 0.f;
+    if (f < 64) w = f < 32 ? p[pi_b2 + f] : p[vf_b2 + f - 32];
+    else if (f < 96) w = p[vf_w3 + f - 64];
+    else { const int a = f - 96; w = a < A ? p[pi_b3 + a] : (a == 31 ? p[vf_b3] : 0.f); }
+    out[e] = __float_as_uint(w);
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float tanh_mufu(float x) {   // MUFU.TANH, |error| <~ 5e-4: the size of the operands' fp16 rounding
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// one thread: the K-steps of one fused-policy layer (A chunks from `a_chunk`, B tile at `b_halves`, D columns from `dcol`)
+template <int N>
+__device__ __forceinline__ void fused_issue(uint32_t a_saddr, uint32_t w_saddr, int a_chunk, int b_halves, uint32_t tmem, int dcol) {
+  const uint64_t abase = umma::smem_desc(a_saddr + (uint32_t)a_chunk * kTile * 16u, kTile * 16u, 128u);
+  const uint64_t bbase = umma::smem_desc(w_saddr + 2u * (uint32_t)b_halves, N * 16u, 128u);
+#pragma unroll
+  for (int s = 0; s < 2; ++s)       // K = 32 = two instructions of K 16 (two 16-byte chunks each)
+    umma::mma_f16(tmem + (uint32_t)dcol, abase + (uint64_t)(((uint32_t)(2 * s) * kTile * 16u) >> 4),
+                  bbase + (uint64_t)(((uint32_t)(2 * s) * N * 16u) >> 4), umma::idesc_f16(N), s > 0 ? 1u : 0u);
 }
 
 // FAST (PHILOX only, chosen by the host when DevConfig::fast holds): boosted accuracies are exactly 1.0,
@@ -357,22 +488,25 @@ tc_logits_kernel(const float* __restrict__ obs13, const uint4* __restrict__ tcw,
 // scheduler's way).  Chosen per launch by launch_step_kind.
 // TCMLP (Env_2's persistent HOT kernel only; full tiles only — the launcher gives a ragged tail to the plain HOT kernel):
 // the embedded policy is evaluated on the tensor cores (tc_mlp_mode above) instead of per-thread FFMA2.
-template <int KIND, int RNG, int LAYOUT, bool FAST, bool HOT = false, bool SMALL = HOT, bool TCMLP = false>
+template <int KIND, int RNG, int LAYOUT, bool FAST, bool HOT = false, bool SMALL = HOT, bool TCMLP = false, bool FUSE = false>
 __global__ void __launch_bounds__(kTile, (KIND == MSORT_ENV_PRESS ? (TCMLP ? MSORT_PRESS_TC_MIN_BLOCKS : MSORT_PRESS_MIN_BLOCKS)   // Env_2 (FFMA2 form) keeps 32 MLP activations in registers
+                                           : FUSE ? MSORT_FUSE_MIN_BLOCKS
                                            : (KIND == MSORT_ENV_MONO && HOT) ? MSORT_HOT_MONO_MIN_BLOCKS : MSORT_STEP_MIN_BLOCKS) * (128 / kTile))
 step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArgs a,
             const __grid_constant__ PolicyParam<KIND> pw) {
   constexpr int D = Dims<KIND>::D, A = Dims<KIND>::A;
   static_assert(!TCMLP || (KIND == MSORT_ENV_PRESS && HOT && MSORT_HOT_PERSIST && kTile == 128), "TCMLP specialises Env_2's persistent HOT kernel");
+  static_assert(!FUSE || (KIND == MSORT_ENV_MONO && HOT && kTile == 128), "FUSE specialises Env_3's HOT kernel");
   // obs tile; with TCMLP the 16 KB MMA A-operand buffer, whose first half the obs tile aliases (the operand is dead
   // once the last layer's MMAs are complete, long before the first obs entry of the tile is written)
   constexpr int kObsBytes = kTile * D * (int)sizeof(float);
-  __shared__ __align__(128) unsigned char s_tile_raw[TCMLP ? (8 * kTile * 16 > kObsBytes ? 8 * kTile * 16 : kObsBytes) : kObsBytes];
+  __shared__ __align__(128) unsigned char s_tile_raw[(TCMLP || FUSE) ? (8 * kTile * 16 > kObsBytes ? 8 * kTile * 16 : kObsBytes) : kObsBytes];
   float* const s_obs = reinterpret_cast<float*>(s_tile_raw);
   __shared__ __align__(16) uint8_t s_mask[kTile * A];
-  __shared__ __align__(128) uint32_t s_tcw[TCMLP ? kTcWords : 4];   // TCMLP: packed fp16 weight tiles + biases
-  __shared__ __align__(8) uint64_t s_mma;                           // TCMLP: MMA completion
-  __shared__ uint32_t s_tmem;                                       // TCMLP: TMEM base address
+  __shared__ __align__(128) uint32_t s_tcw[TCMLP ? kTcWords : (FUSE ? kFwWords : 4)];   // TCMLP / FUSE: packed fp16 weight tiles + biases
+  __shared__ __align__(8) uint64_t s_mma;                           // TCMLP / FUSE: MMA completion
+  __shared__ __align__(8) uint64_t s_wbar;                          // FUSE: the weights have landed (TMA complete_tx)
+  __shared__ uint32_t s_tmem;                                       // TCMLP / FUSE: TMEM base address
   __shared__ double s_accs[RNG == MSORT_RNG_REPLAY ? 4 : 1][RNG == MSORT_RNG_REPLAY ? kTile : 1];  // accuracy_sorter (REPLAY)
   __shared__ double s_stat[kTile / 32][ST_COUNT];   // per-warp partial sums (plain stores: no init, no atomics)
 
@@ -391,12 +525,16 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   // +7 %; Env_1 / Env_3 10-17 % SLOWER than one CTA per tile with the hardware scheduler refilling the SM
   // (second barrier per tile, ~50 more instructions per warp), so they keep that form plus the L2 prefetch.
   constexpr bool PERSIST = HOT && MSORT_HOT_PERSIST && KIND == MSORT_ENV_PRESS;
-  __shared__ __align__(16) uint4 s_in[PERSIST ? 4 * kTile : 1];        // staged state planes C0..C3 of the next tile
-  __shared__ __align__(16) long long s_act[PERSIST ? kTile : 2];       // ... and its actions
+  // TCMLP keeps shared memory at 27.1 KB per CTA (8 resident CTAs per SM): the staging buffer IS the lo half of the MMA
+  // operand buffer (free from the completion of the layer-2 MMAs until the next tile's layer-1 operand is built — the
+  // next tile is staged in exactly that window), and the actions come by plain coalesced loads.
+  __shared__ __align__(16) uint4 s_in_own[PERSIST && !TCMLP ? 4 * kTile : 1];   // staged state planes C0..C3 of the next tile
+  __shared__ __align__(16) long long s_act[PERSIST && !TCMLP ? kTile : 2];      // ... and its actions
+  uint4* const s_in = TCMLP ? reinterpret_cast<uint4*>(s_tile_raw + 4 * kTile * 16) : s_in_own;
   __shared__ __align__(8) uint64_t s_full;                             // "staged tile has landed"
   const long long ntiles = (c.n + kTile - 1) / kTile;
   auto stage_tile = [&](long long t) {                                  // one thread: start the copies of tile t
-    const bool whole = (t + 1) * kTile <= c.n && a.act_tma;
+    const bool whole = !TCMLP && (t + 1) * kTile <= c.n && a.act_tma;
     mbar_expect_tx(&s_full, 4u * kTile * 16u + (whole ? kTile * 8u : 0u));
 #pragma unroll
     for (int p = 0; p < 4; ++p) bulk_load(&s_in[p * kTile], a.state + p * c.n_pad + t * kTile, kTile * 16u, &s_full);
@@ -424,6 +562,17 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     __syncthreads();
     if (TCMLP) { umma::fence_after_sync(); tcm.tmem = s_tmem; }
   }
+  if (FUSE) {   // the weights start their way into shared memory now and land behind the step; 64 TMEM columns
+    if (tid == 0) {
+      mbar_init(&s_wbar, 1);
+      mbar_init(&s_mma, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_expect_tx(&s_wbar, kFwWords * 4u);
+      bulk_load(s_tcw, a.fused_w, kFwWords * 4u, &s_wbar);
+    }
+    if (tid < 32) { __syncwarp(); umma::tmem_alloc(&s_tmem, 64u); umma::fence_before_sync(); }
+  }
+  uint32_t mbits = 0;   // FUSE: this env's press-mask bits for the policy phase
   long long tile = blockIdx.x;
   do {   // one pass unless PERSIST
   const long long row0 = tile * kTile;
@@ -452,14 +601,15 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   Env s;
   long long act = 0;
   if (PERSIST) {
+    if (TCMLP && live) act = a.actions[i];                                                 // in flight while the staged planes are awaited
     mbar_wait(&s_full, phase); phase ^= 1u;
     if (live) {
       load_planes<LAYOUT>(s_in, kTile, tid, s);
-      act = (a.act_tma && rows == kTile) ? s_act[tid] : a.actions[i];
+      if (!TCMLP) act = (a.act_tma && rows == kTile) ? s_act[tid] : a.actions[i];
     }
     if (tid == kStoreTid) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous tile's obs / mask have left shared memory
     __syncthreads();                                                                       // every thread has taken its env out of the staging buffer
-    if (tid == kStageTid && tile + gridDim.x < ntiles) stage_tile(tile + gridDim.x);
+    if (!TCMLP && tid == kStageTid && tile + gridDim.x < ntiles) stage_tile(tile + gridDim.x);   // (TCMLP: after the policy's last MMA)
   } else if (live) {
     load_planes<LAYOUT>(a.state, c.n_pad, i, s);
     act = a.actions[i];
@@ -579,7 +729,8 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
         sort_obs(c, s, kq, so);
         if constexpr (TCMLP) {
           mode = tc_mlp_mode(tcm, so, tid, mma_phase);   // every thread of the (full) tile is here: CTA barriers inside
-          obs_sorting(c, s, prow);                       // the operand buffer is free again: the deferred obs entries
+          // this thread has seen the layer-2 MMAs complete: the operand buffer is dead, its lo half takes the next tile
+          if (tid == kStageTid && tile + gridDim.x < ntiles) stage_tile(tile + gridDim.x);
         } else if constexpr (KIND == MSORT_ENV_PRESS) mode = mlp_sort_mode<HOT>(pw.w, so);
       } else {  // sorting_rules env_super.py:469-482: pA+pC > pB+pD on float64 proportions
         int ac = b4(s.belt4, 0) + b4(s.belt4, 2), bd = b4(s.belt4, 1) + b4(s.belt4, 3);
@@ -988,7 +1139,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
         obs_pdiff(c, kq, orow);
       }
     }
-    if (KIND != MSORT_ENV_SORT) obs_levels_timers(c, s, prow);
+    if (KIND != MSORT_ENV_SORT && !TCMLP) obs_levels_timers(c, s, prow);
 
     a.reward[i] = (float)reward;
     a.terminated[i] = terminated ? 1 : 0;
@@ -1011,6 +1162,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       if (a.episode_length) a.episode_length[i] = (int)s.step;
       if (auto_reset) {
         if (a.terminal_obs) {
+          if (TCMLP) put_press_row(c, s, orow);
           // Episodes of one warp normally end together: then the warp's 32 rows are one contiguous
           // range in the tile and in the tensor, copied with coalesced stores.  (All 32 lanes reach
           // this point in that case, so __activemask() names the whole warp.)
@@ -1034,10 +1186,14 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
         s.episode = ep + 1;
         s.gfirst = (int)(env_draw(c, gid_lo, gid_hi, kBlkReset, s.episode, 0u).x & 1u);
         zero_cold(a.state, c.n_pad, i);
-        env_obs<KIND>(c, s, orow);
+        if (!TCMLP) env_obs<KIND>(c, s, orow);
       }
     }
-    if (want_mask) put_mask_row<A>(s_mask, tid, press_mask_bits(c, s));
+    // TCMLP: the whole 16-wide row is a function of the final state — assembled in registers and stored as four 16-byte
+    // vectors (scalar stores at the row pitch of 64 B are 16-way bank conflicts: they were 57 % of the kernel's
+    // shared-memory store wavefronts)
+    if (TCMLP) put_press_row(c, s, orow);
+    if (want_mask) { mbits = press_mask_bits(c, s); put_mask_row<A>(s_mask, tid, mbits); }
     store_planes<LAYOUT>(a.state, c.n_pad, i, s);
   }
 
@@ -1069,12 +1225,145 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     if (tid == kStoreTid) {
       bulk_store(a.obs + row0 * D, s_obs, kTile * D * (uint32_t)sizeof(float));
       if (want_mask) bulk_store(a.mask + row0 * A, s_mask, kTile * A);
-      if (PERSIST) asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // waited for before the tile is written again
+      if (PERSIST || FUSE) asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // waited for before the tile is written again
       else bulk_commit_and_wait_read();
     }
   } else {  // partial last tile
     flush_tile(s_obs, a.obs + row0 * D, rows * D * (int)sizeof(float));
     if (want_mask) flush_tile(s_mask, a.mask + row0 * A, rows * A);
+  }
+  if constexpr (FUSE) {
+    // ================================================================ the NEXT step's policy on the tile just built
+    // (1) this env's observation row -> the fp16 words of the layer-1 operand (K 0..28 = obs, K 29 = 1.0 for the bias)
+    uint32_t a1[16];
+    {
+      const float* x = &s_obs[tid * D];       // pitch 29 floats: conflict-free
+#pragma unroll
+      for (int q = 0; q < 14; ++q) a1[q] = pack_h2(x[2 * q], x[2 * q + 1]);
+      a1[14] = pack_h2(x[28], 1.0f);
+      a1[15] = 0u;
+    }
+    // (2) the operand buffer aliases the observation tile: its bulk store must have read it out first
+    if (rows == kTile && tid == kStoreTid) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncthreads();
+    uint4* const A4 = reinterpret_cast<uint4*>(s_tile_raw);   // chunk kc (8 K values) of row r at (kc * 128 + r) * 16 B
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) A4[kc * kTile + tid] = make_uint4(a1[4 * kc], a1[4 * kc + 1], a1[4 * kc + 2], a1[4 * kc + 3]);
+    mbar_wait(&s_wbar, 0u);                   // the weights (their fp32 part is read with plain loads below)
+    const uint32_t a_saddr = smem_u32(s_tile_raw), w_saddr = smem_u32(s_tcw);
+    const float* const fw = reinterpret_cast<const float*>(s_tcw);
+    umma::fence_async_proxy();
+    __syncthreads();
+    umma::fence_after_sync();                 // (also orders the TMEM allocation before the first use of its address)
+    const uint32_t tmem = s_tmem;
+    const uint32_t tlane = tmem + ((uint32_t)(tid & ~31) << 16);
+    // ---- layer 1: both towers, N = 64
+    if (tid == 0) { fused_issue<64>(a_saddr, w_saddr, 0, kFwB1, tmem, 0); umma::commit(&s_mma); }
+    mbar_wait(&s_mma, 0u);
+    umma::fence_after_sync();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {             // 64 hidden units -> tanh -> chunks 0..3 (policy tower), 4..7 (value tower)
+      float v[16];
+      umma::tmem_ld16(tlane + 16u * q, v);
+      uint32_t h[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h[j] = pack_h2(tanh_mufu(v[2 * j]), tanh_mufu(v[2 * j + 1]));
+      A4[(2 * q) * kTile + tid] = make_uint4(h[0], h[1], h[2], h[3]);
+      A4[(2 * q + 1) * kTile + tid] = make_uint4(h[4], h[5], h[6], h[7]);
+    }
+    umma::fence_async_proxy();
+    umma::fence_before_sync();
+    __syncthreads();
+    // ---- layer 2: one [32 x 32] product per tower
+    if (tid == 0) {
+      umma::fence_after_sync();
+      fused_issue<32>(a_saddr, w_saddr, 0, kFwB2p, tmem, 0);
+      fused_issue<32>(a_saddr, w_saddr, 4, kFwB2v, tmem, 32);
+      umma::commit(&s_mma);
+    }
+    mbar_wait(&s_mma, 1u);
+    umma::fence_after_sync();
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {             // policy tower: + bias -> tanh -> chunks 0..3
+      float v[16];
+      umma::tmem_ld16(tlane + 16u * q, v);
+      uint32_t h[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 bb = *reinterpret_cast<const float2*>(fw + kFwBias2 + 16 * q + 2 * j);
+        h[j] = pack_h2(tanh_mufu(v[2 * j] + bb.x), tanh_mufu(v[2 * j + 1] + bb.y));
+      }
+      A4[(2 * q) * kTile + tid] = make_uint4(h[0], h[1], h[2], h[3]);
+      A4[(2 * q + 1) * kTile + tid] = make_uint4(h[4], h[5], h[6], h[7]);
+    }
+    float value = fw[kFwBias3 + 31];
+#pragma unroll
+    for (int q = 2; q < 4; ++q) {             // value tower: + bias -> tanh -> the value head's 32 MACs, in fp32
+      float v[16];
+      umma::tmem_ld16(tlane + 16u * q, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float2 bb = *reinterpret_cast<const float2*>(fw + kFwBias2 + 16 * q + 2 * j);
+        const float2 ww = *reinterpret_cast<const float2*>(fw + kFwW3v + 16 * (q - 2) + 2 * j);
+        value = fmaf(tanh_mufu(v[2 * j] + bb.x), ww.x, value);
+        value = fmaf(tanh_mufu(v[2 * j + 1] + bb.y), ww.y, value);
+      }
+    }
+    umma::fence_async_proxy();
+    umma::fence_before_sync();
+    __syncthreads();
+    // ---- layer 3: the 22 logits
+    if (tid == 0) { umma::fence_after_sync(); fused_issue<32>(a_saddr, w_saddr, 0, kFwB3, tmem, 0); umma::commit(&s_mma); }
+    mbar_wait(&s_mma, 0u);
+    umma::fence_after_sync();
+    {
+      float o[32];
+      umma::tmem_ld16(tlane, *reinterpret_cast<float(*)[16]>(&o[0]));
+      umma::tmem_ld16(tlane + 16u, *reinterpret_cast<float(*)[16]>(&o[16]));
+      umma::fence_before_sync();              // TMEM reads done before the columns are given back
+      if (live) {
+        // masked log-softmax (sb3_contrib masks logits with -1e8; action a of Env_3 is valid iff press action a % 11 is)
+        float mx = -3.0e38f;
+#pragma unroll
+        for (int k = 0; k < A; ++k) {
+          o[k] = ((mbits >> (k % 11)) & 1u) ? o[k] + fw[kFwBias3 + k] : -1e8f;
+          mx = fmaxf(mx, o[k]);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < A; ++k) { o[k] = __expf(o[k] - mx); sum += o[k]; }   // o[k]: unnormalised probability
+        int na = 0;
+        if (a.deterministic) {
+          float best = -1.f;
+#pragma unroll
+          for (int k = 0; k < A; ++k) if (o[k] > best) { best = o[k]; na = k; }
+        } else {   // inverse-CDF draw with one Philox uniform keyed by (seed, draw index, global env id) — msort_policy_act's draw
+          const unsigned long long g = (unsigned long long)(c.gid0 + i);
+          const unsigned dt = a.draw_t + (a.draw_t_dev ? *a.draw_t_dev : 0u);
+          const U4 r4 = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), 0xAC70u, dt, a.draw_key0, a.draw_key1);
+          const float u = ((float)(r4.x >> 8) + 0.5f) * (1.0f / 16777216.0f) * sum;   // uniform in (0, sum)
+          float cdf = 0.f;
+          int last = 0;
+          bool found = false;
+#pragma unroll
+          for (int k = 0; k < A; ++k) {
+            cdf += o[k];
+            if (o[k] > 0.f) last = k;
+            if (!found && u < cdf && o[k] > 0.f) { na = k; found = true; }
+          }
+          if (!found) na = last;
+        }
+        float pa = 0.f;
+#pragma unroll
+        for (int k = 0; k < A; ++k) if (k == na) pa = o[k];
+        a.next_actions[i] = na;
+        a.next_logp[i] = __logf(pa) - __logf(sum);
+        a.next_value[i] = value;
+      }
+    }
+    __syncthreads();
+    if (tid < 32) umma::tmem_dealloc(tmem, 64u);
+    if (rows == kTile && tid == kStoreTid) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
   tile += gridDim.x;
   } while (PERSIST && tile < ntiles);
@@ -1547,14 +1836,24 @@ static cudaError_t launch_step_kind(const DevConfig& c, const StepArgs& a, const
     if (policy_host) memcpy(pw.w, policy_host, MSORT_POLICY_WEIGHTS * sizeof(float));
   }
   var = rng == MSORT_RNG_REPLAY ? MSORT_STEP_REPLAY : (c.fast ? MSORT_STEP_FAST : MSORT_STEP_GENERIC);
+  if (a.fused_w && (rng == MSORT_RNG_REPLAY || c.layout != LAYOUT_COMPACT)) return cudaErrorNotSupported;
   if (rng == MSORT_RNG_REPLAY) step_kernel<KIND, MSORT_RNG_REPLAY, LAYOUT_REPLAY, false><<<g, kTile, 0, st>>>(c, a, pw);
   else if (c.layout == LAYOUT_COMPACT) {
     const unsigned want = MSORT_F_ACTION_MASKING | MSORT_F_AUTO_RESET, never = MSORT_F_CHECK_OVERFLOW;
     const bool hot = allow_hot && c.fast && c.one_block && (c.flags & want) == want && !(c.flags & never) && a.mask && !a.any_step_info;
+    if (a.fused_w && !(hot && KIND == MSORT_ENV_MONO)) return cudaErrorNotSupported;   // FUSE exists for Env_3's HOT configuration only
     if (hot) {
       auto kern = c.small_lv ? step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true, true>
                              : step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true, false>;
       var = MSORT_STEP_HOT;
+      if (a.fused_w) {   // Env_3 rollout kernel: step + the next step's policy (launch_step refuses other kinds)
+        if constexpr (KIND == MSORT_ENV_MONO) {
+          var = MSORT_STEP_HOT_FUSED;
+          if (c.small_lv) step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true, true, false, true><<<g, kTile, 0, st>>>(c, a, pw);
+          else step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true, false, false, true><<<g, kTile, 0, st>>>(c, a, pw);
+          return cudaGetLastError();
+        }
+      }
       if constexpr (MSORT_HOT_PERSIST && KIND == MSORT_ENV_PRESS) {
         // persistent: exactly one wave of resident CTAs (per-SM count from the occupancy calculator, cached in the handle)
         var = MSORT_STEP_HOT_PERSISTENT;
@@ -1608,6 +1907,11 @@ cudaError_t launch_step(const DevConfig& c, const StepLaunch& l, int rng, cudaSt
                     a.info_press_action || a.info_invalid || a.info_r_sort || a.info_r_press || a.info_sorted_true;
   a.act_tma = ((uintptr_t)l.actions & 15u) == 0;
   a.policy_tc = reinterpret_cast<const uint4*>(l.policy_tc);
+  const FusedLaunch* fz = l.fused;
+  a.fused_w = fz ? reinterpret_cast<const uint4*>(fz->packed) : nullptr;
+  a.next_actions = fz ? (long long*)fz->next_actions : nullptr; a.next_logp = fz ? fz->next_logp : nullptr; a.next_value = fz ? fz->next_value : nullptr;
+  a.draw_key0 = fz ? (unsigned)(fz->seed & 0xffffffffu) : 0u; a.draw_key1 = fz ? (unsigned)(fz->seed >> 32) : 0u;
+  a.draw_t = fz ? fz->t : 0u; a.draw_t_dev = fz ? fz->t_dev : nullptr; a.deterministic = fz ? fz->deterministic : 0;
   a.terminal_obs = f ? f->terminal_obs : nullptr;
   a.episode_return = f ? f->episode_return : nullptr;
   a.episode_length = f ? f->episode_length : nullptr;
@@ -1623,9 +1927,17 @@ cudaError_t launch_step(const DevConfig& c, const StepLaunch& l, int rng, cudaSt
   }
 }
 
+cudaError_t launch_pack_fused(const float* params, uint32_t* packed, cudaStream_t st) {
+  pack_fused_kernel<<<(kFwWords + 255) / 256, 256, 0, st>>>(params, packed);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_tc_logits(const float* obs13, const uint32_t* tcw, long long n, float* logits, int sm_count, cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
-  const unsigned grid = (unsigned)std::min<long long>((n + kTile - 1) / kTile, 4ll * sm_count);
+  #ifndef MSORT_EXP_TC_CTAS
+#define MSORT_EXP_TC_CTAS 4
+#endif
+  const unsigned grid = (unsigned)std::min<long long>((n + kTile - 1) / kTile, (long long)MSORT_EXP_TC_CTAS * sm_count);
   tc_logits_kernel<<<grid, kTile, 0, st>>>(obs13, reinterpret_cast<const uint4*>(tcw), n, logits);
   return cudaGetLastError();
 }

@@ -10,6 +10,18 @@ namespace msort {
 
 struct DevConfig;
 
+// Env_3's fused rollout kernel (step + the next step's policy): the packed actor-critic and where its outputs go
+struct FusedLaunch {
+  const uint32_t* packed;    // MSORT_ROLLOUT_WEIGHTS words (launch_pack_fused), device memory, 16-byte aligned
+  int64_t* next_actions;
+  float* next_logp;
+  float* next_value;
+  uint64_t seed;
+  uint32_t t;                // draw index (+ *t_dev)
+  const uint32_t* t_dev;
+  int deterministic;
+};
+
 struct StepLaunch {
   void* state;
   const int64_t* actions;
@@ -24,6 +36,7 @@ struct StepLaunch {
   const float* policy_host;  // Env_2 embedded policy (host copy in the paired layout, MSORT_POLICY_WEIGHTS floats) or nullptr
   const uint32_t* policy_tc; // the same policy packed for the tensor-core path (pack_policy_tc; DEVICE memory) or nullptr
   const int* persist_per_sm; // resident CTAs per SM of the persistent Env_2 kernels (query_persist_occupancy)
+  const FusedLaunch* fused = nullptr;   // non-null: the fused rollout kernel (Env_3, HOT configuration only)
 };
 
 void pack_policy_pairs(const float* sb3, float* paired);   // SB3 weight order -> the step kernel's FFMA2 operand order
@@ -31,6 +44,7 @@ bool pack_policy_tc(const float* sb3, uint32_t* words);    // ... -> the tensor-
 int policy_tc_words();                                     // size of that buffer in 32-bit words
 void query_persist_occupancy(int per_sm[4]);               // current device; index = SMALL + 2 * TCMLP
 cudaError_t launch_step(const DevConfig& c, const StepLaunch& l, int rng, cudaStream_t st);
+cudaError_t launch_pack_fused(const float* params, uint32_t* packed, cudaStream_t st);   // flat fp32 parameters -> MSORT_ROLLOUT_WEIGHTS words
 cudaError_t launch_tc_logits(const float* obs13, const uint32_t* tcw, long long n, float* logits, int sm_count, cudaStream_t st);
 cudaError_t launch_reset(const DevConfig& c, void* state, const uint8_t* which, const uint8_t* first_pattern,
                          float* obs, uint8_t* mask, uint32_t reset_flags, cudaStream_t st);

@@ -73,10 +73,13 @@ struct __align__(16) PolicySmem {
 template <int K, int N, class Smem>
 __device__ __forceinline__ void issue_layer(const Smem& sm, int b_off, uint32_t tmem_d, uint64_t* bar) {
   const uint32_t a0 = smem_u32(sm.a), b0 = smem_u32(sm.b + b_off);
+  // the K-steps' descriptors differ only in the 14-bit start-address field (bytes >> 4; never carries out of the field in
+  // < 256 KB of shared memory): one base word per operand, then an immediate add per MMA
+  const uint64_t abase = umma::smem_desc(a0, kRows * 16u, 128u), bbase = umma::smem_desc(b0, N * 16u, 128u);
 #pragma unroll
   for (int s = 0; s < K / 16; ++s) {   // one instruction = K 16 (fp16) = two 16-byte chunks
-    const uint64_t ad = umma::smem_desc(a0 + (uint32_t)(2 * s) * kRows * 16u, kRows * 16u, 128u);
-    const uint64_t bd = umma::smem_desc(b0 + (uint32_t)(2 * s) * N * 16u, N * 16u, 128u);
+    const uint64_t ad = abase + (uint64_t)(((uint32_t)(2 * s) * kRows * 16u) >> 4);
+    const uint64_t bd = bbase + (uint64_t)(((uint32_t)(2 * s) * N * 16u) >> 4);
     umma::mma_f16(tmem_d, ad, bd, umma::idesc_f16(N), s > 0 ? 1u : 0u);
   }
   umma::commit(bar);

@@ -112,7 +112,7 @@ class MaskablePPO:
     def __init__(self, env, n_steps: int = 64, batch_size: int = 8192, n_epochs: int = 10, gamma: float = 0.99,
                  gae_lambda: float = 0.95, clip_range: float = 0.2, ent_coef: float = 0.05, vf_coef: float = 0.5,
                  learning_rate: float = 3e-4, max_grad_norm: float = 0.5, seed: int = 42, fused_act: bool = True,
-                 rollout_streams: int = 2, native_update: bool = True, graph_rollout: bool = True):
+                 rollout_streams: int = 2, native_update: bool = True, graph_rollout: bool = True, fused_rollout: bool = True):
         self.env = env
         # rollout inference: one fused tensor-core kernel (msort_policy_act) instead of ~25 torch kernels/step
         self.fused_act = fused_act and hasattr(env, "policy_act")
@@ -124,6 +124,9 @@ class MaskablePPO:
         self.lib = env.lib if hasattr(env, "lib") else None
         self.native_update = native_update and self.lib is not None
         self.graph_rollout = graph_rollout and fused_act and hasattr(env, "policy_act")
+        # Env_3 in its training configuration: step + the next step's policy as one kernel per env-step (msort_rollout_step)
+        # (the library refuses configurations outside its HOT instantiation: the first rollout then falls back, see _rollout_body)
+        self.fused_rollout = fused_rollout and self.fused_act and getattr(env, "kind", "") == "mono" and hasattr(env, "rollout_step")
         self.flat = flatten_parameters(self.policy)
         self.opt = torch.optim.Adam(self.policy.parameters(), lr=learning_rate, eps=1e-5)
         self.lr = learning_rate
@@ -178,6 +181,29 @@ class MaskablePPO:
         `_tail` pair), every env range on its own stream.  Only stream-ordered device work: capturable as a CUDA graph."""
         env, b = self.env, self.buf
         b["obs"][0].copy_(self._tail[0]); b["mask"][0].copy_(self._tail[1])
+        if self.fused_rollout:
+            # ONE kernel per env-step (msort_rollout_step): step(a_t) and, on the observation tile still on chip, the policy
+            # forward + masked draw for step t+1; only the first action of the rollout needs the stand-alone policy kernel.
+            # Reward / done go straight into their buffer slots (the env's output pointers are aimed at them).
+            T = self.n_steps
+            env.rollout_pack(self.flat, out=self._packed_fused)
+            env.policy_act(packed, seed=self.seed, t=t0, obs=b["obs"][0], mask=b["mask"][0], out=(b["act"][0], b["logp"][0], b["val"][0]))
+            keep = (env.reward, env.terminated)
+            for t in range(T):
+                last = t + 1 == T
+                oo, om = self._tail if last else (b["obs"][t + 1], b["mask"][t + 1])
+                nxt = self._spare if last else (b["act"][t + 1], b["logp"][t + 1], b["val"][t + 1])
+                env.reward, env.terminated = b["rew"][t], b["done"][t]
+                try:
+                    env.rollout_step(b["act"][t], self._packed_fused, self.seed, t0 + t + 1, nxt, out_obs=oo, out_mask=om)
+                except _abi.MsortError as e:
+                    env.reward, env.terminated = keep
+                    if t == 0 and e.code == _abi.E_UNSUPPORTED:       # refused before anything was launched: two kernels per step
+                        self.fused_rollout = False
+                        return self._rollout_body(packed, t0)
+                    raise
+            env.reward, env.terminated = keep
+            return
         cur = torch.cuda.current_stream(self.dev)
         streams = self._streams or [cur]
         for s in self._streams:
@@ -208,6 +234,9 @@ class MaskablePPO:
                 self._tail = (torch.zeros((self.n, self.D), device=self.dev), torch.zeros((self.n, self.A), dtype=torch.bool, device=self.dev))
                 self._tail[0].copy_(self._obs); self._tail[1].copy_(env.action_masks())
                 self._packed = torch.zeros(_abi.POLICY_ACT_WEIGHTS, device=self.dev)
+                self._packed_fused = torch.zeros(_abi.ROLLOUT_WEIGHTS, dtype=torch.int32, device=self.dev)
+                self._spare = (torch.zeros(self.n, dtype=torch.int64, device=self.dev), torch.zeros(self.n, device=self.dev),
+                               torch.zeros(self.n, device=self.dev))
                 if self.graph_rollout:
                     env.set_option(_abi.OPT_DRAW_COUNTER, self._draw_counter.data_ptr())
             packed = pack_actor_critic(self.policy, out=self._packed)

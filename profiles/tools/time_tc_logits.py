@@ -19,3 +19,9 @@ for _ in range(20):
     env.policy_logits_tensor(x)
 e1.record(); torch.cuda.synchronize()
 print(f"{os.path.basename(sys.argv[1]):28s} tc_logits n {n}: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us", flush=True)
+if os.environ.get("TCPROF"):
+    out = env.policy_logits_tensor(x)
+    torch.cuda.synchronize()
+    names = ["start", "A1 built", "sync1", "issued1", "mma1 done", "epilogue1 done", "(A2 built)", "sync2", "issued2", "mma2 done", "-", "epilogue2 done"]
+    v = out.reshape(-1)[:12].tolist()
+    print("   cycles since tile start (CTA 0, last tile): " + ", ".join(f"{n} {int(c)}" for n, c in zip(names, v)), flush=True)

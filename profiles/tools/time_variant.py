@@ -9,7 +9,7 @@ import marl_sortingenv_b200 as ms
 n = int(os.environ.get("N", 1 << 20))
 cls = {"mono": ms.BatchedMonolithEnv, "sort": ms.BatchedSortingEnv, "press": ms.BatchedPressingEnv}[kind]
 env = cls(n, max_steps=50, seed=42, info_level=os.environ.get("INFO", "episode"))
-if kind == 'press':
+if kind == 'press' and not os.environ.get('NOPOLICY'):
     from marl_sortingenv_b200.policy import sb3_style_init
     env.set_sort_policy(sb3_style_init(0, action_gain=float(os.environ.get("GAIN", 0.01))))
     if os.environ.get("TENSOR") is not None:                      # A/B: embedded policy on the tensor cores (1) or FFMA2 (0)
