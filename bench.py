@@ -490,8 +490,32 @@ def measure_rollout(ctx, args, env, W):
     r0.record(); gf.replay(); r1.record()
     ctx.barrier()
     msf = ctx.max_over_ranks(r0.elapsed_time(r1))
+    # ... and as two kernels with the same arithmetic: msort_rollout_policy (128 threads per tile, 8 CTAs per SM) + msort_step
+    gs = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gs):
+        cur = torch.cuda.current_stream(dev)
+        for s_ in streams:
+            s_.wait_stream(cur)
+        for t in range(Kr):
+            for s_, r in zip(streams, ranges):
+                with torch.cuda.stream(s_):
+                    env.rollout_policy(pf, seed=ACTION_SEED, t=W + t, out=out, env_range=r if len(ranges) > 1 else None)
+                    env.step(out[0], env_range=r if len(ranges) > 1 else None)
+        for s_ in streams:
+            cur.wait_stream(s_)
+    gs.replay()
+    ctx.barrier()
+    r0.record(); gs.replay(); r1.record()
+    ctx.barrier()
+    mss = ctx.max_over_ranks(r0.elapsed_time(r1))
+    split = {"value": n * world * Kr / (mss * 1e-3), "unit": "env-steps/s", "steps": Kr, "ms_per_step": mss / Kr,
+             "launches_per_step": 2 * len(ranges), "streams": len(ranges),
+             "what": "per env-step: msort_rollout_policy (the fused kernel's policy half as its own kernel, tiles by TMA) + fused step()"}
+    fused = {"value": n * world * Kr / (msf * 1e-3), "unit": "env-steps/s", "steps": Kr, "ms_per_step": msf / Kr, "launches_per_step": 1}
+    if mss < msf:
+        return dict(split, variant="split", fused_one_kernel=fused, two_kernels_r01=two)
     return {"value": n * world * Kr / (msf * 1e-3), "unit": "env-steps/s", "steps": Kr, "ms_per_step": msf / Kr,
-            "launches_per_step": 1, "streams": 1, "variant": env.step_variant,
+            "launches_per_step": 1, "streams": 1, "variant": env.step_variant, "split": split,
             "what": "per env-step ONE kernel (msort_rollout_step): fused step() + the next step's actor-critic forward "
                     "(29-32-32-{22|1}, tcgen05) and masked categorical draw on the observation tile still in shared memory; "
                     "one msort_policy_act per rollout for the first action",

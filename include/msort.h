@@ -435,6 +435,12 @@ int msort_ppo_update(const msort_ppo_batch_t* batch, const msort_ppo_hparams_t* 
  *  seed, t, deterministic : as msort_policy_act (MSORT_OPT_DRAW_COUNTER is added to t the same way). */
 #define MSORT_ROLLOUT_WEIGHTS 2688
 int msort_rollout_pack(const float* params, uint32_t* packed, void* stream);
+/* The policy half alone on given observations / masks ([N,29] f32, [N,22] u8): what msort_policy_act computes, with the
+ * fused kernel's arithmetic and weights format (one CTA per 128 envs, 8 CTAs per SM; TMA tiles need 16-byte aligned tensors,
+ * others take plain loads).  first_env / num_envs select a range (first_env a multiple of 128) of whole-batch tensors. */
+int msort_rollout_policy(msort_t* h, int64_t first_env, int64_t num_envs, const float* obs, const uint8_t* mask,
+                         const uint32_t* packed, uint64_t seed, uint32_t t, int deterministic, int64_t* actions, float* logp,
+                         float* value, void* stream);
 int msort_rollout_step(msort_t* h, void* state, const int64_t* actions, float* obs, float* reward, uint8_t* terminated,
                        uint8_t* mask, const msort_info_out_t* info, const uint32_t* packed, uint64_t seed, uint32_t t,
                        int deterministic, int64_t* next_actions, float* next_logp, float* next_value, void* stream);

@@ -378,6 +378,29 @@ class BatchedEnv:
         _abi.check(self.lib, rc, "msort_rollout_pack")
         return out
 
+    def rollout_policy(self, packed: torch.Tensor, seed: int = 0, t: int = 0, deterministic: bool = False,
+                       obs: torch.Tensor | None = None, mask: torch.Tensor | None = None, out=None,
+                       env_range: tuple[int, int] | None = None):
+        """`policy_act` in the fused kernel's arithmetic and weights format (`rollout_pack`): actor-critic forward + masked
+        categorical draw for every env of Env_3 (`msort_rollout_policy`: one CTA per 128 envs, 8 CTAs per SM).  Returns
+        (actions int64 [N], log-prob f32 [N], value f32 [N])."""
+        obs = self.obs if obs is None else obs
+        mask = self.mask if mask is None else mask
+        if not (obs.is_contiguous() and mask.is_contiguous() and packed.is_contiguous()):
+            raise ValueError("rollout_policy needs contiguous tensors")
+        if out is None:
+            out = (torch.empty(self.num_envs, dtype=torch.int64, device=self.device),
+                   torch.empty(self.num_envs, dtype=torch.float32, device=self.device),
+                   torch.empty(self.num_envs, dtype=torch.float32, device=self.device))
+        a, lp, v = out
+        first, stop = (0, self.num_envs) if env_range is None else (int(env_range[0]), int(env_range[1]))
+        with torch.cuda.device(self.device):
+            rc = self.lib.msort_rollout_policy(self._h, first, stop - first, _ptr(obs), _ptr(mask), _ptr(packed),
+                                               int(seed) & 0xFFFFFFFFFFFFFFFF, int(t) & 0xFFFFFFFF, 1 if deterministic else 0,
+                                               _ptr(a), _ptr(lp), _ptr(v), self._stream())
+        _abi.check(self.lib, rc, "msort_rollout_policy")
+        return a, lp, v
+
     def rollout_step(self, actions: torch.Tensor, packed: torch.Tensor, seed: int, t: int, next_out,
                      out_obs: torch.Tensor | None = None, out_mask: torch.Tensor | None = None, deterministic: bool = False):
         """One env-step of the MaskablePPO rollout loop as ONE kernel (`msort_rollout_step`; Env_3, training configuration):

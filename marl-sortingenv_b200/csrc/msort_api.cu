@@ -505,6 +505,24 @@ extern "C" int msort_rollout_pack(const float* params, uint32_t* packed, void* s
   return MSORT_OK;
 }
 
+extern "C" int msort_rollout_policy(msort_t* h, int64_t first_env, int64_t num_envs, const float* obs, const uint8_t* mask,
+                                    const uint32_t* packed, uint64_t seed, uint32_t t, int deterministic, int64_t* actions, float* logp,
+                                    float* value, void* stream) {
+  if (!h || !obs || !mask || !packed || !actions || !logp || !value) return fail(MSORT_E_INVALID, "msort_rollout_policy: NULL argument");
+  if (h->dev.kind != MSORT_ENV_MONO) return fail(MSORT_E_UNSUPPORTED, "msort_rollout_policy: Env_3_Monolith (29 observations, 22 actions) only");
+  if (!aligned(obs, 4) || !aligned(packed, 16) || !aligned(actions, 8) || !aligned(logp, 4) || !aligned(value, 4))
+    return fail(MSORT_E_INVALID, "msort_rollout_policy: misaligned buffer");
+  if (first_env < 0 || num_envs <= 0 || first_env + num_envs > h->dev.n || first_env % kTile != 0)
+    return fail(MSORT_E_INVALID, "msort_rollout_policy: range must lie inside the batch and start on a multiple of %d envs", kTile);
+  DevConfig d = h->dev;
+  d.n = num_envs; d.gid0 += first_env;
+  MSORT_TRY_CUDA(launch_rollout_policy(d, obs + first_env * 29, mask + first_env * 22, packed, seed, t, h->draw_counter, deterministic,
+                                       actions + first_env, logp + first_env, value + first_env, (cudaStream_t)stream),
+                 "rollout policy kernel");
+  h->launches += 1;
+  return MSORT_OK;
+}
+
 extern "C" int msort_rollout_step(msort_t* h, void* state, const int64_t* actions, float* obs, float* reward, uint8_t* terminated,
                                   uint8_t* mask, const msort_info_out_t* info, const uint32_t* packed, uint64_t seed, uint32_t t,
                                   int deterministic, int64_t* next_actions, float* next_logp, float* next_value, void* stream) {

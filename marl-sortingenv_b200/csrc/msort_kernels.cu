@@ -477,6 +477,224 @@ __device__ __forceinline__ void fused_issue(uint32_t a_saddr, uint32_t w_saddr, 
                   bbase + (uint64_t)(((uint32_t)(2 * s) * N * 16u) >> 4), umma::idesc_f16(N), s > 0 ? 1u : 0u);
 }
 
+// The policy half of the rollout for one tile of 128 envs (thread = env = TMEM lane); shared by the fused step kernel (FUSE)
+// and the stand-alone rollout_policy_kernel.  On entry: every thread holds its layer-1 operand words `a1` (fp16 pairs: K 0..28 =
+// obs, K 29 = 1.0, K 30..31 = 0) and its 22-bit action mask `m22`; the 16 KB operand buffer `tile_raw` is free (a CTA barrier
+// has passed since its last reader); the weights' TMA completes on `wbar` (phase 0); `tmem_slot` holds the base of 64 TMEM
+// columns (allocated before a CTA barrier).  Contains CTA barriers: all 128 threads call it.
+struct PolicyOut {
+  long long* actions; float* logp; float* value;       // indexed by the tile-local row base the caller applied
+  unsigned key0, key1, t; const unsigned* t_dev; int deterministic;
+};
+__device__ __forceinline__ void rollout_policy_tile(unsigned char* tile_raw, const uint32_t* wsm, uint64_t* wbar, uint64_t* mmabar,
+                                                    const uint32_t* tmem_slot, const uint32_t (&a1)[16], uint32_t m22, bool live,
+                                                    long long i, long long gid, int tid, const PolicyOut& p, uint32_t& tmem_out) {
+  constexpr int A = 22;
+    uint4* const A4 = reinterpret_cast<uint4*>(tile_raw);   // chunk kc (8 K values) of row r at (kc * 128 + r) * 16 B
+#pragma unroll
+    for (int kc = 0; kc < 4; ++kc) A4[kc * kTile + tid] = make_uint4(a1[4 * kc], a1[4 * kc + 1], a1[4 * kc + 2], a1[4 * kc + 3]);
+    mbar_wait(wbar, 0u);                   // the weights (their fp32 part is read with plain loads below)
+    const uint32_t a_saddr = smem_u32(tile_raw), w_saddr = smem_u32(wsm);
+    const float* const fw = reinterpret_cast<const float*>(wsm);
+    umma::fence_async_proxy();
+    __syncthreads();
+    umma::fence_after_sync();                 // (also orders the TMEM allocation before the first use of its address)
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tlane = tmem + ((uint32_t)(tid & ~31) << 16);
+    // ---- layer 1: both towers, N = 64
+    if (tid == 0) { fused_issue<64>(a_saddr, w_saddr, 0, kFwB1, tmem, 0); umma::commit(mmabar); }
+    mbar_wait(mmabar, 0u);
+    umma::fence_after_sync();
+    // (the epilogue loops stay rolled on purpose: the kernel is ~2 400 straight-line instructions per warp and seven CTAs
+    //  sit at different places of it — instruction fetch is a measured stall here, `no_instruction` in profiles/ncu_r02_fused.md)
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {             // 64 hidden units -> tanh -> chunks 0..3 (policy tower), 4..7 (value tower)
+      float v[16];
+      umma::tmem_ld16(tlane + 16u * q, v);
+      uint32_t h[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h[j] = pack_h2(tanh_mufu(v[2 * j]), tanh_mufu(v[2 * j + 1]));
+      A4[(2 * q) * kTile + tid] = make_uint4(h[0], h[1], h[2], h[3]);
+      A4[(2 * q + 1) * kTile + tid] = make_uint4(h[4], h[5], h[6], h[7]);
+    }
+    umma::fence_async_proxy();
+    umma::fence_before_sync();
+    __syncthreads();
+    // ---- layer 2: one [32 x 32] product per tower
+    if (tid == 0) {
+      umma::fence_after_sync();
+      fused_issue<32>(a_saddr, w_saddr, 0, kFwB2p, tmem, 0);
+      fused_issue<32>(a_saddr, w_saddr, 4, kFwB2v, tmem, 32);
+      umma::commit(mmabar);
+    }
+    mbar_wait(mmabar, 1u);
+    umma::fence_after_sync();
+#pragma unroll 1
+    for (int q = 0; q < 2; ++q) {             // policy tower: + bias (LDS.128 broadcasts, packed adds) -> tanh -> chunks 0..3
+      float v[16];
+      umma::tmem_ld16(tlane + 16u * q, v);
+      uint32_t h[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 bb = *reinterpret_cast<const float4*>(fw + kFwBias2 + 16 * q + 4 * j);
+        float z0, z1, z2, z3;
+        umma::fadd2(v[4 * j], v[4 * j + 1], bb.x, bb.y, z0, z1);
+        umma::fadd2(v[4 * j + 2], v[4 * j + 3], bb.z, bb.w, z2, z3);
+        h[2 * j] = pack_h2(tanh_mufu(z0), tanh_mufu(z1));
+        h[2 * j + 1] = pack_h2(tanh_mufu(z2), tanh_mufu(z3));
+      }
+      A4[(2 * q) * kTile + tid] = make_uint4(h[0], h[1], h[2], h[3]);
+      A4[(2 * q + 1) * kTile + tid] = make_uint4(h[4], h[5], h[6], h[7]);
+    }
+    float value = fw[kFwBias3 + 31];
+#pragma unroll 1
+    for (int q = 2; q < 4; ++q) {             // value tower: + bias -> tanh -> the value head's 32 MACs, in fp32
+      float v[16];
+      umma::tmem_ld16(tlane + 16u * q, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 bb = *reinterpret_cast<const float4*>(fw + kFwBias2 + 16 * q + 4 * j);
+        const float4 ww = *reinterpret_cast<const float4*>(fw + kFwW3v + 16 * (q - 2) + 4 * j);
+        float z0, z1, z2, z3;
+        umma::fadd2(v[4 * j], v[4 * j + 1], bb.x, bb.y, z0, z1);
+        umma::fadd2(v[4 * j + 2], v[4 * j + 3], bb.z, bb.w, z2, z3);
+        value = fmaf(tanh_mufu(z0), ww.x, value);
+        value = fmaf(tanh_mufu(z1), ww.y, value);
+        value = fmaf(tanh_mufu(z2), ww.z, value);
+        value = fmaf(tanh_mufu(z3), ww.w, value);
+      }
+    }
+    umma::fence_async_proxy();
+    umma::fence_before_sync();
+    __syncthreads();
+    // ---- layer 3: the 22 logits
+    if (tid == 0) { umma::fence_after_sync(); fused_issue<32>(a_saddr, w_saddr, 0, kFwB3, tmem, 0); umma::commit(mmabar); }
+    mbar_wait(mmabar, 0u);
+    umma::fence_after_sync();
+    {
+      float o[32];
+      umma::tmem_ld16(tlane, *reinterpret_cast<float(*)[16]>(&o[0]));
+      umma::tmem_ld16(tlane + 16u, *reinterpret_cast<float(*)[16]>(&o[16]));
+      umma::fence_before_sync();              // TMEM reads done before the columns are given back
+      if (live) {
+        // masked log-softmax (sb3_contrib masks logits with -1e8 = probability 0 in fp32: here -inf; action a of Env_3 is
+        // valid iff press action a % 11 is).  Everything in the exp2 domain: p_k ~ 2^((l_k - max) log2 e), 2^-inf = 0.
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k4 = 0; k4 < 6; ++k4) {
+          const float4 bb = *reinterpret_cast<const float4*>(fw + kFwBias3 + 4 * k4);
+          const float bk[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int k = 4 * k4 + j;
+            if (k < A) {
+              o[k] = ((m22 >> k) & 1u) ? o[k] + bk[j] : -INFINITY;
+              mx = fmaxf(mx, o[k]);
+            }
+          }
+        }
+        const float nmx = -mx * 1.4426950408889634f;
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < A; ++k) {
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(o[k]) : "f"(fmaf(o[k], 1.4426950408889634f, nmx)));   // unnormalised probability
+          sum += o[k];
+        }
+        int na = 0;
+        float pa = 0.f;
+        if (p.deterministic) {
+#pragma unroll
+          for (int k = 0; k < A; ++k) if (o[k] > pa) { pa = o[k]; na = k; }
+        } else {   // inverse-CDF draw with one Philox uniform keyed by (seed, draw index, global env id) — msort_policy_act's draw
+          const unsigned long long g = (unsigned long long)gid;
+          const unsigned dt = p.t + (p.t_dev ? *p.t_dev : 0u);
+          const U4 r4 = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), 0xAC70u, dt, p.key0, p.key1);
+          // uniform in (0, sum), kept strictly below sum (the cdf's last value is bit-identical to `sum`: same order of adds),
+          // so the first k with cdf_k > u always exists and has p_k > 0
+          const float u = fminf(((float)(r4.x >> 8) + 0.5f) * (1.0f / 16777216.0f) * sum, sum * 0.99999994f);
+          float cdf = 0.f;
+          bool found = false;
+#pragma unroll
+          for (int k = 0; k < A; ++k) {
+            if (!found) { na = k; pa = o[k]; }
+            cdf += o[k];
+            found = found || cdf > u;
+          }
+        }
+        p.actions[i] = na;
+        p.logp[i] = (__log2f(pa) - __log2f(sum)) * 0.6931471805599453f;
+        p.value[i] = value;
+      }
+    }
+  tmem_out = tmem;
+}
+
+// The policy half alone (msort_rollout_policy): the rollout's first action, and the two-kernel form of the loop.  One CTA =
+// one tile of 128 envs: the weights and the observation tile (14.5 KB, contiguous in the [N, 29] tensor) arrive by TMA bulk
+// copies, the 22 mask bytes of each env by eleven 2-byte loads of its own thread (no mask tile: 26.6 KB per CTA = 8 CTAs per
+// SM); each thread turns its row into the layer-1 operand words and its mask bytes into bits; the observation tile's space
+// then becomes the operand buffer, exactly as in the fused kernel.
+__global__ void __launch_bounds__(kTile, 8)
+rollout_policy_kernel(const float* __restrict__ obs, const uint8_t* __restrict__ mask, const uint4* __restrict__ packed, long long n,
+                      long long gid0, const __grid_constant__ PolicyOut po) {
+  constexpr int D = 29, A = 22;
+  __shared__ __align__(128) unsigned char s_tile_raw[8 * kTile * 16];
+  __shared__ __align__(128) uint32_t s_w[kFwWords];
+  __shared__ __align__(8) uint64_t s_wbar, s_mma, s_in;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x;
+  const long long row0 = (long long)blockIdx.x * kTile, i = row0 + tid;
+  const int rows = (int)min((long long)kTile, n - row0);
+  const bool live = i < n;
+  float* const s_obs = reinterpret_cast<float*>(s_tile_raw);
+  // TMA needs 16-byte aligned global addresses: whole tiles of 16-byte aligned tensors (tile sizes are multiples of 16 B)
+  const bool by_tma = rows == kTile && (reinterpret_cast<uintptr_t>(obs) & 15u) == 0;
+  if (tid == 0) {
+    mbar_init(&s_wbar, 1); mbar_init(&s_mma, 1); mbar_init(&s_in, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (by_tma) {
+      mbar_expect_tx(&s_in, (uint32_t)(kTile * D * 4));
+      bulk_load(s_obs, obs + row0 * D, kTile * D * 4u, &s_in);
+    }
+    mbar_expect_tx(&s_wbar, kFwWords * 4u);
+    bulk_load(s_w, packed, kFwWords * 4u, &s_wbar);
+  }
+  if (tid < 32) { __syncwarp(); umma::tmem_alloc(&s_tmem, 64u); umma::fence_before_sync(); }
+  if (!by_tma) {   // ragged last tile / unaligned tensor: plain loads
+    for (int e = tid; e < kTile * D; e += kTile) s_obs[e] = e < rows * D ? obs[row0 * D + e] : 0.f;
+  }
+  uint32_t a1[16], m22 = 0;
+  if (live) {      // this env's 22 mask bytes -> bits (rows are 2-byte aligned when the tensor is; else byte loads)
+    const uint8_t* mrow = mask + i * A;
+    if ((reinterpret_cast<uintptr_t>(mask) & 1u) == 0) {
+      const uint16_t* mr = reinterpret_cast<const uint16_t*>(mrow);
+#pragma unroll
+      for (int k = 0; k < A / 2; ++k) {
+        const uint32_t w = mr[k];
+        m22 |= ((w & 0xffu) ? 1u : 0u) << (2 * k) | ((w >> 8) ? 1u : 0u) << (2 * k + 1);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < A; ++k) m22 |= (mrow[k] ? 1u : 0u) << k;
+    }
+  }
+  __syncthreads();                            // barrier inits / plain loads / the TMEM address are visible
+  if (by_tma) mbar_wait(&s_in, 0u);
+  {
+    const float* x = &s_obs[tid * D];
+#pragma unroll
+    for (int q = 0; q < 14; ++q) a1[q] = pack_h2(x[2 * q], x[2 * q + 1]);
+    a1[14] = pack_h2(x[28], 1.0f);
+    a1[15] = 0u;
+  }
+  __syncthreads();                            // every row has been read: the tile's space becomes the operand buffer
+  uint32_t tmem = 0;
+  PolicyOut p = po;
+  rollout_policy_tile(s_tile_raw, s_w, &s_wbar, &s_mma, &s_tmem, a1, m22, live, i, gid0 + i, tid, p, tmem);
+  __syncthreads();
+  if (tid < 32) umma::tmem_dealloc(tmem, 64u);
+}
+
 // FAST (PHILOX only, chosen by the host when DevConfig::fast holds): boosted accuracies are exactly 1.0,
 // unboosted ones need no clip, and the redistribution classes fit one register of packed bytes.
 // Results are identical to the generic instantiation; only the instruction count differs.
@@ -1246,120 +1464,10 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     // (2) the operand buffer aliases the observation tile: its bulk store must have read it out first
     if (rows == kTile && tid == kStoreTid) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncthreads();
-    uint4* const A4 = reinterpret_cast<uint4*>(s_tile_raw);   // chunk kc (8 K values) of row r at (kc * 128 + r) * 16 B
-#pragma unroll
-    for (int kc = 0; kc < 4; ++kc) A4[kc * kTile + tid] = make_uint4(a1[4 * kc], a1[4 * kc + 1], a1[4 * kc + 2], a1[4 * kc + 3]);
-    mbar_wait(&s_wbar, 0u);                   // the weights (their fp32 part is read with plain loads below)
-    const uint32_t a_saddr = smem_u32(s_tile_raw), w_saddr = smem_u32(s_tcw);
-    const float* const fw = reinterpret_cast<const float*>(s_tcw);
-    umma::fence_async_proxy();
-    __syncthreads();
-    umma::fence_after_sync();                 // (also orders the TMEM allocation before the first use of its address)
-    const uint32_t tmem = s_tmem;
-    const uint32_t tlane = tmem + ((uint32_t)(tid & ~31) << 16);
-    // ---- layer 1: both towers, N = 64
-    if (tid == 0) { fused_issue<64>(a_saddr, w_saddr, 0, kFwB1, tmem, 0); umma::commit(&s_mma); }
-    mbar_wait(&s_mma, 0u);
-    umma::fence_after_sync();
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {             // 64 hidden units -> tanh -> chunks 0..3 (policy tower), 4..7 (value tower)
-      float v[16];
-      umma::tmem_ld16(tlane + 16u * q, v);
-      uint32_t h[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) h[j] = pack_h2(tanh_mufu(v[2 * j]), tanh_mufu(v[2 * j + 1]));
-      A4[(2 * q) * kTile + tid] = make_uint4(h[0], h[1], h[2], h[3]);
-      A4[(2 * q + 1) * kTile + tid] = make_uint4(h[4], h[5], h[6], h[7]);
-    }
-    umma::fence_async_proxy();
-    umma::fence_before_sync();
-    __syncthreads();
-    // ---- layer 2: one [32 x 32] product per tower
-    if (tid == 0) {
-      umma::fence_after_sync();
-      fused_issue<32>(a_saddr, w_saddr, 0, kFwB2p, tmem, 0);
-      fused_issue<32>(a_saddr, w_saddr, 4, kFwB2v, tmem, 32);
-      umma::commit(&s_mma);
-    }
-    mbar_wait(&s_mma, 1u);
-    umma::fence_after_sync();
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {             // policy tower: + bias -> tanh -> chunks 0..3
-      float v[16];
-      umma::tmem_ld16(tlane + 16u * q, v);
-      uint32_t h[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float2 bb = *reinterpret_cast<const float2*>(fw + kFwBias2 + 16 * q + 2 * j);
-        h[j] = pack_h2(tanh_mufu(v[2 * j] + bb.x), tanh_mufu(v[2 * j + 1] + bb.y));
-      }
-      A4[(2 * q) * kTile + tid] = make_uint4(h[0], h[1], h[2], h[3]);
-      A4[(2 * q + 1) * kTile + tid] = make_uint4(h[4], h[5], h[6], h[7]);
-    }
-    float value = fw[kFwBias3 + 31];
-#pragma unroll
-    for (int q = 2; q < 4; ++q) {             // value tower: + bias -> tanh -> the value head's 32 MACs, in fp32
-      float v[16];
-      umma::tmem_ld16(tlane + 16u * q, v);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float2 bb = *reinterpret_cast<const float2*>(fw + kFwBias2 + 16 * q + 2 * j);
-        const float2 ww = *reinterpret_cast<const float2*>(fw + kFwW3v + 16 * (q - 2) + 2 * j);
-        value = fmaf(tanh_mufu(v[2 * j] + bb.x), ww.x, value);
-        value = fmaf(tanh_mufu(v[2 * j + 1] + bb.y), ww.y, value);
-      }
-    }
-    umma::fence_async_proxy();
-    umma::fence_before_sync();
-    __syncthreads();
-    // ---- layer 3: the 22 logits
-    if (tid == 0) { umma::fence_after_sync(); fused_issue<32>(a_saddr, w_saddr, 0, kFwB3, tmem, 0); umma::commit(&s_mma); }
-    mbar_wait(&s_mma, 0u);
-    umma::fence_after_sync();
+    uint32_t tmem = 0;
     {
-      float o[32];
-      umma::tmem_ld16(tlane, *reinterpret_cast<float(*)[16]>(&o[0]));
-      umma::tmem_ld16(tlane + 16u, *reinterpret_cast<float(*)[16]>(&o[16]));
-      umma::fence_before_sync();              // TMEM reads done before the columns are given back
-      if (live) {
-        // masked log-softmax (sb3_contrib masks logits with -1e8; action a of Env_3 is valid iff press action a % 11 is)
-        float mx = -3.0e38f;
-#pragma unroll
-        for (int k = 0; k < A; ++k) {
-          o[k] = ((mbits >> (k % 11)) & 1u) ? o[k] + fw[kFwBias3 + k] : -1e8f;
-          mx = fmaxf(mx, o[k]);
-        }
-        float sum = 0.f;
-#pragma unroll
-        for (int k = 0; k < A; ++k) { o[k] = __expf(o[k] - mx); sum += o[k]; }   // o[k]: unnormalised probability
-        int na = 0;
-        if (a.deterministic) {
-          float best = -1.f;
-#pragma unroll
-          for (int k = 0; k < A; ++k) if (o[k] > best) { best = o[k]; na = k; }
-        } else {   // inverse-CDF draw with one Philox uniform keyed by (seed, draw index, global env id) — msort_policy_act's draw
-          const unsigned long long g = (unsigned long long)(c.gid0 + i);
-          const unsigned dt = a.draw_t + (a.draw_t_dev ? *a.draw_t_dev : 0u);
-          const U4 r4 = philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), 0xAC70u, dt, a.draw_key0, a.draw_key1);
-          const float u = ((float)(r4.x >> 8) + 0.5f) * (1.0f / 16777216.0f) * sum;   // uniform in (0, sum)
-          float cdf = 0.f;
-          int last = 0;
-          bool found = false;
-#pragma unroll
-          for (int k = 0; k < A; ++k) {
-            cdf += o[k];
-            if (o[k] > 0.f) last = k;
-            if (!found && u < cdf && o[k] > 0.f) { na = k; found = true; }
-          }
-          if (!found) na = last;
-        }
-        float pa = 0.f;
-#pragma unroll
-        for (int k = 0; k < A; ++k) if (k == na) pa = o[k];
-        a.next_actions[i] = na;
-        a.next_logp[i] = __logf(pa) - __logf(sum);
-        a.next_value[i] = value;
-      }
+      const PolicyOut po{a.next_actions, a.next_logp, a.next_value, a.draw_key0, a.draw_key1, a.draw_t, a.draw_t_dev, a.deterministic};
+      rollout_policy_tile(s_tile_raw, s_tcw, &s_wbar, &s_mma, &s_tmem, a1, mbits | (mbits << 11), live, i, c.gid0 + i, tid, po, tmem);
     }
     __syncthreads();
     if (tid < 32) umma::tmem_dealloc(tmem, 64u);
@@ -1925,6 +2033,15 @@ cudaError_t launch_step(const DevConfig& c, const StepLaunch& l, int rng, cudaSt
     case MSORT_ENV_PRESS: return launch_step_kind<MSORT_ENV_PRESS>(c, a, l.policy_host, rng, st, l.variant, l.allow_hot, l.persist_per_sm);
     default: return launch_step_kind<MSORT_ENV_MONO>(c, a, l.policy_host, rng, st, l.variant, l.allow_hot, l.persist_per_sm);
   }
+}
+
+cudaError_t launch_rollout_policy(const DevConfig& c, const float* obs, const uint8_t* mask, const uint32_t* packed, uint64_t seed,
+                                  uint32_t t, const uint32_t* t_dev, int deterministic, int64_t* actions, float* logp, float* value,
+                                  cudaStream_t st) {
+  if (c.n <= 0) return cudaSuccess;
+  const PolicyOut po{(long long*)actions, logp, value, (unsigned)(seed & 0xffffffffu), (unsigned)(seed >> 32), t, t_dev, deterministic};
+  rollout_policy_kernel<<<tiles(c.n), kTile, 0, st>>>(obs, mask, reinterpret_cast<const uint4*>(packed), c.n, c.gid0, po);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_pack_fused(const float* params, uint32_t* packed, cudaStream_t st) {

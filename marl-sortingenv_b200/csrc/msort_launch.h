@@ -44,6 +44,9 @@ bool pack_policy_tc(const float* sb3, uint32_t* words);    // ... -> the tensor-
 int policy_tc_words();                                     // size of that buffer in 32-bit words
 void query_persist_occupancy(int per_sm[4]);               // current device; index = SMALL + 2 * TCMLP
 cudaError_t launch_step(const DevConfig& c, const StepLaunch& l, int rng, cudaStream_t st);
+cudaError_t launch_rollout_policy(const DevConfig& c, const float* obs, const uint8_t* mask, const uint32_t* packed, uint64_t seed,
+                                  uint32_t t, const uint32_t* t_dev, int deterministic, int64_t* actions, float* logp, float* value,
+                                  cudaStream_t st);                                            // Env_3 (29, 22): the policy half alone
 cudaError_t launch_pack_fused(const float* params, uint32_t* packed, cudaStream_t st);   // flat fp32 parameters -> MSORT_ROLLOUT_WEIGHTS words
 cudaError_t launch_tc_logits(const float* obs13, const uint32_t* tcw, long long n, float* logits, int sm_count, cudaStream_t st);
 cudaError_t launch_reset(const DevConfig& c, void* state, const uint8_t* which, const uint8_t* first_pattern,

@@ -127,6 +127,10 @@ class MaskablePPO:
         # Env_3 in its training configuration: step + the next step's policy as one kernel per env-step (msort_rollout_step)
         # (the library refuses configurations outside its HOT instantiation: the first rollout then falls back, see _rollout_body)
         self.fused_rollout = fused_rollout and self.fused_act and getattr(env, "kind", "") == "mono" and hasattr(env, "rollout_step")
+        # ... or as two kernels per env-step with the same arithmetic (msort_rollout_policy + msort_step): `fused_rollout="split"`
+        self.split_rollout = fused_rollout == "split" and self.fused_rollout
+        if self.split_rollout:
+            self.fused_rollout = False
         self.flat = flatten_parameters(self.policy)
         self.opt = torch.optim.Adam(self.policy.parameters(), lr=learning_rate, eps=1e-5)
         self.lr = learning_rate
@@ -187,7 +191,8 @@ class MaskablePPO:
             # Reward / done go straight into their buffer slots (the env's output pointers are aimed at them).
             T = self.n_steps
             env.rollout_pack(self.flat, out=self._packed_fused)
-            env.policy_act(packed, seed=self.seed, t=t0, obs=b["obs"][0], mask=b["mask"][0], out=(b["act"][0], b["logp"][0], b["val"][0]))
+            env.rollout_policy(self._packed_fused, seed=self.seed, t=t0, obs=b["obs"][0], mask=b["mask"][0],
+                               out=(b["act"][0], b["logp"][0], b["val"][0]))
             keep = (env.reward, env.terminated)
             for t in range(T):
                 last = t + 1 == T
@@ -206,6 +211,9 @@ class MaskablePPO:
             return
         cur = torch.cuda.current_stream(self.dev)
         streams = self._streams or [cur]
+        split = self.split_rollout                       # Env_3: the 128-thread policy kernel (msort_rollout_policy) + step
+        if split:
+            env.rollout_pack(self.flat, out=self._packed_fused)
         for s in self._streams:
             s.wait_stream(cur)
         for t in range(self.n_steps):
@@ -213,8 +221,12 @@ class MaskablePPO:
             for s, (lo, hi) in zip(streams, self._ranges):
                 with torch.cuda.stream(s):
                     rng = None if len(self._ranges) == 1 else (lo, hi)
-                    env.policy_act(packed, seed=self.seed, t=t0 + t, obs=b["obs"][t], mask=b["mask"][t],
-                                   out=(b["act"][t], b["logp"][t], b["val"][t]), env_range=rng)
+                    if split:
+                        env.rollout_policy(self._packed_fused, seed=self.seed, t=t0 + t, obs=b["obs"][t], mask=b["mask"][t],
+                                           out=(b["act"][t], b["logp"][t], b["val"][t]), env_range=rng)
+                    else:
+                        env.policy_act(packed, seed=self.seed, t=t0 + t, obs=b["obs"][t], mask=b["mask"][t],
+                                       out=(b["act"][t], b["logp"][t], b["val"][t]), env_range=rng)
                     env.step(b["act"][t], out_obs=oo, out_mask=om, env_range=rng)   # fused CUDA step (auto-reset inside)
                     b["rew"][t][lo:hi].copy_(env.reward[lo:hi]); b["done"][t][lo:hi].copy_(env.terminated[lo:hi])
         for s in self._streams:

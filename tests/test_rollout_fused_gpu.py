@@ -120,3 +120,54 @@ def test_ppo_fused_rollout_buffers_replay_through_the_plain_step_kernel(graph):
     m2 = MaskablePPO(env2, n_steps=4, seed=3, graph_rollout=graph)
     m2.collect_rollout(); m2.collect_rollout()
     assert not m2.fused_rollout and m2.num_timesteps == 2 * 4 * 256
+
+
+@pytest.mark.parametrize("n", [128 * 7, 128 * 3 + 50])
+def test_standalone_policy_kernel_equals_the_fused_policy_half(n):
+    """msort_rollout_policy runs the very code of the fused kernel's policy half on tiles loaded from HBM: fed the observation /
+    mask the fused step wrote, it returns bit-identical actions, log-probs and values; ranges compose; unaligned views work."""
+    import torch
+    (fa, _), pol, flat, packed = _pair(n, seed=13)
+    pf = fa.rollout_pack(flat)
+    fa.reset()
+    a, lp, v = fa.rollout_policy(pf, seed=4, t=0)
+    with torch.no_grad():
+        ref = torch.log_softmax(pol.masked_logits(fa.obs, fa.mask), dim=-1)
+        assert torch.allclose(lp, ref.gather(1, a[:, None]).squeeze(1), atol=5e-3)
+        assert torch.allclose(v, pol.vf(fa.obs).squeeze(1), atol=5e-3, rtol=5e-3)
+    assert bool(fa.mask.gather(1, a[:, None]).all())
+    nxt = (torch.empty(n, dtype=torch.int64, device="cuda"), torch.empty(n, device="cuda"), torch.empty(n, device="cuda"))
+    for t in range(6):
+        fa.rollout_step(a, pf, 4, t + 1, nxt)
+        sa, slp, sv = fa.rollout_policy(pf, seed=4, t=t + 1)
+        assert torch.equal(sa, nxt[0]) and torch.equal(slp, nxt[1]) and torch.equal(sv, nxt[2]), t
+        a = nxt[0].clone()
+    # two ranges == the whole batch
+    out = (torch.empty(n, dtype=torch.int64, device="cuda"), torch.empty(n, device="cuda"), torch.empty(n, device="cuda"))
+    fa.rollout_policy(pf, seed=4, t=6, out=out, env_range=(0, 256)); fa.rollout_policy(pf, seed=4, t=6, out=out, env_range=(256, n))
+    assert torch.equal(out[0], sa) and torch.equal(out[1], slp)
+    # tensors that are not 16-byte aligned take the plain-load path
+    ob = torch.empty(n * 29 + 1, device="cuda")[1:].view(n, 29); ob.copy_(fa.obs)
+    mk = torch.empty(n * 22 + 1, dtype=torch.bool, device="cuda")[1:].view(n, 22); mk.copy_(fa.mask)
+    ua, ulp, uv = fa.rollout_policy(pf, seed=4, t=6, obs=ob, mask=mk)
+    assert torch.equal(ua, sa) and torch.equal(ulp, slp) and torch.equal(uv, sv)
+
+
+def test_ppo_split_rollout_equals_fused_rollout():
+    """fused_rollout="split" (msort_rollout_policy + msort_step per env-step, same arithmetic) fills the buffers exactly as the
+    one-kernel rollout does."""
+    import torch
+    import marl_sortingenv_b200 as ms
+    from marl_sortingenv_b200.ppo import MaskablePPO
+    runs = []
+    for mode in (True, "split"):
+        env = ms.BatchedMonolithEnv(128 * 10, max_steps=15, seed=6, info_level="none", track_stats=False)
+        model = MaskablePPO(env, n_steps=10, seed=2, fused_rollout=mode)
+        outs = [model.collect_rollout() for _ in range(3)]
+        torch.cuda.synchronize()
+        assert model.fused_rollout == (mode is True) and model.split_rollout == (mode == "split")
+        runs.append((model.buf, outs, env.state.clone()))
+    (b1, o1, s1), (b2, o2, s2) = runs
+    for k in b1:
+        assert torch.equal(b1[k], b2[k]), k
+    assert torch.equal(s1, s2) and all(torch.equal(x[0], y[0]) for x, y in zip(o1, o2))
