@@ -99,8 +99,8 @@ def ncu_traffic(kind: str, n: int):
         t = re.search(r"DRAM traffic = [\d.]+ \+ [\d.]+ = ([\d.]+) (\w+)", txt)
         if not (k and g and t):
             continue
-        kid = {"sort": "(int)1", "press": "(int)2", "mono": "(int)3"}[kind]
-        if not k.group(1).startswith(f"void msort::step_kernel<{kid}") and f"step_kernel<{kid}" not in k.group(1):
+        num = {"sort": 1, "press": 2, "mono": 3}[kind]                     # first template argument = the env kind
+        if not re.search(rf"step_kernel<(\(int\))?{num},", k.group(1)):
             continue
         if int(float(g.group(1))) != want_grid:
             continue
@@ -391,6 +391,8 @@ def roofline(kind, n, kern_ms, peak, peak_src, variant, launches_per_step, extra
     tr = ncu_traffic(kind, n)
     return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": tr["bytes"] if tr else None, "traffic_source": tr["source"] if tr else None,
+            "traffic_note": ("dram__bytes_read.sum + dram__bytes_write.sum of ONE isolated whole-batch launch of this kernel (ncu --set full, "
+                             "committed summary); the timed step issues the same work as `launches_per_step` env-range launches") if tr else None,
             "kernel": f"msort::step_kernel<{kind.upper()},PHILOX> [{variant} instantiation]",
             "kernel_ms": kern_ms, "launches_per_step": launches_per_step, "algorithmic_bytes_per_launch": algo,
             "bytes_per_env_step": ALGO_BYTES_PER_STEP[kind] + extra_bytes, "peak_source": peak_src}

@@ -486,24 +486,26 @@ struct PolicyOut {
   long long* actions; float* logp; float* value;       // indexed by the tile-local row base the caller applied
   unsigned key0, key1, t; const unsigned* t_dev; int deterministic;
 };
+struct PolicyPhase { uint32_t mma, w; };      // parities of the MMA barrier / "weights seen" flag across the tiles of a persistent CTA
+template <class AfterL3>
 __device__ __forceinline__ void rollout_policy_tile(unsigned char* tile_raw, const uint32_t* wsm, uint64_t* wbar, uint64_t* mmabar,
-                                                    const uint32_t* tmem_slot, const uint32_t (&a1)[16], uint32_t m22, bool live,
-                                                    long long i, long long gid, int tid, const PolicyOut& p, uint32_t& tmem_out) {
+                                                    uint32_t tmem, const uint32_t (&a1)[16], uint32_t m22, bool live,
+                                                    long long i, long long gid, int tid, const PolicyOut& p, PolicyPhase& ph,
+                                                    AfterL3 after_l3) {
   constexpr int A = 22;
     uint4* const A4 = reinterpret_cast<uint4*>(tile_raw);   // chunk kc (8 K values) of row r at (kc * 128 + r) * 16 B
 #pragma unroll
     for (int kc = 0; kc < 4; ++kc) A4[kc * kTile + tid] = make_uint4(a1[4 * kc], a1[4 * kc + 1], a1[4 * kc + 2], a1[4 * kc + 3]);
-    mbar_wait(wbar, 0u);                   // the weights (their fp32 part is read with plain loads below)
+    if (!ph.w) { mbar_wait(wbar, 0u); ph.w = 1u; }   // the weights (their fp32 part is read with plain loads below)
     const uint32_t a_saddr = smem_u32(tile_raw), w_saddr = smem_u32(wsm);
     const float* const fw = reinterpret_cast<const float*>(wsm);
     umma::fence_async_proxy();
     __syncthreads();
-    umma::fence_after_sync();                 // (also orders the TMEM allocation before the first use of its address)
-    const uint32_t tmem = *tmem_slot;
+    umma::fence_after_sync();
     const uint32_t tlane = tmem + ((uint32_t)(tid & ~31) << 16);
     // ---- layer 1: both towers, N = 64
     if (tid == 0) { fused_issue<64>(a_saddr, w_saddr, 0, kFwB1, tmem, 0); umma::commit(mmabar); }
-    mbar_wait(mmabar, 0u);
+    mbar_wait(mmabar, ph.mma); ph.mma ^= 1u;
     umma::fence_after_sync();
     // (the epilogue loops stay rolled on purpose: the kernel is ~2 400 straight-line instructions per warp and seven CTAs
     //  sit at different places of it — instruction fetch is a measured stall here, `no_instruction` in profiles/ncu_r02_fused.md)
@@ -527,7 +529,7 @@ __device__ __forceinline__ void rollout_policy_tile(unsigned char* tile_raw, con
       fused_issue<32>(a_saddr, w_saddr, 4, kFwB2v, tmem, 32);
       umma::commit(mmabar);
     }
-    mbar_wait(mmabar, 1u);
+    mbar_wait(mmabar, ph.mma); ph.mma ^= 1u;
     umma::fence_after_sync();
 #pragma unroll 1
     for (int q = 0; q < 2; ++q) {             // policy tower: + bias (LDS.128 broadcasts, packed adds) -> tanh -> chunks 0..3
@@ -569,8 +571,9 @@ __device__ __forceinline__ void rollout_policy_tile(unsigned char* tile_raw, con
     __syncthreads();
     // ---- layer 3: the 22 logits
     if (tid == 0) { umma::fence_after_sync(); fused_issue<32>(a_saddr, w_saddr, 0, kFwB3, tmem, 0); umma::commit(mmabar); }
-    mbar_wait(mmabar, 0u);
+    mbar_wait(mmabar, ph.mma); ph.mma ^= 1u;
     umma::fence_after_sync();
+    after_l3();                               // the operand buffer has been consumed: the caller may refill it
     {
       float o[32];
       umma::tmem_ld16(tlane, *reinterpret_cast<float(*)[16]>(&o[0]));
@@ -626,7 +629,6 @@ __device__ __forceinline__ void rollout_policy_tile(unsigned char* tile_raw, con
         p.value[i] = value;
       }
     }
-  tmem_out = tmem;
 }
 
 // The policy half alone (msort_rollout_policy): the rollout's first action, and the two-kernel form of the loop.  One CTA =
@@ -643,55 +645,81 @@ rollout_policy_kernel(const float* __restrict__ obs, const uint8_t* __restrict__
   __shared__ __align__(8) uint64_t s_wbar, s_mma, s_in;
   __shared__ uint32_t s_tmem;
   const int tid = threadIdx.x;
-  const long long row0 = (long long)blockIdx.x * kTile, i = row0 + tid;
-  const int rows = (int)min((long long)kTile, n - row0);
-  const bool live = i < n;
   float* const s_obs = reinterpret_cast<float*>(s_tile_raw);
-  // TMA needs 16-byte aligned global addresses: whole tiles of 16-byte aligned tensors (tile sizes are multiples of 16 B)
-  const bool by_tma = rows == kTile && (reinterpret_cast<uintptr_t>(obs) & 15u) == 0;
+  const long long ntiles = (n + kTile - 1) / kTile;
+  // TMA needs 16-byte aligned global addresses: whole tiles of a 16-byte aligned tensor (a tile is a multiple of 16 bytes)
+  const bool obs_aligned = (reinterpret_cast<uintptr_t>(obs) & 15u) == 0, mask_even = (reinterpret_cast<uintptr_t>(mask) & 1u) == 0;
+  auto tile_by_tma = [&](long long tl) { return obs_aligned && (tl + 1) * kTile <= n; };
+  auto fetch_obs = [&](long long tl) {      // one thread: the observation tile of `tl` into the (free) operand buffer
+    if (tl < ntiles && tile_by_tma(tl)) {
+      mbar_expect_tx(&s_in, (uint32_t)(kTile * D * 4));
+      bulk_load(s_obs, obs + tl * kTile * D, kTile * D * 4u, &s_in);
+    }
+  };
+  auto mask_bits = [&](long long tl) -> uint32_t {   // this thread's env of tile `tl`: its 22 mask bytes -> bits
+    const long long r = tl * kTile + tid;
+    uint32_t m = 0;
+    if (tl < ntiles && r < n) {
+      const uint8_t* mrow = mask + r * A;
+      if (mask_even) {                       // rows are 22 bytes: 2-byte aligned
+        const uint16_t* mr = reinterpret_cast<const uint16_t*>(mrow);
+#pragma unroll
+        for (int k = 0; k < A / 2; ++k) {
+          const uint32_t w = mr[k];
+          m |= ((w & 0xffu) ? 1u : 0u) << (2 * k) | ((w >> 8) ? 1u : 0u) << (2 * k + 1);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < A; ++k) m |= (mrow[k] ? 1u : 0u) << k;
+      }
+    }
+    return m;
+  };
   if (tid == 0) {
     mbar_init(&s_wbar, 1); mbar_init(&s_mma, 1); mbar_init(&s_in, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (by_tma) {
-      mbar_expect_tx(&s_in, (uint32_t)(kTile * D * 4));
-      bulk_load(s_obs, obs + row0 * D, kTile * D * 4u, &s_in);
-    }
+    fetch_obs(blockIdx.x);
     mbar_expect_tx(&s_wbar, kFwWords * 4u);
     bulk_load(s_w, packed, kFwWords * 4u, &s_wbar);
   }
   if (tid < 32) { __syncwarp(); umma::tmem_alloc(&s_tmem, 64u); umma::fence_before_sync(); }
-  if (!by_tma) {   // ragged last tile / unaligned tensor: plain loads
-    for (int e = tid; e < kTile * D; e += kTile) s_obs[e] = e < rows * D ? obs[row0 * D + e] : 0.f;
-  }
-  uint32_t a1[16], m22 = 0;
-  if (live) {      // this env's 22 mask bytes -> bits (rows are 2-byte aligned when the tensor is; else byte loads)
-    const uint8_t* mrow = mask + i * A;
-    if ((reinterpret_cast<uintptr_t>(mask) & 1u) == 0) {
-      const uint16_t* mr = reinterpret_cast<const uint16_t*>(mrow);
-#pragma unroll
-      for (int k = 0; k < A / 2; ++k) {
-        const uint32_t w = mr[k];
-        m22 |= ((w & 0xffu) ? 1u : 0u) << (2 * k) | ((w >> 8) ? 1u : 0u) << (2 * k + 1);
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < A; ++k) m22 |= (mrow[k] ? 1u : 0u) << k;
+  uint32_t m22 = mask_bits(blockIdx.x);
+  __syncthreads();                            // barrier inits and the TMEM address are visible
+  umma::fence_after_sync();
+  const uint32_t tmem = s_tmem;
+  PolicyPhase ph{0u, 0u};
+  uint32_t in_phase = 0;
+  // persistent: one wave of resident CTAs, each looping over tiles blockIdx.x, + gridDim.x, ...; the next tile's observations
+  // land in the operand buffer (and its mask bits in a register) while the current tile's softmax / draw epilogue runs
+  for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const long long row0 = tile * kTile, i = row0 + tid;
+    const int rows = (int)min((long long)kTile, n - row0);
+    const bool live = i < n;
+    if (tile_by_tma(tile)) { mbar_wait(&s_in, in_phase); in_phase ^= 1u; }
+    else {                                    // ragged last tile / unaligned tensor: plain loads (the buffer is free: barrier below)
+      for (int e = tid; e < kTile * D; e += kTile) s_obs[e] = e < rows * D ? obs[row0 * D + e] : 0.f;
+      __syncthreads();
     }
-  }
-  __syncthreads();                            // barrier inits / plain loads / the TMEM address are visible
-  if (by_tma) mbar_wait(&s_in, 0u);
-  {
-    const float* x = &s_obs[tid * D];
+    uint32_t a1[16];
+    {
+      const float* x = &s_obs[tid * D];
 #pragma unroll
-    for (int q = 0; q < 14; ++q) a1[q] = pack_h2(x[2 * q], x[2 * q + 1]);
-    a1[14] = pack_h2(x[28], 1.0f);
-    a1[15] = 0u;
+      for (int q = 0; q < 14; ++q) a1[q] = pack_h2(x[2 * q], x[2 * q + 1]);
+      a1[14] = pack_h2(x[28], 1.0f);
+      a1[15] = 0u;
+    }
+    __syncthreads();                          // every row has been read: the tile's space becomes the operand buffer
+    const long long next = tile + gridDim.x;
+    uint32_t m22_next = 0;
+    rollout_policy_tile(s_tile_raw, s_w, &s_wbar, &s_mma, tmem, a1, m22, live, i, gid0 + i, tid, po, ph,
+                        [&]() {               // after the layer-3 MMAs: the operand buffer is free again
+                          if (tid == 0) fetch_obs(next);
+                          m22_next = mask_bits(next);
+                        });
+    m22 = m22_next;
+    umma::fence_before_sync();
+    __syncthreads();                          // all TMEM reads of this tile are done before the next tile's first MMA
   }
-  __syncthreads();                            // every row has been read: the tile's space becomes the operand buffer
-  uint32_t tmem = 0;
-  PolicyOut p = po;
-  rollout_policy_tile(s_tile_raw, s_w, &s_wbar, &s_mma, &s_tmem, a1, m22, live, i, gid0 + i, tid, p, tmem);
-  __syncthreads();
   if (tid < 32) umma::tmem_dealloc(tmem, 64u);
 }
 
@@ -713,7 +741,7 @@ __global__ void __launch_bounds__(kTile, (KIND == MSORT_ENV_PRESS ? (TCMLP ? MSO
 step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArgs a,
             const __grid_constant__ PolicyParam<KIND> pw) {
   constexpr int D = Dims<KIND>::D, A = Dims<KIND>::A;
-  static_assert(!TCMLP || (KIND == MSORT_ENV_PRESS && HOT && MSORT_HOT_PERSIST && kTile == 128), "TCMLP specialises Env_2's persistent HOT kernel");
+  static_assert(!TCMLP || !MSORT_HOT_PERSIST || (KIND == MSORT_ENV_PRESS && HOT && kTile == 128), "TCMLP specialises Env_2's persistent HOT kernel");   // (MSORT_HOT_PERSIST=0 experiment builds never launch it)
   static_assert(!FUSE || (KIND == MSORT_ENV_MONO && HOT && kTile == 128), "FUSE specialises Env_3's HOT kernel");
   // obs tile; with TCMLP the 16 KB MMA A-operand buffer, whose first half the obs tile aliases (the operand is dead
   // once the last layer's MMAs are complete, long before the first obs entry of the tile is written)
@@ -1464,10 +1492,12 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     // (2) the operand buffer aliases the observation tile: its bulk store must have read it out first
     if (rows == kTile && tid == kStoreTid) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncthreads();
-    uint32_t tmem = 0;
+    // (the barrier inside rollout_policy_tile, before its first MMA, also orders the TMEM allocation before this read's use)
+    const uint32_t tmem = s_tmem;
     {
       const PolicyOut po{a.next_actions, a.next_logp, a.next_value, a.draw_key0, a.draw_key1, a.draw_t, a.draw_t_dev, a.deterministic};
-      rollout_policy_tile(s_tile_raw, s_tcw, &s_wbar, &s_mma, &s_tmem, a1, mbits | (mbits << 11), live, i, c.gid0 + i, tid, po, tmem);
+      PolicyPhase ph{0u, 0u};
+      rollout_policy_tile(s_tile_raw, s_tcw, &s_wbar, &s_mma, tmem, a1, mbits | (mbits << 11), live, i, c.gid0 + i, tid, po, ph, []() {});
     }
     __syncthreads();
     if (tid < 32) umma::tmem_dealloc(tmem, 64u);
@@ -2040,7 +2070,8 @@ cudaError_t launch_rollout_policy(const DevConfig& c, const float* obs, const ui
                                   cudaStream_t st) {
   if (c.n <= 0) return cudaSuccess;
   const PolicyOut po{(long long*)actions, logp, value, (unsigned)(seed & 0xffffffffu), (unsigned)(seed >> 32), t, t_dev, deterministic};
-  rollout_policy_kernel<<<tiles(c.n), kTile, 0, st>>>(obs, mask, reinterpret_cast<const uint4*>(packed), c.n, c.gid0, po);
+  const unsigned grid = std::min(tiles(c.n), (unsigned)(8 * c.sm_count));     // one wave of resident CTAs (26.6 KB, 64 registers: 8 per SM)
+  rollout_policy_kernel<<<grid, kTile, 0, st>>>(obs, mask, reinterpret_cast<const uint4*>(packed), c.n, c.gid0, po);
   return cudaGetLastError();
 }
 

@@ -129,8 +129,7 @@ class MaskablePPO:
         self.fused_rollout = fused_rollout and self.fused_act and getattr(env, "kind", "") == "mono" and hasattr(env, "rollout_step")
         # ... or as two kernels per env-step with the same arithmetic (msort_rollout_policy + msort_step): `fused_rollout="split"`
         self.split_rollout = fused_rollout == "split" and self.fused_rollout
-        if self.split_rollout:
-            self.fused_rollout = False
+        self._rollout_auto = fused_rollout is True
         self.flat = flatten_parameters(self.policy)
         self.opt = torch.optim.Adam(self.policy.parameters(), lr=learning_rate, eps=1e-5)
         self.lr = learning_rate
@@ -170,6 +169,13 @@ class MaskablePPO:
         per = -(-per // 128) * 128                                       # ranges start on whole 128-env tiles
         self._ranges = [(lo, min(self.n, lo + per)) for lo in range(0, self.n, per)] if self.fused_act else [(0, self.n)]
         self._streams = [torch.cuda.Stream(device=self.dev) for _ in self._ranges] if len(self._ranges) > 1 else []
+        # measured on one B200 (bench.py `rollout`, 1 048 576 envs): split on two streams 104 us per env-step, one fused kernel
+        # 117 us (its 2 100 straight-line instructions per warp stall on instruction fetch), r01's two kernels 127 us; small
+        # batches are launch-bound and take the one-kernel form
+        if self.fused_rollout and self._rollout_auto and len(self._ranges) > 1:
+            self.split_rollout = True
+        if self.split_rollout:
+            self.fused_rollout = False
 
     # ------------------------------------------------------------------ rollout
     def _batch(self, rows, obs, mask, act, logp=None, adv=None, ret=None):

@@ -29,6 +29,19 @@ def main():
         if w in hdr:
             i = hdr.index(w)
             print(f"| {w} | {units[i]} | " + " | ".join(r[i] for r in data) + " |")
+    for w in ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+              "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+              "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+              "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum",
+              "launch__occupancy_limit_shared_mem", "launch__shared_mem_per_block_static", "launch__waves_per_multiprocessor"):
+        if w in hdr:
+            i = hdr.index(w)
+            print(f"| {w} | {units[i]} | " + " | ".join(r[i] for r in data) + " |")
+    for k, r in enumerate(data):     # warp-state breakdown: average warps per issue slot in each stall state
+        st = sorted(((float(r[i]), h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""))
+                     for i, h in enumerate(hdr) if "smsp__average_warps_issue_stalled" in h and "per_issue_active" in h
+                     and "not_issued" not in h), reverse=True)
+        print(f"\nlaunch {k + 1}: warps per issue slot by state: " + ", ".join(f"{n} {v:.2f}" for v, n in st[:10]))
     rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
     for k, r in enumerate(data):
         print(f"\nlaunch {k + 1}: DRAM traffic = {float(r[rd]):.1f} + {float(r[wr]):.1f} = "
