@@ -796,13 +796,16 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     if (tid == kStageTid) {
       mbar_init(&s_full, 1);
       if (TCMLP) mbar_init(&s_mma, 1);
+      if (TCMLP) mbar_init(&s_wbar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       stage_tile(blockIdx.x);
+      if (TCMLP) {   // once per resident CTA: the packed weights by one TMA bulk copy (lands while the first tile is staged)
+        mbar_expect_tx(&s_wbar, kTcWords * 4u);
+        bulk_load(s_tcw, a.policy_tc, kTcWords * 4u, &s_wbar);
+      }
     }
-    if (TCMLP) {   // once per resident CTA: 32 TMEM columns (warp 0) and the packed weights
+    if (TCMLP) {   // ... and 32 TMEM columns (warp 0)
       if (tid < 32) umma::tmem_alloc(&s_tmem, 32u);
-      for (int e = tid; e < kTcWords / 4; e += kTile) reinterpret_cast<uint4*>(s_tcw)[e] = a.policy_tc[e];
-      umma::fence_async_proxy();
       umma::fence_before_sync();
     }
     __syncthreads();
@@ -819,6 +822,10 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     if (tid < 32) { __syncwarp(); umma::tmem_alloc(&s_tmem, 64u); umma::fence_before_sync(); }
   }
   uint32_t mbits = 0;   // FUSE: this env's press-mask bits for the policy phase
+  // TCMLP: the tile's actions come by plain loads issued one tile ahead (whole tiles only), the weights' TMA is awaited once
+  long long act_ahead = 0;
+  bool weights_seen = false;
+  if (TCMLP) act_ahead = a.actions[(long long)blockIdx.x * kTile + tid];
   long long tile = blockIdx.x;
   do {   // one pass unless PERSIST
   const long long row0 = tile * kTile;
@@ -847,7 +854,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   Env s;
   long long act = 0;
   if (PERSIST) {
-    if (TCMLP && live) act = a.actions[i];                                                 // in flight while the staged planes are awaited
+    if (TCMLP) act = act_ahead;
     mbar_wait(&s_full, phase); phase ^= 1u;
     if (live) {
       load_planes<LAYOUT>(s_in, kTile, tid, s);
@@ -974,9 +981,13 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
         purity_ks(c, s, kq);
         sort_obs(c, s, kq, so);
         if constexpr (TCMLP) {
+          if (!weights_seen) { mbar_wait(&s_wbar, 0u); weights_seen = true; }
           mode = tc_mlp_mode(tcm, so, tid, mma_phase);   // every thread of the (full) tile is here: CTA barriers inside
           // this thread has seen the layer-2 MMAs complete: the operand buffer is dead, its lo half takes the next tile
-          if (tid == kStageTid && tile + gridDim.x < ntiles) stage_tile(tile + gridDim.x);
+          if (tile + gridDim.x < ntiles) {
+            if (tid == kStageTid) stage_tile(tile + gridDim.x);
+            act_ahead = a.actions[(tile + gridDim.x) * kTile + tid];
+          }
         } else if constexpr (KIND == MSORT_ENV_PRESS) mode = mlp_sort_mode<HOT>(pw.w, so);
       } else {  // sorting_rules env_super.py:469-482: pA+pC > pB+pD on float64 proportions
         int ac = b4(s.belt4, 0) + b4(s.belt4, 2), bd = b4(s.belt4, 1) + b4(s.belt4, 3);
