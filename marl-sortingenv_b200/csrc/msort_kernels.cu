@@ -16,6 +16,9 @@
 #ifndef MSORT_PREFETCH_TILES
 #define MSORT_PREFETCH_TILES 296  // L2 prefetch distance of the step kernel in tiles (2 per SM; 0 = off): 148..518 measured alike, +3.4 %
 #endif
+#ifndef MSORT_TC_PERSIST
+#define MSORT_TC_PERSIST 0        // Env_2's tensor-core kernel: 0 = one CTA per tile (weights by TMA per CTA; measured 104.6 vs 109.7 us per 1 048 576 envs), 1 = persistent like the FFMA2 form
+#endif
 #ifndef MSORT_HOT_PERSIST
 #define MSORT_HOT_PERSIST 1       // Env_2's HOT step kernel: 1 = resident CTAs loop over tiles, next tile's state staged by TMA
 #endif
@@ -199,7 +202,9 @@ struct TcMlp {
   uint4* a;            // A operand: hi chunks [4][128] then lo chunks [4][128] (16 KB; the first 8 KB alias the obs tile)
   const uint32_t* w;   // packed weights in shared memory (kTcWords)
   uint64_t* bar;       // MMA completion
-  uint32_t tmem;       // base address of the 32 accumulator columns
+  uint32_t tmem;       // base address of the 32 accumulator columns ...
+  const uint32_t* tmem_slot = nullptr;   // ... or where the allocating warp left it (read after the first CTA barrier of the MLP)
+  uint64_t* wbar = nullptr;              // the weights' TMA barrier, awaited (phase 0) behind that barrier when given
 };
 
 __device__ __forceinline__ float tc_sigmoid2(float zp) {   // 1 / (1 + 2^zp); +inf -> 0, -inf -> 1
@@ -230,7 +235,7 @@ __device__ __forceinline__ void tc_sigmoid2x2(float z0, float z1, float& r0, flo
 
 // one thread: all split products of one layer, smallest terms first, then commit
 template <int KSTEPS, int N, int NTERMS>
-__device__ __forceinline__ void tc_issue_layer(const TcMlp& m, int b_off_halves) {
+__device__ __forceinline__ void tc_issue_layer(const TcMlp& m, uint32_t tmem, int b_off_halves) {
   const uint32_t a0 = smem_u32(m.a), b0 = smem_u32(m.w) + 2u * (uint32_t)b_off_halves;
   constexpr uint32_t kTermBytes = (uint32_t)(KSTEPS * 16 * N * 2), kLoBytes = 4u * kTile * 16u;
   // the descriptors of one layer differ only in the 14-bit start-address field (bytes >> 4; shared memory is < 256 KB, so
@@ -240,7 +245,7 @@ __device__ __forceinline__ void tc_issue_layer(const TcMlp& m, int b_off_halves)
   auto mm = [&](int aterm, int bterm, int s) {
     const uint64_t ad = abase + (uint64_t)(((aterm ? kLoBytes : 0u) + (uint32_t)(2 * s) * kTile * 16u) >> 4);
     const uint64_t bd = bbase + (uint64_t)(((uint32_t)bterm * kTermBytes + (uint32_t)(2 * s) * N * 16u) >> 4);
-    umma::mma_f16(m.tmem, ad, bd, umma::idesc_f16(N), acc);
+    umma::mma_f16(tmem, ad, bd, umma::idesc_f16(N), acc);
     acc = 1u;
   };
 #ifndef MSORT_TC_TERMS
@@ -260,7 +265,7 @@ __device__ __forceinline__ void tc_issue_layer(const TcMlp& m, int b_off_halves)
 }
 
 // hidden-layer epilogue of this thread's env: 32 accumulators -> (+bias) -> r -> fp16 split -> the next A operand
-__device__ __forceinline__ void tc_hidden_epilogue(const TcMlp& m, uint32_t tlane, int tid) {
+__device__ __forceinline__ void tc_hidden_epilogue(const TcMlp& m, uint32_t tlane, int tid) {   // tlane: this thread's TMEM lane, column 0
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     float v[16];
@@ -293,7 +298,7 @@ __device__ long long g_tcprof[16];
 #define TCPROF(k) do { } while (0)
 #endif
 __device__ __forceinline__ void tc_mlp_logits(const TcMlp& m, const float (&so)[13], int tid, uint32_t& phase, float& l0, float& l1) {
-  const uint32_t tlane = m.tmem + ((uint32_t)(tid & ~31) << 16);
+  uint32_t tmem = m.tmem, tlane = tmem + ((uint32_t)(tid & ~31) << 16);
   TCPROF(0);
   {   // layer-1 operand: obs columns 0..12, then 1, 1, 1 (bias terms); the lo part of an exact 1.0 is 0
     uint32_t h[8], l[8];
@@ -313,10 +318,14 @@ __device__ __forceinline__ void tc_mlp_logits(const TcMlp& m, const float (&so)[
     umma::fence_before_sync();       // ... and its TMEM reads are done before the next MMA overwrites the columns
     __syncthreads();
     TCPROF(2 + 5 * layer);
+    if (layer == 0) {                // a CTA that set itself up just before (one CTA per tile): its barriers, TMEM columns and weights
+      if (m.tmem_slot) { umma::fence_after_sync(); tmem = *m.tmem_slot; tlane = tmem + ((uint32_t)(tid & ~31) << 16); }
+      if (m.wbar) mbar_wait(m.wbar, 0u);
+    }
     if (tid == 0) {
       umma::fence_after_sync();
-      if (layer == 0) tc_issue_layer<1, 32, 3>(m, kTcB1);
-      else tc_issue_layer<2, 32, 3>(m, kTcB2);
+      if (layer == 0) tc_issue_layer<1, 32, 3>(m, tmem, kTcB1);
+      else tc_issue_layer<2, 32, 3>(m, tmem, kTcB2);
     }
     TCPROF(3 + 5 * layer);
     mbar_wait(m.bar, phase); phase ^= 1u;
@@ -770,7 +779,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   // on an mbarrier — so no warp waits for DRAM at the top of a tile.  Measured: Env_2 (long, MLP-heavy tiles)
   // +7 %; Env_1 / Env_3 10-17 % SLOWER than one CTA per tile with the hardware scheduler refilling the SM
   // (second barrier per tile, ~50 more instructions per warp), so they keep that form plus the L2 prefetch.
-  constexpr bool PERSIST = HOT && MSORT_HOT_PERSIST && KIND == MSORT_ENV_PRESS;
+  constexpr bool PERSIST = HOT && KIND == MSORT_ENV_PRESS && (TCMLP ? MSORT_TC_PERSIST != 0 : MSORT_HOT_PERSIST != 0);
   // TCMLP keeps shared memory at 27.1 KB per CTA (8 resident CTAs per SM): the staging buffer IS the lo half of the MMA
   // operand buffer (free from the completion of the layer-2 MMAs until the next tile's layer-1 operand is built — the
   // next tile is staged in exactly that window), and the actions come by plain coalesced loads.
@@ -791,6 +800,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   // (and later waits for) the bulk stores.  Without PERSIST everything stays with warp 0: the other warps exit.
   constexpr int kStageTid = 32 % kTile, kStatTid = PERSIST ? 64 % kTile : 0, kStoreTid = PERSIST ? 96 % kTile : 0;
   uint32_t phase = 0, mma_phase = 0;
+  bool weights_seen = false;
   TcMlp tcm{reinterpret_cast<uint4*>(s_tile_raw), s_tcw, &s_mma, 0u};
   if (PERSIST) {
     if (tid == kStageTid) {
@@ -811,6 +821,20 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
     __syncthreads();
     if (TCMLP) { umma::fence_after_sync(); tcm.tmem = s_tmem; }
   }
+  if (TCMLP && !PERSIST) {   // one CTA per tile: barriers, the weights' TMA and 32 TMEM columns per CTA, behind the state loads
+    if (tid == 0) {
+      mbar_init(&s_mma, 1);
+      mbar_init(&s_wbar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_expect_tx(&s_wbar, kTcWords * 4u);
+      bulk_load(s_tcw, a.policy_tc, kTcWords * 4u, &s_wbar);
+    }
+    if (tid < 32) { __syncwarp(); umma::tmem_alloc(&s_tmem, 32u); }
+    umma::fence_before_sync();
+    __syncthreads();       // (taking the TMEM address and the weights behind the MLP's first barrier instead — TcMlp::tmem_slot /
+    umma::fence_after_sync();   //  wbar — measured 3 % SLOWER: 107.3 vs 104.1 us per 1 048 576 envs, more spills at 64 registers)
+    tcm.tmem = s_tmem;
+  }
   if (FUSE) {   // the weights start their way into shared memory now and land behind the step; 64 TMEM columns
     if (tid == 0) {
       mbar_init(&s_wbar, 1);
@@ -824,8 +848,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   uint32_t mbits = 0;   // FUSE: this env's press-mask bits for the policy phase
   // TCMLP: the tile's actions come by plain loads issued one tile ahead (whole tiles only), the weights' TMA is awaited once
   long long act_ahead = 0;
-  bool weights_seen = false;
-  if (TCMLP) act_ahead = a.actions[(long long)blockIdx.x * kTile + tid];
+  if (TCMLP && PERSIST) act_ahead = a.actions[(long long)blockIdx.x * kTile + tid];
   long long tile = blockIdx.x;
   do {   // one pass unless PERSIST
   const long long row0 = tile * kTile;
@@ -984,7 +1007,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
           if (!weights_seen) { mbar_wait(&s_wbar, 0u); weights_seen = true; }
           mode = tc_mlp_mode(tcm, so, tid, mma_phase);   // every thread of the (full) tile is here: CTA barriers inside
           // this thread has seen the layer-2 MMAs complete: the operand buffer is dead, its lo half takes the next tile
-          if (tile + gridDim.x < ntiles) {
+          if (PERSIST && tile + gridDim.x < ntiles) {
             if (tid == kStageTid) stage_tile(tile + gridDim.x);
             act_ahead = a.actions[(tile + gridDim.x) * kTile + tid];
           }
@@ -1520,7 +1543,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   if (TCMLP) {
     umma::fence_before_sync();
     __syncthreads();
-    if (tid < 32) umma::tmem_dealloc(tcm.tmem, 32u);
+    if (tid < 32) umma::tmem_dealloc(s_tmem, 32u);
   }
 }
 
@@ -2016,7 +2039,7 @@ static cudaError_t launch_step_kind(const DevConfig& c, const StepArgs& a, const
             DevConfig cf = c; cf.n = n_full;
             auto tk = c.small_lv ? step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true, true, true>
                                  : step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true, false, true>;
-            tk<<<wave(n_full, 1), kTile, 0, st>>>(cf, a, pw);
+            tk<<<MSORT_TC_PERSIST ? wave(n_full, 1) : tiles(n_full), kTile, 0, st>>>(cf, a, pw);
           }
           if (c.n > n_full) {
             DevConfig ct = c; ct.n = c.n - n_full; ct.gid0 += n_full;
