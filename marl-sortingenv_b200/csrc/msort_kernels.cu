@@ -28,6 +28,9 @@
 #ifndef MSORT_EXP_SIGMOID
 #define MSORT_EXP_SIGMOID 0
 #endif
+#ifndef MSORT_TC_ROLL
+#define MSORT_TC_ROLL 0           // experiment switch: the two 16-column halves of each MLP epilogue as a rolled loop (smaller footprint; measured 106.1 vs 104.4 us: slower)
+#endif
 #ifndef MSORT_PRESS_TC_MIN_BLOCKS
 #define MSORT_PRESS_TC_MIN_BLOCKS 8  // Env_2 with the embedded policy on the tensor cores (TCMLP): 27.1 KB of shared memory per CTA, 64 registers
 #endif
@@ -266,7 +269,11 @@ __device__ __forceinline__ void tc_issue_layer(const TcMlp& m, uint32_t tmem, in
 
 // hidden-layer epilogue of this thread's env: 32 accumulators -> (+bias) -> r -> fp16 split -> the next A operand
 __device__ __forceinline__ void tc_hidden_epilogue(const TcMlp& m, uint32_t tlane, int tid) {   // tlane: this thread's TMEM lane, column 0
+#if MSORT_TC_ROLL
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
   for (int half = 0; half < 2; ++half) {
     float v[16];
     umma::tmem_ld16(tlane + 16u * half, v);
@@ -339,7 +346,11 @@ __device__ __forceinline__ void tc_mlp_logits(const TcMlp& m, const float (&so)[
   const float4* const b2 = reinterpret_cast<const float4*>(fw + kTcBias2);
   const ulonglong2* const w3 = reinterpret_cast<const ulonglong2*>(fw + kTcW3);   // two (logit0, logit1) weight pairs per 16 bytes
   unsigned long long acc = *reinterpret_cast<const unsigned long long*>(fw + kTcBias3);
+#if MSORT_TC_ROLL
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
   for (int half = 0; half < 2; ++half) {
     float v[16];
     umma::tmem_ld16(tlane + 16u * half, v);

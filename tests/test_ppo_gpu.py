@@ -206,3 +206,24 @@ def test_graph_rollout_equals_the_eager_rollout():
     with torch.no_grad():
         lp, _, _ = model.policy.evaluate(b["obs"].reshape(-1, model.D), b["mask"].reshape(-1, model.A), b["act"].reshape(-1))
     assert torch.allclose(lp, b["logp"].reshape(-1), rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("kind", ["sort", "press"])
+def test_ppo_iterations_on_the_other_env_kinds(kind):
+    """The loop is not Env_3-only: Env_1 (13 obs, 2 actions) and Env_2 (16, 11) run the r01 policy kernel in the graph rollout and
+    the native update kernels' other two instantiations; three iterations change the weights and keep everything finite."""
+    import torch
+    import marl_sortingenv_b200 as ms
+    from marl_sortingenv_b200.ppo import MaskablePPO
+    cls = {"sort": ms.BatchedSortingEnv, "press": ms.BatchedPressingEnv}[kind]
+    env = cls(640, max_steps=30, seed=3, info_level="none", track_stats=False)
+    model = MaskablePPO(env, n_steps=16, batch_size=2048, n_epochs=3, seed=1)
+    assert not model.fused_rollout and not model.split_rollout
+    before = model.flat.clone()
+    model.learn(3 * 16 * 640, log_every=1)
+    torch.cuda.synchronize()
+    assert model._graph is not None and model.num_timesteps == 3 * 16 * 640
+    assert torch.isfinite(model.flat).all() and not torch.equal(before, model.flat)
+    assert bool(model.buf["mask"].gather(2, model.buf["act"][..., None]).all())
+    st = model.log[-1]
+    assert all(k in st for k in ("pg", "vf", "ent", "clip_fraction")) and st["ent"] > 0
