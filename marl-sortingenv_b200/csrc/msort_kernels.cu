@@ -40,6 +40,9 @@
 #ifndef MSORT_FUSE_MIN_BLOCKS
 #define MSORT_FUSE_MIN_BLOCKS 7  // Env_3's HOT kernel fused with the rollout policy: 30.4 KB of shared memory per CTA, 72 registers
 #endif
+#ifndef MSORT_HOT_SORT_MIN_BLOCKS
+#define MSORT_HOT_SORT_MIN_BLOCKS 7  // Env_1's HOT kernel (72 registers)
+#endif
 #ifndef MSORT_STEP_MIN_BLOCKS
 #define MSORT_STEP_MIN_BLOCKS 7  // resident CTAs per SM the step kernel is compiled for (register cap)
 #endif
@@ -757,7 +760,8 @@ rollout_policy_kernel(const float* __restrict__ obs, const uint8_t* __restrict__
 template <int KIND, int RNG, int LAYOUT, bool FAST, bool HOT = false, bool SMALL = HOT, bool TCMLP = false, bool FUSE = false>
 __global__ void __launch_bounds__(kTile, (KIND == MSORT_ENV_PRESS ? (TCMLP ? MSORT_PRESS_TC_MIN_BLOCKS : MSORT_PRESS_MIN_BLOCKS)   // Env_2 (FFMA2 form) keeps 32 MLP activations in registers
                                            : FUSE ? MSORT_FUSE_MIN_BLOCKS
-                                           : (KIND == MSORT_ENV_MONO && HOT) ? MSORT_HOT_MONO_MIN_BLOCKS : MSORT_STEP_MIN_BLOCKS) * (128 / kTile))
+                                           : (KIND == MSORT_ENV_MONO && HOT) ? MSORT_HOT_MONO_MIN_BLOCKS
+                                           : (KIND == MSORT_ENV_SORT && HOT) ? MSORT_HOT_SORT_MIN_BLOCKS : MSORT_STEP_MIN_BLOCKS) * (128 / kTile))
 step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArgs a,
             const __grid_constant__ PolicyParam<KIND> pw) {
   constexpr int D = Dims<KIND>::D, A = Dims<KIND>::A;
