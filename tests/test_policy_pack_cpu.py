@@ -44,3 +44,24 @@ def test_packed_layout_reproduces_the_towers(D, A):
     assert not W2[:32, 32:].any() and not W2[32:, :32].any()
     assert not W3[:A, 32:].any() and not W3[A, :32].any() and not W3[A + 1:].any()
     assert not W1[:, D:].any()
+
+
+def test_flatten_parameters_follows_the_layout_of_the_update_kernels():
+    """ppo.flatten_parameters: ONE flat fp32 vector in the order include/msort.h documents for msort_ppo_* / msort_rollout_pack
+    (pi W1 b1 W2 b2 W3 b3 | vf W1 b1 W2 b2 W3 b3, torch Linear layout), every nn.Parameter a view of it."""
+    import torch
+    from marl_sortingenv_b200.ppo import MaskableActorCritic, flatten_parameters
+    torch.manual_seed(0)
+    for D, A in ((29, 22), (16, 11), (13, 2)):
+        pol = MaskableActorCritic(D, A)
+        want = torch.cat([p.detach().reshape(-1).clone() for p in
+                          (pol.pi[0].weight, pol.pi[0].bias, pol.pi[2].weight, pol.pi[2].bias, pol.pi[4].weight, pol.pi[4].bias,
+                           pol.vf[0].weight, pol.vf[0].bias, pol.vf[2].weight, pol.vf[2].bias, pol.vf[4].weight, pol.vf[4].bias)])
+        flat = flatten_parameters(pol)
+        assert flat.numel() == 2 * (32 * D + 32 + 32 * 32 + 32) + (A * 32 + A) + (32 + 1) and torch.equal(flat, want)
+        flat[0] = 123.0                                       # the modules see what the kernels write
+        assert float(pol.pi[0].weight[0, 0]) == 123.0
+        flat[-1] = -7.0
+        assert float(pol.vf[4].bias[0]) == -7.0
+        x = torch.rand(5, D)
+        assert torch.isfinite(pol.pi(x)).all()

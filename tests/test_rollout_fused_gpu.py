@@ -171,3 +171,24 @@ def test_ppo_split_rollout_equals_fused_rollout():
     for k in b1:
         assert torch.equal(b1[k], b2[k]), k
     assert torch.equal(s1, s2) and all(torch.equal(x[0], y[0]) for x, y in zip(o1, o2))
+
+
+def test_fused_step_accumulates_the_same_episode_statistics():
+    """The fused kernel keeps the step kernel's statistics path (per-warp REDUX sums -> one atomic per CTA and slot): after the
+    same 60 steps the 16-slot stats vector, episode returns and lengths equal those of the plain kernel."""
+    import torch
+    n = 128 * 9 + 5
+    (fa, pl), pol, flat, packed = _pair(n, seed=21, max_steps=10)
+    pf = fa.rollout_pack(flat)
+    fa.reset(); pl.reset()
+    a, _, _ = pl.rollout_policy(pf, seed=2, t=0)
+    nxt = (torch.empty(n, dtype=torch.int64, device="cuda"), torch.empty(n, device="cuda"), torch.empty(n, device="cuda"))
+    for t in range(60):
+        fa.rollout_step(a, pf, 2, t + 1, nxt); pl.step(a)
+        a = nxt[0].clone()
+    torch.cuda.synchronize()
+    assert fa.stats is not None and torch.allclose(fa.stats, pl.stats, rtol=1e-12, atol=1e-9)    # (float64 atomics: order-dependent last bits)
+    assert float(fa.stats[0]) == n * 6 and float(fa.stats[3]) == n * 60          # episodes (10 steps each), env-steps
+    for k in ("episode_return", "episode_length", "terminal_observation"):
+        if k in fa.info_buffers and fa.info_buffers[k] is not None:
+            assert torch.equal(fa.info_buffers[k], pl.info_buffers[k]), k
