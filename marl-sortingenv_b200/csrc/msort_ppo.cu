@@ -9,7 +9,8 @@
 //   * one CTA = 128 rows = 128 threads; both towers' weights live in shared memory in input-major order, so a thread
 //     advances 4 output units per LDS.128 (all threads read the same address: a broadcast) — 1 load per 4 FMAs;
 //   * per-row activations / pre-activation gradients go to shared memory in rows of 36 floats (16-byte aligned for the
-//     weight-gradient phase, conflict-free for a thread reading its own row with LDS.128);
+//     weight-gradient phase, conflict-free for a thread reading its own row with LDS.128); five such buffers (the layer-1
+//     gradient rows reuse the layer-3 buffer after its weight gradients are taken) + the weights = 103 KB: two CTAs per SM;
 //   * weight gradients dW[o][i] = sum_r dz[r][o] * act[r][i]: thread (o, i-block of 8) loops over the tile's rows
 //     (dz: one conflict-free load; act: two broadcast LDS.128), then ONE atomicAdd per parameter per CTA.
 // Parameter vector (flat fp32, owned by the caller):
@@ -150,13 +151,15 @@ struct PpoSmem {
   float w1[D * kH], w2[kH * kH], w3[kH * AP];     // the current tower's W^T
   float b1[kH], b2[kH], b3[AP];
   float x[kRows * kLd], h1[kRows * kLd], h2[kRows * kLd];        // per-row activations
-  float dz1[kRows * kLd], dz2[kRows * kLd], dz3[kRows * kLd];    // per-row pre-activation gradients
+  float dz2[kRows * kLd], dz3[kRows * kLd];                      // per-row pre-activation gradients; dz1 takes dz3's place once the
+                                                                 // layer-3 weight gradients have consumed it: 5 row buffers + weights =
+                                                                 // 103 KB per CTA = TWO CTAs per SM (six buffers: one)
   float red[8];
 };
 
 // GRAD = false: forward only, writes log-prob of the row's action and the value.
 template <int D, int A, bool GRAD>
-__global__ void __launch_bounds__(kRows, 1)
+__global__ void __launch_bounds__(kRows, 2)
 ppo_kernel(const __grid_constant__ PpoArgs a) {
   using S = PpoSmem<D, A>;
   constexpr int DP = S::DP, AP = S::AP;
@@ -246,9 +249,6 @@ ppo_kernel(const __grid_constant__ PpoArgs a) {
     row_store<kH>(sm.dz3, tid, dz3);
     // backward through the two tanh layers
     dense_bwd_tanh<kH, AP>(sm.w3, reinterpret_cast<const float(&)[AP]>(dz3), h2row, sm.dz2 + tid * kLd);
-    float dz2[kH];
-    row_load<kH>(sm.dz2, tid, dz2);
-    dense_bwd_tanh<kH, kH>(sm.w2, dz2, h1row, sm.dz1 + tid * kLd);
     // loss statistics: warp sums -> one atomic per warp
     float s0 = live ? -surr : 0.f, s2 = live ? ent : 0.f, s3 = (live && clipped) ? 1.f : 0.f;
 #pragma unroll
@@ -258,8 +258,13 @@ ppo_kernel(const __grid_constant__ PpoArgs a) {
     if ((tid & 31) == 0 && a.stats) { atomicAdd(&a.stats[0], s0); atomicAdd(&a.stats[2], s2); atomicAdd(&a.stats[3], s3); }
     __syncthreads();
     weight_grad<kH, A>(sm.dz3, sm.h2, rows, a.grads + L.pi_w3, a.grads + L.pi_b3, tid);
+    __syncthreads();                                                  // dz3 has been consumed: its rows take dz1
+    float dz2[kH];
+    row_load<kH>(sm.dz2, tid, dz2);
+    dense_bwd_tanh<kH, kH>(sm.w2, dz2, h1row, sm.dz3 + tid * kLd);
+    __syncthreads();
     weight_grad<kH, kH>(sm.dz2, sm.h1, rows, a.grads + L.pi_w2, a.grads + L.pi_b2, tid);
-    weight_grad<D, kH>(sm.dz1, sm.x, rows, a.grads + L.pi_w1, a.grads + L.pi_b1, tid);
+    weight_grad<D, kH>(sm.dz3, sm.x, rows, a.grads + L.pi_w1, a.grads + L.pi_b1, tid);
   }
   __syncthreads();
 
@@ -294,17 +299,19 @@ ppo_kernel(const __grid_constant__ PpoArgs a) {
   for (int k = 0; k < kH / 4; ++k)
     *reinterpret_cast<float4*>(sm.dz3 + tid * kLd + 4 * k) = make_float4(k == 0 ? dz3v[0] : 0.f, 0.f, 0.f, 0.f);
   dense_bwd_tanh<kH, 4>(sm.w3, dz3v, h2row, sm.dz2 + tid * kLd);
-  float dz2[kH];
-  row_load<kH>(sm.dz2, tid, dz2);
-  dense_bwd_tanh<kH, kH>(sm.w2, dz2, h1row, sm.dz1 + tid * kLd);
   float s1 = err * err, s4 = live ? 1.f : 0.f;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s4 += __shfl_xor_sync(0xffffffffu, s4, o); }
   if ((tid & 31) == 0 && a.stats) { atomicAdd(&a.stats[1], s1); atomicAdd(&a.stats[4], s4); }
   __syncthreads();
   weight_grad<kH, 1>(sm.dz3, sm.h2, rows, a.grads + L.vf_w3, a.grads + L.vf_b3, tid);
+  __syncthreads();
+  float dz2[kH];
+  row_load<kH>(sm.dz2, tid, dz2);
+  dense_bwd_tanh<kH, kH>(sm.w2, dz2, h1row, sm.dz3 + tid * kLd);
+  __syncthreads();
   weight_grad<kH, kH>(sm.dz2, sm.h1, rows, a.grads + L.vf_w2, a.grads + L.vf_b2, tid);
-  weight_grad<D, kH>(sm.dz1, sm.x, rows, a.grads + L.vf_w1, a.grads + L.vf_b1, tid);
+  weight_grad<D, kH>(sm.dz3, sm.x, rows, a.grads + L.vf_w1, a.grads + L.vf_b1, tid);
 }
 
 // mean and 1 / (std + 1e-8) (unbiased std, like torch.Tensor.std) of adv[idx[first .. first + count)] -> out[0..1]
