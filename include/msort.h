@@ -456,12 +456,18 @@ int msort_rollout_step(msort_t* h, void* state, const int64_t* actions, float* o
 #define MSORT_STEP_HOT_PERSISTENT 5
 #define MSORT_STEP_HOT_TENSOR 6 /* HOT persistent with Env_2's embedded policy on the tensor cores (tcgen05, fp16-split operands) */
 #define MSORT_STEP_HOT_FUSED 7  /* Env_3 HOT + the next step's rollout policy in the same kernel (msort_rollout_step) */
+#define MSORT_STEP_HOT_TENSOR_SPLIT 8 /* Env_2: tensor-core policy kernel (one mode byte per env) + policy-free HOT step kernel */
 int msort_step_variant(const msort_t* h);
 
 /* Handle options (diagnostics / experiments; defaults are the production choice).
- *  MSORT_OPT_TENSOR_POLICY (default 1): Env_2's embedded sort policy (ref: sort_agent.predict, env_2_press.py:106-109)
- *    is evaluated on the tensor cores when the HOT persistent kernel runs and the weights fit the fp16 split;
- *    0 = always the per-thread fp32 FFMA2 form. */
+ *  MSORT_OPT_TENSOR_POLICY (default MSORT_TENSOR_POLICY_DEFAULT): Env_2's embedded sort policy (ref: sort_agent.predict,
+ *    env_2_press.py:106-109) is evaluated on the tensor cores when the HOT configuration runs and the weights fit the
+ *    fp16 split: 1 = inside the step kernel (one launch per step), 2 = as its own kernel writing one mode byte per env,
+ *    followed by a policy-free step kernel (two launches per step; bit-identical results); 0 = always the per-thread
+ *    fp32 FFMA2 form. */
+#ifndef MSORT_TENSOR_POLICY_DEFAULT
+#define MSORT_TENSOR_POLICY_DEFAULT 1   /* measured on B200: 104.3 us per 1 048 576 envs inside the step kernel, 108.6 us as two kernels */
+#endif
 #define MSORT_OPT_TENSOR_POLICY 1
 /*  MSORT_OPT_PERSIST_CTAS: resident CTAs per SM the persistent Env_2 kernels are launched with (default: what the
  *    kernel's registers and shared memory allow, asked at msort_create); get = the count of the kernel the next

@@ -181,7 +181,7 @@ class BatchedEnv:
     @property
     def step_variant(self) -> str:
         """Which instantiation of the step kernel the last step() launched (include/msort.h MSORT_STEP_*)."""
-        return ("none", "replay", "generic", "fast", "hot", "hot_persistent", "hot_tensor", "hot_fused")[int(self.lib.msort_step_variant(self._h))]
+        return ("none", "replay", "generic", "fast", "hot", "hot_persistent", "hot_tensor", "hot_fused", "hot_tensor_split")[int(self.lib.msort_step_variant(self._h))]
 
     def set_option(self, option: int, value: int):
         """Handle options of include/msort.h (MSORT_OPT_*), e.g. `_abi.OPT_TENSOR_POLICY`."""

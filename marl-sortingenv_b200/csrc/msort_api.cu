@@ -30,7 +30,9 @@ struct msort_handle {
   uint32_t policy_tc_host[kTcWords];        // the same policy packed for the tensor-core path (pack_policy_tc); source of the upload
   uint32_t* policy_tc_dev = nullptr;        // owned device copy (11 KB, allocated by the first msort_set_policy)
   bool policy_tc_ok = false;                // the policy fits the fp16 split (else the FFMA2 kernel evaluates it)
-  bool policy_tc_enabled = true;            // msort_set_option(MSORT_OPT_TENSOR_POLICY)
+  bool policy_tc_enabled = true;            // msort_set_option(MSORT_OPT_TENSOR_POLICY) != 0
+  bool policy_tc_split = MSORT_TENSOR_POLICY_DEFAULT == 2;   // ... == 2: policy kernel + policy-free step kernel instead of the one fused kernel
+  uint8_t* mode_scratch = nullptr;          // owned: one byte per env (n_pad), the split form's sort modes (allocated with the tensor-core policy)
   const uint32_t* draw_counter = nullptr;   // MSORT_OPT_DRAW_COUNTER: device-side offset of msort_policy_act's draw index
   int persist_per_sm[4] = {1, 1, 1, 1};     // resident CTAs per SM of the persistent Env_2 kernels on this handle's device
   // msort_step_host: the library's own streams / events (created by the first call, on the handle's device)
@@ -334,6 +336,7 @@ extern "C" int msort_destroy(msort_t* h) {
   if (!h) return MSORT_OK;
   if (h->lut_dev) cudaFree(h->lut_dev);
   if (h->policy_tc_dev) cudaFree(h->policy_tc_dev);
+  if (h->mode_scratch) cudaFree(h->mode_scratch);
   if (h->host_ready) {
     for (int k = 0; k < msort_handle::kHostStreams; ++k) { cudaStreamDestroy(h->host_stream[k]); cudaEventDestroy(h->host_done[k]); }
     cudaEventDestroy(h->host_start);
@@ -364,7 +367,10 @@ extern "C" int msort_set_seed(msort_t* h, uint64_t seed) {
 extern "C" int msort_set_option(msort_t* h, int option, int64_t value) {
   if (!h) return fail(MSORT_E_INVALID, "msort_set_option: NULL handle");
   switch (option) {
-    case MSORT_OPT_TENSOR_POLICY: h->policy_tc_enabled = value != 0; return MSORT_OK;
+    case MSORT_OPT_TENSOR_POLICY:
+      if (value < 0 || value > 2) return fail(MSORT_E_INVALID, "msort_set_option: MSORT_OPT_TENSOR_POLICY must be 0, 1 or 2");
+      h->policy_tc_enabled = value != 0; h->policy_tc_split = value == 2;
+      return MSORT_OK;
     case MSORT_OPT_DRAW_COUNTER:
       if (value & 3) return fail(MSORT_E_INVALID, "msort_set_option: MSORT_OPT_DRAW_COUNTER must be a 4-byte aligned device pointer");
       h->draw_counter = reinterpret_cast<const uint32_t*>((uintptr_t)value);
@@ -380,7 +386,9 @@ extern "C" int msort_set_option(msort_t* h, int option, int64_t value) {
 extern "C" int msort_get_option(const msort_t* h, int option, int64_t* value) {
   if (!h || !value) return fail(MSORT_E_INVALID, "msort_get_option: NULL argument");
   switch (option) {
-    case MSORT_OPT_TENSOR_POLICY: *value = (h->policy_tc_enabled && h->policy_set && h->policy_tc_ok) ? 1 : 0; return MSORT_OK;
+    case MSORT_OPT_TENSOR_POLICY:
+      *value = (h->policy_tc_enabled && h->policy_set && h->policy_tc_ok) ? ((h->policy_tc_split && h->mode_scratch) ? 2 : 1) : 0;
+      return MSORT_OK;
     case MSORT_OPT_PERSIST_CTAS:
       *value = h->persist_per_sm[(h->dev.small_lv ? 1 : 0) + ((h->policy_tc_enabled && h->policy_set && h->policy_tc_ok) ? 2 : 0)];
       return MSORT_OK;
@@ -468,6 +476,7 @@ static int step_impl(msort_t* h, long long first, long long count, void* state, 
                h->policy_set ? h->policy_host : nullptr,
                (h->policy_set && h->policy_tc_ok && h->policy_tc_enabled) ? h->policy_tc_dev : nullptr, h->persist_per_sm};
   l.fused = fused;
+  if (l.policy_tc && h->policy_tc_split && h->mode_scratch) l.mode_scratch = h->mode_scratch + first;   // this launch's slice of the handle's scratch
   if (fused) {
     cudaError_t e = launch_step(d, l, h->cfg.rng_mode, (cudaStream_t)stream);
     if (e == cudaErrorNotSupported)
@@ -478,7 +487,7 @@ static int step_impl(msort_t* h, long long first, long long count, void* state, 
     return MSORT_OK;
   }
   MSORT_TRY_CUDA(launch_step(d, l, h->cfg.rng_mode, (cudaStream_t)stream), "step kernel");
-  h->launches += 1;
+  h->launches += h->step_variant == MSORT_STEP_HOT_TENSOR_SPLIT ? 2 : 1;
   return MSORT_OK;
 }
 
@@ -638,6 +647,7 @@ extern "C" int msort_set_policy(msort_t* h, const float* weights, int weights_on
   h->policy_tc_ok = pack_policy_tc(sb3, h->policy_tc_host);
   if (h->policy_tc_ok) {
     if (!h->policy_tc_dev) MSORT_TRY_CUDA(cudaMalloc(&h->policy_tc_dev, sizeof(h->policy_tc_host)), "cudaMalloc(tensor-core policy)");
+    if (!h->mode_scratch) MSORT_TRY_CUDA(cudaMalloc(&h->mode_scratch, (size_t)h->dev.n_pad), "cudaMalloc(sort-mode scratch)");
     MSORT_TRY_CUDA(cudaMemcpyAsync(h->policy_tc_dev, h->policy_tc_host, sizeof(h->policy_tc_host), cudaMemcpyHostToDevice,
                                    (cudaStream_t)stream), "cudaMemcpyAsync(tensor-core policy)");
   }

@@ -143,6 +143,7 @@ struct StepArgs {
   int any_step_info;  // any of the six per-step info arrays above is present
   int act_tma;        // actions are 16-byte aligned: the persistent kernel may fetch a tile's actions by TMA
   const uint4* policy_tc;   // Env_2 TCMLP: packed tensor-core policy (kTcWords words, device memory) or nullptr
+  uint8_t* mode_scratch;    // Env_2 split form: one byte per env of THIS launch for the policy kernel's sort modes, or nullptr (fused TCMLP kernel)
   // FUSE (Env_3 rollout kernel): the actor-critic packed by pack_fused_kernel and where the NEXT step's action goes
   const uint4* fused_w;     // kFwWords words (device memory, 16-byte aligned) or nullptr
   long long* next_actions;
@@ -746,6 +747,62 @@ rollout_policy_kernel(const float* __restrict__ obs, const uint8_t* __restrict__
   if (tid < 32) umma::tmem_dealloc(tmem, 64u);
 }
 
+// ---------------------------------------------------------------- Env_2: the embedded policy as its own kernel (split form)
+// ref: sort_agent.predict(self.get_sort_obs(), deterministic=True) env_2_press.py:106-109.  press_policy_kernel reads the 64-byte
+// compact state of every env, rebuilds exactly the 13-wide sort observation the step kernel would show the policy (previous
+// step's accuracies from the Philox counter, stages after the shift, container purities), evaluates the 13-32-32-2 policy on
+// the tensor cores (tc_mlp_mode: the same function the fused TCMLP kernel calls, so the two forms agree bit for bit) and
+// writes ONE mode byte per env; step_kernel<PRESS,...,HOT,EXTMODE> then steps the env with that mode.  Two small kernels
+// instead of one 56 KB one: no spills, 8 CTAs per SM each, the hardware CTA scheduler for both.  Whole tiles only (the
+// launcher gives a ragged tail to the FFMA2 kernel), FAST configurations only (HOT implies FAST).
+__global__ void __launch_bounds__(kTile, 8)
+press_policy_kernel(const __grid_constant__ DevConfig c, const uint4* __restrict__ state, const uint4* __restrict__ tcw,
+                    uint8_t* __restrict__ modes) {
+  __shared__ __align__(128) uint4 s_a[8 * kTile];
+  __shared__ __align__(128) uint32_t s_w[kTcWords];
+  __shared__ __align__(8) uint64_t s_bar, s_wbar;
+  __shared__ uint32_t s_tm;
+  const int tid = threadIdx.x;
+  const long long i = (long long)blockIdx.x * kTile + tid;     // whole tiles: i < c.n
+  if (tid == 0) {
+    mbar_init(&s_bar, 1); mbar_init(&s_wbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(&s_wbar, kTcWords * 4u);
+    bulk_load(s_w, tcw, kTcWords * 4u, &s_wbar);
+  }
+  if (tid < 32) { __syncwarp(); umma::tmem_alloc(&s_tm, 32u); }
+  umma::fence_before_sync();
+  Env s;
+  load_planes<LAYOUT_COMPACT>(state, c.n_pad, i, s);
+  const unsigned long long gid = (unsigned long long)(c.gid0 + i);
+  const uint32_t gid_lo = (uint32_t)gid, gid_hi = (uint32_t)(gid >> 32) & 0xffffu;
+  // exactly the step kernel's preamble for Env_2 (FAST): accuracy_sorter of this step = accuracy_belt of the previous one
+  double acc_a, acc_b;
+  const int pm = s.mode;
+  philox_accuracy2(c, gid_lo, gid_hi, s.episode, s.step - 1, pm, acc_a, acc_b);
+  s.acc[0] = pm ? acc_a : 1.0; s.acc[1] = pm ? 1.0 : acc_a;
+  s.acc[2] = pm ? acc_b : 1.0; s.acc[3] = pm ? 1.0 : acc_b;
+  if (s.step == 0) {
+#pragma unroll
+    for (int m = 0; m < 4; ++m) s.acc[m] = c.base_acc[m];
+  }
+  s.sort4 = s.belt4; s.belt4 = s.in4;             // update_environment's shift (the new input does not enter the sort observation)
+  float so[13];
+  int kq[4];
+  purity_ks(c, s, kq);
+  sort_obs(c, s, kq, so);
+  __syncthreads();                                // barrier inits and the TMEM address are visible
+  umma::fence_after_sync();
+  const TcMlp m{s_a, s_w, &s_bar, s_tm};
+  mbar_wait(&s_wbar, 0u);
+  uint32_t phase = 0;
+  const int mode = tc_mlp_mode(m, so, tid, phase);
+  modes[i] = (uint8_t)mode;
+  umma::fence_before_sync();
+  __syncthreads();
+  if (tid < 32) umma::tmem_dealloc(s_tm, 32u);
+}
+
 // FAST (PHILOX only, chosen by the host when DevConfig::fast holds): boosted accuracies are exactly 1.0,
 // unboosted ones need no clip, and the redistribution classes fit one register of packed bytes.
 // Results are identical to the generic instantiation; only the instruction count differs.
@@ -757,8 +814,8 @@ rollout_policy_kernel(const float* __restrict__ obs, const uint8_t* __restrict__
 // scheduler's way).  Chosen per launch by launch_step_kind.
 // TCMLP (Env_2's persistent HOT kernel only; full tiles only — the launcher gives a ragged tail to the plain HOT kernel):
 // the embedded policy is evaluated on the tensor cores (tc_mlp_mode above) instead of per-thread FFMA2.
-template <int KIND, int RNG, int LAYOUT, bool FAST, bool HOT = false, bool SMALL = HOT, bool TCMLP = false, bool FUSE = false>
-__global__ void __launch_bounds__(kTile, (KIND == MSORT_ENV_PRESS ? (TCMLP ? MSORT_PRESS_TC_MIN_BLOCKS : MSORT_PRESS_MIN_BLOCKS)   // Env_2 (FFMA2 form) keeps 32 MLP activations in registers
+template <int KIND, int RNG, int LAYOUT, bool FAST, bool HOT = false, bool SMALL = HOT, bool TCMLP = false, bool FUSE = false, bool EXTMODE = false>
+__global__ void __launch_bounds__(kTile, (KIND == MSORT_ENV_PRESS ? ((TCMLP || EXTMODE) ? MSORT_PRESS_TC_MIN_BLOCKS : MSORT_PRESS_MIN_BLOCKS)   // Env_2 (FFMA2 form) keeps 32 MLP activations in registers
                                            : FUSE ? MSORT_FUSE_MIN_BLOCKS
                                            : (KIND == MSORT_ENV_MONO && HOT) ? MSORT_HOT_MONO_MIN_BLOCKS
                                            : (KIND == MSORT_ENV_SORT && HOT) ? MSORT_HOT_SORT_MIN_BLOCKS : MSORT_STEP_MIN_BLOCKS) * (128 / kTile))
@@ -767,6 +824,9 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   constexpr int D = Dims<KIND>::D, A = Dims<KIND>::A;
   static_assert(!TCMLP || !MSORT_HOT_PERSIST || (KIND == MSORT_ENV_PRESS && HOT && kTile == 128), "TCMLP specialises Env_2's persistent HOT kernel");   // (MSORT_HOT_PERSIST=0 experiment builds never launch it)
   static_assert(!FUSE || (KIND == MSORT_ENV_MONO && HOT && kTile == 128), "FUSE specialises Env_3's HOT kernel");
+  // EXTMODE: Env_2's HOT kernel with the sort mode of every env given in a.sort_mode_in (written by press_policy_kernel just
+  // before, on the same stream): no embedded policy in this kernel at all — one CTA per tile, 64 registers, 8 CTAs per SM
+  static_assert(!EXTMODE || (KIND == MSORT_ENV_PRESS && HOT && !TCMLP), "EXTMODE specialises Env_2's HOT kernel");
   // obs tile; with TCMLP the 16 KB MMA A-operand buffer, whose first half the obs tile aliases (the operand is dead
   // once the last layer's MMAs are complete, long before the first obs entry of the tile is written)
   constexpr int kObsBytes = kTile * D * (int)sizeof(float);
@@ -784,8 +844,8 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   const bool masking = HOT || (c.flags & MSORT_F_ACTION_MASKING);
   const bool auto_reset = HOT || (c.flags & MSORT_F_AUTO_RESET);
   const bool want_mask = HOT || a.mask != nullptr;
-  const bool use_mlp = TCMLP || (KIND == MSORT_ENV_PRESS && (c.flags & MSORT_F_SORT_POLICY_MLP) &&
-                                 !(RNG == MSORT_RNG_REPLAY && a.sort_mode_in));
+  const bool use_mlp = !EXTMODE && (TCMLP || (KIND == MSORT_ENV_PRESS && (c.flags & MSORT_F_SORT_POLICY_MLP) &&
+                                                !(RNG == MSORT_RNG_REPLAY && a.sort_mode_in)));
   const int tid = threadIdx.x;
 
   // PERSIST (Env_2's HOT instantiation): the grid is one wave of resident CTAs, each looping over tiles
@@ -794,7 +854,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
   // on an mbarrier — so no warp waits for DRAM at the top of a tile.  Measured: Env_2 (long, MLP-heavy tiles)
   // +7 %; Env_1 / Env_3 10-17 % SLOWER than one CTA per tile with the hardware scheduler refilling the SM
   // (second barrier per tile, ~50 more instructions per warp), so they keep that form plus the L2 prefetch.
-  constexpr bool PERSIST = HOT && KIND == MSORT_ENV_PRESS && (TCMLP ? MSORT_TC_PERSIST != 0 : MSORT_HOT_PERSIST != 0);
+  constexpr bool PERSIST = HOT && KIND == MSORT_ENV_PRESS && !EXTMODE && (TCMLP ? MSORT_TC_PERSIST != 0 : MSORT_HOT_PERSIST != 0);
   // TCMLP keeps shared memory at 27.1 KB per CTA (8 resident CTAs per SM): the staging buffer IS the lo half of the MMA
   // operand buffer (free from the completion of the layer-2 MMAs until the next tile's layer-1 operand is built — the
   // next tile is staged in exactly that window), and the actions come by plain coalesced loads.
@@ -1011,7 +1071,7 @@ step_kernel(const __grid_constant__ DevConfig c, const __grid_constant__ StepArg
       if (!masking && !press_action_valid(c, s, pa)) { pa = 0; skip_press = true; invalid = true; }
     } else {
       pa = (int)act;
-      if (RNG == MSORT_RNG_REPLAY && a.sort_mode_in) {
+      if ((RNG == MSORT_RNG_REPLAY || EXTMODE) && a.sort_mode_in) {
         mode = a.sort_mode_in[i] & 1;
       } else if (use_mlp) {
         float so[13];
@@ -2050,7 +2110,15 @@ static cudaError_t launch_step_kind(const DevConfig& c, const StepArgs& a, const
         if (a.policy_tc && (c.flags & MSORT_F_SORT_POLICY_MLP)) {
           // embedded policy on the tensor cores: whole tiles only; a ragged tail goes to the FFMA2 kernel below
           var = MSORT_STEP_HOT_TENSOR;
-          if (n_full > 0) {
+          if (n_full > 0 && a.mode_scratch) {   // split form: the policy kernel writes one mode byte per env, the policy-free step kernel reads it
+            DevConfig cf = c; cf.n = n_full;
+            StepArgs as = a; as.sort_mode_in = a.mode_scratch;
+            press_policy_kernel<<<tiles(n_full), kTile, 0, st>>>(cf, a.state, a.policy_tc, a.mode_scratch);
+            auto sk = c.small_lv ? step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true, true, false, false, true>
+                                 : step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true, false, false, false, true>;
+            sk<<<tiles(n_full), kTile, 0, st>>>(cf, as, pw);
+            var = MSORT_STEP_HOT_TENSOR_SPLIT;
+          } else if (n_full > 0) {
             DevConfig cf = c; cf.n = n_full;
             auto tk = c.small_lv ? step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true, true, true>
                                  : step_kernel<KIND, MSORT_RNG_PHILOX, LAYOUT_COMPACT, true, true, false, true>;
@@ -2094,6 +2162,7 @@ cudaError_t launch_step(const DevConfig& c, const StepLaunch& l, int rng, cudaSt
                     a.info_press_action || a.info_invalid || a.info_r_sort || a.info_r_press || a.info_sorted_true;
   a.act_tma = ((uintptr_t)l.actions & 15u) == 0;
   a.policy_tc = reinterpret_cast<const uint4*>(l.policy_tc);
+  a.mode_scratch = l.mode_scratch;
   const FusedLaunch* fz = l.fused;
   a.fused_w = fz ? reinterpret_cast<const uint4*>(fz->packed) : nullptr;
   a.next_actions = fz ? (long long*)fz->next_actions : nullptr; a.next_logp = fz ? fz->next_logp : nullptr; a.next_value = fz ? fz->next_value : nullptr;

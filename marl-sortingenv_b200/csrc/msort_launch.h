@@ -37,6 +37,7 @@ struct StepLaunch {
   const uint32_t* policy_tc; // the same policy packed for the tensor-core path (pack_policy_tc; DEVICE memory) or nullptr
   const int* persist_per_sm; // resident CTAs per SM of the persistent Env_2 kernels (query_persist_occupancy)
   const FusedLaunch* fused = nullptr;   // non-null: the fused rollout kernel (Env_3, HOT configuration only)
+  uint8_t* mode_scratch = nullptr;      // Env_2 with the tensor-core policy: non-null = the split form (policy kernel -> mode bytes -> step kernel)
 };
 
 void pack_policy_pairs(const float* sb3, float* paired);   // SB3 weight order -> the step kernel's FFMA2 operand order

@@ -208,7 +208,8 @@ def test_persistent_env2_kernel_with_unaligned_actions_and_kernel_variants():
         buf[1:].copy_(a)
         assert buf[1:].data_ptr() % 16 == 8
         envs[0].step(a); envs[1].step(buf[1:]); envs[2].step(a); envs[3].step(a)
-    assert [e.step_variant for e in envs] == ["hot_tensor", "hot_tensor", "fast", "hot_persistent"]
+    tv = "hot_tensor_split" if envs[0].get_option(_abi.OPT_TENSOR_POLICY) == 2 else "hot_tensor"
+    assert [e.step_variant for e in envs] == [tv, tv, "fast", "hot_persistent"]
     assert torch.equal(envs[0].state, envs[1].state) and torch.equal(envs[3].state, envs[2].state)
     assert torch.equal(envs[0].obs, envs[1].obs) and torch.equal(envs[3].obs, envs[2].obs)
     assert torch.equal(envs[3].mask, envs[2].mask) and torch.equal(envs[0].reward, envs[1].reward)

@@ -90,11 +90,16 @@ def test_tensor_policy_is_what_the_hot_kernel_runs_and_can_be_switched_off():
     env.reset(seed=3)
     a = env.sample_actions(1, 0)
     env.step(a)
-    assert env.step_variant == "hot_tensor"
+    assert env.step_variant == ("hot_tensor_split" if env.get_option(_abi.OPT_TENSOR_POLICY) == 2 else "hot_tensor")
     env.set_option(_abi.OPT_TENSOR_POLICY, 0)
     env.step(env.sample_actions(1, 1))
     assert env.step_variant == "hot_persistent"
     env.set_option(_abi.OPT_TENSOR_POLICY, 1)
+    env.step(env.sample_actions(1, 3))
+    assert env.step_variant == "hot_tensor"                 # 1 = inside the step kernel, 2 = policy kernel + step kernel
+    env.set_option(_abi.OPT_TENSOR_POLICY, 2)
+    env.step(env.sample_actions(1, 4))
+    assert env.step_variant == "hot_tensor_split"
     # a policy outside fp16's range cannot be split: the FFMA2 kernel keeps evaluating it
     big = w.copy(); big[5] = 1.0e5
     env.set_sort_policy(torch.as_tensor(big))
@@ -122,11 +127,39 @@ def test_tensor_and_ffma2_forms_walk_the_same_trajectories():
         # masks agree on every env that has not diverged; a diverged env may hold an action the other side's mask
         # forbids — in masked mode the kernel then simply starts that press, which is fine for a divergence count
         a_env.step(act); b_env.step(act)
-    assert a_env.step_variant == "hot_tensor" and b_env.step_variant == "hot_persistent"
+    assert a_env.step_variant in ("hot_tensor", "hot_tensor_split") and b_env.step_variant == "hot_persistent"
     sa = a_env.state.view(torch.int32).reshape(-1, a_env.state.numel() // 4 // 13)    # [13 planes, n_pad * 4 words]
     sb = b_env.state.view(torch.int32).reshape(-1, b_env.state.numel() // 4 // 13)
     diff = (sa != sb).reshape(13, -1, 4).any(dim=2).any(dim=0)[:n]
     n_div = int(diff.sum())
     print(f"tensor vs FFMA2 policy: {n_div} of {n} envs diverged within {T} steps ({n_div / (n * T):.2e} per env-step)")
     assert n_div <= n * T * 2e-6, f"{n_div} envs diverged"
+    a_env.close(); b_env.close()
+
+
+def test_split_form_equals_the_fused_tensor_kernel_bit_for_bit():
+    """MSORT_OPT_TENSOR_POLICY 2 (press_policy_kernel writes one mode byte per env, the policy-free EXTMODE step kernel reads it)
+    and 1 (policy inside the step kernel) call the same tc_mlp_mode on the same 13-wide observation: identical state, obs,
+    reward, mask and statistics after every one of 60 steps, ragged batch and env ranges included."""
+    import torch
+    from marl_sortingenv_b200 import _abi
+    from marl_sortingenv_b200.policy import sb3_style_init
+    n = 128 * 37 + 55
+    w = sb3_style_init(5, action_gain=1.0).numpy()
+    a_env, b_env = _press_env(n, w), _press_env(n, w)
+    a_env.set_option(_abi.OPT_TENSOR_POLICY, 1); b_env.set_option(_abi.OPT_TENSOR_POLICY, 2)
+    a_env.reset(seed=4); b_env.reset(seed=4)
+    act = torch.empty(n, dtype=torch.int64, device="cuda:0")
+    for t in range(60):
+        a_env.sample_actions(6, t, out=act)
+        a_env.step(act)
+        if t % 2:
+            b_env.step(act)
+        else:                                               # two env ranges on the current stream
+            b_env.step(act, env_range=(0, 128 * 20)); b_env.step(act, env_range=(128 * 20, n))
+        assert a_env.step_variant == "hot_tensor" and b_env.step_variant == "hot_tensor_split"
+        assert torch.equal(a_env.state, b_env.state), t
+        assert torch.equal(a_env.obs, b_env.obs) and torch.equal(a_env.reward, b_env.reward) and torch.equal(a_env.mask, b_env.mask), t
+    if a_env.stats is not None:
+        assert torch.allclose(a_env.stats, b_env.stats, rtol=1e-12, atol=1e-9)
     a_env.close(); b_env.close()
