@@ -7,9 +7,9 @@ import collections, re, subprocess, sys
 
 WANT = ["UTCHMMA", "LDTM", "UTCBAR", "UTCATOMSWS", "UBLKCP", "SYNCS", "FFMA2", "FADD2", "FFMA", "HFMA2", "REDUX", "MUFU.TANH", "MUFU.EX2",
         "MUFU.RCP", "MUFU.LG2", "IMAD", "DFMA", "DADD", "DMUL", "LDG", "STG", "LDS", "STS", "BAR", "STL", "LDL"]
-KEEP = ("step_kernelILi3ELi0ELi2ELb1ELb1ELb1ELb0ELb0E", "step_kernelILi3ELi0ELi2ELb1ELb1ELb1ELb0ELb1E", "step_kernelILi2ELi0ELi2ELb1ELb1ELb1ELb1ELb0E",
-        "step_kernelILi2ELi0ELi2ELb1ELb1ELb1ELb0ELb0E", "step_kernelILi1ELi0ELi2ELb1ELb1ELb1ELb0ELb0E", "rollout_policy_kernel", "policy_act_kernelILi29ELi22E",
-        "ppo_kernelILi29ELi22ELb1E", "ppo_kernelILi29ELi22ELb0E", "pack_fused_kernel", "tc_logits_kernel", "adam_kernel", "gae_kernel")
+KEEP = ("step_kernelILi3ELi0ELi2ELb1ELb1ELb1ELb0ELb0ELb0E", "step_kernelILi3ELi0ELi2ELb1ELb1ELb1ELb0ELb1ELb0E", "step_kernelILi2ELi0ELi2ELb1ELb1ELb1ELb1ELb0ELb0E",
+        "step_kernelILi2ELi0ELi2ELb1ELb1ELb1ELb0ELb0ELb0E", "step_kernelILi1ELi0ELi2ELb1ELb1ELb1ELb0ELb0ELb0E", "rollout_policy_kernel", "policy_act_kernelILi29ELi22E",
+        "ppo_kernelILi29ELi22ELb1E", "ppo_kernelILi29ELi22ELb0E", "pack_fused_kernel", "press_policy_kernel", "step_kernelILi2ELi0ELi2ELb1ELb1ELb1ELb0ELb0ELb1E", "tc_logits_kernel", "adam_kernel", "gae_kernel")
 
 def main():
     out = subprocess.run(["cuobjdump", "-sass", sys.argv[1]], capture_output=True, text=True).stdout.split("\n")
