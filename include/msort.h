@@ -315,6 +315,15 @@ int msort_gather_state(msort_t* h, const void* state, const int64_t* env_ids, in
                        msort_env_state_t* out, void* stream);
 int msort_import_state(msort_t* h, void* state, const msort_env_state_t* in, void* stream);
 
+/* The same actor-critic kernels on caller-given rows: any of the three (obs_dim, num_actions) shapes on any handle, rows
+ * `obs_row_stride` floats / `mask_row_stride` bytes apart (e.g. the 13-wide sort part and the 16-wide press part of Env_3's
+ * 29-wide observation: the two agents of Env_3.step(mode='model'), env_monolith.py:186-221), mask NULL = every action
+ * valid.  Dense, 16-byte aligned tensors take the TMA path, everything else plain loads.  The draw of row r is keyed by
+ * (seed, t, global env id of row r of the handle). */
+int msort_policy_eval(msort_t* h, int obs_dim, int num_actions, int64_t num_rows, const float* obs, int64_t obs_row_stride,
+                      const uint8_t* mask, int64_t mask_row_stride, const float* packed_weights, uint64_t seed, uint32_t t,
+                      int deterministic, int64_t* actions, float* logp, float* value, void* stream);
+
 /* State-wide sums for the episode-statistics all-reduce (out16: device, f64[16], overwritten):
  * 0 N, 1 sum container level, 2..6 bales A..E, 7..11 bale size sums A..E, 12 sum mean purity,
  * 13 busy presses, 14 sum running episode return, 15 sum current step. */

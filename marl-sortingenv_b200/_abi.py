@@ -182,6 +182,8 @@ SYMBOLS = {
     "msort_ppo_gradient": (C.c_int, [C.POINTER(MsortPpoBatch), C.POINTER(MsortPpoHparams), _P, _P, _P, C.c_int64, C.c_int64, _P, _P, _P]),
     "msort_ppo_update": (C.c_int, [C.POINTER(MsortPpoBatch), C.POINTER(MsortPpoHparams), _P, _P, _P, _P, _P, _P, C.c_int32,
                                    C.c_int64, _P, _P, _P]),
+    "msort_policy_eval": (C.c_int, [_P, C.c_int, C.c_int, C.c_int64, _P, C.c_int64, _P, C.c_int64, _P, C.c_uint64, C.c_uint32, C.c_int,
+                                    _P, _P, _P, _P]),
     "msort_rollout_pack": (C.c_int, [_P, _P, _P]),
     "msort_rollout_policy": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, C.c_uint64, C.c_uint32, C.c_int, _P, _P, _P, _P]),
     "msort_rollout_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, C.POINTER(MsortInfoOut), _P, C.c_uint64, C.c_uint32, C.c_int,

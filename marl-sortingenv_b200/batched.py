@@ -366,6 +366,29 @@ class BatchedEnv:
         _abi.check(self.lib, rc, "msort_policy_act")
         return a, lp, v
 
+    def policy_eval(self, packed_weights: torch.Tensor, obs: torch.Tensor, mask: torch.Tensor | None = None, *, num_actions: int,
+                    deterministic: bool = True, seed: int = 0, t: int = 0, out=None):
+        """`policy_act`'s kernels on caller-given rows (`msort_policy_eval`): `obs` [K, D] f32 may be a column slice of a wider
+        tensor (row stride > D, e.g. `env.obs[:, :13]`), `mask` [K, A] bool / uint8 likewise or None (every action valid).
+        (D, A) must be one of (13, 2), (16, 11), (29, 22).  Returns (actions int64 [K], log-prob f32 [K], value f32 [K]).
+        ref: the sort / press agents' `predict` inside Env_3.step(mode='model') (env_monolith.py:186-221)."""
+        if obs.dim() != 2 or obs.dtype != torch.float32 or not obs.is_cuda or obs.stride(1) != 1:
+            raise ValueError("policy_eval needs a 2-D float32 CUDA observation tensor with unit column stride")
+        K, D = obs.shape
+        if mask is not None and (mask.dim() != 2 or mask.shape != (K, num_actions) or mask.stride(1) != 1 or mask.element_size() != 1):
+            raise ValueError("policy_eval: mask must be [K, A] bool / uint8 with unit column stride")
+        if out is None:
+            out = (torch.empty(K, dtype=torch.int64, device=self.device), torch.empty(K, dtype=torch.float32, device=self.device),
+                   torch.empty(K, dtype=torch.float32, device=self.device))
+        a, lp, v = out
+        with torch.cuda.device(self.device):
+            rc = self.lib.msort_policy_eval(self._h, int(D), int(num_actions), int(K), _ptr(obs), int(obs.stride(0)),
+                                            _ptr(mask), 0 if mask is None else int(mask.stride(0)), _ptr(packed_weights),
+                                            int(seed) & 0xFFFFFFFFFFFFFFFF, int(t) & 0xFFFFFFFF, 1 if deterministic else 0,
+                                            _ptr(a), _ptr(lp), _ptr(v), self._stream())
+        _abi.check(self.lib, rc, "msort_policy_eval")
+        return a, lp, v
+
     def rollout_pack(self, params: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """The flat fp32 actor-critic parameter vector (`ppo.flatten_parameters`, the layout of `msort_ppo_*`) packed for the
         fused rollout kernel (`msort_rollout_pack`, one small kernel): `_abi.ROLLOUT_WEIGHTS` 32-bit words."""

@@ -742,6 +742,23 @@ extern "C" int msort_policy_act_range(msort_t* h, int64_t first_env, int64_t num
   return policy_act_impl(h, first_env, num_envs, obs, mask, packed_weights, seed, t, deterministic, actions, logp, value, stream);
 }
 
+extern "C" int msort_policy_eval(msort_t* h, int obs_dim, int num_actions, int64_t num_rows, const float* obs, int64_t obs_row_stride,
+                                 const uint8_t* mask, int64_t mask_row_stride, const float* packed_weights, uint64_t seed, uint32_t t,
+                                 int deterministic, int64_t* actions, float* logp, float* value, void* stream) {
+  if (!h || !obs || !packed_weights || !actions || !logp || !value) return fail(MSORT_E_INVALID, "msort_policy_eval: NULL argument");
+  if (!((obs_dim == 29 && num_actions == 22) || (obs_dim == 16 && num_actions == 11) || (obs_dim == 13 && num_actions == 2)))
+    return fail(MSORT_E_UNSUPPORTED, "msort_policy_eval: (obs_dim, num_actions) must be (13,2), (16,11) or (29,22)");
+  if (num_rows < 0 || obs_row_stride < obs_dim || (mask && mask_row_stride < num_actions))
+    return fail(MSORT_E_INVALID, "msort_policy_eval: bad row count / stride");
+  if (!aligned(obs, 4) || !aligned(packed_weights, 16) || !aligned(actions, 8) || !aligned(logp, 4) || !aligned(value, 4))
+    return fail(MSORT_E_INVALID, "msort_policy_eval: misaligned buffer");
+  MSORT_TRY_CUDA(launch_policy_eval(h->dev, obs_dim, num_actions, num_rows, obs, obs_row_stride, mask, mask_row_stride, packed_weights,
+                                    seed, t, deterministic, actions, logp, value, h->sm_count, (cudaStream_t)stream),
+                 "policy_eval kernel");
+  h->launches += 1;
+  return MSORT_OK;
+}
+
 extern "C" int msort_export_state(msort_t* h, const void* state, msort_env_state_t* out, void* stream) {
   if (!h || !state || !out) return fail(MSORT_E_INVALID, "msort_export_state: NULL argument");
   if (!aligned(state, 16) || !aligned(out, 8)) return fail(MSORT_E_INVALID, "msort_export_state: misaligned buffer");

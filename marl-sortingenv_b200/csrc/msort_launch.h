@@ -63,6 +63,9 @@ cudaError_t launch_rule_actions(const DevConfig& c, const void* state, int after
 cudaError_t launch_policy_act(const DevConfig& c, const float* obs, const uint8_t* mask, const float* packed,
                               int D, int A, uint64_t seed, uint32_t t, const uint32_t* t_dev, int deterministic, int64_t* actions,
                               float* logp, float* value, int sm_count, cudaStream_t st);
+cudaError_t launch_policy_eval(const DevConfig& c, int D, int A, long long rows, const float* obs, long long ld_obs, const uint8_t* mask,
+                               long long ld_mask, const float* packed, uint64_t seed, uint32_t t, int deterministic, int64_t* actions,
+                               float* logp, float* value, int sm_count, cudaStream_t st);
 cudaError_t prepare_policy_kernels();                      // current device: opt-in shared-memory sizes of the policy kernels
 cudaError_t launch_export(const DevConfig& c, const void* state, msort_env_state_t* out, cudaStream_t st);
 cudaError_t launch_gather(const DevConfig& c, const void* state, const int64_t* env_ids, long long count,

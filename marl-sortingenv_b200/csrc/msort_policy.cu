@@ -112,7 +112,7 @@ template <int D, int A>
 __global__ void __launch_bounds__(kThreads, 4)
 policy_act_kernel(const float* __restrict__ obs, const uint8_t* __restrict__ mask, const float* __restrict__ packed,
                   long long n, long long gid0, unsigned key0, unsigned key1, unsigned t_in, const unsigned* __restrict__ t_dev,
-                  int deterministic, int use_tma,
+                  int deterministic, int use_tma, long long ld_obs, long long ld_mask,
                   long long* __restrict__ actions, float* __restrict__ logp_out, float* __restrict__ value_out) {
   static_assert(D <= 32 && A <= 31, "padded layer sizes");
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -161,12 +161,18 @@ policy_act_kernel(const float* __restrict__ obs, const uint8_t* __restrict__ mas
   // plain-load fallback for a tile TMA cannot fetch (ragged last tile: its byte count need not be a multiple
   // of 16; or unaligned tensors), executed by `nthr` threads numbered `t0`
   auto plain_load = [&](long long tl, int slot, int t0, int nthr) {
+    // (also the path of msort_policy_eval: rows `ld_obs` floats / `ld_mask` bytes apart — e.g. the 13-wide sort part of a
+    //  29-wide observation — and no mask at all = every action valid)
     const long long r0 = tl * kRows;
     const int rws = (int)min((long long)kRows, n - r0);
-    const float* src = obs + r0 * D;
-    for (int e = t0; e < kRows * D; e += nthr) sm.stage[e] = e < rws * D ? src[e] : 0.f;
-    const uint8_t* ms = mask + r0 * A;
-    for (int e = t0; e < kRows * A; e += nthr) sm.mask[slot][e] = e < rws * A ? ms[e] : (uint8_t)0;
+    for (int e = t0; e < kRows * D; e += nthr) {
+      const int r = e / D, k = e - r * D;
+      sm.stage[e] = r < rws ? obs[(r0 + r) * ld_obs + k] : 0.f;
+    }
+    for (int e = t0; e < kRows * A; e += nthr) {
+      const int r = e / A, k = e - r * A;
+      sm.mask[slot][e] = r < rws ? (mask ? mask[(r0 + r) * ld_mask + k] : (uint8_t)1) : (uint8_t)0;
+    }
   };
   // layer-1 A operand of this thread's row: obs zero-padded to 32 columns, chunks [kc0, kc0 + nkc)
   auto build_a1 = [&](int kc0, int nkc) {
@@ -308,16 +314,17 @@ policy_act_kernel(const float* __restrict__ obs, const uint8_t* __restrict__ mas
 template <int D, int A>
 static cudaError_t launch_policy_act_da(const DevConfig& c, const float* obs, const uint8_t* mask, const float* packed,
                                         uint64_t seed, uint32_t t, const uint32_t* t_dev, int deterministic, int64_t* actions, float* logp,
-                                        float* value, int sm_count, cudaStream_t st) {
+                                        float* value, int sm_count, cudaStream_t st, long long ld_obs = D, long long ld_mask = A) {
   static_assert(sizeof(PolicySmem<D, A>) <= 55 * 1024, "four CTAs per SM");
   const size_t smem = sizeof(PolicySmem<D, A>);   // opt-in size set once per device by prepare_policy_kernels (msort_create)
   const long long ntiles = (c.n + kRows - 1) / kRows;
   const unsigned grid = (unsigned)std::min<long long>(ntiles, 4ll * sm_count);
   // TMA bulk copies need 16-byte aligned tile addresses (tile sizes are multiples of 16 bytes)
-  const int use_tma = ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(mask)) & 15u) == 0;
+  const int use_tma = mask && ld_obs == D && ld_mask == A &&
+                      ((reinterpret_cast<uintptr_t>(obs) | reinterpret_cast<uintptr_t>(mask)) & 15u) == 0;
   policy_act_kernel<D, A><<<grid, kThreads, smem, st>>>(obs, mask, packed, c.n, c.gid0, (unsigned)(seed & 0xffffffffu),
-                                                        (unsigned)(seed >> 32), t, t_dev, deterministic, use_tma, (long long*)actions,
-                                                        logp, value);
+                                                        (unsigned)(seed >> 32), t, t_dev, deterministic, use_tma, ld_obs, ld_mask,
+                                                        (long long*)actions, logp, value);
   return cudaGetLastError();
 }
 
@@ -335,6 +342,19 @@ cudaError_t launch_policy_act(const DevConfig& c, const float* obs, const uint8_
   if (D == 29 && A == 22) return launch_policy_act_da<29, 22>(c, obs, mask, packed, seed, t, t_dev, deterministic, actions, logp, value, sm_count, st);
   if (D == 16 && A == 11) return launch_policy_act_da<16, 11>(c, obs, mask, packed, seed, t, t_dev, deterministic, actions, logp, value, sm_count, st);
   if (D == 13 && A == 2) return launch_policy_act_da<13, 2>(c, obs, mask, packed, seed, t, t_dev, deterministic, actions, logp, value, sm_count, st);
+  return cudaErrorInvalidValue;
+}
+
+// msort_policy_eval: the same kernels on caller-given rows (any env kind's handle; strided observations, optional mask)
+cudaError_t launch_policy_eval(const DevConfig& c, int D, int A, long long rows, const float* obs, long long ld_obs, const uint8_t* mask,
+                               long long ld_mask, const float* packed, uint64_t seed, uint32_t t, int deterministic, int64_t* actions,
+                               float* logp, float* value, int sm_count, cudaStream_t st) {
+  DevConfig d = c;
+  d.n = rows;
+  if (rows <= 0) return cudaSuccess;
+  if (D == 29 && A == 22) return launch_policy_act_da<29, 22>(d, obs, mask, packed, seed, t, nullptr, deterministic, actions, logp, value, sm_count, st, ld_obs, ld_mask);
+  if (D == 16 && A == 11) return launch_policy_act_da<16, 11>(d, obs, mask, packed, seed, t, nullptr, deterministic, actions, logp, value, sm_count, st, ld_obs, ld_mask);
+  if (D == 13 && A == 2) return launch_policy_act_da<13, 2>(d, obs, mask, packed, seed, t, nullptr, deterministic, actions, logp, value, sm_count, st, ld_obs, ld_mask);
   return cudaErrorInvalidValue;
 }
 

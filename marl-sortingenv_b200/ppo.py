@@ -408,17 +408,27 @@ def modular_actions(env, sort_agent=None, press_agent=None, use_action_masking: 
     shift (env_monolith.py:114-115) and both deterministic; a missing agent falls back to a uniform draw — over
     the valid press actions when masking is on (:213-219).  action = 11 * sort_mode + press_action.
     `sort_agent` / `press_agent`: objects with SB3's `predict(obs, deterministic=True[, action_masks=])` that
-    accept batched CUDA tensors (this module's MaskablePPO), or None."""
+    accept batched CUDA tensors, or None.  Agents trained here (this module's MaskablePPO, 13 -> 2 and 16 -> 11) are
+    evaluated IN-BATCH BY THE TENSOR-CORE POLICY KERNEL (`msort_policy_eval`) straight on the 13- and 16-wide column
+    slices of the 29-wide observation and the first 11 mask columns — no copy, no eager PyTorch forward."""
     n, dev = env.num_envs, env.device
     obs = env.observe_after_shift()
     g = torch.Generator(device=dev).manual_seed(int(seed) * 1_000_003 + int(t))
+
+    def act(agent, o, m, A):
+        pol = getattr(agent, "policy", None)
+        if isinstance(pol, MaskableActorCritic) and hasattr(env, "policy_eval") and pol.pi[0].weight.shape[1] == o.shape[1] \
+                and pol.pi[4].weight.shape[0] == A and pol.pi[0].weight.is_cuda:
+            return env.policy_eval(pack_actor_critic(pol), o, m, num_actions=A, deterministic=True)[0]
+        return agent.predict(o, deterministic=True, action_masks=m)[0] if m is not None else agent.predict(o, deterministic=True)[0]
+
     if sort_agent is not None:
-        mode, _ = sort_agent.predict(obs[:, :13], deterministic=True)
+        mode = act(sort_agent, obs[:, :13], None, 2)
     else:
         mode = torch.randint(0, 2, (n,), device=dev, generator=g)
     pmask = env.action_masks()[:, :11]
     if press_agent is not None:
-        press, _ = press_agent.predict(obs[:, 13:], deterministic=True, action_masks=pmask if use_action_masking else None)
+        press = act(press_agent, obs[:, 13:], pmask if use_action_masking else None, 11)
     elif use_action_masking:
         press = torch.multinomial(pmask.float(), 1, generator=g).squeeze(1)
     else:

@@ -142,3 +142,60 @@ def test_env_ranges_on_two_streams_compose_to_the_whole_batch(kind):
     assert torch.allclose(parts.stats, whole.stats, rtol=1e-12, atol=0)      # atomics: order differs, sums agree
     with pytest.raises(Exception):
         parts.step(out_p[0], env_range=(64, 256))                             # not on a tile boundary
+
+
+def test_policy_eval_on_column_slices_and_modular_agents():
+    """`msort_policy_eval`: the actor-critic kernels on strided rows (the 13- and 16-wide parts of Env_3's 29-wide observation),
+    with and without a mask — the in-batch evaluation of the two agents of Env_3.step(mode='model') (env_monolith.py:186-221).
+    Deterministic actions equal the PyTorch fp32 argmax wherever the top-2 logit gap is clear; log-probs / values within 5e-3;
+    `ppo.modular_actions` with two agents trained here takes this path and composes 11 * mode + press."""
+    import torch
+    import marl_sortingenv_b200 as ms
+    from marl_sortingenv_b200.ppo import MaskableActorCritic, MaskablePPO, modular_actions, pack_actor_critic
+    n = 128 * 21 + 19
+    env = ms.BatchedMonolithEnv(n, max_steps=40, seed=12, info_level="episode")
+    env.reset()
+    for t in range(25):
+        env.step(env.sample_actions(3, t))
+    torch.manual_seed(4)
+    obs = env.observe_after_shift()
+    for (D, A, lo) in ((13, 2, 0), (16, 11, 13)):
+        pol = MaskableActorCritic(D, A).cuda()
+        with torch.no_grad():
+            for p in pol.parameters():
+                p.add_(0.3 * torch.randn_like(p))
+        o = obs[:, lo:lo + D]
+        m = env.action_masks()[:, :11] if A == 11 else None
+        assert o.stride(0) == 29 and not o.is_contiguous()
+        a, lp, v = env.policy_eval(pack_actor_critic(pol), o, m, num_actions=A, deterministic=True)
+        with torch.no_grad():
+            mm = m if m is not None else torch.ones((n, A), dtype=torch.bool, device="cuda")
+            lg = pol.masked_logits(o, mm)
+            ref_lp = torch.log_softmax(lg, -1)
+            top2 = lg.topk(2, dim=-1).values
+            clear = (top2[:, 0] - top2[:, 1]) > 2e-2
+            assert torch.equal(a[clear], lg.argmax(-1)[clear]) and int(clear.sum()) > n // 2
+            assert bool(mm.gather(1, a[:, None]).all())
+            assert torch.allclose(lp, ref_lp.gather(1, a[:, None]).squeeze(1), atol=5e-3)
+            assert torch.allclose(v, pol.vf(o).squeeze(1), atol=5e-3, rtol=5e-3)
+        # sampling mode draws valid actions too
+        a2, _, _ = env.policy_eval(pack_actor_critic(pol), o, m, num_actions=A, deterministic=False, seed=5, t=1)
+        assert bool(mm.gather(1, a2[:, None]).all())
+    # modular_actions with agents of this module = the kernel path; with SB3-style stand-ins = predict()
+    sort_env = ms.BatchedSortingEnv(256, max_steps=20, seed=1, info_level="none", track_stats=False)
+    press_env = ms.BatchedPressingEnv(256, max_steps=20, seed=1, info_level="none", track_stats=False)
+    sa, pa = MaskablePPO(sort_env, n_steps=4, seed=1), MaskablePPO(press_env, n_steps=4, seed=2)
+    with torch.no_grad():
+        for p in list(sa.policy.parameters()) + list(pa.policy.parameters()):
+            p.add_(0.3 * torch.randn_like(p))
+    before = env.launch_count
+    act = modular_actions(env, sa, pa, use_action_masking=True)
+    assert env.launch_count - before >= 3            # observe_after_shift + two policy_eval launches
+
+    class Eager:                                     # the same towers through predict(): the fallback path
+        def __init__(self, m): self.m = m
+        def predict(self, o, deterministic=True, action_masks=None): return self.m.predict(o, action_masks=action_masks, deterministic=deterministic)
+    ref = modular_actions(env, Eager(sa), Eager(pa), use_action_masking=True)
+    agree = float((act == ref).float().mean())
+    assert agree > 0.97, agree                       # equal except near-ties of the fp16-operand logits
+    assert bool(((act >= 0) & (act < 22)).all()) and bool(env.action_masks().gather(1, act[:, None]).all())
