@@ -19,9 +19,11 @@ SHAPES = [(32, 13), (32,), (32, 32), (32,), (2, 32), (2,)]
 
 
 def flatten_sort_policy(agent) -> torch.Tensor:
-    """Accepts: flat array/tensor of 1570 floats; a state_dict with SB3's key names; an object
+    """Accepts: flat array/tensor of 1570 floats; the path of a model archive (`.zip` with `policy.pth`); a state_dict with SB3's key names; an object
     with `.policy.state_dict()` (an SB3 PPO model) or `.state_dict()` (an SB3 policy); this package's MaskablePPO / MaskableActorCritic
     trained on BatchedSortingEnv (its policy tower)."""
+    if isinstance(agent, str):                                      # a model archive (SB3's `model.save()` layout / MaskablePPO.save)
+        return load_sb3_zip(agent if agent.endswith(".zip") else agent + ".zip")
     if isinstance(agent, (np.ndarray, list, tuple)):
         agent = torch.as_tensor(np.asarray(agent, dtype=np.float32))
     if isinstance(agent, torch.Tensor):

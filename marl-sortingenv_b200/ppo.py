@@ -388,6 +388,55 @@ class MaskablePPO:
                 self.log.append(st)
         return self
 
+    # ------------------------------------------------------------------ SB3-style archive
+    SB3_STATE_KEYS = (("mlp_extractor.policy_net.0", "pi", 0), ("mlp_extractor.policy_net.2", "pi", 2), ("action_net", "pi", 4),
+                      ("mlp_extractor.value_net.0", "vf", 0), ("mlp_extractor.value_net.2", "vf", 2), ("value_net", "vf", 4))
+
+    def sb3_state_dict(self) -> dict:
+        """The towers under the key names of an SB3 `ActorCriticPolicy.state_dict()` with `net_arch=dict(pi=[32,32], vf=[32,32])`
+        (training.py:115): mlp_extractor.policy_net.{0,2}, action_net, mlp_extractor.value_net.{0,2}, value_net."""
+        sd = {}
+        for name, tower, k in self.SB3_STATE_KEYS:
+            lin = getattr(self.policy, tower)[k]
+            sd[name + ".weight"] = lin.weight.detach().cpu().clone()
+            sd[name + ".bias"] = lin.bias.detach().cpu().clone()
+        return sd
+
+    def save(self, path: str) -> str:
+        """Write `path`(.zip) in the layout `model.save()` of SB3 produces (ref: training.py:271-287 saves
+        `./models/{prefix}_{timesteps}.zip`): a zip holding `policy.pth` (torch state-dict, SB3's key names), `data` (JSON of the
+        hyper-parameters) and `_stable_baselines3_version`.  `policy.load_sb3_zip` / `BatchedPressingEnv.set_agents(sort_agent=path)`
+        read it; `load()` restores it here.  (SB3 itself is not installed in this image, so loading the archive INTO SB3 is untested.)"""
+        import io
+        import json
+        import zipfile
+        if not path.endswith(".zip"):
+            path += ".zip"
+        buf = io.BytesIO()
+        torch.save(self.sb3_state_dict(), buf)
+        data = dict(policy_class="MaskableActorCriticPolicy", net_arch=dict(pi=[32, 32], vf=[32, 32]), activation_fn="tanh",
+                    observation_dim=self.D, num_actions=self.A, n_steps=self.n_steps, batch_size=self.batch_size, n_epochs=self.n_epochs,
+                    gamma=self.gamma, gae_lambda=self.lam, clip_range=self.clip, ent_coef=self.ent_coef, vf_coef=self.vf_coef,
+                    learning_rate=self.lr, max_grad_norm=self.max_grad_norm, num_timesteps=self.num_timesteps, seed=self.seed)
+        with zipfile.ZipFile(path, "w") as z:
+            z.writestr("policy.pth", buf.getvalue())
+            z.writestr("data", json.dumps(data))
+            z.writestr("_stable_baselines3_version", "msort (SB3 policy.pth key layout)")
+        return path
+
+    def load(self, path: str) -> "MaskablePPO":
+        """Restore the towers from an archive written by `save()` or by SB3's `model.save()` (its `policy.pth`)."""
+        import io
+        import zipfile
+        with zipfile.ZipFile(path if path.endswith(".zip") else path + ".zip") as z:
+            with z.open("policy.pth") as f:
+                sd = torch.load(io.BytesIO(f.read()), map_location="cpu", weights_only=True)
+        with torch.no_grad():
+            for name, tower, k in self.SB3_STATE_KEYS:
+                lin = getattr(self.policy, tower)[k]
+                lin.weight.copy_(sd[name + ".weight"]); lin.bias.copy_(sd[name + ".bias"])   # (views of self.flat: the kernels see them)
+        return self
+
     # ------------------------------------------------------------------ SB3-style inference
     @torch.no_grad()
     def predict(self, obs, action_masks=None, deterministic=True):

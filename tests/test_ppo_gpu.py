@@ -227,3 +227,34 @@ def test_ppo_iterations_on_the_other_env_kinds(kind):
     assert bool(model.buf["mask"].gather(2, model.buf["act"][..., None]).all())
     st = model.log[-1]
     assert all(k in st for k in ("pg", "vf", "ent", "clip_fraction")) and st["ent"] > 0
+
+
+def test_sort_agent_archive_round_trip_into_env2(tmp_path):
+    """The reference's pipeline (training.py:271-287 `model.save()` -> main.py loads the sort agent -> Env_2_Pressing.set_agents):
+    a sort agent trained here on Env_1 is saved in SB3's archive layout (policy.pth with SB3's key names), read back by
+    `load_sb3_zip` / `set_agents(sort_agent=<path>)`, and Env_2 then walks exactly the trajectory it walks with the live model."""
+    import torch
+    import marl_sortingenv_b200 as ms
+    from marl_sortingenv_b200.policy import SB3_KEYS, flatten_sort_policy, load_sb3_zip
+    from marl_sortingenv_b200.ppo import MaskablePPO
+    env = ms.BatchedSortingEnv(512, max_steps=50, seed=1, info_level="none", track_stats=False)
+    model = MaskablePPO(env, n_steps=16, batch_size=4096, n_epochs=2, seed=5)
+    model.learn(4 * 16 * 512)
+    path = model.save(str(tmp_path / "sort_32768"))
+    assert path.endswith(".zip")
+    import io, zipfile
+    with zipfile.ZipFile(path) as z:
+        assert {"policy.pth", "data", "_stable_baselines3_version"} <= set(z.namelist())
+        sd = torch.load(io.BytesIO(z.read("policy.pth")), map_location="cpu", weights_only=True)
+    assert set(SB3_KEYS) <= set(sd) and "value_net.weight" in sd and "mlp_extractor.value_net.2.bias" in sd
+    assert torch.equal(load_sb3_zip(path), flatten_sort_policy(model))
+    # a second model restores the towers from the archive (parameters are views of its flat kernel buffer)
+    m2 = MaskablePPO(ms.BatchedSortingEnv(512, max_steps=50, seed=1, info_level="none", track_stats=False), n_steps=16, seed=99).load(path)
+    assert torch.equal(m2.flat, model.flat)
+    a, b = (ms.BatchedPressingEnv(128 * 9 + 3, max_steps=30, seed=8, info_level="episode") for _ in range(2))
+    a.set_agents(sort_agent=path); b.set_agents(sort_agent=model)
+    a.reset(); b.reset()
+    for t in range(40):
+        act = a.sample_actions(4, t)
+        a.step(act); b.step(act)
+    assert torch.equal(a.state, b.state) and torch.equal(a.obs, b.obs)
