@@ -200,20 +200,25 @@ class MaskablePPO:
             env.rollout_policy(self._packed_fused, seed=self.seed, t=t0, obs=b["obs"][0], mask=b["mask"][0],
                                out=(b["act"][0], b["logp"][0], b["val"][0]))
             keep = (env.reward, env.terminated)
-            for t in range(T):
-                last = t + 1 == T
-                oo, om = self._tail if last else (b["obs"][t + 1], b["mask"][t + 1])
-                nxt = self._spare if last else (b["act"][t + 1], b["logp"][t + 1], b["val"][t + 1])
-                env.reward, env.terminated = b["rew"][t], b["done"][t]
-                try:
-                    env.rollout_step(b["act"][t], self._packed_fused, self.seed, t0 + t + 1, nxt, out_obs=oo, out_mask=om)
-                except _abi.MsortError as e:
-                    env.reward, env.terminated = keep
-                    if t == 0 and e.code == _abi.E_UNSUPPORTED:       # refused before anything was launched: two kernels per step
-                        self.fused_rollout = False
-                        return self._rollout_body(packed, t0)
-                    raise
-            env.reward, env.terminated = keep
+            refused = False
+            try:
+                for t in range(T):
+                    last = t + 1 == T
+                    oo, om = self._tail if last else (b["obs"][t + 1], b["mask"][t + 1])
+                    nxt = self._spare if last else (b["act"][t + 1], b["logp"][t + 1], b["val"][t + 1])
+                    env.reward, env.terminated = b["rew"][t], b["done"][t]
+                    try:
+                        env.rollout_step(b["act"][t], self._packed_fused, self.seed, t0 + t + 1, nxt, out_obs=oo, out_mask=om)
+                    except _abi.MsortError as e:
+                        if t == 0 and e.code == _abi.E_UNSUPPORTED:   # refused before anything was launched: two kernels per step
+                            refused = True
+                            break
+                        raise
+            finally:
+                env.reward, env.terminated = keep                     # whatever happens, the env's own output buffers come back
+            if refused:
+                self.fused_rollout = False
+                return self._rollout_body(packed, t0)
             return
         cur = torch.cuda.current_stream(self.dev)
         streams = self._streams or [cur]
