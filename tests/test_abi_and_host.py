@@ -132,3 +132,37 @@ def test_load_sb3_zip_layout(tmp_path):
         z.writestr("data", "{}")
     w = load_sb3_zip(str(path))
     assert w.numel() == 1570 and torch.equal(w[416:448], sd[SB3_KEYS[1]]) and torch.equal(w[1504:1568].reshape(2, 32), sd[SB3_KEYS[4]])
+
+
+def test_handle_free_entry_points_reject_bad_arguments_without_a_gpu():
+    """msort_ppo_* and msort_rollout_pack take no handle: their argument checks run before any CUDA call, so they are testable
+    here — wrong struct sizes, unsupported (obs_dim, num_actions), NULL buffers and misaligned pointers come back as error
+    codes with a message, never as a crash."""
+    import ctypes as C
+    from marl_sortingenv_b200 import _abi
+    lib = _abi.load_library()
+    assert lib.msort_ppo_param_count(29, 22) == 2 * (32 * 29 + 32 + 32 * 32 + 32) + (22 * 32 + 22) + (32 + 1) == 4791
+    assert lib.msort_ppo_param_count(13, 2) == 2 * (32 * 13 + 32 + 32 * 32 + 32) + (2 * 32 + 2) + 33
+    buf = (C.c_float * 64)()
+    p = C.cast(buf, C.c_void_p)
+    good = _abi.MsortPpoBatch(C.sizeof(_abi.MsortPpoBatch), 29, 22, 0, 16, p, p, p, p, p, p)
+    hp = _abi.MsortPpoHparams(C.sizeof(_abi.MsortPpoHparams), 1, 0.2, 0.5, 0.05, 3e-4, 0.9, 0.999, 1e-5, 0.5)
+    assert lib.msort_ppo_forward(None, p, p, p, None) == _abi.E_INVALID
+    assert lib.msort_ppo_forward(C.byref(good), None, p, p, None) == _abi.E_INVALID
+    bad = _abi.MsortPpoBatch(C.sizeof(_abi.MsortPpoBatch) - 4, 29, 22, 0, 16, p, p, p, p, p, p)
+    assert lib.msort_ppo_forward(C.byref(bad), p, p, p, None) == _abi.E_INVALID
+    dims = _abi.MsortPpoBatch(C.sizeof(_abi.MsortPpoBatch), 29, 11, 0, 16, p, p, p, p, p, p)
+    assert lib.msort_ppo_forward(C.byref(dims), p, p, p, None) == _abi.E_UNSUPPORTED
+    assert b"obs_dim" in lib.msort_last_error()
+    noadv = _abi.MsortPpoBatch(C.sizeof(_abi.MsortPpoBatch), 29, 22, 0, 16, p, p, p, p, None, p)
+    assert lib.msort_ppo_gradient(C.byref(noadv), C.byref(hp), p, p, None, 0, 16, p, None, None) == _abi.E_INVALID
+    assert lib.msort_ppo_gradient(C.byref(good), C.byref(hp), p, p, None, 8, 16, p, None, None) == _abi.E_INVALID    # first + count > rows
+    badhp = _abi.MsortPpoHparams(4, 1, 0.2, 0.5, 0.05, 3e-4, 0.9, 0.999, 1e-5, 0.5)
+    assert lib.msort_ppo_gradient(C.byref(good), C.byref(badhp), p, p, None, 0, 16, p, None, None) == _abi.E_INVALID
+    assert lib.msort_ppo_update(C.byref(good), C.byref(hp), p, p, p, p, p, None, 1, 8, p, None, None) == _abi.E_INVALID   # no permutations
+    assert lib.msort_ppo_gae(0, 16, p, p, p, p, 0.99, 0.95, p, p, None) == _abi.E_INVALID
+    assert lib.msort_rollout_pack(None, p, None) == _abi.E_INVALID
+    assert lib.msort_rollout_pack(p, C.c_void_p(C.addressof(buf) + 4), None) == _abi.E_INVALID                      # 16-byte alignment
+    for fn in ("msort_rollout_step", "msort_rollout_policy", "msort_policy_eval"):                                   # NULL handle
+        args = [0 if t in (C.c_int, C.c_int64, C.c_uint32, C.c_uint64) else None for t in _abi.SYMBOLS[fn][1]]
+        assert getattr(lib, fn)(*args) == _abi.E_INVALID, fn
