@@ -412,6 +412,9 @@ typedef struct msort_ppo_hparams {
 } msort_ppo_hparams_t;
 
 int msort_ppo_param_count(int obs_dim, int num_actions);
+/* floats of the `scratch` buffer msort_ppo_gradient / msort_ppo_update need (16-byte aligned device memory): the minibatch's
+ * advantage statistics and both towers' weights transposed into the gradient kernel's shared-memory order */
+int msort_ppo_scratch_floats(int obs_dim, int num_actions);
 /* log-prob of every row's action and the value estimate under `params` (forward only; either output nullable) */
 int msort_ppo_forward(const msort_ppo_batch_t* batch, const float* params, float* logp_out, float* value_out, void* stream);
 /* GAE(lambda): rew / val / done [T, n] (done = terminated, u8), last_val [n] -> adv, ret [T, n] */
@@ -419,7 +422,7 @@ int msort_ppo_gae(int32_t T, int64_t n, const float* rew, const float* val, cons
                   float gamma, float gae_lambda, float* adv, float* ret, void* stream);
 /* Gradient of the PPO loss (clipped surrogate + vf_coef * value MSE - ent_coef * entropy, means over the minibatch) for
  * rows idx[first .. first + count) (idx NULL: the rows themselves), ADDED into grads; stats (nullable, 5 floats) +=
- * {sum surrogate loss, sum squared value error, sum entropy, clipped rows, rows}; scratch: 2 floats. */
+ * {sum surrogate loss, sum squared value error, sum entropy, clipped rows, rows}; scratch: msort_ppo_scratch_floats() floats. */
 int msort_ppo_gradient(const msort_ppo_batch_t* batch, const msort_ppo_hparams_t* hp, const float* params, float* grads,
                        const int64_t* idx, int64_t first, int64_t count, float* scratch, float* stats, void* stream);
 /* The whole update: n_epochs passes over the buffer in minibatches of batch_size rows taken from perms[e] (n_epochs

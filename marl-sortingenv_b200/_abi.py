@@ -177,6 +177,7 @@ SYMBOLS = {
     "msort_launch_count": (C.c_int64, [_P]),
     "msort_step_variant": (C.c_int, [_P]),
     "msort_ppo_param_count": (C.c_int, [C.c_int, C.c_int]),
+    "msort_ppo_scratch_floats": (C.c_int, [C.c_int, C.c_int]),
     "msort_ppo_forward": (C.c_int, [C.POINTER(MsortPpoBatch), _P, _P, _P, _P]),
     "msort_ppo_gae": (C.c_int, [C.c_int32, C.c_int64, _P, _P, _P, _P, C.c_float, C.c_float, _P, _P, _P]),
     "msort_ppo_gradient": (C.c_int, [C.POINTER(MsortPpoBatch), C.POINTER(MsortPpoHparams), _P, _P, _P, C.c_int64, C.c_int64, _P, _P, _P]),

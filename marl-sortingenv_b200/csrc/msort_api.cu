@@ -814,6 +814,7 @@ static int ppo_check_batch(const msort_ppo_batch_t* b, bool update, const char* 
 }
 
 extern "C" int msort_ppo_param_count(int obs_dim, int num_actions) { return ppo_param_count(obs_dim, num_actions); }
+extern "C" int msort_ppo_scratch_floats(int obs_dim, int num_actions) { return ppo_scratch_floats(obs_dim, num_actions); }
 
 extern "C" int msort_ppo_forward(const msort_ppo_batch_t* batch, const float* params, float* logp_out, float* value_out, void* stream) {
   int rc = ppo_check_batch(batch, false, "msort_ppo_forward");
@@ -837,6 +838,7 @@ extern "C" int msort_ppo_gradient(const msort_ppo_batch_t* batch, const msort_pp
   if (!hp || hp->struct_size != sizeof(msort_ppo_hparams_t)) return fail(MSORT_E_INVALID, "msort_ppo_gradient: bad hparams");
   if (!params || !grads || !scratch || count <= 0 || first < 0 || first + count > batch->num_rows)
     return fail(MSORT_E_INVALID, "msort_ppo_gradient: bad argument");
+  if (!aligned(scratch, 16)) return fail(MSORT_E_INVALID, "msort_ppo_gradient: scratch must be 16-byte aligned");
   MSORT_TRY_CUDA(ppo_gradient(*batch, *hp, params, grads, idx, first, count, scratch, stats, (cudaStream_t)stream), "ppo gradient kernel");
   return MSORT_OK;
 }
@@ -849,6 +851,7 @@ extern "C" int msort_ppo_update(const msort_ppo_batch_t* batch, const msort_ppo_
   if (!hp || hp->struct_size != sizeof(msort_ppo_hparams_t)) return fail(MSORT_E_INVALID, "msort_ppo_update: bad hparams");
   if (!params || !grads || !adam_m || !adam_v || !step || !perms || !scratch || n_epochs <= 0 || batch_size <= 0)
     return fail(MSORT_E_INVALID, "msort_ppo_update: bad argument");
+  if (!aligned(scratch, 16)) return fail(MSORT_E_INVALID, "msort_ppo_update: scratch must be 16-byte aligned");
   const int P = ppo_param_count(batch->obs_dim, batch->num_actions);
   const long long N = batch->num_rows;
   for (int e = 0; e < n_epochs; ++e)

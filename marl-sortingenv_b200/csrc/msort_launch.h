@@ -75,6 +75,7 @@ cudaError_t launch_stats(const DevConfig& c, const void* state, double* out16, i
 
 // ---- msort_ppo.cu: the update half of the GPU-resident MaskablePPO loop
 int ppo_param_count(int D, int A);
+int ppo_scratch_floats(int D, int A);
 cudaError_t ppo_forward(const msort_ppo_batch_t& b, const float* params, float* logp_out, float* value_out, cudaStream_t st);
 cudaError_t ppo_gradient(const msort_ppo_batch_t& b, const msort_ppo_hparams_t& hp, const float* params, float* grads,
                          const int64_t* idx, long long first, long long count, float* adv_stats, float* stats, cudaStream_t st);

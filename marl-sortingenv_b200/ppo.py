@@ -138,7 +138,7 @@ class MaskablePPO:
             assert P == self.flat.numel(), (P, self.flat.numel())
             z = lambda *sh, dt=torch.float32: torch.zeros(*sh, dtype=dt, device=self.dev)   # noqa: E731
             self._grads, self._m, self._v, self._step = z(P), z(P), z(P), z(1, dt=torch.int32)
-            self._scratch, self._stats = z(2), z(5)
+            self._scratch, self._stats = z(int(self.lib.msort_ppo_scratch_floats(self.D, self.A))), z(5)
             self._hp = _abi.MsortPpoHparams(C.sizeof(_abi.MsortPpoHparams), 1, clip_range, vf_coef, ent_coef, learning_rate,
                                             0.9, 0.999, 1e-5, max_grad_norm)
         self._graph = None

@@ -143,8 +143,9 @@ def test_handle_free_entry_points_reject_bad_arguments_without_a_gpu():
     lib = _abi.load_library()
     assert lib.msort_ppo_param_count(29, 22) == 2 * (32 * 29 + 32 + 32 * 32 + 32) + (22 * 32 + 22) + (32 + 1) == 4791
     assert lib.msort_ppo_param_count(13, 2) == 2 * (32 * 13 + 32 + 32 * 32 + 32) + (2 * 32 + 2) + 33
+    assert lib.msort_ppo_scratch_floats(29, 22) > 2 * 4791 // 2 and lib.msort_ppo_scratch_floats(29, 11) == 0
     buf = (C.c_float * 64)()
-    p = C.cast(buf, C.c_void_p)
+    p = C.c_void_p((C.addressof(buf) + 15) // 16 * 16)                  # a 16-byte aligned address inside the buffer
     good = _abi.MsortPpoBatch(C.sizeof(_abi.MsortPpoBatch), 29, 22, 0, 16, p, p, p, p, p, p)
     hp = _abi.MsortPpoHparams(C.sizeof(_abi.MsortPpoHparams), 1, 0.2, 0.5, 0.05, 3e-4, 0.9, 0.999, 1e-5, 0.5)
     assert lib.msort_ppo_forward(None, p, p, p, None) == _abi.E_INVALID
@@ -162,7 +163,7 @@ def test_handle_free_entry_points_reject_bad_arguments_without_a_gpu():
     assert lib.msort_ppo_update(C.byref(good), C.byref(hp), p, p, p, p, p, None, 1, 8, p, None, None) == _abi.E_INVALID   # no permutations
     assert lib.msort_ppo_gae(0, 16, p, p, p, p, 0.99, 0.95, p, p, None) == _abi.E_INVALID
     assert lib.msort_rollout_pack(None, p, None) == _abi.E_INVALID
-    assert lib.msort_rollout_pack(p, C.c_void_p(C.addressof(buf) + 4), None) == _abi.E_INVALID                      # 16-byte alignment
+    assert lib.msort_rollout_pack(p, C.c_void_p(p.value + 4), None) == _abi.E_INVALID                                # 16-byte alignment
     for fn in ("msort_rollout_step", "msort_rollout_policy", "msort_policy_eval"):                                   # NULL handle
         args = [0 if t in (C.c_int, C.c_int64, C.c_uint32, C.c_uint64) else None for t in _abi.SYMBOLS[fn][1]]
         assert getattr(lib, fn)(*args) == _abi.E_INVALID, fn

@@ -103,7 +103,7 @@ def test_native_forward_and_gradient_match_torch_autograd(D, A, rows):
     hp = _abi.MsortPpoHparams(C.sizeof(_abi.MsortPpoHparams), 1, 0.2, 0.5, 0.05, 3e-4, 0.9, 0.999, 1e-5, 0.5)
     P = lib.msort_ppo_param_count(D, A)
     assert P == flat.numel()
-    grads, scratch, stats = torch.zeros(P, device="cuda"), torch.zeros(2, device="cuda"), torch.zeros(5, device="cuda")
+    grads, scratch, stats = torch.zeros(P, device="cuda"), torch.zeros(lib.msort_ppo_scratch_floats(D, A), device="cuda"), torch.zeros(5, device="cuda")
     _abi.check(lib, lib.msort_ppo_gradient(C.byref(c["batch"]), C.byref(hp), p(flat), p(grads), p(perm), first, count, p(scratch),
                                            p(stats), st), "gradient")
     idx = perm[first:first + count]
@@ -140,7 +140,7 @@ def test_native_update_matches_torch_adam_steps():
     hp = _abi.MsortPpoHparams(C.sizeof(_abi.MsortPpoHparams), 1, 0.2, 0.5, 0.05, 3e-3, 0.9, 0.999, 1e-5, 0.5)
     P = flat.numel()
     z = lambda k, dt=torch.float32: torch.zeros(k, device="cuda", dtype=dt)      # noqa: E731
-    grads, m, v, step, scratch, stats = z(P), z(P), z(P), z(1, torch.int32), z(2), z(5)
+    grads, m, v, step, scratch, stats = z(P), z(P), z(P), z(1, torch.int32), z(lib.msort_ppo_scratch_floats(D, A)), z(5)
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     _abi.check(lib, lib.msort_ppo_update(C.byref(c["batch"]), C.byref(hp), p(flat), p(grads), p(m), p(v), p(step), p(perms), 2, bs,
                                          p(scratch), p(stats), st), "update")
