@@ -33,7 +33,8 @@ extern "C" {
 
 /* ABI history: 2 telemetry (msort_gather_state, reward terms) and msort_policy_act; 3 msort_observe_after_shift,
  * msort_step_variant, obs / mask must be 16-byte aligned; 4 msort_step_range, msort_policy_act_range;
- * 5 msort_set_option, MSORT_STEP_HOT_TENSOR, msort_step_host, msort_generate_streams, msort_ppo_*, msort_rollout_*. */
+ * 5 msort_set_option, MSORT_STEP_HOT_TENSOR, msort_step_host, msort_generate_streams, msort_ppo_* (scratch sized by
+ * msort_ppo_scratch_floats), msort_rollout_pack / _step / _policy, msort_policy_eval, MSORT_OPT_TENSOR_POLICY 2 (split form). */
 #define MSORT_ABI_VERSION 5
 
 /* ------------------------------------------------------------------ enums */
