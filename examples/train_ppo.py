@@ -7,7 +7,7 @@ Protocol of the reference (main.py:42-52): max_steps=200, noise 0, bale size 200
 deterministic masked policy, 200 steps.  Published returns of the reference (CPU, 100 000
 timesteps): PPO Monolith 32.77 +- 1.12, Rule-Based 44.03 +- 1.10 (utils/benchmark_plot_summary.py).
 On one B200 2 048 envs x 20 M timesteps take ~2.5 s and reach ~85 (round 1: ~30 s): the rollout is one CUDA graph of fused
-policy + step kernels, the update three hand-written kernels per minibatch (marl-sortingenv_b200/csrc/msort_ppo.cu).
+policy + step kernels, the update four hand-written kernels per minibatch (marl-sortingenv_b200/csrc/msort_ppo.cu).
 """
 import os
 import sys
