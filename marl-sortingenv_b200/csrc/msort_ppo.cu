@@ -27,6 +27,9 @@ namespace msort {
 
 namespace {
 
+#ifndef MSORT_EXP_PPO_NOATOMIC
+#define MSORT_EXP_PPO_NOATOMIC 0
+#endif
 constexpr int kRows = 128;     // rows per CTA == threads per CTA
 constexpr int kH = 32;         // hidden width of every tower layer
 constexpr int kLd = 36;        // row stride of the per-row shared buffers
@@ -131,10 +134,17 @@ __device__ __forceinline__ void weight_grad(const float* __restrict__ dz, const 
     accb += d;
   }
   if (o < O) {
+#if MSORT_EXP_PPO_NOATOMIC      // timing experiment: no global traffic for the weight gradients at all (only a NaN would be stored)
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (i0 + k < I && acc[k] != acc[k]) gw[o * I + i0 + k] = acc[k];
+    if (i0 == 0 && accb != accb) gb[o] = accb;
+#else
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       if (i0 + k < I) atomicAdd(&gw[o * I + i0 + k], acc[k]);
     if (i0 == 0) atomicAdd(&gb[o], accb);
+#endif
   }
 }
 
