@@ -55,7 +55,7 @@ struct PpoArgs {
   const float* old_logp; const float* adv; const float* ret;
   const long long* idx;        // minibatch row indices (nullptr: rows first .. first + count)
   long long first, count;
-  const float* adv_stats;      // {mean, 1 / (std + 1e-8)} of the minibatch's advantages, or nullptr (no normalisation)
+  const double* adv_sums;      // {sum a, sum a^2} of the minibatch's advantages (adv_sums_kernel), or nullptr (no normalisation)
   const float* image;          // GRAD: both towers' weights already transposed / padded in the kernel's shared-memory order
                                // (ppo_image_kernel, 2 * PpoSmem::kImage floats) or nullptr (each CTA gathers them from `params`)
   float clip, vf_coef, ent_coef, inv_count;
@@ -191,6 +191,7 @@ ppo_image_kernel(const float* __restrict__ params, float* __restrict__ image) {
   constexpr int AP = S::AP, N = S::kImage;
   const PpoLayout L = ppo_layout(D, A);
   const int e0 = blockIdx.x * 256 + threadIdx.x;
+  if (e0 == 0) { double* sums = reinterpret_cast<double*>(image) - 2; sums[0] = 0.0; sums[1] = 0.0; }   // the advantage sums in front of the image
   if (e0 >= 2 * N) return;
   const int tower = e0 / N;
   int e = e0 - tower * N;
@@ -293,7 +294,11 @@ ppo_kernel(const __grid_constant__ PpoArgs a) {
     if (live && a.logp_out) a.logp_out[row] = logp_a;
   } else {
     float advn = live ? a.adv[row] : 0.f;
-    if (a.adv_stats) advn = (advn - a.adv_stats[0]) * a.adv_stats[1];
+    if (a.adv_sums) {        // (a - mean) / (std + 1e-8), unbiased std like torch.Tensor.std
+      const double sa = a.adv_sums[0], mean = sa / (double)a.count;
+      const double var = a.count > 1 ? fmax(0.0, (a.adv_sums[1] - sa * mean) / (double)(a.count - 1)) : 0.0;
+      advn = (advn - (float)mean) * (float)(1.0 / (sqrt(var) + 1e-8));
+    }
     const float ratio = __expf(logp_a - (live ? a.old_logp[row] : 0.f));
     const bool clipped = (advn > 0.f && ratio > 1.f + a.clip) || (advn < 0.f && ratio < 1.f - a.clip);
     const float surr = fminf(advn * ratio, advn * fminf(fmaxf(ratio, 1.f - a.clip), 1.f + a.clip));
@@ -381,12 +386,13 @@ ppo_kernel(const __grid_constant__ PpoArgs a) {
   weight_grad<D, kH>(sm.dz3, sm.x, rows, a.grads + L.vf_w1, a.grads + L.vf_b1, sm.gstage, tid);
 }
 
-// mean and 1 / (std + 1e-8) (unbiased std, like torch.Tensor.std) of adv[idx[first .. first + count)] -> out[0..1]
+// sum and sum of squares of adv[idx[first .. first + count)] added into out[0..1] (float64; zeroed by ppo_image_kernel, which runs
+// just before on the same stream): a grid of CTAs with a grid-stride loop — one CTA alone needed ~0.25 us per 1 024 rows
 __global__ void __launch_bounds__(1024)
-adv_stats_kernel(const float* __restrict__ adv, const long long* __restrict__ idx, long long first, long long count, float* __restrict__ out) {
+adv_sums_kernel(const float* __restrict__ adv, const long long* __restrict__ idx, long long first, long long count, double* __restrict__ out) {
   __shared__ double sh[2][32];
   double s = 0.0, q = 0.0;
-  for (long long j = threadIdx.x; j < count; j += 1024) {
+  for (long long j = (long long)blockIdx.x * 1024 + threadIdx.x; j < count; j += (long long)gridDim.x * 1024) {
     const double v = (double)adv[idx ? idx[first + j] : first + j];
     s += v; q += v * v;
   }
@@ -394,13 +400,11 @@ adv_stats_kernel(const float* __restrict__ adv, const long long* __restrict__ id
   for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
   if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = q; }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    s = 0.0; q = 0.0;
-    for (int w = 0; w < 32; ++w) { s += sh[0][w]; q += sh[1][w]; }
-    const double mean = s / (double)count;
-    const double var = count > 1 ? fmax(0.0, (q - s * mean) / (double)(count - 1)) : 0.0;
-    out[0] = (float)mean;
-    out[1] = (float)(1.0 / (sqrt(var) + 1e-8));
+  if (threadIdx.x < 32) {
+    s = sh[0][threadIdx.x]; q = sh[1][threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if (threadIdx.x == 0) { atomicAdd(&out[0], s); atomicAdd(&out[1], q); }
   }
 }
 
@@ -507,12 +511,7 @@ cudaError_t ppo_forward(const msort_ppo_batch_t& b, const float* params, float* 
 
 cudaError_t ppo_gradient(const msort_ppo_batch_t& b, const msort_ppo_hparams_t& hp, const float* params, float* grads,
                          const int64_t* idx, long long first, long long count, float* adv_stats, float* stats, cudaStream_t st) {
-  if (hp.normalize_advantage) {
-    adv_stats_kernel<<<1, 1024, 0, st>>>(b.adv, (const long long*)idx, first, count, adv_stats);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-  }
-  float* image = adv_stats + 4;              // 16-byte aligned when the scratch buffer is
+  float* image = adv_stats + 4;              // scratch: two float64 advantage sums (16 bytes), then the weight image
   {
     const int D = b.obs_dim, A = b.num_actions, n = ppo_image_floats(D, A);
     const unsigned g = (unsigned)((n + 255) / 256);
@@ -522,10 +521,16 @@ cudaError_t ppo_gradient(const msort_ppo_batch_t& b, const msort_ppo_hparams_t& 
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
   }
+  if (hp.normalize_advantage) {              // after the image kernel: it zeroes the sums
+    const unsigned g = (unsigned)std::min<long long>(64, (count + 4095) / 4096);
+    adv_sums_kernel<<<g, 1024, 0, st>>>(b.adv, (const long long*)idx, first, count, reinterpret_cast<double*>(adv_stats));
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
   PpoArgs a = make_args(b, params);
   a.image = image;
   a.grads = grads; a.idx = (const long long*)idx; a.first = first; a.count = count;
-  a.adv_stats = hp.normalize_advantage ? adv_stats : nullptr;
+  a.adv_sums = hp.normalize_advantage ? reinterpret_cast<const double*>(adv_stats) : nullptr;
   a.clip = hp.clip_range; a.vf_coef = hp.vf_coef; a.ent_coef = hp.ent_coef; a.inv_count = 1.0f / (float)count; a.stats = stats;
   return launch_ppo_da<true>(b.obs_dim, b.num_actions, a, st);
 }
