@@ -8,7 +8,8 @@ import marl_sortingenv_b200 as ms
 kind = sys.argv[1] if len(sys.argv) > 1 else "mono"
 n = 1 << 20
 cls = {"mono": ms.BatchedMonolithEnv, "sort": ms.BatchedSortingEnv, "press": ms.BatchedPressingEnv}[kind]
-env = cls(n, max_steps=50, seed=42, info_level="episode")
+import os
+env = cls(n, max_steps=50, seed=42, info_level="none", track_stats=False) if os.environ.get("NOSTATS") else cls(n, max_steps=50, seed=42, info_level="episode")
 if kind == "press":
     from marl_sortingenv_b200.policy import sb3_style_init
     env.set_sort_policy(sb3_style_init(0))
